@@ -1,0 +1,221 @@
+// Internal declarations shared by the translation units of libathena_cuda.
+// Nothing here is part of the ABI (see include/athena_cuda.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "athena_cuda.h"
+
+#define ATHENA_API extern "C" __attribute__((visibility("default")))
+
+namespace athena {
+
+void set_error(const char* fmt, ...);
+
+#define ATH_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (expr);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      ::athena::set_error("%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                          __LINE__);                                                \
+      return ATHENA_ERR_CUDA;                                                       \
+    }                                                                               \
+  } while (0)
+
+#define ATH_REQUIRE(cond, code, ...)     \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::athena::set_error(__VA_ARGS__);  \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+#define ATH_TRY(expr)          \
+  do {                         \
+    int rc_ = (expr);          \
+    if (rc_ != 0) return rc_;  \
+  } while (0)
+
+struct Context {
+  bool ready = false;
+  int device = 0;
+  int sm_count = 0;
+  size_t total_mem = 0;
+  size_t max_smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  std::atomic<int64_t> launches{0};
+  cudaEvent_t ev_start[16] = {};
+  cudaEvent_t ev_stop[16] = {};
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  bool profiling = false;
+};
+Context& ctx();
+int ensure_init();
+
+void prof_mark(const char* tag);  // no-op unless profiling is on
+
+// Count + check a kernel launch.  Use right after <<<>>>.
+#define ATH_LAUNCHED() ATH_LAUNCHED_T(__func__)
+#define ATH_LAUNCHED_T(tag)                                                    \
+  do {                                                                         \
+    ::athena::ctx().launches.fetch_add(1, std::memory_order_relaxed);          \
+    if (::athena::ctx().profiling) ::athena::prof_mark(tag);                   \
+    cudaError_t e_ = cudaPeekAtLastError();                                    \
+    if (e_ != cudaSuccess) {                                                   \
+      ::athena::set_error("kernel launch: %s (%s:%d)", cudaGetErrorString(e_), \
+                          __FILE__, __LINE__);                                 \
+      return ATHENA_ERR_CUDA;                                                  \
+    }                                                                          \
+  } while (0)
+
+// Grow-only device buffer: layers keep their activations in these so that a
+// training loop performs no cudaMalloc after the first (largest) batch.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+enum class Kind : int { Batch = 1, Layer = 2, Network = 3 };
+
+struct Object {
+  Kind kind;
+  explicit Object(Kind k) : kind(k) {}
+  virtual ~Object() {}
+};
+
+athena_handle_t register_object(Object* obj);  // takes ownership
+Object* lookup_object(athena_handle_t h, Kind kind);
+int destroy_object(athena_handle_t h, Kind kind);
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
+
+// ---------------------------------------------------------------------------
+// graph batch (batch.cu)
+// ---------------------------------------------------------------------------
+struct BucketSet {
+  int min_deg = 0, max_deg = 0, D = 0;
+  DevBuf bkt;      // [V]   0-based bucket id
+  DevBuf perm;     // [V]   stable bucket permutation
+  DevBuf bkt_ptr;  // [D+1]
+  DevBuf scratch;  // block histograms
+};
+
+struct Batch : Object {
+  Batch() : Object(Kind::Batch) {}
+  int32_t B = 0;
+  int64_t V = 0, Z = 0, E = 0;
+  DevBuf meta;  // int32: nv[B], ne[B], voff[B+1], zoff[B+1], eoff[B+1]
+  const int32_t* nv = nullptr;
+  const int32_t* ne = nullptr;
+  const int32_t* voff = nullptr;
+  const int32_t* zoff = nullptr;
+  const int32_t* eoff = nullptr;
+  DevBuf raw;  // staging of adj_ia / adj_ja when they arrive from the host
+  DevBuf ints; // row_ptr, col, eid, deg, vgraph, csc_ptr, csc_src, csc_ent, cursor
+  int32_t* row_ptr = nullptr;
+  int32_t* col = nullptr;
+  int32_t* eid = nullptr;
+  int32_t* deg = nullptr;
+  int32_t* vgraph = nullptr;
+  int32_t* csc_ptr = nullptr;
+  int32_t* csc_src = nullptr;
+  int32_t* csc_ent = nullptr;
+  DevBuf coef_buf;
+  float* coef = nullptr;
+  DevBuf scratch;
+  DevBuf status;  // int32[4]: [0] first bad graph + 1, [1] long-column count
+  std::vector<std::unique_ptr<BucketSet>> buckets;
+  BucketSet* find_buckets(int min_deg, int max_deg) const;
+};
+int batch_bucketize(Batch* b, int min_deg, int max_deg, BucketSet** out);
+
+// ---------------------------------------------------------------------------
+// kernels (spmm.cu / dense.cu / misc.cu): host launchers, all on ctx().stream
+// ---------------------------------------------------------------------------
+
+// out[v, 0:F] (+)= sum_{w in row v} c_w * X[col[w], 0:F]   (entries with col < 0 skipped)
+// coef == nullptr -> c_w = 1.  accumulate != 0 -> adds to the existing out.
+// tail != nullptr  -> out[v, F:F+tail_n] = tail[v, 0:tail_n]  (plain copy).
+int launch_aggregate(const int32_t* row_ptr, const int32_t* col, const float* coef,
+                     const float* X, int ldx, int F, float* out, int ldo, int64_t V,
+                     int accumulate, const float* tail, int tail_n);
+
+struct GroupDesc {
+  // rows are visited through perm (nullptr = identity) in tiles that never
+  // straddle a group boundary; group g owns rows [ptr[g], ptr[g+1]) of the
+  // permuted order and weight matrix Wbase + g * wstride.
+  const int32_t* perm = nullptr;
+  const int32_t* ptr = nullptr;  // device [D+1]; nullptr = single group [0, M)
+  int D = 1;
+  int64_t wstride = 0;
+  int scale_by_group = 0;  // divide the A rows (NN/TN) or the result (NT) by (g+1)
+};
+
+// C[m, 0:N] = act( (A[m, 0:K] / s_m) . W_g[K, N] )          (row-major W)
+int launch_gemm_nn(const float* A, int lda, const float* W, float* C, int ldc, int64_t M,
+                   int N, int K, int act, const GroupDesc& gd);
+// C[m, 0:N] = ( A[m, 0:K] . W_g[N, K]^T ) / s_m              (row-major W, transposed use)
+int launch_gemm_nt(const float* A, int lda, const float* W, float* C, int ldc, int64_t M,
+                   int N, int K, const GroupDesc& gd);
+// dW_g[k, n] += sum_{m in group g} (A[m, k] / s_m) * G[m, n]  (deterministic two-pass)
+int launch_gemm_tn(const float* A, int lda, const float* G, int ldg, float* dW, int64_t M,
+                   int N, int K, const GroupDesc& gd, DevBuf& scratch);
+
+// elementwise / row-wise helpers
+int launch_act_bwd(int act, const float* Y, const float* G, float* out, int64_t M, int N);
+int launch_softmax_rows(float* Y, int64_t M, int N);
+// out[s, 0:N] (+)= sum_{v in graph s} Y[v, 0:N]
+int launch_segment_sum(const float* Y, int N, const int32_t* voff, int32_t B, float* out,
+                       int accumulate);
+// dY[v, :] = act_bwd(S[v, :], gout[vgraph[v], :])
+int launch_readout_bwd(int act, const float* S, const float* gout, const int32_t* vgraph,
+                       float* dY, int64_t V, int N);
+int launch_add_inplace(float* dst, const float* src, int64_t n);
+
+// loss (misc.cu)
+// graph output: L = sum_s mean_{F,V_s}((p-e)^2)/2 ; g = (p-e)/(F*V_s).  loss_acc[0] += L.
+int launch_mse_graph(const float* pred, const float* target, const int32_t* vgraph,
+                     const int32_t* nv, int F, int64_t V, float* grad, float* loss_acc,
+                     DevBuf& scratch);
+// array output [B, N]: L = sum((p-e)^2)/(2*N*global_B) ; g = (p-e)/(N*global_B)
+int launch_mse_array(const float* pred, const float* target, int64_t n, float denom,
+                     float* grad, float* loss_acc, DevBuf& scratch);
+
+struct OptimState {
+  athena_optimiser_desc d{};
+  float lr = 0.f;
+  int64_t iter = 0;
+  DevBuf s1, s2;   // velocity | m, v
+  DevBuf scratch;  // norm partials
+};
+// clip + optimiser step + zero the gradients (athena_network_sub.f90:2904-2927)
+int launch_update(float* params, float* grads, int64_t n, OptimState& st);
+
+// comm (comm.cc)
+int comm_allreduce_sum(float* buf, int64_t n);  // no-op when no communicator
+int comm_world_size();
+
+}  // namespace athena

@@ -1,0 +1,643 @@
+// K1: graph_type batch -> device CSR / CSC / degrees / normalisation
+// coefficients / degree buckets.  Replaces the per-sample host deep copies of
+// msgpass_layer_type%set_graph (athena_msgpass_layer_sub.f90:144-174) with one
+// device build per mini-batch that all layers and both passes share.
+//
+// Integer results are bit-exact against oracle_batch_build / oracle_bucketize
+// (oracle/athena_oracle.c): counting uses integer atomics (order-independent
+// totals); the CSC fill claims slots in arbitrary order and every column is
+// then sorted by CSR entry index, which yields the unique stable order.
+#include <climits>
+
+#include "athena_internal.h"
+
+namespace athena {
+
+// largest s in [0, n) with off[s] <= x   (off is non-decreasing, off[0] == 0)
+__device__ __forceinline__ int find_segment(const int32_t* __restrict__ off, int n, int x) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (__ldg(off + mid) <= x) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void k_convert_rows(int B, int V, int Z, const int32_t* __restrict__ nz,
+                               const int32_t* __restrict__ voff,
+                               const int32_t* __restrict__ zoff,
+                               const int32_t* __restrict__ ia_cat, int32_t* __restrict__ row_ptr,
+                               int32_t* __restrict__ deg, int32_t* __restrict__ vgraph,
+                               int32_t* __restrict__ status) {
+  int gv = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gv == 0) row_ptr[V] = Z;
+  if (gv >= V) return;
+  int s = find_segment(voff, B, gv);
+  int i = gv - voff[s];
+  const int32_t* ia = ia_cat + voff[s] + s;  // each graph contributes nv+1 row pointers
+  int a0 = ia[i], a1 = ia[i + 1];
+  int nvs = voff[s + 1] - voff[s];
+  bool bad = (a1 < a0) || (a0 < 1) || (a1 - 1 > nz[s]) || (i == 0 && a0 != 1) ||
+             (i == nvs - 1 && a1 - 1 != nz[s]);
+  if (bad) {
+    atomicMin(status, s);
+    a0 = 1;
+    a1 = 1;
+  }
+  row_ptr[gv] = zoff[s] + a0 - 1;
+  deg[gv] = a1 - a0;
+  vgraph[gv] = s;
+}
+
+__global__ void k_convert_entries(int B, int Z, const int32_t* __restrict__ nv,
+                                  const int32_t* __restrict__ ne,
+                                  const int32_t* __restrict__ voff,
+                                  const int32_t* __restrict__ zoff,
+                                  const int32_t* __restrict__ eoff,
+                                  const int2* __restrict__ ja_cat, int32_t* __restrict__ col,
+                                  int32_t* __restrict__ eid, int32_t* __restrict__ csc_cnt,
+                                  int32_t* __restrict__ status) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= Z) return;
+  int s = find_segment(zoff, B, w);
+  int2 p = ja_cat[w];
+  int nb = p.x;
+  if (nb < 1 || nb > nv[s]) {
+    atomicMin(status, s);
+    nb = 1;  // keep later kernels in bounds; the batch is flagged invalid
+  }
+  int c = voff[s] + nb - 1;
+  col[w] = c;
+  eid[w] = (p.y >= 1 && p.y <= ne[s]) ? eoff[s] + p.y - 1 : -1;
+  atomicAdd(csc_cnt + c, 1);
+}
+
+// ---- exclusive scan of int32 (three small kernels) -------------------------
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_exclusive_scan(int x, int* total) {
+  __shared__ int warp_sums[32];
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int nw = blockDim.x >> 5;
+    int ws = lane < nw ? warp_sums[lane] : 0;
+    int wi = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += y;
+    }
+    warp_sums[lane] = wi - ws;  // exclusive warp offsets
+    if (lane == 31) *total = wi;
+  }
+  __syncthreads();
+  int res = incl - x + warp_sums[warp];
+  __syncthreads();
+  return res;
+}
+
+// in may alias out (no __restrict__ on purpose)
+__global__ void k_scan_tiles(const int32_t* in, int32_t* out, int n,
+                             int32_t* __restrict__ tile_sums) {
+  __shared__ int total;
+  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    s += v[k];
+  }
+  int ex = block_exclusive_scan(s, &total);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) out[base + k] = ex;
+    ex += v[k];
+  }
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the tile sums in place; writes the grand total
+__global__ void k_scan_sums(int32_t* __restrict__ tile_sums, int ntiles,
+                            int32_t* __restrict__ grand_total) {
+  __shared__ int total;
+  int carry = 0;
+  for (int base = 0; base < ntiles; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    int x = i < ntiles ? tile_sums[i] : 0;
+    int ex = block_exclusive_scan(x, &total);
+    if (i < ntiles) tile_sums[i] = ex + carry;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void k_scan_add(int32_t* __restrict__ out, int n,
+                           const int32_t* __restrict__ tile_sums) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] += tile_sums[i / SCAN_TILE];
+}
+
+// out[0..n) = exclusive scan of in[0..n);  out[n] = total.  in may alias out.
+static int exclusive_scan(const int32_t* in, int32_t* out, int n, int32_t* tile_sums) {
+  cudaStream_t st = ctx().stream;
+  int ntiles = (int)cdiv(n, SCAN_TILE);
+  if (ntiles == 0) {
+    ATH_CUDA(cudaMemsetAsync(out, 0, sizeof(int32_t), st));
+    return ATHENA_OK;
+  }
+  k_scan_tiles<<<ntiles, SCAN_THREADS, 0, st>>>(in, out, n, tile_sums);
+  ATH_LAUNCHED();
+  k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, ntiles, out + n);
+  ATH_LAUNCHED();
+  k_scan_add<<<(int)cdiv(n, 256), 256, 0, st>>>(out, n, tile_sums);
+  ATH_LAUNCHED();
+  return ATHENA_OK;
+}
+
+// ---- coefficients + CSC fill ------------------------------------------------
+// 8 lanes per CSR row.  coef follows athena_diffstruc_extd_sub_kipf.f90:39-42:
+// integer degree product, converted to real32, raised to -1/2.
+__global__ void k_coef_and_csc_fill(int V, const int32_t* __restrict__ row_ptr,
+                                    const int32_t* __restrict__ col,
+                                    const int32_t* __restrict__ deg, float* __restrict__ coef,
+                                    int32_t* __restrict__ cursor, int32_t* __restrict__ csc_ent,
+                                    int32_t* __restrict__ csc_src) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int lane = (int)(t & 7);
+  if ((t >> 3) >= V) return;
+  int v = (int)(t >> 3);
+  int beg = row_ptr[v], end = row_ptr[v + 1];
+  int dv = deg[v];
+  for (int w = beg + lane; w < end; w += 8) {
+    int u = col[w];
+    int prod = dv * __ldg(deg + u);
+    coef[w] = 1.0f / sqrtf((float)prod);
+    int pos = atomicAdd(cursor + u, 1);
+    csc_ent[pos] = w;
+    csc_src[pos] = v;
+  }
+}
+
+// warp per CSC column: rank sort by entry index for columns of <= 32 entries;
+// longer columns are queued for k_csc_sort_long.
+__global__ void k_csc_sort_short(int V, const int32_t* __restrict__ csc_ptr,
+                                 int32_t* __restrict__ csc_ent, int32_t* __restrict__ csc_src,
+                                 int32_t* __restrict__ long_list, int32_t* __restrict__ long_count) {
+  long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (gw >= V) return;
+  int warp = (int)gw;
+  int beg = csc_ptr[warp];
+  int len = csc_ptr[warp + 1] - beg;
+  if (len <= 1) return;
+  if (len > 32) {
+    if (lane == 0) long_list[atomicAdd(long_count, 1)] = warp;
+    return;
+  }
+  int key = lane < len ? csc_ent[beg + lane] : INT_MAX;
+  int val = lane < len ? csc_src[beg + lane] : 0;
+  int rank = 0;
+  for (int j = 0; j < len; ++j) rank += (__shfl_sync(0xffffffffu, key, j) < key) ? 1 : 0;
+  __syncwarp();
+  if (lane < len) {
+    csc_ent[beg + rank] = key;
+    csc_src[beg + rank] = val;
+  }
+}
+
+// Ascending-only bitonic network (mirror step + half cleaners) so that virtual
+// +inf padding above n never has to move.
+template <class Swap>
+__device__ __forceinline__ void bitonic_network(int n, Swap swap_if) {
+  int P = 1;
+  while (P < n) P <<= 1;
+  for (int k = 2; k <= P; k <<= 1) {
+    int half = k >> 1;
+    for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+      int grp = t / half, off = t - grp * half;
+      int i = grp * k + off, l = grp * k + k - 1 - off;
+      if (l < n) swap_if(i, l);
+    }
+    __syncthreads();
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        int i = 2 * j * (t / j) + (t % j), l = i + j;
+        if (l < n) swap_if(i, l);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+constexpr int LONG_SMEM_KEYS = 16384;  // 128 KB of 64-bit keys
+
+__global__ void __launch_bounds__(1024)
+k_csc_sort_long(const int32_t* __restrict__ csc_ptr, int32_t* __restrict__ csc_ent,
+                int32_t* __restrict__ csc_src, const int32_t* __restrict__ long_list,
+                const int32_t* __restrict__ long_count) {
+  extern __shared__ unsigned long long keys[];
+  int count = *long_count;
+  for (int q = blockIdx.x; q < count; q += gridDim.x) {
+    int u = long_list[q];
+    int beg = csc_ptr[u];
+    int n = csc_ptr[u + 1] - beg;
+    int32_t* ent = csc_ent + beg;
+    int32_t* src = csc_src + beg;
+    if (n <= LONG_SMEM_KEYS) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x)
+        keys[i] = ((unsigned long long)(unsigned)ent[i] << 32) | (unsigned)src[i];
+      __syncthreads();
+      bitonic_network(
+          n, [&](int i, int l) {
+            unsigned long long a = keys[i], b = keys[l];
+            if (b < a) {
+              keys[i] = b;
+              keys[l] = a;
+            }
+          });
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        ent[i] = (int)(keys[i] >> 32);
+        src[i] = (int)(keys[i] & 0xffffffffu);
+      }
+      __syncthreads();
+    } else {
+      __syncthreads();
+      bitonic_network(
+          n, [&](int i, int l) {
+            int a = ent[i], b = ent[l];
+            if (b < a) {
+              ent[i] = b;
+              ent[l] = a;
+              int sa = src[i];
+              src[i] = src[l];
+              src[l] = sa;
+            }
+          });
+    }
+  }
+}
+
+// ---- degree buckets -----------------------------------------------------------
+constexpr int BKT_THREADS = 1024;
+constexpr int BKT_MAX_D = 256;
+
+__device__ __forceinline__ int bucket_of(int deg, int min_deg, int max_deg) {
+  return max(min_deg, min(deg, max_deg)) - min_deg;  // 0-based
+}
+
+// pass 0: bucket ids + per-block histograms.  pass 1: stable scatter.
+template <int PASS>
+__global__ void __launch_bounds__(BKT_THREADS)
+k_bucket_pass(int V, int D, int min_deg, int max_deg, const int32_t* __restrict__ deg,
+              int32_t* __restrict__ bkt, int32_t* __restrict__ block_hist,
+              int32_t* __restrict__ perm) {
+  extern __shared__ int warp_cnt[];  // [32][D]
+  int v = blockIdx.x * BKT_THREADS + threadIdx.x;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 32 * D; i += BKT_THREADS) warp_cnt[i] = 0;
+  __syncthreads();
+  bool live = v < V;
+  int b = live ? bucket_of(deg[v], min_deg, max_deg) : -1;
+  unsigned peers = __match_any_sync(0xffffffffu, b);
+  int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+  if (live && rank_in_warp == 0) warp_cnt[warp * D + b] = __popc(peers);
+  __syncthreads();
+  if (PASS == 0) {
+    if (live) bkt[v] = b;
+    for (int d = threadIdx.x; d < D; d += BKT_THREADS) {
+      int s = 0;
+      for (int w = 0; w < 32; ++w) s += warp_cnt[w * D + d];
+      block_hist[(size_t)blockIdx.x * D + d] = s;
+    }
+  } else if (live) {
+    int off = block_hist[(size_t)blockIdx.x * D + b];  // global base of (block, bucket)
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w * D + b];
+    perm[off + rank_in_warp] = v;
+  }
+}
+
+// single block: block_hist[blk][d] -> global base offsets, bkt_ptr[D+1]
+__global__ void k_bucket_scan(int nblocks, int D, int32_t* __restrict__ block_hist,
+                              int32_t* __restrict__ bkt_ptr) {
+  __shared__ int totals[BKT_MAX_D + 1];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    int run = 0;
+    for (int b = 0; b < nblocks; ++b) {
+      int c = block_hist[(size_t)b * D + d];
+      block_hist[(size_t)b * D + d] = run;
+      run += c;
+    }
+    totals[d] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int d = 0; d < D; ++d) {
+      int c = totals[d];
+      totals[d] = run;
+      bkt_ptr[d] = run;
+      run += c;
+    }
+    bkt_ptr[D] = run;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    int base = totals[d];
+    for (int b = 0; b < nblocks; ++b) block_hist[(size_t)b * D + d] += base;
+  }
+}
+
+BucketSet* Batch::find_buckets(int min_deg, int max_deg) const {
+  for (auto& bs : buckets)
+    if (bs->min_deg == min_deg && bs->max_deg == max_deg) return bs.get();
+  return nullptr;
+}
+
+int batch_bucketize(Batch* b, int min_deg, int max_deg, BucketSet** out) {
+  ATH_REQUIRE(max_deg >= min_deg && min_deg >= 1, ATHENA_ERR_ARG,
+              "bucketize: need 1 <= min_vertex_degree <= max_vertex_degree (got %d, %d)", min_deg,
+              max_deg);
+  int D = max_deg - min_deg + 1;
+  ATH_REQUIRE(D <= BKT_MAX_D, ATHENA_ERR_ARG, "bucketize: %d degree buckets > supported %d", D,
+              BKT_MAX_D);
+  if (BucketSet* hit = b->find_buckets(min_deg, max_deg)) {
+    if (out) *out = hit;
+    return ATHENA_OK;
+  }
+  std::unique_ptr<BucketSet> bs(new BucketSet);
+  bs->min_deg = min_deg;
+  bs->max_deg = max_deg;
+  bs->D = D;
+  int V = (int)b->V;
+  int nblocks = (int)cdiv(V, BKT_THREADS);
+  ATH_TRY(bs->bkt.reserve(sizeof(int32_t) * (size_t)(V + 1)));
+  ATH_TRY(bs->perm.reserve(sizeof(int32_t) * (size_t)(V + 1)));
+  ATH_TRY(bs->bkt_ptr.reserve(sizeof(int32_t) * (size_t)(D + 1)));
+  ATH_TRY(bs->scratch.reserve(sizeof(int32_t) * (size_t)(nblocks + 1) * D));
+  cudaStream_t st = ctx().stream;
+  size_t smem = sizeof(int) * 32 * (size_t)D;
+  if (V > 0) {
+    k_bucket_pass<0><<<nblocks, BKT_THREADS, smem, st>>>(V, D, min_deg, max_deg, b->deg,
+                                                         bs->bkt.as<int32_t>(),
+                                                         bs->scratch.as<int32_t>(), nullptr);
+    ATH_LAUNCHED();
+  }
+  k_bucket_scan<<<1, 256, 0, st>>>(nblocks, D, bs->scratch.as<int32_t>(),
+                                   bs->bkt_ptr.as<int32_t>());
+  ATH_LAUNCHED();
+  if (V > 0) {
+    k_bucket_pass<1><<<nblocks, BKT_THREADS, smem, st>>>(V, D, min_deg, max_deg, b->deg,
+                                                         bs->bkt.as<int32_t>(),
+                                                         bs->scratch.as<int32_t>(),
+                                                         bs->perm.as<int32_t>());
+    ATH_LAUNCHED();
+  }
+  if (out) *out = bs.get();
+  b->buckets.push_back(std::move(bs));
+  return ATHENA_OK;
+}
+
+}  // namespace athena
+
+using namespace athena;
+
+ATHENA_API int athena_cuda_batch_create(athena_handle_t* batch, int32_t num_graphs,
+                                        const int32_t* num_vertices, const int32_t* num_edges,
+                                        const int32_t* num_entries, const int32_t* adj_ia,
+                                        const int32_t* adj_ja, int32_t mem, int32_t validate) {
+  ATH_TRY(ensure_init());
+  ATH_REQUIRE(batch && num_vertices && num_edges && num_entries && adj_ia, ATHENA_ERR_ARG,
+              "batch_create: null argument");
+  ATH_REQUIRE(num_graphs >= 1, ATHENA_ERR_ARG, "batch_create: num_graphs = %d", num_graphs);
+  ATH_REQUIRE(mem == ATHENA_MEM_HOST || mem == ATHENA_MEM_DEVICE, ATHENA_ERR_ARG,
+              "batch_create: bad mem %d", mem);
+  const int B = num_graphs;
+  std::vector<int32_t> meta((size_t)5 * B + 3);
+  int32_t* h_nv = meta.data();
+  int32_t* h_ne = h_nv + B;
+  int32_t* h_nz = h_ne + B;
+  int32_t* h_voff = h_nz + B;
+  int32_t* h_zoff = h_voff + B + 1;
+  // eoff appended below (needs its own B+1)
+  std::vector<int32_t> eoffv((size_t)B + 1);
+  int64_t V = 0, Z = 0, E = 0;
+  for (int s = 0; s < B; ++s) {
+    ATH_REQUIRE(num_vertices[s] >= 0 && num_edges[s] >= 0 && num_entries[s] >= 0, ATHENA_ERR_ARG,
+                "batch_create: negative size in graph %d", s);
+    h_nv[s] = num_vertices[s];
+    h_ne[s] = num_edges[s];
+    h_nz[s] = num_entries[s];
+    h_voff[s] = (int32_t)V;
+    h_zoff[s] = (int32_t)Z;
+    eoffv[s] = (int32_t)E;
+    V += num_vertices[s];
+    Z += num_entries[s];
+    E += num_edges[s];
+  }
+  ATH_REQUIRE(V < INT32_MAX - 2 && Z < INT32_MAX - 2 && E < INT32_MAX - 2, ATHENA_ERR_ARG,
+              "batch_create: batch exceeds int32 indexing (V=%lld Z=%lld E=%lld)", (long long)V,
+              (long long)Z, (long long)E);
+  ATH_REQUIRE(Z == 0 || adj_ja, ATHENA_ERR_ARG, "batch_create: null adj_ja");
+  h_voff[B] = (int32_t)V;
+  h_zoff[B] = (int32_t)Z;
+  eoffv[B] = (int32_t)E;
+
+  std::unique_ptr<Batch> b(new Batch);
+  b->B = B;
+  b->V = V;
+  b->Z = Z;
+  b->E = E;
+  cudaStream_t st = ctx().stream;
+
+  // meta on the device: nv | ne | nz | voff | zoff | eoff
+  size_t meta_ints = (size_t)3 * B + 3 * ((size_t)B + 1);
+  ATH_TRY(b->meta.reserve(sizeof(int32_t) * meta_ints));
+  int32_t* d_meta = b->meta.as<int32_t>();
+  ATH_CUDA(cudaMemcpyAsync(d_meta, meta.data(), sizeof(int32_t) * ((size_t)5 * B + 2),
+                           cudaMemcpyHostToDevice, st));
+  ATH_CUDA(cudaMemcpyAsync(d_meta + 5 * (size_t)B + 2, eoffv.data(),
+                           sizeof(int32_t) * ((size_t)B + 1), cudaMemcpyHostToDevice, st));
+  b->nv = d_meta;
+  b->ne = d_meta + B;
+  const int32_t* d_nz = d_meta + 2 * (size_t)B;
+  b->voff = d_meta + 3 * (size_t)B;
+  b->zoff = b->voff + B + 1;
+  b->eoff = b->zoff + B + 1;
+
+  // raw adjacency on the device
+  const int32_t* d_ia = adj_ia;
+  const int32_t* d_ja = adj_ja;
+  if (mem == ATHENA_MEM_HOST) {
+    size_t ia_ints = (size_t)V + B, ja_ints = 2 * (size_t)Z;
+    size_t ia_pad = (size_t)round_up((int64_t)ia_ints, 4);
+    ATH_TRY(b->raw.reserve(sizeof(int32_t) * (ia_pad + ja_ints + 4)));
+    int32_t* r = b->raw.as<int32_t>();
+    ATH_CUDA(cudaMemcpyAsync(r, adj_ia, sizeof(int32_t) * ia_ints, cudaMemcpyHostToDevice, st));
+    if (Z > 0)
+      ATH_CUDA(cudaMemcpyAsync(r + ia_pad, adj_ja, sizeof(int32_t) * ja_ints,
+                               cudaMemcpyHostToDevice, st));
+    d_ia = r;
+    d_ja = r + ia_pad;
+  } else {
+    ATH_REQUIRE((reinterpret_cast<uintptr_t>(adj_ja) & 7) == 0, ATHENA_ERR_ARG,
+                "batch_create: device adj_ja must be 8-byte aligned");
+  }
+
+  // integer structures, one allocation
+  size_t Vp = (size_t)round_up(V + 1, 4), Zp = (size_t)round_up(Z + 1, 4);
+  size_t total = 5 * Vp /* row_ptr deg vgraph csc_ptr cursor */ + 4 * Zp /* col eid src ent */ +
+                 Vp /* long list */;
+  ATH_TRY(b->ints.reserve(sizeof(int32_t) * total));
+  int32_t* p = b->ints.as<int32_t>();
+  b->row_ptr = p; p += Vp;
+  b->deg = p; p += Vp;
+  b->vgraph = p; p += Vp;
+  b->csc_ptr = p; p += Vp;
+  int32_t* cursor = p; p += Vp;
+  int32_t* long_list = p; p += Vp;
+  b->col = p; p += Zp;
+  b->eid = p; p += Zp;
+  b->csc_src = p; p += Zp;
+  b->csc_ent = p; p += Zp;
+  ATH_TRY(b->coef_buf.reserve(sizeof(float) * Zp));
+  b->coef = b->coef_buf.as<float>();
+  int ntiles = (int)cdiv(V + 1, SCAN_TILE) + 1;
+  ATH_TRY(b->scratch.reserve(sizeof(int32_t) * (size_t)ntiles));
+  ATH_TRY(b->status.reserve(sizeof(int32_t) * 4));
+  int32_t* status = b->status.as<int32_t>();
+  const int32_t status_init[4] = {INT_MAX, 0, 0, 0};
+  ATH_CUDA(cudaMemcpyAsync(status, status_init, sizeof(status_init), cudaMemcpyHostToDevice, st));
+
+  ATH_CUDA(cudaMemsetAsync(b->csc_ptr, 0, sizeof(int32_t) * Vp, st));
+  k_convert_rows<<<(int)cdiv(V + 1, 256), 256, 0, st>>>(B, (int)V, (int)Z, d_nz, b->voff, b->zoff,
+                                                       d_ia, b->row_ptr, b->deg, b->vgraph,
+                                                       status);
+  ATH_LAUNCHED();
+  if (Z > 0) {
+    k_convert_entries<<<(int)cdiv(Z, 256), 256, 0, st>>>(
+        B, (int)Z, b->nv, b->ne, b->voff, b->zoff, b->eoff, reinterpret_cast<const int2*>(d_ja),
+        b->col, b->eid, b->csc_ptr, status);
+    ATH_LAUNCHED();
+  }
+  // csc_ptr currently holds per-column counts in [0, V)
+  ATH_TRY(exclusive_scan(b->csc_ptr, b->csc_ptr, (int)V, b->scratch.as<int32_t>()));
+  if (V > 0 && Z > 0) {
+    ATH_CUDA(cudaMemcpyAsync(cursor, b->csc_ptr, sizeof(int32_t) * (size_t)V,
+                             cudaMemcpyDeviceToDevice, st));
+    k_coef_and_csc_fill<<<(int)cdiv(V * 8, 256), 256, 0, st>>>((int)V, b->row_ptr, b->col, b->deg,
+                                                              b->coef, cursor, b->csc_ent,
+                                                              b->csc_src);
+    ATH_LAUNCHED();
+    k_csc_sort_short<<<(int)cdiv(V * 32, 256), 256, 0, st>>>((int)V, b->csc_ptr, b->csc_ent,
+                                                            b->csc_src, long_list, status + 1);
+    ATH_LAUNCHED();
+    static bool attr_set = false;
+    size_t smem = sizeof(unsigned long long) * LONG_SMEM_KEYS;
+    if (!attr_set) {
+      ATH_CUDA(cudaFuncSetAttribute(k_csc_sort_long, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+      attr_set = true;
+    }
+    k_csc_sort_long<<<ctx().sm_count, 1024, smem, st>>>(b->csc_ptr, b->csc_ent, b->csc_src,
+                                                        long_list, status + 1);
+    ATH_LAUNCHED();
+  }
+  Batch* raw = b.release();
+  athena_handle_t h = register_object(raw);
+  *batch = h;
+  if (validate) {
+    int rc = athena_cuda_batch_status(h);
+    if (rc != ATHENA_OK) {
+      destroy_object(h, Kind::Batch);
+      *batch = 0;
+      return rc;
+    }
+  }
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_batch_destroy(athena_handle_t batch) {
+  return destroy_object(batch, Kind::Batch);
+}
+
+ATHENA_API int athena_cuda_batch_status(athena_handle_t batch) {
+  Batch* b = static_cast<Batch*>(lookup_object(batch, Kind::Batch));
+  if (!b) return ATHENA_ERR_HANDLE;
+  int32_t st[4];
+  ATH_CUDA(cudaMemcpyAsync(st, b->status.p, sizeof(st), cudaMemcpyDeviceToHost, ctx().stream));
+  ATH_CUDA(cudaStreamSynchronize(ctx().stream));
+  ATH_REQUIRE(st[0] == INT_MAX, ATHENA_ERR_GRAPH,
+              "graph adjacency matrix has indices greater than the number of vertices "
+              "(or inconsistent adj_ia) in sample %d",
+              st[0] + 1);
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_batch_info(athena_handle_t batch, int32_t* num_graphs,
+                                      int64_t* num_vertices, int64_t* num_entries,
+                                      int64_t* num_edges) {
+  Batch* b = static_cast<Batch*>(lookup_object(batch, Kind::Batch));
+  if (!b) return ATHENA_ERR_HANDLE;
+  if (num_graphs) *num_graphs = b->B;
+  if (num_vertices) *num_vertices = b->V;
+  if (num_entries) *num_entries = b->Z;
+  if (num_edges) *num_edges = b->E;
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_batch_bucketize(athena_handle_t batch, int32_t min_degree,
+                                           int32_t max_degree) {
+  Batch* b = static_cast<Batch*>(lookup_object(batch, Kind::Batch));
+  if (!b) return ATHENA_ERR_HANDLE;
+  return batch_bucketize(b, min_degree, max_degree, nullptr);
+}
+
+ATHENA_API int athena_cuda_batch_export(athena_handle_t batch, int32_t what, void* host_out,
+                                        int64_t count) {
+  Batch* b = static_cast<Batch*>(lookup_object(batch, Kind::Batch));
+  if (!b) return ATHENA_ERR_HANDLE;
+  ATH_REQUIRE(host_out, ATHENA_ERR_ARG, "batch_export: null output");
+  const void* src = nullptr;
+  int64_t n = 0;
+  BucketSet* bs = b->buckets.empty() ? nullptr : b->buckets.back().get();
+  switch (what) {
+    case ATHENA_BATCH_ROW_PTR: src = b->row_ptr; n = b->V + 1; break;
+    case ATHENA_BATCH_COL: src = b->col; n = b->Z; break;
+    case ATHENA_BATCH_EID: src = b->eid; n = b->Z; break;
+    case ATHENA_BATCH_DEG: src = b->deg; n = b->V; break;
+    case ATHENA_BATCH_VGRAPH: src = b->vgraph; n = b->V; break;
+    case ATHENA_BATCH_CSC_PTR: src = b->csc_ptr; n = b->V + 1; break;
+    case ATHENA_BATCH_CSC_SRC: src = b->csc_src; n = b->Z; break;
+    case ATHENA_BATCH_CSC_ENT: src = b->csc_ent; n = b->Z; break;
+    case ATHENA_BATCH_COEF: src = b->coef; n = b->Z; break;
+    case ATHENA_BATCH_BUCKET:
+    case ATHENA_BATCH_PERM:
+    case ATHENA_BATCH_BUCKET_PTR:
+      ATH_REQUIRE(bs, ATHENA_ERR_STATE, "batch_export: call athena_cuda_batch_bucketize first");
+      if (what == ATHENA_BATCH_BUCKET) { src = bs->bkt.p; n = b->V; }
+      else if (what == ATHENA_BATCH_PERM) { src = bs->perm.p; n = b->V; }
+      else { src = bs->bkt_ptr.p; n = bs->D + 1; }
+      break;
+    default:
+      ATH_REQUIRE(false, ATHENA_ERR_ARG, "batch_export: unknown selector %d", what);
+  }
+  ATH_REQUIRE(count == n, ATHENA_ERR_ARG, "batch_export: selector %d has %lld elements, got %lld",
+              what, (long long)n, (long long)count);
+  if (n > 0)
+    ATH_CUDA(cudaMemcpyAsync(host_out, src, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost,
+                             ctx().stream));
+  ATH_CUDA(cudaStreamSynchronize(ctx().stream));
+  return ATHENA_OK;
+}

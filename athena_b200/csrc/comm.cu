@@ -1,0 +1,155 @@
+// Data-parallel plumbing: one process per GPU, graphs sharded across ranks,
+// one in-stream NCCL all-reduce over the flat gradient vector (+ the loss
+// slot).  The reference has no collective at all; its semantic template is
+// network_type%reduce (athena_network_sub.f90:36-62), which sums the
+// gradients of two replicas.
+//
+// NCCL is resolved with dlopen at comm_init time so that libathena_cuda has
+// no link-time dependency on it (single-GPU users never load it, and inside
+// a PyTorch process the already-loaded libnccl.so.2 is reused).
+#include <dlfcn.h>
+
+#include "athena_internal.h"
+
+namespace athena {
+
+// Minimal mirror of the NCCL C API (stable since NCCL 2.0).
+typedef struct ncclComm* ncclComm_t;
+typedef struct {
+  char internal[128];
+} ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat32 = 7 };
+enum { ncclSum = 0 };
+
+struct Nccl {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  ncclComm_t comm = nullptr;
+  int world = 1, rank = 0;
+};
+static Nccl g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.lib) return ATHENA_OK;
+  const char* names[] = {getenv("ATHENA_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* n : names) {
+    if (!n) continue;
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  ATH_REQUIRE(lib, ATHENA_ERR_COMM, "cannot dlopen libnccl.so.2 (%s); set ATHENA_NCCL_LIB",
+              dlerror());
+#define ATH_SYM(field, name)                                                   \
+  g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name));   \
+  ATH_REQUIRE(g_nccl.field, ATHENA_ERR_COMM, "libnccl: missing symbol %s", name)
+  ATH_SYM(GetUniqueId, "ncclGetUniqueId");
+  ATH_SYM(CommInitRank, "ncclCommInitRank");
+  ATH_SYM(AllReduce, "ncclAllReduce");
+  ATH_SYM(CommDestroy, "ncclCommDestroy");
+  ATH_SYM(GetErrorString, "ncclGetErrorString");
+#undef ATH_SYM
+  g_nccl.lib = lib;
+  return ATHENA_OK;
+}
+
+#define ATH_NCCL(expr)                                                                   \
+  do {                                                                                   \
+    int r_ = (expr);                                                                     \
+    if (r_ != ncclSuccess) {                                                             \
+      set_error("%s: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+      return ATHENA_ERR_COMM;                                                            \
+    }                                                                                    \
+  } while (0)
+
+int comm_world_size() { return g_nccl.comm ? g_nccl.world : 1; }
+
+int comm_allreduce_sum(float* buf, int64_t n) {
+  if (!g_nccl.comm || g_nccl.world == 1 || n == 0) return ATHENA_OK;
+  ATH_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclSum, g_nccl.comm, ctx().stream));
+  ctx().launches.fetch_add(1, std::memory_order_relaxed);
+  return ATHENA_OK;
+}
+
+}  // namespace athena
+
+using namespace athena;
+
+ATHENA_API int athena_cuda_comm_unique_id(char id[ATHENA_COMM_ID_BYTES]) {
+  ATH_REQUIRE(id, ATHENA_ERR_ARG, "comm_unique_id: null");
+  ATH_TRY(ensure_init());
+  ATH_TRY(nccl_load());
+  ncclUniqueId u;
+  ATH_NCCL(g_nccl.GetUniqueId(&u));
+  static_assert(sizeof(u) == ATHENA_COMM_ID_BYTES, "id size");
+  memcpy(id, &u, sizeof(u));
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_comm_init(int32_t world_size, int32_t rank,
+                                     const char id[ATHENA_COMM_ID_BYTES]) {
+  ATH_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, ATHENA_ERR_ARG,
+              "comm_init: bad world_size/rank %d/%d", world_size, rank);
+  ATH_TRY(ensure_init());
+  ATH_REQUIRE(!g_nccl.comm, ATHENA_ERR_STATE, "comm_init: communicator already exists");
+  g_nccl.world = world_size;
+  g_nccl.rank = rank;
+  if (world_size == 1) return ATHENA_OK;
+  ATH_REQUIRE(id, ATHENA_ERR_ARG, "comm_init: null id");
+  ATH_TRY(nccl_load());
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof(u));
+  ATH_NCCL(g_nccl.CommInitRank(&g_nccl.comm, world_size, u, rank));
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_comm_destroy(void) {
+  if (g_nccl.comm) {
+    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    g_nccl.CommDestroy(g_nccl.comm);
+    g_nccl.comm = nullptr;
+  }
+  g_nccl.world = 1;
+  g_nccl.rank = 0;
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_comm_info(int32_t* world_size, int32_t* rank) {
+  if (world_size) *world_size = g_nccl.world;
+  if (rank) *rank = g_nccl.rank;
+  return ATHENA_OK;
+}
+
+// Contiguous partition of B graphs over `world_size` ranks, balanced by CSR
+// entries (the per-graph cost of aggregation): boundary r is placed at the
+// first graph whose running entry count reaches r/world of the total.
+// Deterministic, pure host code; every rank computes the same answer.
+ATHENA_API int athena_cuda_shard_graphs(int32_t num_graphs, const int64_t* entries_per_graph,
+                                        int32_t world_size, int32_t* first_graph) {
+  ATH_REQUIRE(num_graphs >= 0 && world_size >= 1 && first_graph &&
+                  (entries_per_graph || num_graphs == 0),
+              ATHENA_ERR_ARG, "shard_graphs: bad argument");
+  int64_t total = 0;
+  for (int32_t s = 0; s < num_graphs; ++s) {
+    ATH_REQUIRE(entries_per_graph[s] >= 0, ATHENA_ERR_ARG, "shard_graphs: negative weight");
+    total += entries_per_graph[s] + 1;  // +1 keeps empty graphs spread out
+  }
+  first_graph[0] = 0;
+  int64_t run = 0;
+  int32_t s = 0;
+  for (int32_t r = 1; r < world_size; ++r) {
+    // smallest s with run >= total * r / world
+    while (s < num_graphs && run * world_size < total * r) {
+      run += entries_per_graph[s] + 1;
+      ++s;
+    }
+    first_graph[r] = s;
+  }
+  first_graph[world_size] = num_graphs;
+  return ATHENA_OK;
+}

@@ -1,0 +1,723 @@
+// Host orchestration of the message-passing layers and the train-step
+// skeleton around them.  Mirrors (and replaces the bodies of)
+//   update_message_kipf        athena_kipf_msgpass_layer.f90:915-959
+//   update_message_duvenaud    athena_duvenaud_msgpass_layer.f90:755-817
+//   update_readout_duvenaud    athena_duvenaud_msgpass_layer.f90:822-859
+//   the reverse sweep loss%grad_reverse performs through them
+//   network%forward/train/update athena_network_sub.f90:2639-2929,3611-3670
+// The whole mini-batch is processed as ONE block-diagonal graph, so the
+// reference's serial `do s = 1, batch` loops become single kernel launches.
+#include <algorithm>
+
+#include "athena_internal.h"
+
+namespace athena {
+
+struct Layer : Object {
+  Layer() : Object(Kind::Layer) {}
+  int kind = 0;  // 0 kipf, 1 duvenaud
+  int T = 0;
+  std::vector<int> nvf;  // (0:T)
+  int nef = 0, min_deg = 1, max_deg = 1, n_out = 0, act = 0, ract = 0;
+  int64_t num_params = 0;
+  std::vector<int64_t> poff;  // flat offset of params(i)
+  DevBuf own_params, own_grads;
+  float* params = nullptr;
+  float* grads = nullptr;
+  bool adopted = false;  // parameters live in a network's flat buffer
+  // saved by forward for the reverse sweep
+  std::vector<std::unique_ptr<DevBuf>> P, H, S, GZ;
+  DevBuf Ae, out_buf, g0, g1, g2, tn_scratch, stage_x, stage_e, stage_g, stage_gin;
+  Batch* fwd_batch = nullptr;
+  int64_t fwd_V = -1;
+
+  int ldA(int t) const { return (int)round_up(nvf[t - 1] + nef, 4); }
+  int out_width() const { return kind == 0 ? nvf[T] : n_out; }
+  int64_t out_rows(const Batch* b) const { return kind == 0 ? b->V : b->B; }
+};
+
+static void layer_layout(Layer* L) {
+  L->poff.clear();
+  int64_t off = 0;
+  if (L->kind == 0) {
+    for (int t = 1; t <= L->T; ++t) {
+      L->poff.push_back(off);
+      off += (int64_t)L->nvf[t] * L->nvf[t - 1];
+    }
+  } else {
+    int D = L->max_deg - L->min_deg + 1;
+    for (int t = 1; t <= L->T; ++t) {
+      L->poff.push_back(off);
+      off += (int64_t)L->nvf[t] * (L->nvf[t - 1] + L->nef) * D;
+    }
+    for (int t = 1; t <= L->T; ++t) {
+      L->poff.push_back(off);
+      off += (int64_t)L->n_out * L->nvf[t];
+    }
+  }
+  L->num_params = off;
+  L->P.clear();
+  L->H.clear();
+  L->S.clear();
+  L->GZ.clear();
+  for (int t = 0; t < L->T; ++t) {
+    L->P.emplace_back(new DevBuf);
+    L->H.emplace_back(new DevBuf);
+    L->S.emplace_back(new DevBuf);
+    L->GZ.emplace_back(new DevBuf);
+  }
+}
+
+static int layer_alloc_params(Layer* L) {
+  size_t bytes = sizeof(float) * (size_t)std::max<int64_t>(L->num_params, 1);
+  ATH_TRY(L->own_params.reserve(bytes));
+  ATH_TRY(L->own_grads.reserve(bytes));
+  ATH_CUDA(cudaMemsetAsync(L->own_params.p, 0, bytes, ctx().stream));
+  ATH_CUDA(cudaMemsetAsync(L->own_grads.p, 0, bytes, ctx().stream));
+  L->params = L->own_params.as<float>();
+  L->grads = L->own_grads.as<float>();
+  return ATHENA_OK;
+}
+
+// ---- forward ---------------------------------------------------------------------
+
+static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out) {
+  const int64_t V = b->V;
+  const float* in = x;
+  for (int t = 1; t <= L->T; ++t) {
+    const int Fi = L->nvf[t - 1], Fo = L->nvf[t];
+    DevBuf& P = *L->P[t - 1];
+    DevBuf& H = *L->H[t - 1];
+    ATH_TRY(P.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fi, 1)));
+    ATH_TRY(H.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fo, 1)));
+    // P = D^-1/2 A D^-1/2 . in      (kipf_propagate)
+    ATH_TRY(launch_aggregate(b->row_ptr, b->col, b->coef, in, Fi, Fi, P.as<float>(), Fi, V, 0,
+                             nullptr, 0));
+    // H = act( P . W_t )            (matmul + activation%apply)
+    ATH_TRY(launch_gemm_nn(P.as<float>(), Fi, L->params + L->poff[t - 1], H.as<float>(), Fo, V,
+                           Fo, Fi, L->act, GroupDesc{}));
+    in = H.as<float>();
+  }
+  *out = in;
+  return ATHENA_OK;
+}
+
+static int duvenaud_forward(Layer* L, Batch* b, const float* x, const float* e,
+                            const float** out) {
+  const int64_t V = b->V;
+  BucketSet* bs = nullptr;
+  ATH_TRY(batch_bucketize(b, L->min_deg, L->max_deg, &bs));
+  const int D = bs->D;
+  const float* tail = nullptr;
+  if (L->nef > 0) {
+    ATH_REQUIRE(e != nullptr, ATHENA_ERR_ARG, "duvenaud forward: edge_features is null");
+    ATH_TRY(L->Ae.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * L->nef, 1)));
+    // time-step invariant: sum_w E(:, ja(2,w))
+    ATH_TRY(launch_aggregate(b->row_ptr, b->eid, nullptr, e, L->nef, L->nef, L->Ae.as<float>(),
+                             L->nef, V, 0, nullptr, 0));
+    tail = L->Ae.as<float>();
+  }
+  const float* in = x;
+  for (int t = 1; t <= L->T; ++t) {
+    const int Fi = L->nvf[t - 1], Fo = L->nvf[t], K = Fi + L->nef, ld = L->ldA(t);
+    DevBuf& A = *L->P[t - 1];
+    DevBuf& Zt = *L->H[t - 1];
+    ATH_TRY(A.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * ld, 1)));
+    ATH_TRY(Zt.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fo, 1)));
+    // A = [ sum_w in(:,ja(1,w)) ; sum_w E(:,ja(2,w)) ]      (duvenaud_propagate)
+    ATH_TRY(launch_aggregate(b->row_ptr, b->col, nullptr, in, Fi, Fi, A.as<float>(), ld, V, 0, tail,
+                             L->nef));
+    // z = act( W_d(v) . A(:,v)/d(v) )                       (duvenaud_update + activation)
+    GroupDesc gd;
+    gd.perm = bs->perm.as<int32_t>();
+    gd.ptr = bs->bkt_ptr.as<int32_t>();
+    gd.D = D;
+    gd.wstride = (int64_t)Fo * K;
+    gd.scale_by_group = 1;
+    ATH_TRY(launch_gemm_nn(A.as<float>(), ld, L->params + L->poff[t - 1], Zt.as<float>(), Fo, V,
+                           Fo, K, L->act, gd));
+    in = Zt.as<float>();
+  }
+  // readout: out(:,s) = sum_t sum_v ract( R_t . z_t )(:,v)
+  const int no = L->n_out;
+  ATH_TRY(L->out_buf.reserve(sizeof(float) * (size_t)b->B * no));
+  for (int t = 1; t <= L->T; ++t) {
+    const int Fo = L->nvf[t];
+    DevBuf& St = *L->S[t - 1];
+    ATH_TRY(St.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * no, 1)));
+    ATH_TRY(launch_gemm_nn(L->H[t - 1]->as<float>(), Fo, L->params + L->poff[L->T + t - 1],
+                           St.as<float>(), no, V, no, Fo, L->ract, GroupDesc{}));
+    ATH_TRY(launch_segment_sum(St.as<float>(), no, b->voff, b->B, L->out_buf.as<float>(), t > 1));
+  }
+  *out = L->out_buf.as<float>();
+  return ATHENA_OK;
+}
+
+int layer_forward_dev(Layer* L, Batch* b, const float* x, const float* e, const float** out) {
+  ATH_REQUIRE(x != nullptr || b->V == 0, ATHENA_ERR_ARG, "forward: vertex_features is null");
+  L->fwd_batch = b;
+  L->fwd_V = b->V;
+  if (L->kind == 0) return kipf_forward(L, b, x, out);
+  return duvenaud_forward(L, b, x, e, out);
+}
+
+// ---- backward --------------------------------------------------------------------
+
+static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin) {
+  const int64_t V = b->V;
+  const float* g = gout;
+  int Fmax = 0;
+  for (int t = 0; t <= L->T; ++t) Fmax = std::max(Fmax, L->nvf[t]);
+  size_t bytes = sizeof(float) * (size_t)std::max<int64_t>(V * Fmax, 1);
+  ATH_TRY(L->g0.reserve(bytes));
+  ATH_TRY(L->g1.reserve(bytes));
+  ATH_TRY(L->g2.reserve(bytes));
+  for (int t = L->T; t >= 1; --t) {
+    const int Fi = L->nvf[t - 1], Fo = L->nvf[t];
+    const float* gy = g;
+    if (L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR) {
+      ATH_TRY(launch_act_bwd(L->act, L->H[t - 1]->as<float>(), g, L->g0.as<float>(), V, Fo));
+      gy = L->g0.as<float>();
+    }
+    // dW_t(o,i) += sum_v gY(o,v) P(i,v)
+    ATH_TRY(launch_gemm_tn(L->P[t - 1]->as<float>(), Fi, gy, Fo, L->grads + L->poff[t - 1], V, Fo,
+                           Fi, GroupDesc{}, L->tn_scratch));
+    if (t > 1 || gin) {
+      // dP = W_t^T gY
+      ATH_TRY(launch_gemm_nt(gy, Fo, L->params + L->poff[t - 1], L->g1.as<float>(), Fi, V, Fi, Fo,
+                             GroupDesc{}));
+      // dH(:,u) += dP(:,v) for every CSR entry (v,u): gather over the CSC, NO coefficient
+      float* dst = (t > 1) ? L->g2.as<float>() : gin;
+      ATH_TRY(launch_aggregate(b->csc_ptr, b->csc_src, nullptr, L->g1.as<float>(), Fi, Fi, dst, Fi,
+                               V, 0, nullptr, 0));
+      g = dst;
+    }
+  }
+  return ATHENA_OK;
+}
+
+static int duvenaud_backward(Layer* L, Batch* b, const float* gout, float* gin) {
+  const int64_t V = b->V;
+  BucketSet* bs = nullptr;
+  ATH_TRY(batch_bucketize(b, L->min_deg, L->max_deg, &bs));
+  const int no = L->n_out, T = L->T;
+  int Wmax = no;
+  for (int t = 1; t <= T; ++t) Wmax = std::max(Wmax, std::max(L->nvf[t], L->ldA(t)));
+  size_t bytes = sizeof(float) * (size_t)std::max<int64_t>(V * Wmax, 1);
+  ATH_TRY(L->g0.reserve(bytes));
+  ATH_TRY(L->g1.reserve(bytes));
+  // readout share of d z_t
+  for (int t = 1; t <= T; ++t) {
+    const int Fo = L->nvf[t];
+    const float* R = L->params + L->poff[T + t - 1];
+    DevBuf& GZ = *L->GZ[t - 1];
+    ATH_TRY(GZ.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fo, 1)));
+    ATH_TRY(launch_readout_bwd(L->ract, L->S[t - 1]->as<float>(), gout, b->vgraph,
+                               L->g0.as<float>(), V, no));
+    ATH_TRY(launch_gemm_tn(L->H[t - 1]->as<float>(), Fo, L->g0.as<float>(), no,
+                           L->grads + L->poff[T + t - 1], V, no, Fo, GroupDesc{}, L->tn_scratch));
+    ATH_TRY(launch_gemm_nt(L->g0.as<float>(), no, R, GZ.as<float>(), Fo, V, Fo, no, GroupDesc{}));
+  }
+  for (int t = T; t >= 1; --t) {
+    const int Fi = L->nvf[t - 1], Fo = L->nvf[t], K = Fi + L->nef, ld = L->ldA(t);
+    const float* gz = L->GZ[t - 1]->as<float>();
+    const float* gzp = gz;
+    if (L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR) {
+      ATH_TRY(launch_act_bwd(L->act, L->H[t - 1]->as<float>(), gz, L->g0.as<float>(), V, Fo));
+      gzp = L->g0.as<float>();
+    }
+    GroupDesc gd;
+    gd.perm = bs->perm.as<int32_t>();
+    gd.ptr = bs->bkt_ptr.as<int32_t>();
+    gd.D = bs->D;
+    gd.wstride = (int64_t)Fo * K;
+    gd.scale_by_group = 1;
+    // dW_d(i,j) += gZ(i,v) A(j,v)/d
+    ATH_TRY(launch_gemm_tn(L->P[t - 1]->as<float>(), ld, gzp, Fo, L->grads + L->poff[t - 1], V, Fo,
+                           K, gd, L->tn_scratch));
+    if (t > 1 || gin) {
+      // dA(:,v) = (W_d^T gZ(:,v)) / d
+      ATH_TRY(launch_gemm_nt(gzp, Fo, L->params + L->poff[t - 1], L->g1.as<float>(), ld, V, K, Fo,
+                             gd));
+      // d in(:,u) += dA(1:F,v) over the CSC
+      if (t > 1)
+        ATH_TRY(launch_aggregate(b->csc_ptr, b->csc_src, nullptr, L->g1.as<float>(), ld, Fi,
+                                 L->GZ[t - 2]->as<float>(), Fi, V, 1, nullptr, 0));
+      else
+        ATH_TRY(launch_aggregate(b->csc_ptr, b->csc_src, nullptr, L->g1.as<float>(), ld, Fi, gin,
+                                 Fi, V, 0, nullptr, 0));
+    }
+  }
+  return ATHENA_OK;
+}
+
+int layer_backward_dev(Layer* L, Batch* b, const float* gout, float* gin) {
+  ATH_REQUIRE(L->fwd_batch == b && L->fwd_V == b->V, ATHENA_ERR_STATE,
+              "backward: no forward pass on this batch");
+  ATH_REQUIRE(gout != nullptr, ATHENA_ERR_ARG, "backward: grad_output is null");
+  if (L->kind == 0) return kipf_backward(L, b, gout, gin);
+  return duvenaud_backward(L, b, gout, gin);
+}
+
+// ---- network ---------------------------------------------------------------------
+
+struct Network : Object {
+  Network() : Object(Kind::Network) {}
+  std::vector<athena_handle_t> handles;
+  std::vector<Layer*> layers;
+  bool compiled = false;
+  int64_t n = 0;
+  DevBuf flat_params, flat_grads;  // grads has n + 1 (+pad) floats: [n] = batch loss
+  OptimState opt;
+  DevBuf stage_x, stage_e, stage_t, gbuf, loss_scratch;
+  std::vector<std::unique_ptr<DevBuf>> gin;  // input gradient of layer l (l >= 1)
+  float* pinned_loss = nullptr;
+  ~Network() {
+    if (pinned_loss) cudaFreeHost(pinned_loss);
+  }
+};
+
+static int stage_in(DevBuf& buf, const float* src, int64_t count, int mem, const float** out) {
+  if (src == nullptr || mem == ATHENA_MEM_DEVICE) {
+    *out = src;
+    return ATHENA_OK;
+  }
+  ATH_TRY(buf.reserve(sizeof(float) * (size_t)std::max<int64_t>(count, 1)));
+  if (count > 0)
+    ATH_CUDA(cudaMemcpyAsync(buf.p, src, sizeof(float) * (size_t)count, cudaMemcpyHostToDevice,
+                             ctx().stream));
+  *out = buf.as<float>();
+  return ATHENA_OK;
+}
+
+static int net_forward_dev(Network* N, Batch* b, const float* x, const float* e,
+                           const float** out) {
+  const float* in = x;
+  for (size_t l = 0; l < N->layers.size(); ++l) {
+    const float* o = nullptr;
+    ATH_TRY(layer_forward_dev(N->layers[l], b, in, e, &o));
+    in = o;
+  }
+  *out = in;
+  return ATHENA_OK;
+}
+
+static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, const float* tgt,
+                          int mem, int global_batch, float* loss) {
+  ATH_REQUIRE(N->compiled, ATHENA_ERR_STATE, "network is not compiled");
+  ATH_REQUIRE(tgt != nullptr, ATHENA_ERR_ARG, "train: target is null");
+  Layer* first = N->layers.front();
+  Layer* last = N->layers.back();
+  const float *dx, *de, *dt, *out;
+  ATH_TRY(stage_in(N->stage_x, x, b->V * first->nvf[0], mem, &dx));
+  ATH_TRY(stage_in(N->stage_e, e, b->E * last->nef, mem, &de));
+  const int64_t out_n = last->out_rows(b) * last->out_width();
+  ATH_TRY(stage_in(N->stage_t, tgt, out_n, mem, &dt));
+  float* gflat = N->flat_grads.as<float>();
+  cudaStream_t st = ctx().stream;
+  ATH_CUDA(cudaMemsetAsync(gflat + N->n, 0, sizeof(float), st));
+  ATH_TRY(net_forward_dev(N, b, dx, de, &out));
+  ATH_TRY(N->gbuf.reserve(sizeof(float) * (size_t)std::max<int64_t>(out_n, 1)));
+  if (last->kind == 0) {
+    ATH_TRY(launch_mse_graph(out, dt, b->vgraph, b->nv, last->nvf[last->T], b->V,
+                             N->gbuf.as<float>(), gflat + N->n, N->loss_scratch));
+  } else {
+    int gb = global_batch > 0 ? global_batch : b->B;
+    ATH_TRY(launch_mse_array(out, dt, out_n, (float)((int64_t)last->n_out * gb),
+                             N->gbuf.as<float>(), gflat + N->n, N->loss_scratch));
+  }
+  const float* g = N->gbuf.as<float>();
+  for (int l = (int)N->layers.size() - 1; l >= 0; --l) {
+    float* gi = nullptr;
+    if (l > 0) {
+      DevBuf& buf = *N->gin[l];
+      ATH_TRY(buf.reserve(sizeof(float) *
+                          (size_t)std::max<int64_t>(b->V * N->layers[l]->nvf[0], 1)));
+      gi = buf.as<float>();
+    }
+    ATH_TRY(layer_backward_dev(N->layers[l], b, g, gi));
+    g = gi;
+  }
+  ATH_TRY(comm_allreduce_sum(gflat, N->n + 1));
+  if (loss) {
+    ATH_CUDA(cudaMemcpyAsync(N->pinned_loss, gflat + N->n, sizeof(float), cudaMemcpyDeviceToHost,
+                             st));
+    ATH_CUDA(cudaStreamSynchronize(st));
+    *loss = *N->pinned_loss;
+  }
+  return ATHENA_OK;
+}
+
+}  // namespace athena
+
+using namespace athena;
+
+// ---- layer ABI ---------------------------------------------------------------------
+
+static int check_act(int a) { return a >= ATHENA_ACT_NONE && a <= ATHENA_ACT_SOFTMAX; }
+
+ATHENA_API int athena_cuda_kipf_layer_create(athena_handle_t* layer, int32_t num_time_steps,
+                                             const int32_t* num_vertex_features,
+                                             int32_t activation) {
+  ATH_TRY(ensure_init());
+  ATH_REQUIRE(layer && num_vertex_features, ATHENA_ERR_ARG, "kipf_layer_create: null argument");
+  // "Number of time steps must be at least 1": athena_kipf_msgpass_layer.f90:271-274
+  ATH_REQUIRE(num_time_steps >= 1, ATHENA_ERR_ARG,
+              "kipf_layer_create: num_time_steps must be >= 1 (got %d)", num_time_steps);
+  ATH_REQUIRE(check_act(activation), ATHENA_ERR_ARG, "kipf_layer_create: unknown activation %d",
+              activation);
+  std::unique_ptr<Layer> L(new Layer);
+  L->kind = 0;
+  L->T = num_time_steps;
+  L->act = activation;
+  for (int t = 0; t <= num_time_steps; ++t) {
+    ATH_REQUIRE(num_vertex_features[t] >= 1, ATHENA_ERR_ARG,
+                "kipf_layer_create: num_vertex_features(%d) = %d", t, num_vertex_features[t]);
+    L->nvf.push_back(num_vertex_features[t]);
+  }
+  layer_layout(L.get());
+  ATH_TRY(layer_alloc_params(L.get()));
+  *layer = register_object(L.release());
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_duvenaud_layer_create(athena_handle_t* layer, int32_t num_time_steps,
+                                                 const int32_t* num_vertex_features,
+                                                 int32_t num_edge_features,
+                                                 int32_t min_vertex_degree,
+                                                 int32_t max_vertex_degree, int32_t num_outputs,
+                                                 int32_t message_activation,
+                                                 int32_t readout_activation) {
+  ATH_TRY(ensure_init());
+  ATH_REQUIRE(layer && num_vertex_features, ATHENA_ERR_ARG,
+              "duvenaud_layer_create: null argument");
+  ATH_REQUIRE(num_time_steps >= 1, ATHENA_ERR_ARG,
+              "duvenaud_layer_create: num_time_steps must be >= 1 (got %d)", num_time_steps);
+  ATH_REQUIRE(num_edge_features >= 0 && num_outputs >= 1, ATHENA_ERR_ARG,
+              "duvenaud_layer_create: bad num_edge_features/num_outputs");
+  ATH_REQUIRE(min_vertex_degree >= 1 && max_vertex_degree >= min_vertex_degree, ATHENA_ERR_ARG,
+              "duvenaud_layer_create: need 1 <= min_vertex_degree <= max_vertex_degree");
+  ATH_REQUIRE(check_act(message_activation) && check_act(readout_activation), ATHENA_ERR_ARG,
+              "duvenaud_layer_create: unknown activation");
+  std::unique_ptr<Layer> L(new Layer);
+  L->kind = 1;
+  L->T = num_time_steps;
+  L->nef = num_edge_features;
+  L->min_deg = min_vertex_degree;
+  L->max_deg = max_vertex_degree;
+  L->n_out = num_outputs;
+  L->act = message_activation;
+  L->ract = readout_activation;
+  for (int t = 0; t <= num_time_steps; ++t) {
+    ATH_REQUIRE(num_vertex_features[t] >= 1, ATHENA_ERR_ARG,
+                "duvenaud_layer_create: num_vertex_features(%d) = %d", t, num_vertex_features[t]);
+    L->nvf.push_back(num_vertex_features[t]);
+  }
+  layer_layout(L.get());
+  ATH_TRY(layer_alloc_params(L.get()));
+  *layer = register_object(L.release());
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_layer_destroy(athena_handle_t layer) {
+  Layer* L = static_cast<Layer*>(lookup_object(layer, Kind::Layer));
+  if (!L) return ATHENA_ERR_HANDLE;
+  ATH_REQUIRE(!L->adopted, ATHENA_ERR_STATE,
+              "layer_destroy: layer belongs to a network; destroy the network instead");
+  return destroy_object(layer, Kind::Layer);
+}
+
+ATHENA_API int athena_cuda_layer_num_params(athena_handle_t layer, int64_t* n) {
+  Layer* L = static_cast<Layer*>(lookup_object(layer, Kind::Layer));
+  if (!L) return ATHENA_ERR_HANDLE;
+  if (n) *n = L->num_params;
+  return ATHENA_OK;
+}
+
+static int layer_copy(athena_handle_t layer, float* host_out, const float* host_in, int64_t n,
+                      bool grads) {
+  Layer* L = static_cast<Layer*>(lookup_object(layer, Kind::Layer));
+  if (!L) return ATHENA_ERR_HANDLE;
+  ATH_REQUIRE(n == L->num_params, ATHENA_ERR_ARG, "layer has %lld parameters, caller passed %lld",
+              (long long)L->num_params, (long long)n);
+  float* dev = grads ? L->grads : L->params;
+  cudaStream_t st = ctx().stream;
+  if (host_in) {
+    ATH_CUDA(cudaMemcpyAsync(dev, host_in, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+    ATH_CUDA(cudaStreamSynchronize(st));
+  } else {
+    ATH_CUDA(cudaMemcpyAsync(host_out, dev, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    ATH_CUDA(cudaStreamSynchronize(st));
+  }
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_layer_set_params(athena_handle_t layer, const float* host, int64_t n) {
+  ATH_REQUIRE(host, ATHENA_ERR_ARG, "set_params: null");
+  return layer_copy(layer, nullptr, host, n, false);
+}
+ATHENA_API int athena_cuda_layer_get_params(athena_handle_t layer, float* host, int64_t n) {
+  ATH_REQUIRE(host, ATHENA_ERR_ARG, "get_params: null");
+  return layer_copy(layer, host, nullptr, n, false);
+}
+ATHENA_API int athena_cuda_layer_set_gradients(athena_handle_t layer, const float* host,
+                                               int64_t n) {
+  ATH_REQUIRE(host, ATHENA_ERR_ARG, "set_gradients: null");
+  return layer_copy(layer, nullptr, host, n, true);
+}
+ATHENA_API int athena_cuda_layer_get_gradients(athena_handle_t layer, float* host, int64_t n) {
+  ATH_REQUIRE(host, ATHENA_ERR_ARG, "get_gradients: null");
+  return layer_copy(layer, host, nullptr, n, true);
+}
+ATHENA_API int athena_cuda_layer_zero_gradients(athena_handle_t layer) {
+  Layer* L = static_cast<Layer*>(lookup_object(layer, Kind::Layer));
+  if (!L) return ATHENA_ERR_HANDLE;
+  ATH_CUDA(cudaMemsetAsync(L->grads, 0, sizeof(float) * (size_t)L->num_params, ctx().stream));
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_layer_forward(athena_handle_t layer, athena_handle_t batch,
+                                         const float* vertex_features, const float* edge_features,
+                                         float* output, int32_t mem) {
+  Layer* L = static_cast<Layer*>(lookup_object(layer, Kind::Layer));
+  Batch* b = static_cast<Batch*>(lookup_object(batch, Kind::Batch));
+  if (!L || !b) return ATHENA_ERR_HANDLE;
+  const float *dx, *de, *out;
+  ATH_TRY(stage_in(L->stage_x, vertex_features, b->V * L->nvf[0], mem, &dx));
+  ATH_TRY(stage_in(L->stage_e, edge_features, b->E * L->nef, mem, &de));
+  ATH_TRY(layer_forward_dev(L, b, dx, de, &out));
+  if (output) {
+    size_t bytes = sizeof(float) * (size_t)(L->out_rows(b) * L->out_width());
+    cudaStream_t st = ctx().stream;
+    if (mem == ATHENA_MEM_HOST) {
+      ATH_CUDA(cudaMemcpyAsync(output, out, bytes, cudaMemcpyDeviceToHost, st));
+      ATH_CUDA(cudaStreamSynchronize(st));
+    } else {
+      ATH_CUDA(cudaMemcpyAsync(output, out, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_layer_backward(athena_handle_t layer, athena_handle_t batch,
+                                          const float* grad_output, float* grad_input,
+                                          int32_t mem) {
+  Layer* L = static_cast<Layer*>(lookup_object(layer, Kind::Layer));
+  Batch* b = static_cast<Batch*>(lookup_object(batch, Kind::Batch));
+  if (!L || !b) return ATHENA_ERR_HANDLE;
+  const float* dg;
+  ATH_TRY(stage_in(L->stage_g, grad_output, L->out_rows(b) * L->out_width(), mem, &dg));
+  float* dgi = grad_input;
+  int64_t gin_n = b->V * L->nvf[0];
+  if (grad_input && mem == ATHENA_MEM_HOST) {
+    ATH_TRY(L->stage_gin.reserve(sizeof(float) * (size_t)std::max<int64_t>(gin_n, 1)));
+    dgi = L->stage_gin.as<float>();
+  }
+  ATH_TRY(layer_backward_dev(L, b, dg, dgi));
+  if (grad_input && mem == ATHENA_MEM_HOST) {
+    cudaStream_t st = ctx().stream;
+    ATH_CUDA(cudaMemcpyAsync(grad_input, dgi, sizeof(float) * (size_t)gin_n,
+                             cudaMemcpyDeviceToHost, st));
+    ATH_CUDA(cudaStreamSynchronize(st));
+  }
+  return ATHENA_OK;
+}
+
+// ---- network ABI -------------------------------------------------------------------
+
+ATHENA_API int athena_cuda_network_create(athena_handle_t* net) {
+  ATH_TRY(ensure_init());
+  ATH_REQUIRE(net, ATHENA_ERR_ARG, "network_create: null");
+  *net = register_object(new Network);
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_network_destroy(athena_handle_t net) {
+  Network* N = static_cast<Network*>(lookup_object(net, Kind::Network));
+  if (!N) return ATHENA_ERR_HANDLE;
+  std::vector<athena_handle_t> hs = N->handles;
+  ATH_TRY(destroy_object(net, Kind::Network));
+  for (athena_handle_t h : hs) destroy_object(h, Kind::Layer);
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_network_add(athena_handle_t net, athena_handle_t layer) {
+  Network* N = static_cast<Network*>(lookup_object(net, Kind::Network));
+  Layer* L = static_cast<Layer*>(lookup_object(layer, Kind::Layer));
+  if (!N || !L) return ATHENA_ERR_HANDLE;
+  ATH_REQUIRE(!N->compiled, ATHENA_ERR_STATE, "network_add: network already compiled");
+  ATH_REQUIRE(!L->adopted, ATHENA_ERR_STATE, "network_add: layer already belongs to a network");
+  if (!N->layers.empty()) {
+    Layer* prev = N->layers.back();
+    ATH_REQUIRE(prev->kind == 0, ATHENA_ERR_ARG,
+                "network_add: a Duvenaud layer emits a graph-level output and must be last");
+    ATH_REQUIRE(prev->nvf[prev->T] == L->nvf[0], ATHENA_ERR_ARG,
+                "network_add: layer expects %d vertex features, previous layer emits %d",
+                L->nvf[0], prev->nvf[prev->T]);
+  }
+  L->adopted = true;
+  N->layers.push_back(L);
+  N->handles.push_back(layer);
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_network_compile(athena_handle_t net,
+                                           const athena_optimiser_desc* optimiser) {
+  Network* N = static_cast<Network*>(lookup_object(net, Kind::Network));
+  if (!N) return ATHENA_ERR_HANDLE;
+  ATH_REQUIRE(optimiser, ATHENA_ERR_ARG, "network_compile: null optimiser");
+  ATH_REQUIRE(!N->layers.empty(), ATHENA_ERR_STATE, "network_compile: no layers");
+  ATH_REQUIRE(!N->compiled, ATHENA_ERR_STATE, "network_compile: already compiled");
+  ATH_REQUIRE(optimiser->kind == ATHENA_OPT_SGD || optimiser->kind == ATHENA_OPT_ADAM,
+              ATHENA_ERR_ARG, "network_compile: unknown optimiser kind %d", optimiser->kind);
+  int64_t n = 0;
+  for (Layer* L : N->layers) n += L->num_params;
+  N->n = n;
+  size_t bytes = sizeof(float) * (size_t)(n + 4);
+  ATH_TRY(N->flat_params.reserve(bytes));
+  ATH_TRY(N->flat_grads.reserve(bytes));
+  cudaStream_t st = ctx().stream;
+  ATH_CUDA(cudaMemsetAsync(N->flat_grads.p, 0, bytes, st));
+  // re-home every layer's parameters into the flat buffer, layer order x params order
+  // (athena_base_layer_sub.f90:545-571, athena_network_sub.f90:2847-2903)
+  int64_t off = 0;
+  for (Layer* L : N->layers) {
+    ATH_CUDA(cudaMemcpyAsync(N->flat_params.as<float>() + off, L->params,
+                             sizeof(float) * (size_t)L->num_params, cudaMemcpyDeviceToDevice, st));
+    L->params = N->flat_params.as<float>() + off;
+    L->grads = N->flat_grads.as<float>() + off;
+    off += L->num_params;
+  }
+  ATH_CUDA(cudaStreamSynchronize(st));
+  for (Layer* L : N->layers) {
+    L->own_params.release();
+    L->own_grads.release();
+  }
+  N->gin.clear();
+  for (size_t l = 0; l < N->layers.size(); ++l) N->gin.emplace_back(new DevBuf);
+  N->opt.d = *optimiser;
+  N->opt.lr = optimiser->learning_rate;
+  N->opt.iter = 0;
+  ATH_CUDA(cudaHostAlloc((void**)&N->pinned_loss, sizeof(float) * 4, cudaHostAllocDefault));
+  N->compiled = true;
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_network_num_params(athena_handle_t net, int64_t* n) {
+  Network* N = static_cast<Network*>(lookup_object(net, Kind::Network));
+  if (!N) return ATHENA_ERR_HANDLE;
+  int64_t s = 0;
+  for (Layer* L : N->layers) s += L->num_params;
+  if (n) *n = s;
+  return ATHENA_OK;
+}
+
+static int net_copy(athena_handle_t net, float* host_out, const float* host_in, int64_t n,
+                    bool grads) {
+  Network* N = static_cast<Network*>(lookup_object(net, Kind::Network));
+  if (!N) return ATHENA_ERR_HANDLE;
+  ATH_REQUIRE(N->compiled, ATHENA_ERR_STATE, "network is not compiled");
+  ATH_REQUIRE(n == N->n, ATHENA_ERR_ARG, "network has %lld parameters, caller passed %lld",
+              (long long)N->n, (long long)n);
+  float* dev = grads ? N->flat_grads.as<float>() : N->flat_params.as<float>();
+  cudaStream_t st = ctx().stream;
+  if (host_in)
+    ATH_CUDA(cudaMemcpyAsync(dev, host_in, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+  else
+    ATH_CUDA(cudaMemcpyAsync(host_out, dev, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  ATH_CUDA(cudaStreamSynchronize(st));
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_network_set_params(athena_handle_t net, const float* host, int64_t n) {
+  ATH_REQUIRE(host, ATHENA_ERR_ARG, "set_params: null");
+  return net_copy(net, nullptr, host, n, false);
+}
+ATHENA_API int athena_cuda_network_get_params(athena_handle_t net, float* host, int64_t n) {
+  ATH_REQUIRE(host, ATHENA_ERR_ARG, "get_params: null");
+  return net_copy(net, host, nullptr, n, false);
+}
+ATHENA_API int athena_cuda_network_get_gradients(athena_handle_t net, float* host, int64_t n) {
+  ATH_REQUIRE(host, ATHENA_ERR_ARG, "get_gradients: null");
+  return net_copy(net, host, nullptr, n, true);
+}
+
+ATHENA_API int athena_cuda_network_set_learning_rate(athena_handle_t net, float lr) {
+  Network* N = static_cast<Network*>(lookup_object(net, Kind::Network));
+  if (!N) return ATHENA_ERR_HANDLE;
+  N->opt.lr = lr;
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_network_forward(athena_handle_t net, athena_handle_t batch,
+                                           const float* vertex_features,
+                                           const float* edge_features, float* output,
+                                           int32_t mem) {
+  Network* N = static_cast<Network*>(lookup_object(net, Kind::Network));
+  Batch* b = static_cast<Batch*>(lookup_object(batch, Kind::Batch));
+  if (!N || !b) return ATHENA_ERR_HANDLE;
+  ATH_REQUIRE(!N->layers.empty(), ATHENA_ERR_STATE, "network_forward: no layers");
+  Layer* first = N->layers.front();
+  Layer* last = N->layers.back();
+  const float *dx, *de, *out;
+  ATH_TRY(stage_in(N->stage_x, vertex_features, b->V * first->nvf[0], mem, &dx));
+  ATH_TRY(stage_in(N->stage_e, edge_features, b->E * last->nef, mem, &de));
+  ATH_TRY(net_forward_dev(N, b, dx, de, &out));
+  if (output) {
+    size_t bytes = sizeof(float) * (size_t)(last->out_rows(b) * last->out_width());
+    cudaStream_t st = ctx().stream;
+    if (mem == ATHENA_MEM_HOST) {
+      ATH_CUDA(cudaMemcpyAsync(output, out, bytes, cudaMemcpyDeviceToHost, st));
+      ATH_CUDA(cudaStreamSynchronize(st));
+    } else {
+      ATH_CUDA(cudaMemcpyAsync(output, out, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_network_loss_and_gradients(athena_handle_t net, athena_handle_t batch,
+                                                      const float* vertex_features,
+                                                      const float* edge_features,
+                                                      const float* target, int32_t mem,
+                                                      int32_t global_batch, float* loss) {
+  Network* N = static_cast<Network*>(lookup_object(net, Kind::Network));
+  Batch* b = static_cast<Batch*>(lookup_object(batch, Kind::Batch));
+  if (!N || !b) return ATHENA_ERR_HANDLE;
+  return net_loss_grads(N, b, vertex_features, edge_features, target, mem, global_batch, loss);
+}
+
+ATHENA_API int athena_cuda_network_update(athena_handle_t net) {
+  Network* N = static_cast<Network*>(lookup_object(net, Kind::Network));
+  if (!N) return ATHENA_ERR_HANDLE;
+  ATH_REQUIRE(N->compiled, ATHENA_ERR_STATE, "network is not compiled");
+  return launch_update(N->flat_params.as<float>(), N->flat_grads.as<float>(), N->n, N->opt);
+}
+
+ATHENA_API int athena_cuda_network_train_step(athena_handle_t net, athena_handle_t batch,
+                                              const float* vertex_features,
+                                              const float* edge_features, const float* target,
+                                              int32_t mem, int32_t global_batch, float* loss) {
+  Network* N = static_cast<Network*>(lookup_object(net, Kind::Network));
+  Batch* b = static_cast<Batch*>(lookup_object(batch, Kind::Batch));
+  if (!N || !b) return ATHENA_ERR_HANDLE;
+  // the loss read-back (if requested) is deferred until the step is queued,
+  // so the host does not stall between backward and update
+  ATH_TRY(net_loss_grads(N, b, vertex_features, edge_features, target, mem, global_batch,
+                         nullptr));
+  ATH_TRY(launch_update(N->flat_params.as<float>(), N->flat_grads.as<float>(), N->n, N->opt));
+  if (loss) return athena_cuda_network_last_loss(net, loss);
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_network_last_loss(athena_handle_t net, float* loss) {
+  Network* N = static_cast<Network*>(lookup_object(net, Kind::Network));
+  if (!N) return ATHENA_ERR_HANDLE;
+  ATH_REQUIRE(N->compiled && loss, ATHENA_ERR_STATE, "last_loss: network not compiled / null");
+  cudaStream_t st = ctx().stream;
+  ATH_CUDA(cudaMemcpyAsync(N->pinned_loss, N->flat_grads.as<float>() + N->n, sizeof(float),
+                           cudaMemcpyDeviceToHost, st));
+  ATH_CUDA(cudaStreamSynchronize(st));
+  *loss = *N->pinned_loss;
+  return ATHENA_OK;
+}

@@ -1,0 +1,231 @@
+// MSE loss (+ its gradient seed) and the clip + optimiser step.
+//   compute_mse            athena_loss.f90:393-430   (mean over all elements / 2,
+//                          summed over cells; pinned by test/test_loss.f90:59-67,135-143)
+//   clip_type%apply        athena_clipper.f90:165-207
+//   minimise_sgd           athena_optimiser.f90:634-673
+//   minimise_adam          athena_optimiser.f90:1027-1091
+//   network%update         athena_network_sub.f90:2816-2929 (clip -> minimise -> zero grads)
+// All reductions are two-pass with a fixed grid, so results are run-to-run
+// identical (no float atomics).
+#include <algorithm>
+#include <cmath>
+
+#include "athena_internal.h"
+
+namespace athena {
+
+constexpr int RED_THREADS = 256;
+
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float ws[RED_THREADS / 32];
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) ws[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (warp == 0) {
+    r = lane < RED_THREADS / 32 ? ws[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  __syncthreads();
+  return r;  // valid in warp 0
+}
+
+// graph-output MSE: cell s = graph s, N_cell = F * nv[s]
+__global__ void __launch_bounds__(RED_THREADS)
+k_mse_graph(const float* __restrict__ pred, const float* __restrict__ target,
+            const int32_t* __restrict__ vgraph, const int32_t* __restrict__ nv, int F, long long n,
+            float* __restrict__ grad, float* __restrict__ partial) {
+  float local = 0.f;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    long long v = i / F;
+    float denom = (float)(F * __ldg(nv + __ldg(vgraph + v)));
+    float d = pred[i] - target[i];
+    grad[i] = d / denom;
+    local += d * d / denom;
+  }
+  float s = block_sum(local);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_mse_array(const float* __restrict__ pred, const float* __restrict__ target, long long n,
+            float denom, float* __restrict__ grad, float* __restrict__ partial) {
+  float local = 0.f;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float d = pred[i] - target[i];
+    grad[i] = d / denom;
+    local += d * d / denom;
+  }
+  float s = block_sum(local);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// loss_acc[0] += 0.5 * sum(partial)   (single block, fixed order)
+__global__ void __launch_bounds__(RED_THREADS)
+k_loss_finish(const float* __restrict__ partial, int nb, float* __restrict__ loss_acc) {
+  float local = 0.f;
+  for (int i = threadIdx.x; i < nb; i += RED_THREADS) local += partial[i];
+  float s = block_sum(local);
+  if (threadIdx.x == 0) loss_acc[0] += 0.5f * s;
+}
+
+static int red_blocks(int64_t n) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, RED_THREADS * 4), 1024));
+}
+
+int launch_mse_graph(const float* pred, const float* target, const int32_t* vgraph,
+                     const int32_t* nv, int F, int64_t V, float* grad, float* loss_acc,
+                     DevBuf& scratch) {
+  int64_t n = V * F;
+  if (n == 0) return ATHENA_OK;
+  int nb = red_blocks(n);
+  ATH_TRY(scratch.reserve(sizeof(float) * 1024));
+  cudaStream_t st = ctx().stream;
+  k_mse_graph<<<nb, RED_THREADS, 0, st>>>(pred, target, vgraph, nv, F, n, grad,
+                                          scratch.as<float>());
+  ATH_LAUNCHED_T("mse_graph");
+  k_loss_finish<<<1, RED_THREADS, 0, st>>>(scratch.as<float>(), nb, loss_acc);
+  ATH_LAUNCHED_T("loss_finish");
+  return ATHENA_OK;
+}
+
+int launch_mse_array(const float* pred, const float* target, int64_t n, float denom, float* grad,
+                     float* loss_acc, DevBuf& scratch) {
+  if (n == 0) return ATHENA_OK;
+  int nb = red_blocks(n);
+  ATH_TRY(scratch.reserve(sizeof(float) * 1024));
+  cudaStream_t st = ctx().stream;
+  k_mse_array<<<nb, RED_THREADS, 0, st>>>(pred, target, n, denom, grad, scratch.as<float>());
+  ATH_LAUNCHED_T("mse_array");
+  k_loss_finish<<<1, RED_THREADS, 0, st>>>(scratch.as<float>(), nb, loss_acc);
+  ATH_LAUNCHED_T("loss_finish");
+  return ATHENA_OK;
+}
+
+// ---- clip + step ---------------------------------------------------------------
+
+// elementwise clamp (written back) + partial sums of squares
+__global__ void __launch_bounds__(RED_THREADS)
+k_clip_sumsq(float* __restrict__ g, long long n, int clamp, float cmin, float cmax,
+             float* __restrict__ partial) {
+  float local = 0.f;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float x = g[i];
+    if (clamp) {
+      x = fmaxf(cmin, fminf(cmax, x));
+      g[i] = x;
+    }
+    local += x * x;
+  }
+  float s = block_sum(local);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+struct StepArgs {
+  int kind;
+  float lr, beta1, beta2, eps, momentum;
+  int nesterov;
+  int norm_on;
+  float clip_norm;
+  float bc1, bc2;
+};
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_step(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
+       float* __restrict__ s2, long long n, const float* __restrict__ partial, int nb,
+       StepArgs a) {
+  __shared__ float scale_sh;
+  if (a.norm_on) {
+    // every block re-derives the same total in the same order
+    float local = 0.f;
+    for (int i = threadIdx.x; i < nb; i += RED_THREADS) local += partial[i];
+    float tot = block_sum(local);
+    if (threadIdx.x == 0) scale_sh = fminf(1.f, a.clip_norm / sqrtf(tot));
+  } else if (threadIdx.x == 0) {
+    scale_sh = 1.f;
+  }
+  __syncthreads();
+  const float scale = scale_sh;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float gr = g[i];
+    if (scale < 1.f) gr = gr * scale;
+    if (a.kind == ATHENA_OPT_SGD) {
+      gr = -a.lr * gr;
+      if (a.momentum > 1e-8f) {
+        float vel = a.momentum * s1[i] + gr;
+        s1[i] = vel;
+        p[i] = a.nesterov ? p[i] + a.momentum * vel + gr : p[i] + vel;
+      } else {
+        s1[i] = gr;
+        p[i] = p[i] + gr;
+      }
+    } else {
+      float m = a.beta1 * s1[i] + (1.f - a.beta1) * gr;
+      float v = a.beta2 * s2[i] + (1.f - a.beta2) * gr * gr;
+      s1[i] = m;
+      s2[i] = v;
+      float mh = m / a.bc1, vh = v / a.bc2;
+      p[i] = p[i] - a.lr * (mh / (sqrtf(vh) + a.eps));
+    }
+    g[i] = 0.f;  // reset_gradients, athena_network_sub.f90:2927
+  }
+}
+
+static float powi(float b, int64_t e) {  // real ** integer
+  float r = 1.f, x = b;
+  while (e > 0) {
+    if (e & 1) r *= x;
+    x *= x;
+    e >>= 1;
+  }
+  return r;
+}
+
+int launch_update(float* params, float* grads, int64_t n, OptimState& st) {
+  if (n == 0) return ATHENA_OK;
+  cudaStream_t s = ctx().stream;
+  if (!st.s1.p) {
+    ATH_TRY(st.s1.reserve(sizeof(float) * (size_t)n));
+    ATH_TRY(st.s2.reserve(sizeof(float) * (size_t)n));
+    ATH_CUDA(cudaMemsetAsync(st.s1.p, 0, sizeof(float) * (size_t)n, s));
+    ATH_CUDA(cudaMemsetAsync(st.s2.p, 0, sizeof(float) * (size_t)n, s));
+  }
+  ATH_TRY(st.scratch.reserve(sizeof(float) * 1024));
+  st.iter += 1;  // incremented BEFORE the step, athena_network_sub.f90:2834-2841
+  int nb = red_blocks(n);
+  const athena_optimiser_desc& d = st.d;
+  if (d.clip_min_max || d.clip_norm_on) {
+    k_clip_sumsq<<<nb, RED_THREADS, 0, s>>>(grads, n, d.clip_min_max, d.clip_min, d.clip_max,
+                                            st.scratch.as<float>());
+    ATH_LAUNCHED_T("clip_sumsq");
+  }
+  StepArgs a;
+  a.kind = d.kind;
+  a.lr = st.lr;
+  a.beta1 = d.beta1;
+  a.beta2 = d.beta2;
+  a.eps = d.epsilon;
+  a.momentum = d.momentum;
+  a.nesterov = d.nesterov;
+  a.norm_on = d.clip_norm_on;
+  a.clip_norm = d.clip_norm;
+  a.bc1 = 1.f - powi(d.beta1, st.iter);
+  a.bc2 = 1.f - powi(d.beta2, st.iter);
+  k_step<<<nb, RED_THREADS, 0, s>>>(params, grads, st.s1.as<float>(), st.s2.as<float>(), n,
+                                    st.scratch.as<float>(), nb, a);
+  ATH_LAUNCHED_T("optimiser_step");
+  return ATHENA_OK;
+}
+
+}  // namespace athena

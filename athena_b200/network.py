@@ -1,0 +1,238 @@
+"""Python mirror of the slice of network_type that drives the message-passing
+layers: add / compile / train / forward / predict / update and the flat
+parameter accessors (athena_network.f90:142-223; bodies
+athena_network_sub.f90:2639-2929, 3387-3905, 4226-4303).  Optimisers and the
+clipper are plain descriptors (athena_optimiser.f90, athena_clipper.f90); the
+arithmetic runs in libathena_cuda.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _lib
+from ._lib import AthenaCudaError, OptimiserDesc, check, lib, ptr
+from .graph import PackedGraphs, graph_type, pack_graphs
+from .layers import GraphBatch, msgpass_layer_type
+
+
+class clip_type:
+    """clip_type(clip_min, clip_max, clip_norm) -- athena_clipper.f90:30-120."""
+
+    def __init__(self, clip_min: Optional[float] = None, clip_max: Optional[float] = None,
+                 clip_norm: Optional[float] = None):
+        self.l_min_max = clip_min is not None or clip_max is not None
+        big = float(np.finfo(np.float32).max)
+        self.min = -big if clip_min is None else float(clip_min)
+        self.max = big if clip_max is None else float(clip_max)
+        self.l_norm = clip_norm is not None
+        self.norm = 0.0 if clip_norm is None else float(clip_norm)
+
+
+class base_optimiser_type:
+    kind = _lib.OPT_SGD
+
+    def __init__(self, learning_rate: float = 0.01, clip_dict: Optional[clip_type] = None):
+        self.learning_rate = float(learning_rate)
+        self.clip_dict = clip_dict or clip_type()
+        self.iter = 0
+
+    def desc(self) -> OptimiserDesc:
+        d = OptimiserDesc()
+        d.kind = self.kind
+        d.learning_rate = self.learning_rate
+        d.beta1, d.beta2, d.epsilon = 0.9, 0.999, 1e-8
+        d.momentum, d.nesterov = 0.0, 0
+        c = self.clip_dict
+        d.clip_min_max, d.clip_min, d.clip_max = int(c.l_min_max), c.min, c.max
+        d.clip_norm_on, d.clip_norm = int(c.l_norm), c.norm
+        return d
+
+
+class sgd_optimiser_type(base_optimiser_type):
+    """sgd_optimiser_type(learning_rate, momentum, nesterov) -- athena_optimiser.f90:560-673."""
+    kind = _lib.OPT_SGD
+
+    def __init__(self, learning_rate: float = 0.01, momentum: float = 0.0, nesterov: bool = False,
+                 clip_dict: Optional[clip_type] = None):
+        super().__init__(learning_rate, clip_dict)
+        self.momentum, self.nesterov = float(momentum), bool(nesterov)
+
+    def desc(self):
+        d = super().desc()
+        d.momentum, d.nesterov = self.momentum, int(self.nesterov)
+        return d
+
+
+class adam_optimiser_type(base_optimiser_type):
+    """adam_optimiser_type(learning_rate, beta1, beta2, epsilon) -- athena_optimiser.f90:940-1091."""
+    kind = _lib.OPT_ADAM
+
+    def __init__(self, learning_rate: float = 0.01, beta1: float = 0.9, beta2: float = 0.999,
+                 epsilon: float = 1e-8, clip_dict: Optional[clip_type] = None):
+        super().__init__(learning_rate, clip_dict)
+        self.beta1, self.beta2, self.epsilon = float(beta1), float(beta2), float(epsilon)
+
+    def desc(self):
+        d = super().desc()
+        d.beta1, d.beta2, d.epsilon = self.beta1, self.beta2, self.epsilon
+        return d
+
+
+class network_type:
+    def __init__(self):
+        h = C.c_int64()
+        check(lib().athena_cuda_network_create(C.byref(h)))
+        self.handle = h.value
+        self.model: List[msgpass_layer_type] = []
+        self.batch_size = 0
+        self.loss_val = 0.0
+        self.epoch = 0
+        self.optimiser: Optional[base_optimiser_type] = None
+        self.compiled = False
+
+    # -- construction -------------------------------------------------------
+    def add(self, layer: msgpass_layer_type):
+        check(lib().athena_cuda_network_add(self.handle, layer.handle))
+        layer._owned = False  # the network owns the device object now
+        self.model.append(layer)
+
+    def compile(self, optimiser: base_optimiser_type, loss_method: str = "mse",
+                accuracy_method: str = "mse", metrics=None, batch_size: int = 1, verbose: int = 0):
+        if loss_method != "mse":
+            raise AthenaCudaError(-2, f"loss_method '{loss_method}' is outside the CUDA path (mse only)")
+        d = optimiser.desc()
+        check(lib().athena_cuda_network_compile(self.handle, C.byref(d)))
+        self.optimiser = optimiser
+        self.batch_size = int(batch_size)
+        self.compiled = True
+
+    @property
+    def num_layers(self) -> int:
+        return len(self.model) + 1  # + the implicit input layer, as the reference counts
+
+    @property
+    def num_params(self) -> int:
+        n = C.c_int64()
+        check(lib().athena_cuda_network_num_params(self.handle, C.byref(n)))
+        return n.value
+
+    def get_num_params(self) -> int:
+        return self.num_params
+
+    def get_params(self) -> np.ndarray:
+        out = np.empty(self.num_params, np.float32)
+        check(lib().athena_cuda_network_get_params(self.handle, ptr(out), out.size))
+        return out
+
+    def set_params(self, params):
+        a = np.ascontiguousarray(params, np.float32)
+        check(lib().athena_cuda_network_set_params(self.handle, ptr(a), a.size))
+
+    def get_gradients(self) -> np.ndarray:
+        out = np.empty(self.num_params, np.float32)
+        check(lib().athena_cuda_network_get_gradients(self.handle, ptr(out), out.size))
+        return out
+
+    def set_learning_rate(self, lr: float):
+        check(lib().athena_cuda_network_set_learning_rate(self.handle, float(lr)))
+
+    # -- one iteration of the batch loop ------------------------------------
+    def _out_shape(self, batch: GraphBatch):
+        last = self.model[-1]
+        if last.name == "kipf":
+            return (batch.V, last.num_vertex_features[-1])
+        return (batch.B, last.num_outputs)
+
+    def forward(self, graphs: Union[Sequence[graph_type], PackedGraphs, GraphBatch],
+                vertex_features=None, edge_features=None) -> np.ndarray:
+        batch = graphs if isinstance(graphs, GraphBatch) else GraphBatch(graphs)
+        p = batch.packed
+        x = np.ascontiguousarray(p.x if vertex_features is None else vertex_features, np.float32)
+        e = p.e if edge_features is None else edge_features
+        e = None if e is None else np.ascontiguousarray(e, np.float32)
+        out = np.empty(self._out_shape(batch), np.float32)
+        check(lib().athena_cuda_network_forward(self.handle, batch.handle, ptr(x), ptr(e), ptr(out),
+                                                _lib.MEM_HOST))
+        return out
+
+    predict = forward
+
+    def train_step(self, batch: GraphBatch, target, global_batch: int = 0,
+                   vertex_features=None, edge_features=None, want_loss: bool = True) -> float:
+        p = batch.packed
+        x = np.ascontiguousarray(p.x if vertex_features is None else vertex_features, np.float32)
+        e = p.e if edge_features is None else edge_features
+        e = None if e is None else np.ascontiguousarray(e, np.float32)
+        t = np.ascontiguousarray(target, np.float32)
+        assert t.size == int(np.prod(self._out_shape(batch))), "target shape mismatch"
+        loss = C.c_float()
+        check(lib().athena_cuda_network_train_step(
+            self.handle, batch.handle, ptr(x), ptr(e), ptr(t), _lib.MEM_HOST, int(global_batch),
+            C.byref(loss) if want_loss else None))
+        self.loss_val = float(loss.value)
+        return self.loss_val
+
+    def loss_and_gradients(self, batch: GraphBatch, target, global_batch: int = 0) -> float:
+        p = batch.packed
+        t = np.ascontiguousarray(target, np.float32)
+        loss = C.c_float()
+        check(lib().athena_cuda_network_loss_and_gradients(
+            self.handle, batch.handle, ptr(p.x), ptr(p.e), ptr(t), _lib.MEM_HOST,
+            int(global_batch), C.byref(loss)))
+        return float(loss.value)
+
+    def update(self):
+        check(lib().athena_cuda_network_update(self.handle))
+
+    # -- network%train -------------------------------------------------------
+    def train(self, input: Union[Sequence[graph_type], PackedGraphs], output, num_epochs: int = 1,
+              batch_size: Optional[int] = None, shuffle_batches: bool = True, verbose: int = 0,
+              seed: int = 0) -> List[float]:
+        """Batch loop of athena_network_sub.f90:3575-3670.  `output` is the
+        target: for a Kipf-last network the per-vertex target [V_tot, F_T] (the
+        reference passes graph_type targets); for a Duvenaud-last network
+        [num_samples, num_outputs]."""
+        if not self.compiled:
+            raise AthenaCudaError(-5, "network is not compiled")
+        packed = input if isinstance(input, PackedGraphs) else pack_graphs(input)
+        bs = int(batch_size or self.batch_size or packed.B)
+        num_samples = packed.B
+        num_batches = (num_samples + bs - 1) // bs
+        order = np.arange(num_batches)
+        rng = np.random.default_rng(seed)
+        target = np.ascontiguousarray(output, np.float32)
+        kipf_last = self.model[-1].name == "kipf"
+        voff = np.concatenate([[0], np.cumsum(packed.nv, dtype=np.int64)])
+        history = []
+        for epoch in range(1, num_epochs + 1):
+            self.epoch = epoch
+            if shuffle_batches:
+                rng.shuffle(order)
+            avg = 0.0
+            for b in order:
+                s0, s1 = int(b) * bs, min((int(b) + 1) * bs, num_samples)
+                batch = GraphBatch(packed.slice(s0, s1))
+                tgt = target[voff[s0]:voff[s1]] if kipf_last else target[s0:s1]
+                avg += self.train_step(batch, tgt)
+                batch.destroy()
+            self.loss_val = avg / num_batches
+            history.append(self.loss_val)
+            if verbose:
+                print(f"epoch {epoch}: loss {self.loss_val:.6e}")
+        return history
+
+    def destroy(self):
+        if self.handle:
+            lib().athena_cuda_network_destroy(self.handle)
+            self.handle = 0
+            for layer in self.model:
+                layer.handle = 0
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

@@ -1,0 +1,386 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against
+the CPU oracle on the same seeded inputs.
+
+  - integer structures (CSR / CSC / degrees / buckets / permutation): bit-exact
+  - forward activations and gradients (fp32): <= 1e-5 relative
+  - parameters after N training steps: <= 1e-4 relative
+(BASELINE.json north_star).  Relative = max|a-b| / max|ref| (see helpers.rel_err).
+"""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import athena_b200 as ab
+from athena_b200 import synth
+from helpers import (RTOL_ACT, RTOL_PARAM, duvenaud_spec, kipf_spec, random_params, rel_err,
+                     to_oracle_batch)
+from oracle.oracle import Batch, OptimSpec
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ---------------------------------------------------------------------------
+# K1: batch build, bit-exact
+# ---------------------------------------------------------------------------
+def _check_batch(cuda, oracle32, p, buckets=((1, 10), (2, 5), (1, 1))):
+    ref = oracle32.batch_build(p.nv, p.ne, p.ia, p.ja)
+    gb = ab.GraphBatch(p)
+    for k in ("row_ptr", "col", "eid", "deg", "vgraph", "csc_ptr", "csc_src", "csc_ent"):
+        got = gb.export(k)
+        assert np.array_equal(got, ref[k]), k
+    # coefficient: float regime (powf vs 1/sqrtf), 1e-6 relative
+    v_of = np.repeat(np.arange(p.V), ref["deg"])
+    coef_ref = 1.0 / np.sqrt((ref["deg"][v_of].astype(np.float64) * ref["deg"][ref["col"]]))
+    assert rel_err(gb.export("coef"), coef_ref) <= 1e-6
+    for mn, mx in buckets:
+        gb.bucketize(mn, mx)
+        bkt, perm, ptr = oracle32.bucketize(ref["deg"], mn, mx)
+        assert np.array_equal(gb.export("bucket"), bkt)
+        assert np.array_equal(gb.export("perm"), perm)
+        assert np.array_equal(gb.export("bucket_ptr"), ptr)
+    gb.destroy()
+
+
+def test_batch_build_reference_fixture_graphs(cuda, oracle32):
+    # test/test_kipf_msgpass_layer.f90:83-90 (6 v / 8 e) and test_msgpass_network.f90:268-273 (5 v / 6 e)
+    g1 = ab.graph_type(); g1.set_num_vertices(6, 3); g1.set_num_edges(8, 1)
+    g1.generate_adjacency([[1, 2], [1, 3], [2, 3], [2, 4], [3, 5], [4, 5], [4, 6], [5, 6]])
+    g2 = ab.graph_type(); g2.set_num_vertices(5, 3); g2.set_num_edges(6, 1)
+    g2.generate_adjacency([[1, 2], [1, 3], [2, 3], [2, 4], [3, 5], [4, 5]])
+    g2.add_self_loops()
+    _check_batch(cuda, oracle32, ab.pack_graphs([g1, g2, g1]))
+
+
+def test_batch_build_ragged_and_empty_graphs(cuda, oracle32):
+    rng = np.random.default_rng(1)
+    p = synth.molecular_batch(300, 4, 2, rng, nv_range=(1, 40))
+    _check_batch(cuda, oracle32, p)
+    # graphs with zero vertices at the ends and in the middle
+    nv = np.array([0, 3, 0, 2, 0], np.int32)
+    ne = np.array([0, 2, 0, 1, 0], np.int32)
+    nz = np.array([0, 4, 0, 2, 0], np.int32)
+    # graph 1: rows {2,3},{1},{1}; graph 3: rows {2},{1}; empty graphs contribute adj_ia = [1]
+    ia = np.array([1, 1, 3, 4, 5, 1, 1, 2, 3, 1], np.int32)
+    ja = np.array([[2, 1], [3, 2], [1, 1], [1, 2], [2, 1], [1, 1]], np.int32)
+    _check_batch(cuda, oracle32, ab.PackedGraphs(nv, ne, nz, ia, ja))
+
+
+def test_batch_build_directed_and_multi_edges(cuda, oracle32):
+    rng = np.random.default_rng(2)
+    nv = np.array([50, 70], np.int64)
+    src = np.concatenate([rng.integers(0, 50, 400), 50 + rng.integers(0, 70, 900)])
+    dst = np.concatenate([rng.integers(0, 50, 400), 50 + rng.integers(0, 70, 900)])
+    p, _ = synth.packed_from_edges(nv, src, dst, directed=True, add_self_loops=False)
+    _check_batch(cuda, oracle32, p)
+
+
+def test_batch_build_power_law_long_columns(cuda, oracle32):
+    rng = np.random.default_rng(3)
+    p = synth.powerlaw_batch(3, 20000, 4, rng, max_degree=10000)
+    deg = oracle32.batch_build(p.nv, p.ne, p.ia, p.ja)["deg"]
+    assert deg.max() > 1000          # exercises the block-sort path for long CSC columns
+    _check_batch(cuda, oracle32, p, buckets=((1, 10), (3, 64)))
+
+
+def test_batch_build_one_huge_column(cuda, oracle32):
+    # star graph: hub column longer than the shared-memory sort capacity (16384)
+    n = 40000
+    p, _ = synth.packed_from_edges(np.array([n]), np.zeros(n - 1, np.int64), np.arange(1, n))
+    _check_batch(cuda, oracle32, p, buckets=((1, 4),))
+
+
+def test_batch_build_rejects_bad_adjacency(cuda):
+    nv = np.array([2], np.int32); ne = np.array([0], np.int32); nz = np.array([2], np.int32)
+    ia = np.array([1, 2, 3], np.int32)
+    ja = np.array([[1, 0], [3, 0]], np.int32)        # neighbour 3 > num_vertices
+    with pytest.raises(ab.AthenaCudaError) as ei:
+        ab.GraphBatch(ab.PackedGraphs(nv, ne, nz, ia, ja))
+    assert ei.value.code == -4 and "greater than the number of vertices" in str(ei.value)
+
+
+# ---------------------------------------------------------------------------
+# Kipf layer: forward / backward
+# ---------------------------------------------------------------------------
+def test_kipf_identity_graph_known_answer(cuda):
+    """test/test_diffstruc_extd_kipf.f90:23-45 through the layer with W = I."""
+    g = ab.graph_type(); g.set_num_vertices(2, 2); g.set_num_edges(0, 0)
+    g.adj_ia = np.array([1, 2, 3], np.int32); g.adj_ja = np.array([[1, 0], [2, 0]], np.int32)
+    g.vertex_features = np.array([[1, 2], [3, 4]], np.float32)
+    L = ab.kipf_msgpass_layer_type([2, 2], 1)
+    L.set_params(np.eye(2, dtype=np.float32).ravel())
+    L.set_graph([g])
+    out = L.forward()
+    assert np.abs(out - g.vertex_features).max() <= 1e-6
+    gin = L.backward(np.ones((2, 2), np.float32), want_input_grad=True)
+    assert np.abs(gin - 1.0).max() <= 1e-6
+
+
+KIPF_CASES = [
+    # nvf, T, act, generator
+    ([5, 5], 1, "none", "mol"),
+    ([3, 6, 5], 2, "relu", "mol"),
+    ([7, 7, 7, 7], 3, "sigmoid", "mol"),
+    ([8, 4], 1, "softmax", "mol"),
+    ([16, 32, 8], 2, "tanh", "reg"),
+    ([64, 64, 64], 2, "leaky_relu", "reg"),
+    ([33, 65], 1, "relu", "reg"),
+    ([128, 128], 1, "none", "reg"),
+    ([130, 20], 1, "sigmoid", "mol"),
+]
+
+
+def _make(gen, F, rng, Fe=0):
+    if gen == "mol":
+        return synth.molecular_batch(37, F, Fe, rng, nv_range=(2, 30))
+    return synth.regular_batch(24, 64, 6, F, rng, Fe=Fe, self_loop_features=bool(Fe))
+
+
+@pytest.mark.parametrize("nvf,T,act,gen", KIPF_CASES)
+def test_kipf_layer_forward_backward_parity(cuda, oracle32, oracle64, nvf, T, act, gen):
+    rng = np.random.default_rng(zlib.crc32(repr((nvf, T, act)).encode()))
+    p = _make(gen, nvf[0], rng)
+    spec = kipf_spec(nvf, T, act)
+    n = oracle32.num_params([spec])
+    params = random_params(n, rng, 0.4)
+    g_out = rng.standard_normal((p.V, nvf[-1])).astype(np.float32)
+    ob = to_oracle_batch(p)
+    out_ref, dp_ref, dx_ref = oracle32.layer_fwd_bwd(spec, params, ob, g_out, want_dx=True)
+    out64, dp64, dx64 = oracle64.layer_fwd_bwd(spec, params, ob, g_out, want_dx=True)
+
+    L = ab.kipf_msgpass_layer_type(nvf, T, activation=act)
+    assert L.num_params == n
+    L.set_params(params)
+    L.set_graph(p)
+    out = L.forward()
+    assert rel_err(out, out_ref) <= RTOL_ACT
+    L.zero_gradients()
+    dx = L.backward(g_out, want_input_grad=True)
+    dp = L.get_gradients()
+    assert rel_err(dp, dp_ref) <= RTOL_ACT
+    assert rel_err(dx, dx_ref) <= RTOL_ACT
+    # the CUDA path is as close to exact arithmetic as the fp32 oracle is
+    assert rel_err(out, out64) <= 4 * max(rel_err(out_ref, out64), 5e-7)
+    assert rel_err(dp, dp64) <= 4 * max(rel_err(dp_ref, dp64), 5e-7)
+    # gradients accumulate (params(t)%grad +=): second backward doubles them
+    L.backward(g_out)
+    assert rel_err(L.get_gradients(), 2 * dp) <= 1e-6
+    # get/set round trip (test/test_kipf_msgpass_layer.f90:115-146)
+    L.set_gradients(np.full(n, 0.1, np.float32))
+    assert np.allclose(L.get_gradients(), 0.1)
+    assert np.array_equal(L.get_params(), params)
+
+
+def test_kipf_forward_shape_matches_reference_test(cuda):
+    """test/test_kipf_msgpass_layer.f90:148-165: 6 vertices, [5 -> 5], params = 1."""
+    g = ab.graph_type(); g.set_num_vertices(6, 5); g.set_num_edges(8, 1)
+    g.vertex_features[:] = 1.0
+    g.generate_adjacency([[1, 2], [1, 3], [2, 3], [2, 4], [3, 5], [4, 5], [4, 6], [5, 6]])
+    L = ab.kipf_msgpass_layer_type([5, 5], 1)
+    L.set_params(np.ones(L.num_params, np.float32))
+    L.set_graph([g])
+    assert L.forward().shape == (6, 5)
+
+
+# ---------------------------------------------------------------------------
+# Duvenaud layer
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["chem", "mindeg2"])
+def test_duvenaud_matches_reference_python_golden(cuda, name):
+    d = np.load(os.path.join(GOLD, f"duvenaud_ref_{name}.npz"))
+    fv, fe, T, no, mn, mx = [int(v) for v in d["hyper"]]
+    nv, ne = d["nv"], d["ne"]
+    ia, ja = d["ia"], d["ja"].reshape(-1, 2)
+    nz = np.array([ia[o + n] - 1 for o, n in zip(np.cumsum(np.r_[0, nv[:-1] + 1]), nv)], np.int32)
+    p = ab.PackedGraphs(nv, ne, nz, ia, ja, d["x"], d["e"])
+    L = ab.duvenaud_msgpass_layer_type([fv], [fe], T, mx, no, min_vertex_degree=mn)
+    L.set_params(d["params"])
+    L.set_graph(p)
+    out = L.forward()
+    assert rel_err(out, d["out"]) <= RTOL_ACT
+    L.zero_gradients()
+    dx = L.backward(d["g_out"], want_input_grad=True)
+    assert rel_err(L.get_gradients(), d["dparams"]) <= RTOL_ACT
+    assert rel_err(dx, d["dx"]) <= RTOL_ACT
+
+
+DUV_CASES = [
+    # nvf, nef, T, min, max, n_out, act, ract, gen
+    ([6], 1, 4, 1, 10, 10, "sigmoid", "softmax", "mol"),
+    ([4, 8, 4], 2, 2, 2, 4, 3, "sigmoid", "softmax", "mol"),
+    ([8], 1, 2, 1, 4, 3, "sigmoid", "linear", "mol"),       # test_msgpass_network.f90:97-107
+    ([32], 4, 2, 1, 6, 32, "relu", "softmax", "mol"),        # cfg4 dims
+    ([64], 3, 1, 10, 14, 16, "tanh", "softmax", "reg"),      # all vertices in bucket 13-10
+    ([5], 0, 2, 1, 3, 4, "sigmoid", "softmax", "mol"),       # no edge features
+]
+
+
+@pytest.mark.parametrize("nvf,nef,T,mn,mx,no,act,ract,gen", DUV_CASES)
+def test_duvenaud_layer_forward_backward_parity(cuda, oracle32, nvf, nef, T, mn, mx, no, act, ract,
+                                                gen):
+    rng = np.random.default_rng(zlib.crc32(repr((nvf, nef, T, mn, mx, no)).encode()))
+    p = _make(gen, nvf[0], rng, Fe=nef)
+    full = nvf * (T + 1) if len(nvf) == 1 else nvf
+    spec = duvenaud_spec(full, nef, T, mn, mx, no, act, ract)
+    n = oracle32.num_params([spec])
+    params = random_params(n, rng, 0.3)
+    g_out = rng.standard_normal((p.B, no)).astype(np.float32)
+    out_ref, dp_ref, dx_ref = oracle32.layer_fwd_bwd(spec, params, to_oracle_batch(p), g_out,
+                                                     want_dx=True)
+    L = ab.duvenaud_msgpass_layer_type(nvf, [nef], T, mx, no, min_vertex_degree=mn,
+                                       message_activation=act, readout_activation=ract)
+    assert L.num_params == n
+    L.set_params(params)
+    L.set_graph(p)
+    out = L.forward()
+    assert out.shape == (p.B, no)
+    assert rel_err(out, out_ref) <= RTOL_ACT
+    L.zero_gradients()
+    dx = L.backward(g_out, want_input_grad=True)
+    assert rel_err(L.get_gradients(), dp_ref) <= RTOL_ACT
+    assert rel_err(dx, dx_ref) <= RTOL_ACT
+
+
+def test_duvenaud_self_loop_without_edge_feature(cuda, oracle32):
+    """adj_ja(2,w) = 0 (add_self_loops marker) contributes a zero edge feature."""
+    rng = np.random.default_rng(11)
+    p = synth.chemical_batch(8, rng)
+    assert (p.ja[:, 1] == 0).sum() == p.V
+    spec = duvenaud_spec([6] * 5, 1, 4, 1, 10, 10)
+    params = random_params(oracle32.num_params([spec]), rng, 0.3)
+    out_ref, _, _ = oracle32.layer_fwd_bwd(spec, params, to_oracle_batch(p))
+    L = ab.duvenaud_msgpass_layer_type([6], [1], 4, 10, 10)
+    L.set_params(params)
+    L.set_graph(p)
+    assert rel_err(L.forward(), out_ref) <= RTOL_ACT
+
+
+# ---------------------------------------------------------------------------
+# network: loss, gradients, optimiser steps
+# ---------------------------------------------------------------------------
+def _train_compare(cuda, oracle32, specs, layers, p, target, optim: OptimSpec, ab_opt, steps=5):
+    net = ab.network_type()
+    for L in layers:
+        net.add(L)
+    net.compile(ab_opt, loss_method="mse", batch_size=p.B)
+    n = oracle32.num_params(specs)
+    assert net.num_params == n
+    rng = np.random.default_rng(123)
+    params = random_params(n, rng, 0.3)
+    net.set_params(params)
+    batch = ab.GraphBatch(p)
+    # loss + gradients of the first step
+    ob = to_oracle_batch(p)
+    loss_ref, out_ref, g_ref = oracle32.stack_fwd_bwd(specs, params, ob, target)
+    loss = net.loss_and_gradients(batch, target)
+    assert abs(loss - loss_ref) <= 1e-5 * max(1.0, abs(loss_ref))
+    assert rel_err(net.get_gradients(), g_ref) <= RTOL_ACT
+    assert rel_err(net.forward(batch), out_ref) <= RTOL_ACT
+    net.update()                                   # consumes those gradients (step 1)
+    ref = params.copy()
+    s1 = np.zeros(n, np.float32); s2 = np.zeros(n, np.float32)
+    l0, _ = oracle32.train_step(specs, ref, ob, target, optim, s1, s2, 1)
+    assert rel_err(net.get_params(), ref) <= RTOL_PARAM
+    assert np.all(net.get_gradients() == 0)        # reset_gradients
+    losses = []
+    for it in range(2, steps + 1):
+        lr_, _ = oracle32.train_step(specs, ref, ob, target, optim, s1, s2, it)
+        l = net.train_step(batch, target)
+        losses.append((l, lr_))
+    for l, lr_ in losses:
+        assert abs(l - lr_) <= 1e-4 * max(1.0, abs(lr_))
+    assert rel_err(net.get_params(), ref) <= RTOL_PARAM
+    net.destroy()
+
+
+def test_kipf_network_sgd_training_parity(cuda, oracle32):
+    """Shape of test/test_msgpass_network.f90:40-88: Kipf net, SGD lr 0.01, graph target."""
+    rng = np.random.default_rng(5)
+    p = synth.molecular_batch(9, 8, 0, rng, nv_range=(3, 9), self_loop_features=False)
+    spec = kipf_spec([8, 8, 8], 2)
+    target = p.x.copy()                            # train(graph, graph): the target is the input graph
+    _train_compare(cuda, oracle32, [spec], [ab.kipf_msgpass_layer_type([8, 8, 8], 2)], p, target,
+                   OptimSpec("sgd", lr=0.01), ab.sgd_optimiser_type(learning_rate=0.01))
+
+
+def test_kipf_two_layer_relu_momentum(cuda, oracle32):
+    rng = np.random.default_rng(6)
+    p = synth.regular_batch(16, 64, 6, 64, rng)
+    specs = [kipf_spec([64, 64], 1, "relu"), kipf_spec([64, 64], 1, "none")]
+    layers = [ab.kipf_msgpass_layer_type([64, 64], 1, "relu"),
+              ab.kipf_msgpass_layer_type([64, 64], 1, "none")]
+    target = rng.standard_normal((p.V, 64)).astype(np.float32)
+    _train_compare(cuda, oracle32, specs, layers, p, target,
+                   OptimSpec("sgd", lr=0.05, momentum=0.9, nesterov=True),
+                   ab.sgd_optimiser_type(0.05, momentum=0.9, nesterov=True))
+
+
+def test_duvenaud_network_adam_clip_training_parity(cuda, oracle32):
+    """example/msgpass_chemical dims (main.f90:129-192): T=4, Fv=6, Fe=1, D=10, n_out=10,
+    Adam lr 1e-2, clip_norm 0.1, batch 8."""
+    rng = np.random.default_rng(7)
+    p = synth.chemical_batch(8, rng)
+    spec = duvenaud_spec([6] * 5, 1, 4, 1, 10, 10)
+    target = rng.random((8, 10)).astype(np.float32)
+    _train_compare(cuda, oracle32, [spec], [ab.duvenaud_msgpass_layer_type([6], [1], 4, 10, 10)],
+                   p, target, OptimSpec("adam", lr=1e-2, clip_norm=0.1),
+                   ab.adam_optimiser_type(1e-2, clip_dict=ab.clip_type(clip_norm=0.1)), steps=8)
+
+
+def test_kipf_duvenaud_stack_training_parity(cuda, oracle32):
+    """cfg4 wiring: Kipf(32->32) x2 -> Duvenaud(T=2, D=6, n_out=32), Adam, min/max clip."""
+    rng = np.random.default_rng(8)
+    p = synth.molecular_batch(40, 32, 4, rng)
+    specs = [kipf_spec([32, 32], 1, "relu"), kipf_spec([32, 32], 1, "relu"),
+             duvenaud_spec([32] * 3, 4, 2, 1, 6, 32)]
+    layers = [ab.kipf_msgpass_layer_type([32, 32], 1, "relu"),
+              ab.kipf_msgpass_layer_type([32, 32], 1, "relu"),
+              ab.duvenaud_msgpass_layer_type([32], [4], 2, 6, 32)]
+    target = rng.random((40, 32)).astype(np.float32)
+    _train_compare(cuda, oracle32, specs, layers, p, target,
+                   OptimSpec("adam", lr=5e-3, clip_min=-0.05, clip_max=0.05),
+                   ab.adam_optimiser_type(5e-3, clip_dict=ab.clip_type(-0.05, 0.05)))
+
+
+def test_network_train_loop_runs_epochs(cuda):
+    """network%train batch loop with a ragged last batch (athena_network_sub.f90:3575-3670)."""
+    rng = np.random.default_rng(9)
+    p = synth.chemical_batch(19, rng)
+    net = ab.network_type()
+    net.add(ab.duvenaud_msgpass_layer_type([6], [1], 2, 10, 4))
+    net.compile(ab.adam_optimiser_type(1e-2), batch_size=8)
+    target = rng.random((19, 4)).astype(np.float32)
+    hist = net.train(p, target, num_epochs=6, shuffle_batches=False)
+    assert len(hist) == 6 and hist[-1] < hist[0] and np.isfinite(hist).all()
+
+
+def test_shard_sum_equals_full_batch_gradient(cuda, oracle32):
+    """The N>1 decomposition on one GPU: gradients of contiguous graph shards (with the
+    global-batch normalisation) sum to the full-batch gradient."""
+    rng = np.random.default_rng(10)
+    p = synth.molecular_batch(64, 32, 4, rng)
+    target = rng.random((64, 8)).astype(np.float32)
+    full = ab.GraphBatch(p)
+    first = np.zeros(5, np.int32)
+    ab.check(ab.lib().athena_cuda_shard_graphs(64, ab.ptr(p.nz.astype(np.int64)), 4, ab.ptr(first)))
+    net = ab.network_type()
+    for L in (ab.kipf_msgpass_layer_type([32, 32], 1, "relu"),
+              ab.duvenaud_msgpass_layer_type([32], [4], 2, 6, 8)):
+        net.add(L)
+    net.compile(ab.sgd_optimiser_type(0.0), batch_size=64)   # lr = 0: update only zeroes grads
+    params = random_params(net.num_params, rng, 0.3)
+    net.set_params(params)
+    g_sum = np.zeros(net.num_params, np.float32)
+    loss_sum = 0.0
+    loss_full = net.loss_and_gradients(full, target)
+    g_full = net.get_gradients().copy()
+    net.update()
+    for r in range(4):
+        sh = ab.GraphBatch(p.slice(first[r], first[r + 1]))
+        loss_sum += net.loss_and_gradients(sh, target[first[r]:first[r + 1]], global_batch=64)
+        g_sum += net.get_gradients()
+        net.update()
+    assert abs(loss_sum - loss_full) <= 1e-5 * abs(loss_full)
+    assert rel_err(g_sum, g_full) <= RTOL_ACT

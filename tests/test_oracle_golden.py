@@ -1,0 +1,195 @@
+"""Pin the CPU oracle (oracle/athena_oracle.c) against every known-answer the
+reference holds for this path and against the golden
+vectors generated from the reference's own Python restatement
+(tests/golden/make_golden.py).  CPU only.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import duvenaud_spec, kipf_spec, rel_err
+from oracle.oracle import Batch, LayerSpec, OptimSpec
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# -- test/test_diffstruc_extd_kipf.f90:23-45,70-91 ----------------------------
+def test_kipf_identity_graph_forward_and_grad(oracle32):
+    x = np.array([[1, 2], [3, 4]], np.float32)       # val(:,1)=[1,2]; val(:,2)=[3,4]
+    ia = [1, 2, 3]
+    ja = [[1, 0], [2, 0]]                            # self-loop only, edge id 0
+    out = oracle32.kipf_propagate(x, ia, ja)
+    assert np.abs(out - x).max() <= 1e-6
+    g = oracle32.kipf_propagate_bwd(np.ones_like(x), ia, ja)   # grad_reverse seeds ones
+    assert np.abs(g - 1.0).max() <= 1e-6
+    up = np.array([[5, 6], [7, 8]], np.float32)
+    assert np.abs(oracle32.kipf_propagate_bwd(up, ia, ja) - up).max() <= 1e-6
+
+
+def test_kipf_backward_is_unnormalised(oracle32):
+    """The live backward has NO (deg_v deg_u)^-1/2 factor
+    (athena_diffstruc_extd_sub_kipf.f90:101-109 vs :39-44)."""
+    ia = [1, 3, 5]
+    ja = [[1, 0], [2, 1], [1, 1], [2, 0]]            # 2 vertices, edge + self loops
+    x = np.array([[1.0], [10.0]], np.float32)
+    fwd = oracle32.kipf_propagate(x, ia, ja)
+    assert np.allclose(fwd[:, 0], [0.5 * 1 + 0.5 * 10, 0.5 * 1 + 0.5 * 10])
+    g = oracle32.kipf_propagate_bwd(np.array([[1.0], [100.0]], np.float32), ia, ja)
+    assert np.allclose(g[:, 0], [101.0, 101.0])      # plain sums, not 50.5
+
+
+# -- test/test_loss.f90:59-67 and :135-143 ----------------------------------------
+def test_mse_matches_reference_known_answer(oracle32):
+    rng = np.random.default_rng(0)
+    p = rng.random((3, 3)).astype(np.float32)
+    e = rng.random((3, 3)).astype(np.float32)
+    expected = (((p - e) ** 2) / 2.0).sum() / 9.0     # sum(expected_loss) / 9.0
+    assert abs(oracle32.mse_cell(p, e) - expected) <= 1e-6
+    # multi-cell: cells of ONE element each -> sum((p-e)^2 / 2)
+    cells = sum(oracle32.mse_cell(p.ravel()[i:i + 1], e.ravel()[i:i + 1]) for i in range(9))
+    assert abs(cells - (((p - e) ** 2) / 2.0).sum()) <= 5e-6
+
+
+# -- test/test_clipper.f90:95-99 ----------------------------------------------
+def test_clipper_known_answer(oracle32):
+    g, b = oracle32.clip(np.full(10, 2.0), clip_min=-0.5, clip_max=0.5, bias=np.full(3, 7.0))
+    assert np.abs(g - 0.5).max() <= 1e-6 and np.abs(b - 0.5).max() <= 1e-6
+    # norm clipping: scale = min(1, norm / sqrt(sum g^2 + (sum bias_)^2)), bias_ = [0]
+    g = oracle32.clip(np.array([3.0, 4.0]), clip_norm=1.0)
+    assert np.allclose(g, [0.6, 0.8], atol=1e-6)
+    g = oracle32.clip(np.array([0.3, 0.4]), clip_norm=1.0)
+    assert np.allclose(g, [0.3, 0.4])
+
+
+# -- test/test_diffstruc_extd.f90:33-45: shared operands sum their gradients --
+def test_shared_operand_gradient_is_summed_over_positions(oracle32):
+    # W [1x1] shared by 4 columns, upstream ones, P = ones -> dW = 4 (like bias grad = 2 there)
+    dw = np.zeros(1, np.float32)
+    gy = np.ones((4, 1), np.float32)
+    p = np.ones((4, 1), np.float32)
+    import ctypes as C
+    oracle32.lib.oracle_matmul_bwd_left(1, 1, 4, oracle32.rp(gy), oracle32.rp(p), oracle32.rp(dw))
+    assert dw[0] == 4.0
+
+
+# -- example/adam_benchmark/compare_fortran_pytorch.py:14-20,52-71 ------------
+@pytest.mark.parametrize("prob", ["scalar", "multi"])
+def test_adam_equals_torch_adam(oracle32, prob):
+    d = np.load(os.path.join(GOLD, "adam_ref.npz"))
+    lr, b1, b2, eps = [float(v) for v in d["hyper"]]
+    params, grads = d[f"{prob}_params"], d[f"{prob}_grads"]
+    x = np.zeros(params.shape[1], np.float32) if prob == "scalar" else np.array([0.0, 2.0], np.float32)
+    m = np.zeros_like(x)
+    v = np.zeros_like(x)
+    for step in range(params.shape[0]):
+        g = 2.0 * (x - np.array([3.0, -1.0], np.float32)[:x.size])
+        assert np.abs(g - grads[step]).max() <= 1e-5
+        x, m, v = oracle32.adam(x, g, m, v, lr, b1, b2, eps, step + 1)   # iter pre-incremented
+        assert np.abs(x - params[step]).max() <= 2e-6, step
+
+
+def test_sgd_variants(oracle32):
+    p, v = oracle32.sgd(np.ones(3), np.full(3, 2.0), np.zeros(3), 0.1)
+    assert np.allclose(p, 0.8) and np.allclose(v, -0.2)
+    p, v = oracle32.sgd(np.ones(3), np.full(3, 2.0), np.full(3, 1.0), 0.1, momentum=0.5)
+    assert np.allclose(v, 0.5 - 0.2) and np.allclose(p, 1.3)
+    p, v = oracle32.sgd(np.ones(3), np.full(3, 2.0), np.full(3, 1.0), 0.1, momentum=0.5, nesterov=True)
+    assert np.allclose(p, 1 + 0.5 * 0.3 - 0.2)
+
+
+# -- golden vectors from the reference's own PyTorch restatement ----------------
+@pytest.mark.parametrize("name", ["chem", "mindeg2"])
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_duvenaud_matches_reference_python(name, prec, oracle32, oracle64):
+    o = oracle32 if prec == "f32" else oracle64
+    d = np.load(os.path.join(GOLD, f"duvenaud_ref_{name}.npz"))
+    fv, fe, T, no, mn, mx = [int(v) for v in d["hyper"]]
+    L = duvenaud_spec([fv] * (T + 1), fe, T, mn, mx, no)
+    b = Batch(d["nv"], d["ne"], d["ia"], d["ja"].reshape(-1, 2), d["x"], d["e"])
+    out, dp, dx = o.layer_fwd_bwd(L, d["params"], b, d["g_out"], want_dx=True)
+    assert rel_err(out, d["out"]) <= 1e-6
+    assert rel_err(dp, d["dparams"]) <= 1e-6
+    assert rel_err(dx, d["dx"]) <= 1e-6
+
+
+# -- self-consistency: analytic gradients vs central differences (float64) --------
+def _fd_check(o, layers, params, b, target, idx, eps=1e-6):
+    _, _, g = o.stack_fwd_bwd(layers, params, b, target)
+    for i in idx:
+        pp = params.copy(); pp[i] += eps
+        pm = params.copy(); pm[i] -= eps
+        lp, _, _ = o.stack_fwd_bwd(layers, pp, b, target, want_grads=False)
+        lm, _, _ = o.stack_fwd_bwd(layers, pm, b, target, want_grads=False)
+        fd = (lp - lm) / (2 * eps)
+        assert abs(fd - g[i]) <= 1e-6 * max(1.0, abs(fd)), (i, fd, g[i])
+
+
+def _toy_batch(rng, B=3, F=4, Fe=2):
+    from athena_b200 import synth
+    p = synth.molecular_batch(B, F, Fe, rng, nv_range=(4, 7))
+    return Batch(p.nv, p.ne, p.ia, p.ja, p.x.astype(np.float64), p.e.astype(np.float64))
+
+
+def test_duvenaud_gradients_are_true_gradients(oracle64):
+    rng = np.random.default_rng(3)
+    b = _toy_batch(rng)
+    L = duvenaud_spec([4, 4, 4], 2, 2, 1, 3, 5)
+    n = oracle64.num_params([L])
+    params = rng.standard_normal(n) * 0.5
+    target = rng.random((b.B, 5))
+    _fd_check(oracle64, [L], params, b, target, rng.choice(n, 12, replace=False))
+
+
+def test_kipf_single_step_weight_gradient_is_true_gradient(oracle64):
+    """With T = 1 the un-normalised propagate backward is never used, so dW is exact."""
+    rng = np.random.default_rng(4)
+    b = _toy_batch(rng)
+    L = kipf_spec([4, 3], 1, "tanh")
+    n = oracle64.num_params([L])
+    params = rng.standard_normal(n) * 0.5
+    target = rng.random((b.V, 3))
+    _fd_check(oracle64, [L], params, b, target, range(n))
+
+
+def test_kipf_two_step_gradient_reproduces_reference_quirk(oracle64):
+    """For T = 2 the first step's dW goes through the un-normalised backward, so it is
+    NOT the finite-difference gradient -- parity means reproducing the reference."""
+    rng = np.random.default_rng(5)
+    b = _toy_batch(rng)
+    L = kipf_spec([4, 4, 4], 2, "none")
+    n = oracle64.num_params([L])
+    params = rng.standard_normal(n) * 0.5
+    target = rng.random((b.V, 4))
+    _, _, g = oracle64.stack_fwd_bwd([L], params, b, target)
+    eps = 1e-6
+    pp = params.copy(); pp[0] += eps
+    pm = params.copy(); pm[0] -= eps
+    fd = (oracle64.stack_fwd_bwd([L], pp, b, target, want_grads=False)[0] -
+          oracle64.stack_fwd_bwd([L], pm, b, target, want_grads=False)[0]) / (2 * eps)
+    assert abs(fd - g[0]) > 1e-4 * abs(fd)           # first-step weight: differs (quirk)
+    pp = params.copy(); pp[-1] += eps
+    pm = params.copy(); pm[-1] -= eps
+    fd = (oracle64.stack_fwd_bwd([L], pp, b, target, want_grads=False)[0] -
+          oracle64.stack_fwd_bwd([L], pm, b, target, want_grads=False)[0]) / (2 * eps)
+    assert abs(fd - g[-1]) <= 1e-6 * max(1.0, abs(fd))  # last-step weight: exact
+
+
+def test_integer_structures_small_example(oracle32):
+    # two graphs: a path 1-2-3 with self loops, and a single vertex with a self loop
+    nv, ne = [3, 1], [2, 0]
+    ia = [1, 3, 6, 8, 1, 2]
+    ja = [[1, 0], [2, 1], [1, 1], [2, 0], [3, 2], [2, 2], [3, 0], [1, 0]]
+    o = oracle32.batch_build(nv, ne, ia, np.array(ja, np.int32))
+    assert o["row_ptr"].tolist() == [0, 2, 5, 7, 8]
+    assert o["col"].tolist() == [0, 1, 0, 1, 2, 1, 2, 3]
+    assert o["eid"].tolist() == [-1, 0, 0, -1, 1, 1, -1, -1]
+    assert o["deg"].tolist() == [2, 3, 2, 1]
+    assert o["vgraph"].tolist() == [0, 0, 0, 1]
+    assert o["csc_ptr"].tolist() == [0, 2, 5, 7, 8]
+    assert o["csc_src"].tolist() == [0, 1, 0, 1, 2, 1, 2, 3]
+    assert o["csc_ent"].tolist() == [0, 2, 1, 3, 5, 4, 6, 7]
+    bkt, perm, ptr = oracle32.bucketize(o["deg"], 2, 3)
+    assert bkt.tolist() == [0, 1, 0, 0] and perm.tolist() == [0, 2, 3, 1] and ptr.tolist() == [0, 3, 4]
+    with pytest.raises(ValueError):
+        oracle32.batch_build([2], [0], [1, 2, 3], np.array([[1, 0], [3, 0]], np.int32))
