@@ -57,16 +57,18 @@ def lib() -> C.CDLL:
                                   "(python -c 'import __graft_entry__ as g; g.build()')")
     L = C.CDLL(LIB_PATH)
     H, I32, I64, F32, P = C.c_int64, C.c_int32, C.c_int64, C.c_float, C.c_void_p
-    PH, PI32, PI64, PF = C.POINTER(H), C.POINTER(I32), C.POINTER(I64), C.POINTER(F32)
+    # every pointer parameter is declared void* so that numpy buffers, device addresses and
+    # byref(scalar) are all accepted
+    PH = PI32 = PI64 = PF = P
     sig = {
         "athena_cuda_init": [I32],
         "athena_cuda_shutdown": [],
         "athena_cuda_version": [PI32, PI32],
         "athena_cuda_device_info": [PI32, PI32, PI64],
         "athena_cuda_synchronize": [],
-        "athena_cuda_malloc": [C.POINTER(P), C.c_size_t],
+        "athena_cuda_malloc": [P, C.c_size_t],
         "athena_cuda_free": [P],
-        "athena_cuda_host_alloc": [C.POINTER(P), C.c_size_t],
+        "athena_cuda_host_alloc": [P, C.c_size_t],
         "athena_cuda_host_free": [P],
         "athena_cuda_memcpy_h2d": [P, P, C.c_size_t],
         "athena_cuda_memcpy_d2h": [P, P, C.c_size_t],
@@ -77,7 +79,7 @@ def lib() -> C.CDLL:
         "athena_cuda_flush_l2": [],
         "athena_cuda_profile_begin": [],
         "athena_cuda_profile_end": [PI32],
-        "athena_cuda_profile_get": [I32, C.c_char_p, I32, PI64, PF],
+        "athena_cuda_profile_get": [I32, P, I32, PI64, PF],
         "athena_cuda_batch_create": [PH, I32, P, P, P, P, P, I32, I32],
         "athena_cuda_batch_destroy": [H],
         "athena_cuda_batch_status": [H],
@@ -98,7 +100,7 @@ def lib() -> C.CDLL:
         "athena_cuda_network_create": [PH],
         "athena_cuda_network_destroy": [H],
         "athena_cuda_network_add": [H, H],
-        "athena_cuda_network_compile": [H, C.POINTER(OptimiserDesc)],
+        "athena_cuda_network_compile": [H, P],
         "athena_cuda_network_num_params": [H, PI64],
         "athena_cuda_network_set_params": [H, P, I64],
         "athena_cuda_network_get_params": [H, P, I64],
