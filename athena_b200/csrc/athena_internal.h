@@ -115,6 +115,9 @@ static inline int64_t round_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
 // ---------------------------------------------------------------------------
 // graph batch (batch.cu)
 // ---------------------------------------------------------------------------
+constexpr int TILE_ROWS = 128;      // vertices per fused-kernel tile (= UMMA M)
+constexpr int TILE_ENTRIES = 3072;  // CSR entries per tile that fit the shared-memory ring
+
 struct BucketSet {
   int min_deg = 0, max_deg = 0, D = 0;
   DevBuf bkt;      // [V]   0-based bucket id
@@ -147,6 +150,14 @@ struct Batch : Object {
   float* coef = nullptr;
   DevBuf scratch;
   DevBuf status;  // int32[4]: [0] first bad graph + 1, [1] long-column count
+  // Graph-aligned row tiles for the fused gather kernels (pipe_tc.cu): a tile is
+  // a run of whole graphs with <= TILE_ROWS vertices and <= TILE_ENTRIES CSR
+  // entries, so every neighbour of a tile row lies inside the tile (the batch is
+  // block diagonal) and the tile's features can be staged once in shared memory.
+  // Built on the host from num_vertices / num_entries (no device sync); valid for
+  // the CSR and the CSC alike.  num_tiles == 0: batch not tileable (a graph too big).
+  DevBuf tiles;   // int4 {first row, rows, first entry, entries}
+  int32_t num_tiles = 0;
   std::vector<std::unique_ptr<BucketSet>> buckets;
   BucketSet* find_buckets(int min_deg, int max_deg) const;
 };
@@ -183,6 +194,25 @@ int launch_gemm_nt(const float* A, int lda, const float* W, float* C, int ldc, i
 // dW_g[k, n] += sum_{m in group g} (A[m, k] / s_m) * G[m, n]  (deterministic two-pass)
 int launch_gemm_tn(const float* A, int lda, const float* G, int ldg, float* dW, int64_t M,
                    int N, int K, const GroupDesc& gd, DevBuf& scratch);
+
+// tcgen05 path (gemm_tc.cu): dense row-major operands, feature widths 32/64.
+// Hact != nullptr fuses the activation derivative into the operand load:
+// the operand becomes A .* act_in'(Hact).
+bool tc_rows_supported(int K, int N, int lda, int ldc, const void* A, const void* C);
+bool tc_tn_supported(int K, int N, int lda1, int lda2, const void* A1, const void* A2);
+int launch_tc_rows(bool transb, const float* A, int lda, const float* Hact, int act_in,
+                   const float* W, float* C, int ldc, int64_t M, int N, int K, int act_out);
+int launch_tc_tn(const float* A1, int lda1, const float* A2, int lda2, const float* Hact,
+                 int act_in, float* dW, int64_t M, int N, int K, DevBuf& scratch);
+
+// fused warp-specialised tcgen05 kernels for batches of small graphs (pipe_tc.cu)
+bool pipe_gather_supported(const Batch* b, int F, int N);
+bool pipe_tn_supported(int K, int N);
+int launch_pipe_gather_fwd(const Batch* b, const float* X, const float* W, float* P, float* out,
+                           int F, int N, int act);
+int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const float* Hin,
+                           float* out, int F, int N, int act);
+int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int N, DevBuf& scratch);
 
 // elementwise / row-wise helpers
 int launch_act_bwd(int act, const float* Y, const float* G, float* out, int64_t M, int N);

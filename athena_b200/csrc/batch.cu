@@ -461,6 +461,34 @@ ATHENA_API int athena_cuda_batch_create(athena_handle_t* batch, int32_t num_grap
   b->E = E;
   cudaStream_t st = ctx().stream;
 
+  // graph-aligned tiles (greedy packing of whole graphs), see Batch::tiles
+  {
+    std::vector<int32_t> tiles;
+    tiles.reserve((size_t)(V / TILE_ROWS + B / 8 + 4) * 4);
+    bool ok = true;
+    int32_t r0 = 0, e0 = 0, rows = 0, ents = 0;
+    for (int s = 0; s < B && ok; ++s) {
+      const int32_t nvs = num_vertices[s], nzs = num_entries[s];
+      if (nvs > TILE_ROWS || nzs > TILE_ENTRIES) ok = false;
+      if (rows + nvs > TILE_ROWS || ents + nzs > TILE_ENTRIES) {
+        if (rows > 0) tiles.insert(tiles.end(), {r0, rows, e0, ents});
+        r0 += rows;
+        e0 += ents;
+        rows = 0;
+        ents = 0;
+      }
+      rows += nvs;
+      ents += nzs;
+    }
+    if (ok && rows > 0) tiles.insert(tiles.end(), {r0, rows, e0, ents});
+    if (ok && !tiles.empty()) {
+      b->num_tiles = (int32_t)(tiles.size() / 4);
+      ATH_TRY(b->tiles.reserve(sizeof(int32_t) * tiles.size()));
+      ATH_CUDA(cudaMemcpyAsync(b->tiles.p, tiles.data(), sizeof(int32_t) * tiles.size(),
+                               cudaMemcpyHostToDevice, st));
+    }
+  }
+
   // meta on the device: nv | ne | nz | voff | zoff | eoff
   size_t meta_ints = (size_t)3 * B + 3 * ((size_t)B + 1);
   ATH_TRY(b->meta.reserve(sizeof(int32_t) * meta_ints));

@@ -90,12 +90,25 @@ static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out) {
     DevBuf& H = *L->H[t - 1];
     ATH_TRY(P.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fi, 1)));
     ATH_TRY(H.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fo, 1)));
+    if (L->act != ATHENA_ACT_SOFTMAX && pipe_gather_supported(b, Fi, Fo)) {
+      // propagate + transform + activation in one fused tcgen05 kernel
+      ATH_TRY(launch_pipe_gather_fwd(b, in, L->params + L->poff[t - 1], P.as<float>(),
+                                     H.as<float>(), Fi, Fo, L->act));
+      in = H.as<float>();
+      continue;
+    }
     // P = D^-1/2 A D^-1/2 . in      (kipf_propagate)
     ATH_TRY(launch_aggregate(b->row_ptr, b->col, b->coef, in, Fi, Fi, P.as<float>(), Fi, V, 0,
                              nullptr, 0));
     // H = act( P . W_t )            (matmul + activation%apply)
-    ATH_TRY(launch_gemm_nn(P.as<float>(), Fi, L->params + L->poff[t - 1], H.as<float>(), Fo, V,
-                           Fo, Fi, L->act, GroupDesc{}));
+    if (L->act != ATHENA_ACT_SOFTMAX &&
+        tc_rows_supported(Fi, Fo, Fi, Fo, P.as<float>(), H.as<float>())) {
+      ATH_TRY(launch_tc_rows(false, P.as<float>(), Fi, nullptr, 0, L->params + L->poff[t - 1],
+                             H.as<float>(), Fo, V, Fo, Fi, L->act));
+    } else {
+      ATH_TRY(launch_gemm_nn(P.as<float>(), Fi, L->params + L->poff[t - 1], H.as<float>(), Fo, V,
+                             Fo, Fi, L->act, GroupDesc{}));
+    }
     in = H.as<float>();
   }
   *out = in;
@@ -165,33 +178,68 @@ int layer_forward_dev(Layer* L, Batch* b, const float* x, const float* e, const 
 
 static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin) {
   const int64_t V = b->V;
-  const float* g = gout;
   int Fmax = 0;
   for (int t = 0; t <= L->T; ++t) Fmax = std::max(Fmax, L->nvf[t]);
   size_t bytes = sizeof(float) * (size_t)std::max<int64_t>(V * Fmax, 1);
   ATH_TRY(L->g0.reserve(bytes));
   ATH_TRY(L->g1.reserve(bytes));
   ATH_TRY(L->g2.reserve(bytes));
+  const bool nonlinear = L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR;
+  const float* g = gout;   // gradient w.r.t. the step output H_t ...
+  bool preact = false;     // ... or already w.r.t. the pre-activation (gY_t) when true
   for (int t = L->T; t >= 1; --t) {
     const int Fi = L->nvf[t - 1], Fo = L->nvf[t];
+    const float* Pt = L->P[t - 1]->as<float>();
+    const float* Ht = L->H[t - 1]->as<float>();
+    const float* Wt = L->params + L->poff[t - 1];
+    float* dWt = L->grads + L->poff[t - 1];
+    const bool need_dp = (t > 1 || gin);
+    const bool need_act = nonlinear && !preact;
+    // fused path: one tcgen05 kernel gathers gY_t over the CSC, multiplies by W_t^T and applies
+    // act'(H_{t-1}); the un-normalised scatter commutes with the linear map
+    const bool fused_dp = need_dp && L->act != ATHENA_ACT_SOFTMAX && pipe_gather_supported(b, Fo, Fi);
+    const bool fused_tn = Fi == 64 && pipe_tn_supported(Fi, Fo);
+    const bool tn_tc = !fused_tn && tc_tn_supported(Fi, Fo, Fi, Fo, Pt, g);
+    const bool nt_tc = need_dp && !fused_dp && tc_rows_supported(Fo, Fi, Fo, Fi, g, L->g1.as<float>());
+    // the unfused tensor-core kernels can apply act'(H) while loading gH
+    const bool fuse_act = need_act && L->act != ATHENA_ACT_SOFTMAX && !fused_dp && !fused_tn &&
+                          tn_tc && (!need_dp || nt_tc);
+    const float* Hact = fuse_act ? Ht : nullptr;
     const float* gy = g;
-    if (L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR) {
-      ATH_TRY(launch_act_bwd(L->act, L->H[t - 1]->as<float>(), g, L->g0.as<float>(), V, Fo));
-      gy = L->g0.as<float>();
+    if (need_act && !fuse_act) {
+      float* dst = (g == L->g0.as<float>()) ? L->g2.as<float>() : L->g0.as<float>();
+      ATH_TRY(launch_act_bwd(L->act, Ht, g, dst, V, Fo));
+      gy = dst;
     }
     // dW_t(o,i) += sum_v gY(o,v) P(i,v)
-    ATH_TRY(launch_gemm_tn(L->P[t - 1]->as<float>(), Fi, gy, Fo, L->grads + L->poff[t - 1], V, Fo,
-                           Fi, GroupDesc{}, L->tn_scratch));
-    if (t > 1 || gin) {
-      // dP = W_t^T gY
-      ATH_TRY(launch_gemm_nt(gy, Fo, L->params + L->poff[t - 1], L->g1.as<float>(), Fi, V, Fi, Fo,
-                             GroupDesc{}));
-      // dH(:,u) += dP(:,v) for every CSR entry (v,u): gather over the CSC, NO coefficient
-      float* dst = (t > 1) ? L->g2.as<float>() : gin;
+    if (fused_tn) {
+      ATH_TRY(launch_pipe_tn(Pt, gy, dWt, V, Fo, L->tn_scratch));
+    } else if (tn_tc) {
+      ATH_TRY(launch_tc_tn(Pt, Fi, gy, Fo, Hact, L->act, dWt, V, Fo, Fi, L->tn_scratch));
+    } else {
+      ATH_TRY(launch_gemm_tn(Pt, Fi, gy, Fo, dWt, V, Fo, Fi, GroupDesc{}, L->tn_scratch));
+    }
+    if (!need_dp) continue;
+    float* dst = gin;
+    if (t > 1) dst = (gy == L->g2.as<float>()) ? L->g0.as<float>() : L->g2.as<float>();
+    if (fused_dp) {
+      const bool act_next = nonlinear && t > 1;
+      ATH_TRY(launch_pipe_gather_bwd(b, gy, Wt, act_next ? L->H[t - 2]->as<float>() : nullptr, dst,
+                                     Fo, Fi, act_next ? L->act : ATHENA_ACT_NONE));
+      preact = t > 1;  // dst already is gY_{t-1}
+    } else {
+      // dP = W_t^T gY, then dH(:,u) += dP(:,v) for every CSR entry (v,u): CSC gather, NO coefficient
+      if (nt_tc) {
+        ATH_TRY(launch_tc_rows(true, gy, Fo, Hact, L->act, Wt, L->g1.as<float>(), Fi, V, Fi, Fo,
+                               ATHENA_ACT_NONE));
+      } else {
+        ATH_TRY(launch_gemm_nt(gy, Fo, Wt, L->g1.as<float>(), Fi, V, Fi, Fo, GroupDesc{}));
+      }
       ATH_TRY(launch_aggregate(b->csc_ptr, b->csc_src, nullptr, L->g1.as<float>(), Fi, Fi, dst, Fi,
                                V, 0, nullptr, 0));
-      g = dst;
+      preact = false;
     }
+    g = dst;
   }
   return ATHENA_OK;
 }

@@ -1,0 +1,210 @@
+// Hand-written sm_100a tensor-core plumbing: mbarrier, TMEM allocation,
+// tcgen05.mma (kind::tf32, operands from shared memory, accumulator in TMEM),
+// tcgen05.commit / tcgen05.ld, and the shared-memory operand layout.
+//
+// Operand tiles use the 128-byte-swizzled canonical layout.  A [rows x 32]
+// fp32 block is stored as 8-row groups of 1024 B; row r of a group sits at
+// r*128 B and its eight 16-byte chunks are XOR-permuted with (r % 8):
+//     off(r, c) = (r / 8) * 1024 + (r % 8) * 128 + ((c / 4) ^ (r % 8)) * 16 + (c % 4) * 4
+// The SAME bytes serve two roles:
+//   * K-major operand   (rows = M or N index, columns = K)   -> SBO = 1024
+//   * MN-major operand  (columns = M or N index, rows = K)   -> SBO = 1024,
+//     LBO = byte distance between consecutive 32-column blocks
+// which lets one staged [vertices x features] tile feed both  Y = P.W
+// (vertices = M, features = K) and dW = P^T.G (features = M, vertices = K).
+//
+// fp32 accuracy on a tf32 pipe: every operand is split x = hi + lo with
+// hi = x & 0xffffe000 (exactly representable in tf32) and lo = x - hi; the
+// hi/lo halves of one operand are stacked along M or N so that two MMAs
+// produce all four partial products, which the epilogue adds (error ~2^-22).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace athena {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier ------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(addr),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive + announce `tx_bytes` of asynchronous copies that will complete on this barrier
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t tx_bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(tx_bytes)
+               : "memory");
+}
+// TMA bulk copy (1-D, contiguous): global -> shared, completion counted on `bar`.
+// size must be a multiple of 16; src/dst 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// generic-proxy shared-memory writes -> visible to the async proxy (UMMA reads)
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- TMEM ----------------------------------------------------------------------
+// One full warp; writes the base address (lane << 16 | column) to *smem_dst.
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {
+  static_assert(NCOLS == 32 || NCOLS == 64 || NCOLS == 128 || NCOLS == 256 || NCOLS == 512, "");
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "r"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(NCOLS)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// ---- descriptors ---------------------------------------------------------------
+// Shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                              uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);             // [0,14)  start address
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;    // [16,30) leading byte offset
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;    // [32,46) stride byte offset
+  d |= static_cast<uint64_t>(1) << 46;                             // [46,48) version
+  d |= static_cast<uint64_t>(2) << 61;                             // [61,64) SWIZZLE_128B
+  return d;
+}
+
+// MN-major operands of 32-bit types must use the "128B swizzle with 32B base"
+// layout (layout type 1): rows (= K index) of 128 B, 4-row atoms of 512 B,
+// the four 32-byte granules of a row XOR-permuted with (row % 4).
+//   LBO = byte distance between consecutive 32-column (128 B) blocks along MN
+//   SBO = byte distance between consecutive 4-row atoms along K
+__device__ __forceinline__ uint64_t make_desc_mn32(uint32_t saddr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(1) << 61;                             // SWIZZLE_128B_BASE32B
+  return d;
+}
+// byte offset of 16-byte chunk c16 (0..7) of row r in a [rows x 32 fp32] block
+// stored in that layout
+__device__ __forceinline__ uint32_t sw128b32_off(int r, int c16) {
+  return static_cast<uint32_t>((r >> 2) * 512 + (r & 3) * 128 + ((((c16 >> 1) ^ (r & 3)) << 5)) +
+                               ((c16 & 1) << 4));
+}
+
+// Instruction descriptor for kind::tf32, fp32 accumulate, dense.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major,
+                                                  bool b_mn_major) {
+  return (1u << 4)                                   // c_format  = F32
+         | (2u << 7)                                 // a_format  = TF32
+         | (2u << 10)                                // b_format  = TF32
+         | ((a_mn_major ? 1u : 0u) << 15)            // a_major
+         | ((b_mn_major ? 1u : 0u) << 16)            // b_major
+         | (static_cast<uint32_t>(N >> 3) << 17)     // n_dim
+         | (static_cast<uint32_t>(M >> 4) << 24);    // m_dim
+}
+
+// D[tmem] (+)= A[smem] . B[smem]   -- issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// All previously issued MMAs of this thread arrive on `bar` when complete
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns: thread t of the warp gets lane
+// (taddr.lane + t), columns taddr.col .. +31.  Warp w may only touch lanes
+// 32*(w%4) .. +31.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- operand staging -----------------------------------------------------------
+// byte offset of the 16-byte chunk `c16` (0..7) of row `r` inside one
+// [rows x 32 fp32] swizzled block
+__device__ __forceinline__ uint32_t sw128_off(int r, int c16) {
+  return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+  hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+  hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+  hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+  lo.x = x.x - hi.x;
+  lo.y = x.y - hi.y;
+  lo.z = x.z - hi.z;
+  lo.w = x.w - hi.w;
+}
+
+}  // namespace tc
+}  // namespace athena

@@ -14,8 +14,8 @@ import pytest
 
 import athena_b200 as ab
 from athena_b200 import synth
-from helpers import (RTOL_ACT, RTOL_PARAM, duvenaud_spec, kipf_spec, random_params, rel_err,
-                     to_oracle_batch)
+from helpers import (RTOL_ACT, RTOL_PARAM, assert_parity, duvenaud_spec, kipf_spec,
+                     random_params, rel_err, to_oracle_batch)
 from oracle.oracle import Batch, OptimSpec
 
 pytestmark = pytest.mark.gpu
@@ -132,6 +132,11 @@ KIPF_CASES = [
     ([33, 65], 1, "relu", "reg"),
     ([128, 128], 1, "none", "reg"),
     ([130, 20], 1, "sigmoid", "mol"),
+    # tensor-core (tcgen05) shapes: 32/64 wide, ragged vertex counts
+    ([64, 64], 1, "relu", "mol"),
+    ([64, 32, 64], 2, "sigmoid", "mol"),
+    ([32, 32, 32], 2, "tanh", "mol"),
+    ([32, 64], 1, "none", "reg"),
 ]
 
 
@@ -174,6 +179,37 @@ def test_kipf_layer_forward_backward_parity(cuda, oracle32, oracle64, nvf, T, ac
     L.set_gradients(np.full(n, 0.1, np.float32))
     assert np.allclose(L.get_gradients(), 0.1)
     assert np.array_equal(L.get_params(), params)
+
+
+def test_kipf_tensor_core_path_many_tiles(cuda, oracle32, oracle64):
+    """More 128-row tiles than resident CTAs: exercises the persistent loops, the mbarrier
+    phase flips and the double-buffered dW kernel of the tcgen05 path.  tanh (smooth) so that
+    the comparison is not dominated by relu'(0) sign flips; dW is a 64000-term fp32 reduction,
+    so the float64 shadow arbitrates (helpers.assert_parity)."""
+    rng = np.random.default_rng(77)
+    p = synth.regular_batch(1000, 64, 6, 64, rng)          # V = 64000 = 500 tiles of 128
+    spec = kipf_spec([64, 64, 64], 2, "tanh")
+    params = random_params(oracle32.num_params([spec]), rng, 0.2)
+    g_out = rng.standard_normal((p.V, 64)).astype(np.float32)
+    ob = to_oracle_batch(p)
+    out_ref, dp_ref, dx_ref = oracle32.layer_fwd_bwd(spec, params, ob, g_out, want_dx=True)
+    out64, dp64, dx64 = oracle64.layer_fwd_bwd(spec, params, ob, g_out, want_dx=True)
+    L = ab.kipf_msgpass_layer_type([64, 64, 64], 2, activation="tanh")
+    L.set_params(params)
+    L.set_graph(p)
+    out = L.forward()
+    assert_parity(out, out_ref, out64, what="out")
+    L.zero_gradients()
+    dx = L.backward(g_out, want_input_grad=True)
+    dp = L.get_gradients()
+    assert_parity(dp, dp_ref, dp64, what="dW")
+    assert_parity(dx, dx_ref, dx64, what="dx")
+    # bitwise run-to-run determinism (no float atomics anywhere)
+    out2 = L.forward()
+    L.zero_gradients()
+    dx2 = L.backward(g_out, want_input_grad=True)
+    assert np.array_equal(out, out2) and np.array_equal(dx, dx2)
+    assert np.array_equal(dp, L.get_gradients())
 
 
 def test_kipf_forward_shape_matches_reference_test(cuda):
