@@ -227,8 +227,9 @@ int launch_add_inplace(float* dst, const float* src, int64_t n);
 
 // loss (misc.cu)
 // graph output: L = sum_s mean_{F,V_s}((p-e)^2)/2 ; g = (p-e)/(F*V_s).  loss_acc[0] += L.
+// act != NONE: grad is additionally multiplied by act'(pred) (layer-boundary fusion)
 int launch_mse_graph(const float* pred, const float* target, const int32_t* vgraph,
-                     const int32_t* nv, int F, int64_t V, float* grad, float* loss_acc,
+                     const int32_t* nv, int F, int64_t V, int act, float* grad, float* loss_acc,
                      DevBuf& scratch);
 // array output [B, N]: L = sum((p-e)^2)/(2*N*global_B) ; g = (p-e)/(N*global_B)
 int launch_mse_array(const float* pred, const float* target, int64_t n, float denom,

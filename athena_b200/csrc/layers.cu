@@ -30,6 +30,7 @@ struct Layer : Object {
   DevBuf Ae, out_buf, g0, g1, g2, tn_scratch, stage_x, stage_e, stage_g, stage_gin;
   Batch* fwd_batch = nullptr;
   int64_t fwd_V = -1;
+  const float* fwd_x = nullptr;  // device input of the last forward (valid until the next one)
 
   int ldA(int t) const { return (int)round_up(nvf[t - 1] + nef, 4); }
   int out_width() const { return kind == 0 ? nvf[T] : n_out; }
@@ -170,13 +171,26 @@ int layer_forward_dev(Layer* L, Batch* b, const float* x, const float* e, const 
   ATH_REQUIRE(x != nullptr || b->V == 0, ATHENA_ERR_ARG, "forward: vertex_features is null");
   L->fwd_batch = b;
   L->fwd_V = b->V;
+  L->fwd_x = x;
   if (L->kind == 0) return kipf_forward(L, b, x, out);
   return duvenaud_forward(L, b, x, e, out);
 }
 
 // ---- backward --------------------------------------------------------------------
 
-static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin) {
+// Layer-boundary fusion of the reverse sweep:
+//   gout_is_preact  gout already carries act'(H_T) of THIS layer (folded into the loss
+//                   gradient or into the next layer's epilogue)
+//   fold_act        activation of the layer that produced this layer's input; when the
+//                   fused kernel is used, grad_input is returned already multiplied by
+//                   fold_act'(input) and *folded is set
+struct BwdOpts {
+  bool gout_is_preact = false;
+  int fold_act = ATHENA_ACT_NONE;
+  bool* folded = nullptr;
+};
+
+static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, const BwdOpts& opt) {
   const int64_t V = b->V;
   int Fmax = 0;
   for (int t = 0; t <= L->T; ++t) Fmax = std::max(Fmax, L->nvf[t]);
@@ -185,8 +199,9 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin) {
   ATH_TRY(L->g1.reserve(bytes));
   ATH_TRY(L->g2.reserve(bytes));
   const bool nonlinear = L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR;
-  const float* g = gout;   // gradient w.r.t. the step output H_t ...
-  bool preact = false;     // ... or already w.r.t. the pre-activation (gY_t) when true
+  const float* g = gout;                // gradient w.r.t. the step output H_t ...
+  bool preact = opt.gout_is_preact;     // ... or already w.r.t. the pre-activation (gY_t)
+  if (opt.folded) *opt.folded = false;
   for (int t = L->T; t >= 1; --t) {
     const int Fi = L->nvf[t - 1], Fo = L->nvf[t];
     const float* Pt = L->P[t - 1]->as<float>();
@@ -223,9 +238,18 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin) {
     float* dst = gin;
     if (t > 1) dst = (gy == L->g2.as<float>()) ? L->g0.as<float>() : L->g2.as<float>();
     if (fused_dp) {
-      const bool act_next = nonlinear && t > 1;
-      ATH_TRY(launch_pipe_gather_bwd(b, gy, Wt, act_next ? L->H[t - 2]->as<float>() : nullptr, dst,
-                                     Fo, Fi, act_next ? L->act : ATHENA_ACT_NONE));
+      const float* Hin = nullptr;
+      int act_e = ATHENA_ACT_NONE;
+      if (t > 1 && nonlinear) {
+        Hin = L->H[t - 2]->as<float>();
+        act_e = L->act;
+      } else if (t == 1 && opt.fold_act != ATHENA_ACT_NONE && opt.fold_act != ATHENA_ACT_LINEAR &&
+                 opt.fold_act != ATHENA_ACT_SOFTMAX && L->fwd_x != nullptr) {
+        Hin = L->fwd_x;  // the producing layer's output
+        act_e = opt.fold_act;
+        if (opt.folded) *opt.folded = true;
+      }
+      ATH_TRY(launch_pipe_gather_bwd(b, gy, Wt, Hin, dst, Fo, Fi, act_e));
       preact = t > 1;  // dst already is gY_{t-1}
     } else {
       // dP = W_t^T gY, then dH(:,u) += dP(:,v) for every CSR entry (v,u): CSC gather, NO coefficient
@@ -299,11 +323,14 @@ static int duvenaud_backward(Layer* L, Batch* b, const float* gout, float* gin) 
   return ATHENA_OK;
 }
 
-int layer_backward_dev(Layer* L, Batch* b, const float* gout, float* gin) {
+int layer_backward_dev(Layer* L, Batch* b, const float* gout, float* gin,
+                       const BwdOpts& opt = BwdOpts{}) {
   ATH_REQUIRE(L->fwd_batch == b && L->fwd_V == b->V, ATHENA_ERR_STATE,
               "backward: no forward pass on this batch");
   ATH_REQUIRE(gout != nullptr, ATHENA_ERR_ARG, "backward: grad_output is null");
-  if (L->kind == 0) return kipf_backward(L, b, gout, gin);
+  if (opt.folded) *opt.folded = false;
+  if (L->kind == 0) return kipf_backward(L, b, gout, gin, opt);
+  ATH_REQUIRE(!opt.gout_is_preact, ATHENA_ERR_STATE, "duvenaud backward: unexpected pre-activation gradient");
   return duvenaud_backward(L, b, gout, gin);
 }
 
@@ -366,9 +393,17 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
   ATH_CUDA(cudaMemsetAsync(gflat + N->n, 0, sizeof(float), st));
   ATH_TRY(net_forward_dev(N, b, dx, de, &out));
   ATH_TRY(N->gbuf.reserve(sizeof(float) * (size_t)std::max<int64_t>(out_n, 1)));
+  // the activation derivative of the last Kipf layer is folded into the loss gradient
+  auto foldable = [](const Layer* L) {
+    return L->kind == 0 && L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR &&
+           L->act != ATHENA_ACT_SOFTMAX;
+  };
+  bool g_preact = false;
   if (last->kind == 0) {
+    g_preact = foldable(last);
     ATH_TRY(launch_mse_graph(out, dt, b->vgraph, b->nv, last->nvf[last->T], b->V,
-                             N->gbuf.as<float>(), gflat + N->n, N->loss_scratch));
+                             g_preact ? last->act : ATHENA_ACT_NONE, N->gbuf.as<float>(),
+                             gflat + N->n, N->loss_scratch));
   } else {
     int gb = global_batch > 0 ? global_batch : b->B;
     ATH_TRY(launch_mse_array(out, dt, out_n, (float)((int64_t)last->n_out * gb),
@@ -383,7 +418,13 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
                           (size_t)std::max<int64_t>(b->V * N->layers[l]->nvf[0], 1)));
       gi = buf.as<float>();
     }
-    ATH_TRY(layer_backward_dev(N->layers[l], b, g, gi));
+    BwdOpts opt;
+    bool folded = false;
+    opt.gout_is_preact = g_preact;
+    opt.fold_act = (l > 0 && foldable(N->layers[l - 1])) ? N->layers[l - 1]->act : ATHENA_ACT_NONE;
+    opt.folded = &folded;
+    ATH_TRY(layer_backward_dev(N->layers[l], b, g, gi, opt));
+    g_preact = folded;
     g = gi;
   }
   ATH_TRY(comm_allreduce_sum(gflat, N->n + 1));

@@ -33,20 +33,50 @@ __device__ __forceinline__ float block_sum(float v) {
   return r;  // valid in warp 0
 }
 
-// graph-output MSE: cell s = graph s, N_cell = F * nv[s]
+__device__ __forceinline__ float mse_act_grad(int act, float y, float g) {
+  switch (act) {
+    case ATHENA_ACT_RELU: return y > 0.f ? g : 0.f;
+    case ATHENA_ACT_LEAKY_RELU: return y > 0.f ? g : g * 0.01f;
+    case ATHENA_ACT_SIGMOID: return g * (y * (1.f - y));
+    case ATHENA_ACT_TANH: return g * (1.f - y * y);
+    default: return g;
+  }
+}
+
+// graph-output MSE: cell s = graph s, N_cell = F * nv[s].  VEC elements per thread step
+// (VEC = 4 needs F % 4 == 0 so that a float4 never straddles two vertices).
+// act != NONE folds act'(pred) of the producing layer into the gradient seed.
+template <int VEC>
 __global__ void __launch_bounds__(RED_THREADS)
 k_mse_graph(const float* __restrict__ pred, const float* __restrict__ target,
             const int32_t* __restrict__ vgraph, const int32_t* __restrict__ nv, int F, long long n,
-            float* __restrict__ grad, float* __restrict__ partial) {
+            int act, float* __restrict__ grad, float* __restrict__ partial) {
   float local = 0.f;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  const long long stride = (long long)gridDim.x * blockDim.x * VEC;
   for (; i < n; i += stride) {
-    long long v = i / F;
-    float denom = (float)(F * __ldg(nv + __ldg(vgraph + v)));
-    float d = pred[i] - target[i];
-    grad[i] = d / denom;
-    local += d * d / denom;
+    const long long v = i / F;
+    const float denom = (float)(F * __ldg(nv + __ldg(vgraph + v)));
+    float p[VEC], t[VEC], g[VEC];
+    if (VEC == 4) {
+      const float4 p4 = *reinterpret_cast<const float4*>(pred + i);
+      const float4 t4 = *reinterpret_cast<const float4*>(target + i);
+      p[0] = p4.x; p[1] = p4.y; p[2] = p4.z; p[3] = p4.w;
+      t[0] = t4.x; t[1] = t4.y; t[2] = t4.z; t[3] = t4.w;
+    } else {
+      p[0] = pred[i];
+      t[0] = target[i];
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float d = p[k] - t[k];
+      g[k] = mse_act_grad(act, p[k], d / denom);
+      local += d * d / denom;
+    }
+    if (VEC == 4)
+      *reinterpret_cast<float4*>(grad + i) = make_float4(g[0], g[1], g[2], g[3]);
+    else
+      grad[i] = g[0];
   }
   float s = block_sum(local);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
@@ -81,15 +111,22 @@ static int red_blocks(int64_t n) {
 }
 
 int launch_mse_graph(const float* pred, const float* target, const int32_t* vgraph,
-                     const int32_t* nv, int F, int64_t V, float* grad, float* loss_acc,
+                     const int32_t* nv, int F, int64_t V, int act, float* grad, float* loss_acc,
                      DevBuf& scratch) {
   int64_t n = V * F;
   if (n == 0) return ATHENA_OK;
-  int nb = red_blocks(n);
   ATH_TRY(scratch.reserve(sizeof(float) * 1024));
   cudaStream_t st = ctx().stream;
-  k_mse_graph<<<nb, RED_THREADS, 0, st>>>(pred, target, vgraph, nv, F, n, grad,
-                                          scratch.as<float>());
+  const bool vec4 = (F % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(target) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(grad) & 15) == 0);
+  int nb = red_blocks(vec4 ? n / 4 : n);
+  if (vec4)
+    k_mse_graph<4><<<nb, RED_THREADS, 0, st>>>(pred, target, vgraph, nv, F, n, act, grad,
+                                               scratch.as<float>());
+  else
+    k_mse_graph<1><<<nb, RED_THREADS, 0, st>>>(pred, target, vgraph, nv, F, n, act, grad,
+                                               scratch.as<float>());
   ATH_LAUNCHED_T("mse_graph");
   k_loss_finish<<<1, RED_THREADS, 0, st>>>(scratch.as<float>(), nb, loss_acc);
   ATH_LAUNCHED_T("loss_finish");

@@ -75,11 +75,11 @@ struct GatherArgs {
 template <int F, int N>
 struct GatherCfg {
   static constexpr int NS = 2;                                   // ring stages
-  static constexpr int GATHER_THREADS = 256;
-  static constexpr int EPI_WARP0 = 8;                            // warps 8..11
-  static constexpr int PRODUCER_WARP = 12;
-  static constexpr int MMA_WARP = 13;
-  static constexpr int THREADS = 14 * 32;
+  static constexpr int GATHER_THREADS = 512;                     // warps 0..15
+  static constexpr int EPI_WARP0 = 16;                           // warps 16..19 (warp % 4 = lane quarter)
+  static constexpr int PRODUCER_WARP = 20;
+  static constexpr int MMA_WARP = 21;
+  static constexpr int THREADS = 22 * 32;
   static constexpr int LPR = F / 4;                              // lanes per row
   static constexpr int GROUPS = GATHER_THREADS / LPR;
   static constexpr int RPG = TILE_ROWS / GROUPS;                 // rows per group
@@ -110,18 +110,18 @@ __device__ __forceinline__ void epilogue_rows(uint32_t tacc, int q, int lane, bo
                                               float* __restrict__ orow,
                                               const float* __restrict__ hrow, uint64_t* acc_empty) {
 #pragma unroll
-  for (int cg = 0; cg < N / 32; ++cg) {
-    float vh[32], vl[32];
-    const uint32_t taddr = tacc + (static_cast<uint32_t>(q * 32) << 16) + cg * 32;
-    tmem_ld32(taddr, vh);
-    tmem_ld32(taddr + N, vl);
-    if (cg == N / 32 - 1) {
+  for (int cg = 0; cg < N / 16; ++cg) {
+    float vh[16], vl[16];
+    const uint32_t taddr = tacc + (static_cast<uint32_t>(q * 32) << 16) + cg * 16;
+    tmem_ld16(taddr, vh);
+    tmem_ld16(taddr + N, vl);
+    if (cg == N / 16 - 1) {
       tc_fence_before();
       mbar_arrive(acc_empty);  // the accumulator buffer may be overwritten now
     }
     if (valid) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
+      for (int i = 0; i < 16; i += 4) {
         float4 o;
         if (EPI == EPI_ACT) {
           o = make_float4(act_fwd<ACT>(vh[i] + vl[i]), act_fwd<ACT>(vh[i + 1] + vl[i + 1]),
@@ -130,12 +130,12 @@ __device__ __forceinline__ void epilogue_rows(uint32_t tacc, int q, int lane, bo
           o = make_float4(vh[i] + vl[i], vh[i + 1] + vl[i + 1], vh[i + 2] + vl[i + 2],
                           vh[i + 3] + vl[i + 3]);
         } else {
-          const float4 h = __ldg(reinterpret_cast<const float4*>(hrow + cg * 32 + i));
+          const float4 h = __ldg(reinterpret_cast<const float4*>(hrow + cg * 16 + i));
           o = make_float4(act_bwd<ACT>(h.x, vh[i] + vl[i]), act_bwd<ACT>(h.y, vh[i + 1] + vl[i + 1]),
                           act_bwd<ACT>(h.z, vh[i + 2] + vl[i + 2]),
                           act_bwd<ACT>(h.w, vh[i + 3] + vl[i + 3]));
         }
-        *reinterpret_cast<float4*>(orow + cg * 32 + i) = o;
+        *reinterpret_cast<float4*>(orow + cg * 16 + i) = o;
       }
     }
   }
@@ -351,7 +351,7 @@ template <int N>
 struct Tn2Cfg {
   static constexpr int K = 64;
   static constexpr int RS = 64;                              // rows per stage
-  static constexpr int NS = 4;
+  static constexpr int NS = 3;
   static constexpr int XFORM_THREADS = 256;
   static constexpr int PRODUCER_WARP = 8;
   static constexpr int MMA_WARP = 9;
@@ -362,8 +362,8 @@ struct Tn2Cfg {
   static constexpr int BLK = RS * 128;                       // [64 rows x 32 feats]
   static constexpr int A1_BYTES = 2 * (K / 32) * BLK;
   static constexpr int A2_HALF = (N / 32) * BLK;
-  static constexpr int OPS_BYTES = A1_BYTES + 2 * A2_HALF;
-  static constexpr int OFF_RING = OPS_BYTES;
+  static constexpr int OPS_BYTES = A1_BYTES + 2 * A2_HALF;   // one operand buffer (two exist)
+  static constexpr int OFF_RING = 2 * OPS_BYTES;
   static constexpr int OFF_BAR = OFF_RING + NS * STAGE_BYTES;
   static constexpr int SMEM = 1024 + OFF_BAR + 256;
   static constexpr int TMEM_COLS = (N <= 32 ? 32 : 64);
@@ -377,16 +377,13 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
   constexpr int K = Cfg::K;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA1 = smem;
-  uint8_t* sA2hi = sA1 + Cfg::A1_BYTES;
-  uint8_t* sA2lo = sA2hi + Cfg::A2_HALF;
   uint8_t* ring = smem + Cfg::OFF_RING;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::NS;
-  uint64_t* ops_ready = bars + 2 * Cfg::NS;
-  uint64_t* ops_free = ops_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ops_free + 1);
+  uint64_t* ops_ready = bars + 2 * Cfg::NS;  // [2]
+  uint64_t* ops_free = ops_ready + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ops_free + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == Cfg::MMA_WARP) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -395,8 +392,10 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], Cfg::XFORM_THREADS);
     }
-    mbar_init(ops_ready, Cfg::XFORM_THREADS);
-    mbar_init(ops_free, 1);
+    for (int ob = 0; ob < 2; ++ob) {
+      mbar_init(&ops_ready[ob], Cfg::XFORM_THREADS);
+      mbar_init(&ops_free[ob], 1);
+    }
     mbar_fence_init();
   }
   tc_fence_before();
@@ -425,9 +424,11 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
   } else if (warp == Cfg::MMA_WARP) {
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc(128, N, true, true);
-      const uint32_t a1 = smem_u32(sA1), b_hi = smem_u32(sA2hi), b_lo = smem_u32(sA2lo);
       for (int j = 0; j < my_tiles; ++j) {
-        mbar_wait(ops_ready, j & 1);
+        const int ob = j & 1;
+        const uint32_t a1 = smem_u32(smem + ob * Cfg::OPS_BYTES);
+        const uint32_t b_hi = a1 + Cfg::A1_BYTES, b_lo = b_hi + Cfg::A2_HALF;
+        mbar_wait(&ops_ready[ob], (j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < Cfg::RS / 8; ++ks) {
@@ -437,11 +438,12 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
           umma_tf32(tmem, da, dbh, IDESC, (j | ks) ? 1u : 0u);
           umma_tf32(tmem, da, dbl, IDESC, 1u);
         }
-        umma_commit(ops_free);
+        umma_commit(&ops_free[ob]);
       }
     }
   } else {
     // transform warps: raw row-major tiles -> hi/lo, MN-major 32B-base swizzle
+    // (two operand buffers: the stores of tile j+1 overlap the MMAs of tile j)
     constexpr int CH1 = K / 4, CH2 = N / 4, CHT = CH1 + CH2;
     constexpr int LOADS = Cfg::RS * CHT / Cfg::XFORM_THREADS;
     static_assert(Cfg::RS * CHT % Cfg::XFORM_THREADS == 0, "loader mapping");
@@ -466,7 +468,11 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
         }
       }
       mbar_arrive(&empty[s]);
-      mbar_wait(ops_free, (j & 1) ^ 1u);
+      const int ob = j & 1;
+      uint8_t* sA1 = smem + ob * Cfg::OPS_BYTES;
+      uint8_t* sA2hi = sA1 + Cfg::A1_BYTES;
+      uint8_t* sA2lo = sA2hi + Cfg::A2_HALF;
+      mbar_wait(&ops_free[ob], ((j >> 1) & 1) ^ 1u);  // MMAs of tile j-2 have read this buffer
 #pragma unroll
       for (int i = 0; i < LOADS; ++i) {
         const int idx = tid + Cfg::XFORM_THREADS * i;
@@ -485,10 +491,10 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
         }
       }
       fence_async_smem();
-      mbar_arrive(ops_ready);
+      mbar_arrive(&ops_ready[ob]);
     }
     // the last commit covers every MMA (in-order completion)
-    if (my_tiles > 0) mbar_wait(ops_free, (my_tiles - 1) & 1);
+    if (my_tiles > 0) mbar_wait(&ops_free[(my_tiles - 1) & 1], ((my_tiles - 1) >> 1) & 1);
   }
   tc_fence_before();
   __syncthreads();
