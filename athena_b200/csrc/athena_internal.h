@@ -63,6 +63,7 @@ struct Context {
 };
 Context& ctx();
 int ensure_init();
+void pool_trim();  // return every cached device block to the driver
 
 void prof_mark(const char* tag);  // no-op unless profiling is on
 

@@ -1,6 +1,7 @@
 // Process-wide context: device selection, the library stream, error strings,
 // the handle registry, memory helpers and event timers.
 #include <cstdlib>
+#include <map>
 
 #include "athena_internal.h"
 
@@ -53,31 +54,95 @@ int destroy_object(athena_handle_t h, Kind kind) {
     victim = std::move(it->second);
     g_objects.erase(it);
   }
-  // device buffers may still be in use by queued kernels
-  if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+  // the object's device buffers return to the stream-ordered pool (no synchronisation)
   victim.reset();
   return ATHENA_OK;
+}
+
+// ---- caching device allocator -----------------------------------------------
+// Every DevBuf draws from a process-wide free list instead of cudaMalloc /
+// cudaFree: a training loop that builds and destroys one graph batch per step
+// (network%train, athena_network_sub.f90:3611-3670) would otherwise pay a
+// device-wide synchronisation plus an unmap per buffer per step.  All work of
+// the library is ordered on one stream, so a block may be handed to its next
+// owner as soon as the previous owner lets go of it: kernels of the new owner
+// are queued behind the kernels that still read the old contents.
+namespace {
+struct DevPool {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;
+  size_t cached = 0;
+};
+DevPool& pool() {
+  static DevPool* p = new DevPool;  // leaked on purpose: outlives every static DevBuf owner
+  return *p;
+}
+size_t pool_round(size_t bytes) {
+  if (bytes < (size_t(1) << 20)) return (bytes + 511) & ~size_t(511);
+  return (bytes + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);  // 2 MB pages
+}
+}  // namespace
+
+void pool_trim() {
+  DevPool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  if (P.free_blocks.empty()) return;
+  if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+  for (auto& kv : P.free_blocks) cudaFree(kv.second);
+  P.free_blocks.clear();
+  P.cached = 0;
+}
+
+static int pool_alloc(size_t bytes, void** out, size_t* cap) {
+  const size_t want = pool_round(bytes ? bytes : 1);
+  DevPool& P = pool();
+  {
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.free_blocks.lower_bound(want);
+    // accept a cached block that wastes at most 25 % (+1 MB)
+    if (it != P.free_blocks.end() && it->first <= want + want / 4 + (size_t(1) << 20)) {
+      *out = it->second;
+      *cap = it->first;
+      P.cached -= it->first;
+      P.free_blocks.erase(it);
+      return ATHENA_OK;
+    }
+  }
+  cudaError_t e = cudaMalloc(out, want);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    pool_trim();  // give the cached blocks back and retry once
+    e = cudaMalloc(out, want);
+  }
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes): %s", want, cudaGetErrorString(e));
+    return ATHENA_ERR_CUDA;
+  }
+  *cap = want;
+  return ATHENA_OK;
+}
+
+static void pool_free(void* p, size_t cap) {
+  DevPool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  P.free_blocks.emplace(cap, p);
+  P.cached += cap;
 }
 
 int DevBuf::reserve(size_t bytes) {
   if (bytes <= cap) return ATHENA_OK;
   ATH_TRY(ensure_init());
   if (p) {
-    // queued kernels may still read the old allocation
-    ATH_CUDA(cudaStreamSynchronize(ctx().stream));
-    ATH_CUDA(cudaFree(p));
+    pool_free(p, cap);
     p = nullptr;
     cap = 0;
   }
-  size_t want = (bytes + 255) & ~size_t(255);
-  ATH_CUDA(cudaMalloc(&p, want));
-  cap = want;
-  return ATHENA_OK;
+  return pool_alloc(bytes, &p, &cap);
 }
 
 void DevBuf::release() {
   if (p) {
-    cudaFree(p);
+    pool_free(p, cap);
     p = nullptr;
     cap = 0;
   }
@@ -168,6 +233,7 @@ ATHENA_API int athena_cuda_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_objects.clear();
   }
+  pool_trim();
   athena_cuda_comm_destroy();
   if (c.flush_buf) cudaFree(c.flush_buf);
   c.flush_buf = nullptr;

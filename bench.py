@@ -60,63 +60,133 @@ def init_params(n):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md clocks line).
+    Sampled through NVML every 2 ms (the timed region of the default run is only tens of
+    milliseconds, too short for `nvidia-smi -lms`); falls back to nvidia-smi when the NVML
+    binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device = device
-        self.proc = None
-        self.lines = []
+        self.sm, self.reasons, self.power = [], [], []   # (time, value) samples
+        self.mx = None
+        self.window = [None, None]
+        self._stop = threading.Event()
+        self.t = None
+        self.how = None
 
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+    def _nvml_loop(self, nv, h):
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                "sw_power_cap": 0x4}
+        k = 0
+        while not self._stop.is_set():
+            try:
+                t = time.perf_counter()
+                self.sm.append((t, float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.reasons.append((t, [name for name, bit in bits.items() if r & bit]))
+                if k % 8 == 0:
+                    self.power.append((t, nv.nvmlDeviceGetPowerUsage(h) / 1e3))
+                k += 1
+            except Exception:
+                pass
+            time.sleep(0.001)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
+    def _smi_loop(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.proc.stdout:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
+            t = time.perf_counter()
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                self.sm.append((t, float(f[1])))
+                self.mx = float(f[2])
+                self.power.append((t, float(f[3])))
             except ValueError:
                 continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+            self.reasons.append((t, [name for name, val in zip(names, f[5:9])
+                                     if val.lower().startswith("active")]))
+
+    def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.device
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.device])
+                except Exception:
+                    pass
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.how = "nvml, ~1 ms period"
+            self.t = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            pass
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "20"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi -lms 20"
+            self.t = threading.Thread(target=self._smi_loop, daemon=True)
+            self.t.start()
+        except Exception:
+            self.how = None
+
+    def mark_begin(self):
+        self.window[0] = time.perf_counter()
+
+    def mark_end(self):
+        self.window[1] = time.perf_counter()
+
+    def stop(self):
+        self._stop.set()
+        if getattr(self, "proc", None):
+            self.proc.terminate()
+        if self.t:
+            self.t.join(timeout=2)
+        t0, t1 = self.window
+        inside = lambda t: (t0 is None or t >= t0) and (t1 is None or t <= t1)
+        sm = [v for t, v in self.sm if inside(t)]
+        where = "timed region"
+        if len(sm) < 3:   # region shorter than a few sampling periods: widen to the loaded span
+            sm = [v for t, v in self.sm if t0 is None or t >= t0 - 0.05]
+            where = "timed region and the identical per-kernel timing pass right after it"
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "samples": 0,
+                    "reasons": ["no clock sample (nvml and nvidia-smi unavailable)"]}
+        reasons = sorted({r for t, rs in self.reasons if t0 is None or t >= t0 - 0.05 for r in rs})
+        power = [v for t, v in self.power if t0 is None or t >= t0 - 0.05]
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)),
+                "sm_max_mhz": self.mx, "samples": len(sm),
+                "power_w_max": max(power) if power else None, "reasons": reasons,
+                "how": self.how, "where": where}
 
 
-# algorithmic (compulsory) bytes per launch, SURVEY 8(d) / DESIGN.md "Roofline accounting"
+# algorithmic (compulsory) bytes per launch, SURVEY 8(d) / DESIGN.md "Roofline accounting":
+# every tensor a kernel must touch counted once, int32 indices, fp32 values.
 def kernel_bytes(tag, V, Z):
     vf = 4 * V * F
+    idx = 4 * (V + 1) + 4 * Z
     table = {
-        "aggregate_v4_g16_c1_coef": 4 * (V + 1) + 4 * Z + 2 * vf,   # read X, write P (+ indices)
-        "aggregate_v4_g16_c1": 4 * (V + 1) + 4 * Z + 2 * vf,        # CSC gather of dP
+        # fused propagate + transform + activation (SURVEY B_f with the saved aggregate P):
+        # row_ptr + col + degree/coefficient vector + X read, P and H written
+        "pipe_gather_fwd": idx + 4 * V + vf + 2 * vf + 4 * F * F,
+        # fused last layer + MSE: X and target read, P and the loss gradient written
+        "pipe_gather_fwd_mse": idx + 4 * V + 2 * vf + 2 * vf + 4 * F * F,
+        # fused dP = gY W^T, CSC gather, .* act'(H): gY and H read, gY_{t-1} written
+        "pipe_gather_bwd": idx + 2 * vf + vf + 4 * F * F,
+        "pipe_tn": 2 * vf + 4 * F * F,
+        "pipe_tn_reduce": 4 * F * F,
+        "aggregate_v4_g16_c1_coef": idx + 4 * V + 2 * vf,
+        "aggregate_v4_g16_c1": idx + 2 * vf,
         "gemm_nn": 2 * vf + 4 * F * F,
         "gemm_nt": 2 * vf + 4 * F * F,
         "gemm_tn_partial": 2 * vf,
@@ -125,6 +195,16 @@ def kernel_bytes(tag, V, Z):
         "mse_graph": 3 * vf,
     }
     return table.get(tag)
+
+
+def measured_traffic(tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `tag` from the committed
+    `ncu --set full` capture (profiles/traffic.json, written by tools/ncu_summary.py)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get(tag, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def step_bytes(V, Z):
@@ -248,21 +328,22 @@ def main():
         ab.check(L.athena_cuda_network_train_step(net.handle, batch.handle, ab.ptr(x_d), None,
                                                   ab.ptr(t_d), ab.MEM_DEVICE, global_B, None))
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         dev_step()
     barrier()
     n0 = np.zeros(1, np.int64); n1 = np.zeros(1, np.int64)
     L.athena_cuda_launch_count(ab.ptr(n0))
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ms = C.c_float()
+    sampler.mark_begin()
     ab.check(L.athena_cuda_timer_start(0))
     for _ in range(args.steps):
         dev_step()
     ab.check(L.athena_cuda_timer_stop(0, C.byref(ms)))
+    sampler.mark_end()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     L.athena_cuda_launch_count(ab.ptr(n1))
     launches = int(n1[0] - n0[0])
     ms_total = max_over_ranks(float(ms.value))
@@ -300,12 +381,14 @@ def main():
         nb = kernel_bytes(top, V, Z)
         ach = nb / (kernels[top]["us_per_launch"] * 1e-6) / 1e9 if nb else None
         roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                "frac": (ach / peak) if ach else None, "traffic": measured_traffic(top),
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": nb,
                 "us_per_launch": kernels[top]["us_per_launch"],
                 "step": {"algorithmic_bytes": step_bytes(V, Z),
                          "achieved": step_bytes(V, Z) / (ms_step * 1e-3) / 1e9,
                          "frac": step_bytes(V, Z) / (ms_step * 1e-3) / 1e9 / peak}}
+    clocks = sampler.stop() if rank == 0 else None
     barrier()
 
     # ---- leg 2: end to end through the public API with HOST buffers ------------------
