@@ -159,6 +159,13 @@ struct Batch : Object {
   // the CSR and the CSC alike.  num_tiles == 0: batch not tileable (a graph too big).
   DevBuf tiles;   // int4 {first row, rows, first entry, entries}
   int32_t num_tiles = 0;
+  // per-tile compact operands of the fused kernels (built only when num_tiles > 0):
+  // neighbour index RELATIVE to the tile's first row (< TILE_ROWS, one byte per entry)
+  // for the CSR and for the CSC, and deg(v)^-1/2 per vertex
+  DevBuf tile_ops;
+  uint8_t* col8 = nullptr;   // [Z] CSR neighbour - tile first row
+  uint8_t* csc8 = nullptr;   // [Z] CSC source    - tile first row
+  float* rsdeg = nullptr;    // [V]
   std::vector<std::unique_ptr<BucketSet>> buckets;
   BucketSet* find_buckets(int min_deg, int max_deg) const;
 };
@@ -211,6 +218,9 @@ bool pipe_gather_supported(const Batch* b, int F, int N);
 bool pipe_tn_supported(int K, int N);
 int launch_pipe_gather_fwd(const Batch* b, const float* X, const float* W, float* P, float* out,
                            int F, int N, int act);
+int launch_pipe_gather_fwd_mse(const Batch* b, const float* X, const float* W, float* P,
+                               const float* target, float* grad, int F, int N, int act,
+                               float* loss_part, int* num_parts);
 int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const float* Hin,
                            float* out, int F, int N, int act);
 int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int N, DevBuf& scratch);
@@ -232,6 +242,8 @@ int launch_add_inplace(float* dst, const float* src, int64_t n);
 int launch_mse_graph(const float* pred, const float* target, const int32_t* vgraph,
                      const int32_t* nv, int F, int64_t V, int act, float* grad, float* loss_acc,
                      DevBuf& scratch);
+// loss_acc[0] += 0.5 * sum(partial[0..nb))   (single block, fixed order)
+int launch_loss_finish(const float* partial, int nb, float* loss_acc);
 // array output [B, N]: L = sum((p-e)^2)/(2*N*global_B) ; g = (p-e)/(N*global_B)
 int launch_mse_array(const float* pred, const float* target, int64_t n, float denom,
                      float* grad, float* loss_acc, DevBuf& scratch);

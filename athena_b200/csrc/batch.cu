@@ -289,6 +289,22 @@ k_csc_sort_long(const int32_t* __restrict__ csc_ptr, int32_t* __restrict__ csc_e
   }
 }
 
+// ---- compact per-tile operands of the fused kernels ----------------------------
+// one CTA per tile: tile-local neighbour indices (CSR and CSC entry ranges of a tile of
+// whole graphs coincide), and deg^-1/2 of the tile's rows
+__global__ void k_tile_operands(const int4* __restrict__ tiles, const int32_t* __restrict__ col,
+                                const int32_t* __restrict__ csc_src,
+                                const int32_t* __restrict__ deg, uint8_t* __restrict__ col8,
+                                uint8_t* __restrict__ csc8, float* __restrict__ rsdeg) {
+  const int4 ti = tiles[blockIdx.x];
+  for (int e = threadIdx.x; e < ti.w; e += blockDim.x) {
+    col8[ti.z + e] = static_cast<uint8_t>(col[ti.z + e] - ti.x);
+    csc8[ti.z + e] = static_cast<uint8_t>(csc_src[ti.z + e] - ti.x);
+  }
+  for (int r = threadIdx.x; r < ti.y; r += blockDim.x)
+    rsdeg[ti.x + r] = 1.0f / sqrtf(static_cast<float>(deg[ti.x + r]));
+}
+
 // ---- degree buckets -----------------------------------------------------------
 constexpr int BKT_THREADS = 1024;
 constexpr int BKT_MAX_D = 256;
@@ -580,6 +596,16 @@ ATHENA_API int athena_cuda_batch_create(athena_handle_t* batch, int32_t num_grap
     }
     k_csc_sort_long<<<ctx().sm_count, 1024, smem, st>>>(b->csc_ptr, b->csc_ent, b->csc_src,
                                                         long_list, status + 1);
+    ATH_LAUNCHED();
+  }
+  if (b->num_tiles > 0) {
+    const size_t z16 = (size_t)round_up(Z + 32, 16);
+    ATH_TRY(b->tile_ops.reserve(2 * z16 + sizeof(float) * (size_t)round_up(V + 8, 4)));
+    b->col8 = b->tile_ops.as<uint8_t>();
+    b->csc8 = b->col8 + z16;
+    b->rsdeg = reinterpret_cast<float*>(b->csc8 + z16);
+    k_tile_operands<<<b->num_tiles, 256, 0, st>>>(b->tiles.as<int4>(), b->col, b->csc_src, b->deg,
+                                                 b->col8, b->csc8, b->rsdeg);
     ATH_LAUNCHED();
   }
   Batch* raw = b.release();

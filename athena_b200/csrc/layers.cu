@@ -82,7 +82,19 @@ static int layer_alloc_params(Layer* L) {
 
 // ---- forward ---------------------------------------------------------------------
 
-static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out) {
+// Network-level fusion of the last Kipf step with the graph-output MSE (train step only):
+// when the fused kernel applies, the layer output is never materialised; `grad` receives
+// d loss / d pre-activation and `loss_part[0..*num_parts)` the per-CTA loss sums.
+struct FwdOpts {
+  const float* mse_target = nullptr;
+  float* mse_grad = nullptr;
+  float* loss_part = nullptr;
+  int num_parts = 0;
+  bool fused = false;
+};
+
+static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out,
+                        FwdOpts* fo = nullptr) {
   const int64_t V = b->V;
   const float* in = x;
   for (int t = 1; t <= L->T; ++t) {
@@ -91,6 +103,15 @@ static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out) {
     DevBuf& H = *L->H[t - 1];
     ATH_TRY(P.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fi, 1)));
     ATH_TRY(H.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fo, 1)));
+    if (fo && fo->mse_target && t == L->T && L->act != ATHENA_ACT_SOFTMAX &&
+        pipe_gather_supported(b, Fi, Fo)) {
+      ATH_TRY(launch_pipe_gather_fwd_mse(b, in, L->params + L->poff[t - 1], P.as<float>(),
+                                         fo->mse_target, fo->mse_grad, Fi, Fo, L->act,
+                                         fo->loss_part, &fo->num_parts));
+      fo->fused = true;
+      in = nullptr;  // H_T is not materialised
+      continue;
+    }
     if (L->act != ATHENA_ACT_SOFTMAX && pipe_gather_supported(b, Fi, Fo)) {
       // propagate + transform + activation in one fused tcgen05 kernel
       ATH_TRY(launch_pipe_gather_fwd(b, in, L->params + L->poff[t - 1], P.as<float>(),
@@ -167,12 +188,13 @@ static int duvenaud_forward(Layer* L, Batch* b, const float* x, const float* e,
   return ATHENA_OK;
 }
 
-int layer_forward_dev(Layer* L, Batch* b, const float* x, const float* e, const float** out) {
+int layer_forward_dev(Layer* L, Batch* b, const float* x, const float* e, const float** out,
+                      FwdOpts* fo = nullptr) {
   ATH_REQUIRE(x != nullptr || b->V == 0, ATHENA_ERR_ARG, "forward: vertex_features is null");
   L->fwd_batch = b;
   L->fwd_V = b->V;
   L->fwd_x = x;
-  if (L->kind == 0) return kipf_forward(L, b, x, out);
+  if (L->kind == 0) return kipf_forward(L, b, x, out, fo);
   return duvenaud_forward(L, b, x, e, out);
 }
 
@@ -366,11 +388,12 @@ static int stage_in(DevBuf& buf, const float* src, int64_t count, int mem, const
 }
 
 static int net_forward_dev(Network* N, Batch* b, const float* x, const float* e,
-                           const float** out) {
+                           const float** out, FwdOpts* fo = nullptr) {
   const float* in = x;
   for (size_t l = 0; l < N->layers.size(); ++l) {
     const float* o = nullptr;
-    ATH_TRY(layer_forward_dev(N->layers[l], b, in, e, &o));
+    ATH_TRY(layer_forward_dev(N->layers[l], b, in, e, &o,
+                              l + 1 == N->layers.size() ? fo : nullptr));
     in = o;
   }
   *out = in;
@@ -391,15 +414,26 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
   float* gflat = N->flat_grads.as<float>();
   cudaStream_t st = ctx().stream;
   ATH_CUDA(cudaMemsetAsync(gflat + N->n, 0, sizeof(float), st));
-  ATH_TRY(net_forward_dev(N, b, dx, de, &out));
   ATH_TRY(N->gbuf.reserve(sizeof(float) * (size_t)std::max<int64_t>(out_n, 1)));
+  ATH_TRY(N->loss_scratch.reserve(sizeof(float) * 1024));
+  FwdOpts fo;
+  if (last->kind == 0 && b->V > 0) {
+    fo.mse_target = dt;
+    fo.mse_grad = N->gbuf.as<float>();
+    fo.loss_part = N->loss_scratch.as<float>();
+  }
+  ATH_TRY(net_forward_dev(N, b, dx, de, &out, &fo));
   // the activation derivative of the last Kipf layer is folded into the loss gradient
   auto foldable = [](const Layer* L) {
     return L->kind == 0 && L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR &&
            L->act != ATHENA_ACT_SOFTMAX;
   };
   bool g_preact = false;
-  if (last->kind == 0) {
+  if (fo.fused) {
+    // the last layer's kernel already produced d loss / d pre-activation and the loss sums
+    g_preact = true;
+    ATH_TRY(launch_loss_finish(fo.loss_part, fo.num_parts, gflat + N->n));
+  } else if (last->kind == 0) {
     g_preact = foldable(last);
     ATH_TRY(launch_mse_graph(out, dt, b->vgraph, b->nv, last->nvf[last->T], b->V,
                              g_preact ? last->act : ATHENA_ACT_NONE, N->gbuf.as<float>(),

@@ -133,6 +133,12 @@ int launch_mse_graph(const float* pred, const float* target, const int32_t* vgra
   return ATHENA_OK;
 }
 
+int launch_loss_finish(const float* partial, int nb, float* loss_acc) {
+  k_loss_finish<<<1, RED_THREADS, 0, ctx().stream>>>(partial, nb, loss_acc);
+  ATH_LAUNCHED_T("loss_finish");
+  return ATHENA_OK;
+}
+
 int launch_mse_array(const float* pred, const float* target, int64_t n, float denom, float* grad,
                      float* loss_acc, DevBuf& scratch) {
   if (n == 0) return ATHENA_OK;

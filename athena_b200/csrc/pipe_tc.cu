@@ -18,10 +18,13 @@
 //   producer warp   1 lane issues TMA bulk copies (cp.async.bulk) of the tile's feature
 //                   rows, CSR row pointers, column indices and coefficients into a
 //                   shared-memory ring; completion is counted on "full" mbarriers
-//   gather warps    256 threads: walk each row's entries in ascending order (the
-//                   reference's summation order), gathering neighbour rows from the
-//                   staged tile; split the result hi/lo and store it as the swizzled
-//                   K-major A operand; store P
+//   gather warps    512 threads, FOUR lanes per row, 16 features per lane: walk the row's
+//                   entries in ascending order (the reference's summation order); column
+//                   indices / coefficients are read four entries at a time (one LDS.128
+//                   per array), neighbour rows with four LDS.128 per entry whose 64-byte
+//                   halves alternate between the two rows of a quarter-warp, so every
+//                   shared-memory access is conflict-free; split the result hi/lo and
+//                   store it as the swizzled K-major A operand; store P
 //   MMA warp        1 lane issues tcgen05.mma.kind::tf32 into a double-buffered TMEM
 //                   accumulator and commits to mbarriers
 //   epilogue warps  128 threads: tcgen05.ld, hi+lo, activation (or act'), row stores
@@ -55,21 +58,46 @@ __device__ __forceinline__ float act_bwd(float y, float g) {
   return g;
 }
 
+// 16-byte shared-memory load that is not issued (and yields 0) when `p` is false
+__device__ __forceinline__ float4 lds128_pred(uint32_t addr, bool p) {
+  float4 v;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "mov.f32 %0, 0f00000000;\n\t"
+      "mov.f32 %1, 0f00000000;\n\t"
+      "mov.f32 %2, 0f00000000;\n\t"
+      "mov.f32 %3, 0f00000000;\n\t"
+      "@q ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
+      "}"
+      : "=&f"(v.x), "=&f"(v.y), "=&f"(v.z), "=&f"(v.w)
+      : "r"(addr), "r"(static_cast<uint32_t>(p))
+      : "memory");
+  return v;
+}
+
 constexpr int EPI_ACT = 0;      // out = act(v)
 constexpr int EPI_ACTGRAD = 1;  // out = v * act'(Hin)
+constexpr int EPI_MSE = 2;      // out = d MSE / d pre-activation; the loss is reduced per CTA
 
 struct GatherArgs {
   const int4* tiles;
   int num_tiles;
-  const int32_t* row_ptr;
-  const int32_t* col;
-  const float* coef;  // nullptr -> unit coefficients
-  const float* X;     // [V][F]
+  const int32_t* row_ptr;  // CSR row pointers or CSC column pointers
+  const uint8_t* col8;     // neighbour index relative to the tile's first row (Batch::col8/csc8)
+  const float* rs;         // deg^-1/2 per vertex; nullptr -> unit coefficients
+  const float* X;          // [V][F]
   const float* W;
-  float* P;           // optional [V][F]
-  float* out;         // [V][N]
-  const float* Hin;   // EPI_ACTGRAD: [V][N]
+  float* P;                // optional [V][F]
+  float* out;              // [V][N]
+  const float* aux;        // EPI_ACTGRAD: [V][N] saved activations (nullptr: act' == 1);
+                           // EPI_MSE: [V][N] target
   int act;
+  // EPI_MSE (mse_loss_type%compute for graph outputs, athena_loss.f90:416-427)
+  const int32_t* vgraph;  // [V] graph of a vertex
+  const int32_t* nv;      // [B] vertices per graph
+  float* loss_part;       // [gridDim.x] sum over this CTA's rows of (p-e)^2 / (N * nv_s)
 };
 
 template <int F, int N>
@@ -80,15 +108,17 @@ struct GatherCfg {
   static constexpr int PRODUCER_WARP = 20;
   static constexpr int MMA_WARP = 21;
   static constexpr int THREADS = 22 * 32;
-  static constexpr int LPR = F / 4;                              // lanes per row
-  static constexpr int GROUPS = GATHER_THREADS / LPR;
-  static constexpr int RPG = TILE_ROWS / GROUPS;                 // rows per group
+  static constexpr int LPR = 4;                                  // lanes per row
+  static constexpr int CPL = F / (4 * LPR);                      // 16-byte chunks per lane
+  // one ring stage: feature rows | tile-local neighbour bytes | row pointers | deg^-1/2
   static constexpr int X_BYTES = TILE_ROWS * F * 4;
-  static constexpr int IDX_ELEMS = TILE_ENTRIES + 8;
-  static constexpr int IDX_BYTES = IDX_ELEMS * 4;
+  static constexpr int C8_BYTES = TILE_ENTRIES + 32;
   static constexpr int RP_ELEMS = TILE_ROWS + 8;
   static constexpr int RP_BYTES = RP_ELEMS * 4;
-  static constexpr int STAGE_RAW = X_BYTES + 2 * IDX_BYTES + RP_BYTES;
+  static constexpr int OFF_C8 = X_BYTES;
+  static constexpr int OFF_RP = OFF_C8 + C8_BYTES;
+  static constexpr int OFF_RS = OFF_RP + RP_BYTES;
+  static constexpr int STAGE_RAW = OFF_RS + RP_BYTES;
   static constexpr int STAGE_BYTES = (STAGE_RAW + 127) / 128 * 128;
   static constexpr int KB = F / 32;
   static constexpr int A_BYTES = KB * 16384;
@@ -97,48 +127,98 @@ struct GatherCfg {
   static constexpr int OFF_OPS = 0;                              // A hi | A lo (1024-aligned)
   static constexpr int OFF_B = 2 * A_BYTES;
   static constexpr int OFF_RING = OFF_B + B_BYTES;
-  static constexpr int OFF_BAR = OFF_RING + NS * STAGE_BYTES;
-  static constexpr int SMEM = 1024 + OFF_BAR + 256;
+  static constexpr int OFF_AUX = OFF_RING + NS * STAGE_BYTES;    // [128][N + 4] epilogue operand tile
+  static constexpr int AUX_BYTES = TILE_ROWS * (N + 4) * 4;
+  static constexpr int OFF_BAR = OFF_AUX + AUX_BYTES;
+  static constexpr int OFF_EPI = OFF_BAR + 256 + 512;            // 4 epilogue transposition patches
+  static constexpr int SMEM = 1024 + OFF_EPI + 4 * (32 * 36) * 4;
+  static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(C8_BYTES % 16 == 0 && OFF_RP % 16 == 0 && OFF_RS % 16 == 0, "TMA alignment");
   static constexpr int ACC_COLS = 2 * N;                         // hi|lo stacked along N
   static constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128
                                    : 2 * ACC_COLS <= 256 ? 256 : 512;
-  static_assert(TILE_ROWS % GROUPS == 0, "row mapping");
+  static_assert(GATHER_THREADS == TILE_ROWS * LPR && CPL == 4 && F == 64, "row mapping");
+  static_assert(TILE_ROWS <= 256, "tile-local neighbour index must fit one byte");
 };
 
+// Epilogue of one 128-row tile for the warp that owns TMEM lanes 32q .. 32q+31.
+// tcgen05.ld hands every thread one ROW of the accumulator.  All arithmetic happens in
+// that layout; the second operand (saved activations / target) is this thread's row of a
+// padded shared-memory tile (pitch 272 B: conflict-free row-per-thread LDS.128) that the
+// thread itself prefetches with a 256-byte TMA bulk copy one tile ahead.  A row-per-thread
+// global store would touch 32 different 128-byte lines per instruction, so the warp
+// transposes the result through a private padded patch, 32 columns at a time:
+// row-per-thread STS.128 (pitch 144 B), then LDS.128 / STG.128 with eight lanes per row
+// segment, i.e. four full 128-byte lines per instruction.
+//   EPI_ACT      out = act(v)
+//   EPI_ACTGRAD  out = v .* act'(aux),  aux = saved activations (USE_AUX = false: out = v)
+//   EPI_MSE      out = act'(p) .* (p - aux) * row_scale,  p = act(v), aux = target;
+//                returns this row's sum (p - aux)^2 * row_scale
+//                (the caller halves the total: athena_loss.f90:414-427)
+constexpr int EPI_PITCH = 36;                 // floats per staged row (32 + 4 pad)
+constexpr int EPI_PATCH = 32 * EPI_PITCH;
+constexpr int AUX_PITCH = 68;                 // floats per operand row (64 + 4 pad)
 template <int ACT, int EPI, int N>
-__device__ __forceinline__ void epilogue_rows(uint32_t tacc, int q, int lane, bool valid,
-                                              float* __restrict__ orow,
-                                              const float* __restrict__ hrow, uint64_t* acc_empty) {
+__device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, int nrows,
+                                               float* __restrict__ out_tile,
+                                               const float* aux_row /* shared memory */,
+                                               float row_scale, float* patch,
+                                               uint64_t* acc_empty) {
+  float lsum = 0.f;
+  float* srow = patch + lane * EPI_PITCH;
 #pragma unroll
-  for (int cg = 0; cg < N / 16; ++cg) {
-    float vh[16], vl[16];
-    const uint32_t taddr = tacc + (static_cast<uint32_t>(q * 32) << 16) + cg * 16;
-    tmem_ld16(taddr, vh);
-    tmem_ld16(taddr + N, vl);
-    if (cg == N / 16 - 1) {
-      tc_fence_before();
-      mbar_arrive(acc_empty);  // the accumulator buffer may be overwritten now
-    }
-    if (valid) {
+  for (int half = 0; half < N / 32; ++half) {
+#pragma unroll
+    for (int cg = 0; cg < 2; ++cg) {
+      float vh[16], vl[16];
+      const int col0 = half * 32 + cg * 16;
+      const uint32_t taddr = tacc + (static_cast<uint32_t>(q * 32) << 16) + col0;
+      tmem_ld16(taddr, vh);
+      tmem_ld16(taddr + N, vl);
+      if (half == N / 32 - 1 && cg == 1) {
+        tc_fence_before();
+        mbar_arrive(acc_empty);  // the accumulator buffer may be overwritten now
+      }
 #pragma unroll
       for (int i = 0; i < 16; i += 4) {
-        float4 o;
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = vh[i + k] + vl[i + k];
         if (EPI == EPI_ACT) {
-          o = make_float4(act_fwd<ACT>(vh[i] + vl[i]), act_fwd<ACT>(vh[i + 1] + vl[i + 1]),
-                          act_fwd<ACT>(vh[i + 2] + vl[i + 2]), act_fwd<ACT>(vh[i + 3] + vl[i + 3]));
-        } else if (ACT == ATHENA_ACT_NONE) {
-          o = make_float4(vh[i] + vl[i], vh[i + 1] + vl[i + 1], vh[i + 2] + vl[i + 2],
-                          vh[i + 3] + vl[i + 3]);
-        } else {
-          const float4 h = __ldg(reinterpret_cast<const float4*>(hrow + cg * 16 + i));
-          o = make_float4(act_bwd<ACT>(h.x, vh[i] + vl[i]), act_bwd<ACT>(h.y, vh[i + 1] + vl[i + 1]),
-                          act_bwd<ACT>(h.z, vh[i + 2] + vl[i + 2]),
-                          act_bwd<ACT>(h.w, vh[i + 3] + vl[i + 3]));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[k] = act_fwd<ACT>(o[k]);
+        } else if (EPI == EPI_MSE) {
+          const float4 t4 = *reinterpret_cast<const float4*>(aux_row + col0 + i);
+          const float t[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float pk = act_fwd<ACT>(o[k]);
+            const float d = pk - t[k];
+            lsum += d * d * row_scale;
+            o[k] = act_bwd<ACT>(pk, d * row_scale);
+          }
+        } else if (ACT != ATHENA_ACT_NONE) {
+          const float4 h4 = *reinterpret_cast<const float4*>(aux_row + col0 + i);
+          const float h[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[k] = act_bwd<ACT>(h[k], o[k]);
         }
-        *reinterpret_cast<float4*>(orow + cg * 16 + i) = o;
+        *reinterpret_cast<float4*>(srow + cg * 16 + i) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = it * 32 + lane;
+      const int r = idx >> 3, c = idx & 7;
+      const int trow = q * 32 + r;
+      if (trow < nrows)
+        *reinterpret_cast<float4*>(out_tile + static_cast<size_t>(trow) * N + half * 32 + c * 4) =
+            *reinterpret_cast<const float4*>(patch + r * EPI_PITCH + c * 4);
+    }
+    __syncwarp();
   }
+  return lsum;
 }
 
 template <int F, int N, bool TRANSB, int EPI>
@@ -157,7 +237,10 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
   uint64_t* ops_free = ops_ready + 1;
   uint64_t* acc_full = ops_free + 1;     // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* aux_full = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 1);
+  float* loss_red = reinterpret_cast<float*>(smem + Cfg::OFF_BAR + 256);  // [128], EPI_MSE
+  float* sAux = reinterpret_cast<float*>(smem + Cfg::OFF_AUX);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == Cfg::MMA_WARP) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -172,19 +255,26 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 128);
     }
+    mbar_init(aux_full, 128);
     mbar_fence_init();
   }
-  // stacked weight operand [hi(W') ; lo(W')] with W' = op(W) as [N][F] K-major
-  for (int idx = tid; idx < F * N; idx += Cfg::THREADS) {
-    int k, n;
-    if (!TRANSB) { k = idx / N; n = idx - k * N; } else { n = idx / F; k = idx - n * F; }
-    const float w = __ldg(a.W + idx);
-    const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
-    const float lo = w - hi;
-    uint8_t* blk = sB + (k >> 5) * Cfg::B_BLK;
-    const int c = k & 31;
-    *reinterpret_cast<float*>(blk + sw128_off(n, c >> 2) + (c & 3) * 4) = hi;
-    *reinterpret_cast<float*>(blk + sw128_off(N + n, c >> 2) + (c & 3) * 4) = lo;
+  // stacked weight operand [hi(W') ; lo(W')] with W' = op(W) as [N][F] K-major.  One item =
+  // one 16-byte chunk (4 consecutive k) of one row n; the lanes of a quarter-warp write
+  // the eight chunks of one swizzled 128-byte line (conflict-free).
+  for (int item = tid; item < N * (F / 4); item += Cfg::THREADS) {
+    const int n = item / (F / 4), kc = item - n * (F / 4);
+    float4 w;
+    if (!TRANSB) {  // W row-major [F][N]: W'[n][k] = W[k][n]
+      const float* src = a.W + (kc * 4) * N + n;
+      w = make_float4(__ldg(src), __ldg(src + N), __ldg(src + 2 * N), __ldg(src + 3 * N));
+    } else {        // W row-major [N][F] used as is
+      w = __ldg(reinterpret_cast<const float4*>(a.W + n * F + kc * 4));
+    }
+    float4 hi, lo;
+    split_tf32(w, hi, lo);
+    uint8_t* blk = sB + (kc >> 3) * Cfg::B_BLK;
+    *reinterpret_cast<float4*>(blk + sw128_off(n, kc & 7)) = hi;
+    *reinterpret_cast<float4*>(blk + sw128_off(N + n, kc & 7)) = lo;
   }
   fence_async_smem();
   tc_fence_before();
@@ -202,17 +292,15 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
         mbar_wait(&empty[s], ph ^ 1u);
         const int4 ti = __ldg(a.tiles + t);
         const int r0 = ti.x, nrows = ti.y, e0 = ti.z, nent = ti.w;
-        const int ea = e0 & ~3, ecnt = (e0 + nent - ea + 3) & ~3;
+        const int ea = e0 & ~15, ebytes = (e0 + nent - ea + 15) & ~15;
         const int ra = r0 & ~3, rcnt = (r0 + nrows + 1 - ra + 3) & ~3;
         uint8_t* st = ring + s * Cfg::STAGE_BYTES;
-        const uint32_t xb = nrows * F * 4, eb = ecnt * 4, rb = rcnt * 4;
-        mbar_arrive_expect_tx(&full[s], xb + rb + (a.coef ? 2 * eb : eb));
+        const uint32_t xb = nrows * F * 4, eb = ebytes, rb = rcnt * 4;
+        mbar_arrive_expect_tx(&full[s], xb + eb + (a.rs ? 2 * rb : rb));
         bulk_g2s(st, a.X + static_cast<size_t>(r0) * F, xb, &full[s]);
-        if (eb) {
-          bulk_g2s(st + Cfg::X_BYTES, a.col + ea, eb, &full[s]);
-          if (a.coef) bulk_g2s(st + Cfg::X_BYTES + Cfg::IDX_BYTES, a.coef + ea, eb, &full[s]);
-        }
-        bulk_g2s(st + Cfg::X_BYTES + 2 * Cfg::IDX_BYTES, a.row_ptr + ra, rb, &full[s]);
+        if (eb) bulk_g2s(st + Cfg::OFF_C8, a.col8 + ea, eb, &full[s]);
+        bulk_g2s(st + Cfg::OFF_RP, a.row_ptr + ra, rb, &full[s]);
+        if (a.rs) bulk_g2s(st + Cfg::OFF_RS, a.rs + ra, rb, &full[s]);
       }
     }
   } else if (warp == Cfg::MMA_WARP) {
@@ -245,98 +333,191 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
   } else if (warp >= Cfg::EPI_WARP0) {
     // ===================== epilogue: TMEM -> registers -> global rows ==================
     const int q = warp - Cfg::EPI_WARP0;  // == warp % 4: TMEM lane quarter
+    float* patch = reinterpret_cast<float*>(smem + Cfg::OFF_EPI) + q * EPI_PATCH;
+    const bool use_aux = (EPI != EPI_ACT) && a.aux != nullptr;
+    const int my_row = q * 32 + lane;
+    float* aux_row = sAux + my_row * AUX_PITCH;
+    // every epilogue thread prefetches ITS OWN row of the operand tile (256 B), so no thread
+    // ever waits for another one before re-filling the buffer
+    auto issue_aux = [&](int t) {
+      const int4 ti = __ldg(a.tiles + t);
+      if (my_row < ti.y) {
+        mbar_arrive_expect_tx(aux_full, N * 4);
+        bulk_g2s(aux_row, a.aux + (static_cast<size_t>(ti.x) + my_row) * N, N * 4, aux_full);
+      } else {
+        mbar_arrive(aux_full);
+      }
+    };
+    if (use_aux && static_cast<int>(blockIdx.x) < a.num_tiles) issue_aux(blockIdx.x);
     int j = 0;
+    float lsum = 0.f;
     for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++j) {
       const int b = j & 1;
       const int4 ti = __ldg(a.tiles + t);
-      const int row = q * 32 + lane;
-      const bool valid = row < ti.y;
-      const size_t grow = static_cast<size_t>(ti.x) + row;
-      float* orow = a.out + grow * N;
-      const float* hrow = (EPI == EPI_ACTGRAD) ? a.Hin + grow * N : nullptr;
+      float* out_tile = a.out + static_cast<size_t>(ti.x) * N;
+      float scale = 0.f;
+      if (EPI == EPI_MSE && my_row < ti.y)
+        scale = 1.f / static_cast<float>(N * __ldg(a.nv + __ldg(a.vgraph + ti.x + my_row)));
       mbar_wait(&acc_full[b], (j >> 1) & 1);
       tc_fence_after();
+      if (use_aux) mbar_wait(aux_full, j & 1);
       const uint32_t tacc = tmem + b * Cfg::ACC_COLS;
-      switch (a.act) {
+      const int act = use_aux || EPI == EPI_ACT ? a.act : ATHENA_ACT_NONE;
+      switch (act) {
         case ATHENA_ACT_RELU:
-          epilogue_rows<ATHENA_ACT_RELU, EPI, N>(tacc, q, lane, valid, orow, hrow, &acc_empty[b]);
+          lsum += epilogue_tile<ATHENA_ACT_RELU, EPI, N>(tacc, q, lane, ti.y, out_tile, aux_row,
+                                                         scale, patch, &acc_empty[b]);
           break;
         case ATHENA_ACT_LEAKY_RELU:
-          epilogue_rows<ATHENA_ACT_LEAKY_RELU, EPI, N>(tacc, q, lane, valid, orow, hrow,
-                                                       &acc_empty[b]);
+          lsum += epilogue_tile<ATHENA_ACT_LEAKY_RELU, EPI, N>(tacc, q, lane, ti.y, out_tile,
+                                                               aux_row, scale, patch,
+                                                               &acc_empty[b]);
           break;
         case ATHENA_ACT_SIGMOID:
-          epilogue_rows<ATHENA_ACT_SIGMOID, EPI, N>(tacc, q, lane, valid, orow, hrow,
-                                                    &acc_empty[b]);
+          lsum += epilogue_tile<ATHENA_ACT_SIGMOID, EPI, N>(tacc, q, lane, ti.y, out_tile, aux_row,
+                                                            scale, patch, &acc_empty[b]);
           break;
         case ATHENA_ACT_TANH:
-          epilogue_rows<ATHENA_ACT_TANH, EPI, N>(tacc, q, lane, valid, orow, hrow, &acc_empty[b]);
+          lsum += epilogue_tile<ATHENA_ACT_TANH, EPI, N>(tacc, q, lane, ti.y, out_tile, aux_row,
+                                                         scale, patch, &acc_empty[b]);
           break;
         default:
-          epilogue_rows<ATHENA_ACT_NONE, EPI, N>(tacc, q, lane, valid, orow, hrow, &acc_empty[b]);
+          lsum += epilogue_tile<ATHENA_ACT_NONE, EPI, N>(tacc, q, lane, ti.y, out_tile, aux_row,
+                                                         scale, patch, &acc_empty[b]);
           break;
       }
+      // this thread is done with its operand row: prefetch the next tile's
+      if (use_aux && t + static_cast<int>(gridDim.x) < a.num_tiles) issue_aux(t + gridDim.x);
     }
+    if (EPI == EPI_MSE) loss_red[my_row] = lsum;
   } else {
     // ===================== gather warps ================================================
-    constexpr int LPR = Cfg::LPR;
-    const int g = tid / LPR, l = tid % LPR;
+    // quad (4 lanes) per row; the two quads of a quarter-warp own rows r and r + 8 (equal
+    // r % 8 => complementary halves of the swizzled operand line too)
+    const int quad = lane >> 2, ql = lane & 3, par = quad & 1;
+    const int row = (warp >> 1) * 16 + (warp & 1) * 4 + (quad >> 1) + 8 * par;
+    // float offsets of this lane's four 16-byte chunks inside a feature row:
+    //   step s reads chunk 4 * (s ^ par) + ql
+    const int offa = par * 16 + ql * 4;        // steps 0 (and 2: + 32)
+    const int offb = (par ^ 1) * 16 + ql * 4;  // steps 1 (and 3: + 32)
     int j = 0;
     for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++j) {
       const int s = j % Cfg::NS;
       const uint32_t ph = (j / Cfg::NS) & 1;
       const int4 ti = __ldg(a.tiles + t);
       const int r0 = ti.x, nrows = ti.y, e0 = ti.z;
-      const int ea = e0 & ~3, ra = r0 & ~3;
+      const int ea = e0 & ~15, ra = r0 & ~3;
       const uint8_t* st = ring + s * Cfg::STAGE_BYTES;
-      const float* Xs = reinterpret_cast<const float*>(st);
-      const int32_t* cols = reinterpret_cast<const int32_t*>(st + Cfg::X_BYTES);
-      const float* coefs = reinterpret_cast<const float*>(st + Cfg::X_BYTES + Cfg::IDX_BYTES);
-      const int32_t* rps =
-          reinterpret_cast<const int32_t*>(st + Cfg::X_BYTES + 2 * Cfg::IDX_BYTES) + (r0 - ra);
-      const bool has_coef = a.coef != nullptr;
+      const uint8_t* cols8 = st + Cfg::OFF_C8;
+      const int32_t* rps = reinterpret_cast<const int32_t*>(st + Cfg::OFF_RP) + (r0 - ra);
+      const float* rss = reinterpret_cast<const float*>(st + Cfg::OFF_RS) + (r0 - ra);
+      const bool has_coef = a.rs != nullptr;
       mbar_wait(&full[s], ph);
-      float4 acc[Cfg::RPG];
+      float4 acc[4];
 #pragma unroll
-      for (int k = 0; k < Cfg::RPG; ++k) {
-        const int row = g + Cfg::GROUPS * k;
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < nrows) {
-          const int beg = rps[row] - ea, end = rps[row + 1] - ea;
-#pragma unroll 4
-          for (int e = beg; e < end; ++e) {
-            const int c = cols[e] - r0;
-            const float w = has_coef ? coefs[e] : 1.f;
-            const float4 x = *reinterpret_cast<const float4*>(Xs + c * F + l * 4);
-            r.x = fmaf(w, x.x, r.x);
-            r.y = fmaf(w, x.y, r.y);
-            r.z = fmaf(w, x.z, r.z);
-            r.w = fmaf(w, x.w, r.w);
+      for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < nrows) {
+        const int beg = rps[row] - ea, end = rps[row + 1] - ea;
+        const uint32_t xs = smem_u32(st);
+        int e4 = beg & ~3;
+        uint32_t c4 = 0;
+        if (e4 < end) c4 = *reinterpret_cast<const uint32_t*>(cols8 + e4);
+        // Branch-free walk over aligned groups of four entries (four neighbour bytes = one
+        // LDS.32).  Entries outside [beg, end) issue no feature load (predicated off, value
+        // 0) and carry coefficient 0, so every accumulator sees exactly the row's entries
+        // in ascending order.  The loads of entry k + 1 are issued before the FMAs of
+        // entry k.  Coefficient: deg_u^-1/2 per entry, deg_v^-1/2 once per row
+        // (athena_diffstruc_extd_sub_kipf.f90:39-44 up to the rounding of the product).
+        while (e4 < end) {
+          const int en = e4 + 4;
+          uint32_t cn = c4;
+          if (en < end) cn = *reinterpret_cast<const uint32_t*>(cols8 + en);  // prefetch
+          float4 x[2][4];
+          float w[2];
+          auto issue = [&](int k) {
+            const int e = e4 + k;
+            const bool v = (e >= beg) && (e < end);
+            const uint32_t c = (c4 >> (8 * k)) & 0xffu;
+            const uint32_t xr = xs + c * (F * 4);
+            x[k & 1][0] = lds128_pred(xr + offa * 4, v);
+            x[k & 1][1] = lds128_pred(xr + offb * 4, v);
+            x[k & 1][2] = lds128_pred(xr + offa * 4 + 128, v);
+            x[k & 1][3] = lds128_pred(xr + offb * 4 + 128, v);
+            const float wu = has_coef ? rss[c & 127u] : 1.f;
+            w[k & 1] = v ? wu : 0.f;
+          };
+          auto consume = [&](int k) {
+            const float wk = w[k & 1];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 xv = x[k & 1][c];
+              acc[c].x = fmaf(wk, xv.x, acc[c].x);
+              acc[c].y = fmaf(wk, xv.y, acc[c].y);
+              acc[c].z = fmaf(wk, xv.z, acc[c].z);
+              acc[c].w = fmaf(wk, xv.w, acc[c].w);
+            }
+          };
+          issue(0);
+          issue(1);
+          consume(0);
+          issue(2);
+          consume(1);
+          issue(3);
+          consume(2);
+          consume(3);
+          c4 = cn;
+          e4 = en;
+        }
+        if (has_coef) {
+          const float wv = rss[row];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            acc[c].x *= wv;
+            acc[c].y *= wv;
+            acc[c].z *= wv;
+            acc[c].w *= wv;
           }
         }
-        acc[k] = r;
       }
       mbar_arrive(&empty[s]);  // raw stage consumed
-      if (a.P != nullptr) {
-#pragma unroll
-        for (int k = 0; k < Cfg::RPG; ++k) {
-          const int row = g + Cfg::GROUPS * k;
-          if (row < nrows)
-            *reinterpret_cast<float4*>(a.P + (static_cast<size_t>(r0) + row) * F + l * 4) = acc[k];
-        }
+      // chunk index of step k: 4 * (k ^ par) + ql
+      const int ch0 = 4 * par + ql, ch1 = 4 * (par ^ 1) + ql;
+      if (a.P != nullptr && row < nrows) {
+        float* prow = a.P + (static_cast<size_t>(r0) + row) * F;
+        *reinterpret_cast<float4*>(prow + ch0 * 4) = acc[0];
+        *reinterpret_cast<float4*>(prow + ch1 * 4) = acc[1];
+        *reinterpret_cast<float4*>(prow + ch0 * 4 + 32) = acc[2];
+        *reinterpret_cast<float4*>(prow + ch1 * 4 + 32) = acc[3];
       }
       mbar_wait(ops_free, (j & 1) ^ 1u);  // MMAs of the previous tile have read the operands
-#pragma unroll
-      for (int k = 0; k < Cfg::RPG; ++k) {
-        const int row = g + Cfg::GROUPS * k;
+      {
+        const uint32_t o0 = sw128_off(row, ch0), o1 = sw128_off(row, ch1);
         float4 hi, lo;
-        split_tf32(acc[k], hi, lo);
-        const uint32_t off = (l >> 3) * 16384 + sw128_off(row, l & 7);
-        *reinterpret_cast<float4*>(sAhi + off) = hi;
-        *reinterpret_cast<float4*>(sAlo + off) = lo;
+        split_tf32(acc[0], hi, lo);
+        *reinterpret_cast<float4*>(sAhi + o0) = hi;
+        *reinterpret_cast<float4*>(sAlo + o0) = lo;
+        split_tf32(acc[1], hi, lo);
+        *reinterpret_cast<float4*>(sAhi + o1) = hi;
+        *reinterpret_cast<float4*>(sAlo + o1) = lo;
+        split_tf32(acc[2], hi, lo);
+        *reinterpret_cast<float4*>(sAhi + 16384 + o0) = hi;
+        *reinterpret_cast<float4*>(sAlo + 16384 + o0) = lo;
+        split_tf32(acc[3], hi, lo);
+        *reinterpret_cast<float4*>(sAhi + 16384 + o1) = hi;
+        *reinterpret_cast<float4*>(sAlo + 16384 + o1) = lo;
       }
       fence_async_smem();
       mbar_arrive(ops_ready);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (EPI == EPI_MSE) {
+    // fixed-order reduction of the 128 per-thread partial sums of this CTA
+    if (tid == 0) {
+      float tot = 0.f;
+      for (int i = 0; i < 128; ++i) tot += loss_red[i];
+      a.loss_part[blockIdx.x] = tot;
     }
   }
   tc_fence_before();
@@ -557,7 +738,8 @@ int launch_gather_t(const GatherArgs& a) {
   }
   const int grid = std::min(a.num_tiles, ctx().sm_count);
   k_pipe_gather<F, N, TRANSB, EPI><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(a);
-  ATH_LAUNCHED_T(EPI == EPI_ACT ? "pipe_gather_fwd" : "pipe_gather_bwd");
+  ATH_LAUNCHED_T(EPI == EPI_ACT ? "pipe_gather_fwd"
+                 : EPI == EPI_MSE ? "pipe_gather_fwd_mse" : "pipe_gather_bwd");
   return ATHENA_OK;
 }
 
@@ -576,16 +758,42 @@ int launch_pipe_gather_fwd(const Batch* b, const float* X, const float* W, float
   a.tiles = b->tiles.as<int4>();
   a.num_tiles = b->num_tiles;
   a.row_ptr = b->row_ptr;
-  a.col = b->col;
-  a.coef = b->coef;
+  a.col8 = b->col8;
+  a.rs = b->rsdeg;
   a.X = X;
   a.W = W;
   a.P = P;
   a.out = out;
-  a.Hin = nullptr;
+  a.aux = nullptr;
   a.act = act;
   ATH_REQUIRE(F == 64 && N == 64, ATHENA_ERR_ARG, "pipe_gather_fwd: unsupported shape");
   return launch_gather_t<64, 64, false, EPI_ACT>(a);
+}
+
+// last layer of a training step: forward fused with the graph-output MSE.
+//   grad[v,:]  = d loss / d pre-activation = act'(p) .* (p - target) / (N nv_s),  p = act(P W)
+//   loss_part[c] = sum over the rows of CTA c of (p - target)^2 / (N nv_s)   (c < *num_parts)
+int launch_pipe_gather_fwd_mse(const Batch* b, const float* X, const float* W, float* P,
+                               const float* target, float* grad, int F, int N, int act,
+                               float* loss_part, int* num_parts) {
+  GatherArgs a{};
+  a.tiles = b->tiles.as<int4>();
+  a.num_tiles = b->num_tiles;
+  a.row_ptr = b->row_ptr;
+  a.col8 = b->col8;
+  a.rs = b->rsdeg;
+  a.X = X;
+  a.W = W;
+  a.P = P;
+  a.out = grad;
+  a.aux = target;
+  a.act = act;
+  a.vgraph = b->vgraph;
+  a.nv = b->nv;
+  a.loss_part = loss_part;
+  ATH_REQUIRE(F == 64 && N == 64, ATHENA_ERR_ARG, "pipe_gather_fwd_mse: unsupported shape");
+  *num_parts = std::min(b->num_tiles, ctx().sm_count);
+  return launch_gather_t<64, 64, false, EPI_MSE>(a);
 }
 
 // backward: out = ( (A^T-gather of G) W^T ) .* act'(Hin)      (W row-major [N][F]: W_t as stored)
@@ -595,13 +803,13 @@ int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const
   a.tiles = b->tiles.as<int4>();
   a.num_tiles = b->num_tiles;
   a.row_ptr = b->csc_ptr;
-  a.col = b->csc_src;
-  a.coef = nullptr;
+  a.col8 = b->csc8;
+  a.rs = nullptr;
   a.X = G;
   a.W = W;
   a.P = nullptr;
   a.out = out;
-  a.Hin = Hin;
+  a.aux = (act != ATHENA_ACT_NONE && act != ATHENA_ACT_LINEAR) ? Hin : nullptr;
   a.act = act;
   ATH_REQUIRE(F == 64 && N == 64, ATHENA_ERR_ARG, "pipe_gather_bwd: unsupported shape");
   return launch_gather_t<64, 64, true, EPI_ACTGRAD>(a);
