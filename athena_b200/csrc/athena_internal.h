@@ -174,6 +174,7 @@ int batch_bucketize(Batch* b, int min_deg, int max_deg, BucketSet** out);
 // ---------------------------------------------------------------------------
 // kernels (spmm.cu / dense.cu / misc.cu): host launchers, all on ctx().stream
 // ---------------------------------------------------------------------------
+struct DeferList;
 
 // out[v, 0:F] (+)= sum_{w in row v} c_w * X[col[w], 0:F]   (entries with col < 0 skipped)
 // coef == nullptr -> c_w = 1.  accumulate != 0 -> adds to the existing out.
@@ -223,7 +224,9 @@ int launch_pipe_gather_fwd_mse(const Batch* b, const float* X, const float* W, f
                                float* loss_part, int* num_parts);
 int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const float* Hin,
                            float* out, int F, int N, int act);
-int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int N, DevBuf& scratch);
+// defer != nullptr: the fold of the per-CTA partials into dW is queued instead of launched
+int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int N, DevBuf& scratch,
+                   DeferList* defer = nullptr);
 
 // elementwise / row-wise helpers
 int launch_act_bwd(int act, const float* Y, const float* G, float* out, int64_t M, int N);
@@ -257,6 +260,20 @@ struct OptimState {
 };
 // clip + optimiser step + zero the gradients (athena_network_sub.f90:2904-2927)
 int launch_update(float* params, float* grads, int64_t n, OptimState& st);
+
+// Partial weight-gradient reductions whose final fold into the flat gradient vector is
+// deferred to ONE launch at the end of the reverse sweep (launch_finalize).
+struct DeferJob {
+  const float* part;  // [nparts][count] per-CTA partial sums
+  int nparts, count;
+  float* dst;         // += into this block of the flat gradient vector
+};
+struct DeferList {
+  std::vector<DeferJob> jobs;
+};
+bool finalize_can_step(const OptimState& st);
+int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts, float* loss_acc,
+                    float* params, float* grads, int64_t n, OptimState* st);
 
 // comm (comm.cc)
 int comm_allreduce_sum(float* buf, int64_t n);  // no-op when no communicator

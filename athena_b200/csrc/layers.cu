@@ -26,7 +26,7 @@ struct Layer : Object {
   float* grads = nullptr;
   bool adopted = false;  // parameters live in a network's flat buffer
   // saved by forward for the reverse sweep
-  std::vector<std::unique_ptr<DevBuf>> P, H, S, GZ;
+  std::vector<std::unique_ptr<DevBuf>> P, H, S, GZ, TN;  // TN: per-step dW partials (fused path)
   DevBuf Ae, out_buf, g0, g1, g2, tn_scratch, stage_x, stage_e, stage_g, stage_gin;
   Batch* fwd_batch = nullptr;
   int64_t fwd_V = -1;
@@ -61,7 +61,9 @@ static void layer_layout(Layer* L) {
   L->H.clear();
   L->S.clear();
   L->GZ.clear();
+  L->TN.clear();
   for (int t = 0; t < L->T; ++t) {
+    L->TN.emplace_back(new DevBuf);
     L->P.emplace_back(new DevBuf);
     L->H.emplace_back(new DevBuf);
     L->S.emplace_back(new DevBuf);
@@ -210,6 +212,7 @@ struct BwdOpts {
   bool gout_is_preact = false;
   int fold_act = ATHENA_ACT_NONE;
   bool* folded = nullptr;
+  DeferList* defer = nullptr;  // queue the dW partial folds for launch_finalize
 };
 
 static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, const BwdOpts& opt) {
@@ -250,7 +253,7 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
     }
     // dW_t(o,i) += sum_v gY(o,v) P(i,v)
     if (fused_tn) {
-      ATH_TRY(launch_pipe_tn(Pt, gy, dWt, V, Fo, L->tn_scratch));
+      ATH_TRY(launch_pipe_tn(Pt, gy, dWt, V, Fo, *L->TN[t - 1], opt.defer));
     } else if (tn_tc) {
       ATH_TRY(launch_tc_tn(Pt, Fi, gy, Fo, Hact, L->act, dWt, V, Fo, Fi, L->tn_scratch));
     } else {
@@ -400,8 +403,12 @@ static int net_forward_dev(Network* N, Batch* b, const float* x, const float* e,
   return ATHENA_OK;
 }
 
+// step_too: also perform network%update when nothing (gradient exchange, clipping) has to
+// happen between the reverse sweep and the step; *stepped reports whether it did.
 static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, const float* tgt,
-                          int mem, int global_batch, float* loss) {
+                          int mem, int global_batch, float* loss, bool step_too = false,
+                          bool* stepped = nullptr) {
+  if (stepped) *stepped = false;
   ATH_REQUIRE(N->compiled, ATHENA_ERR_STATE, "network is not compiled");
   ATH_REQUIRE(tgt != nullptr, ATHENA_ERR_ARG, "train: target is null");
   Layer* first = N->layers.front();
@@ -429,10 +436,11 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
            L->act != ATHENA_ACT_SOFTMAX;
   };
   bool g_preact = false;
+  DeferList defer;
   if (fo.fused) {
-    // the last layer's kernel already produced d loss / d pre-activation and the loss sums
+    // the last layer's kernel already produced d loss / d pre-activation and the per-CTA
+    // loss sums, which launch_finalize folds into the loss slot
     g_preact = true;
-    ATH_TRY(launch_loss_finish(fo.loss_part, fo.num_parts, gflat + N->n));
   } else if (last->kind == 0) {
     g_preact = foldable(last);
     ATH_TRY(launch_mse_graph(out, dt, b->vgraph, b->nv, last->nvf[last->T], b->V,
@@ -457,9 +465,17 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
     opt.gout_is_preact = g_preact;
     opt.fold_act = (l > 0 && foldable(N->layers[l - 1])) ? N->layers[l - 1]->act : ATHENA_ACT_NONE;
     opt.folded = &folded;
+    opt.defer = &defer;
     ATH_TRY(layer_backward_dev(N->layers[l], b, g, gi, opt));
     g_preact = folded;
     g = gi;
+  }
+  if (!defer.jobs.empty() || fo.fused) {
+    const bool fuse_step = step_too && finalize_can_step(N->opt);
+    ATH_TRY(launch_finalize(defer, fo.fused ? fo.loss_part : nullptr, fo.num_parts, gflat + N->n,
+                            N->flat_params.as<float>(), gflat, N->n,
+                            fuse_step ? &N->opt : nullptr));
+    if (stepped) *stepped = fuse_step;
   }
   ATH_TRY(comm_allreduce_sum(gflat, N->n + 1));
   if (loss) {
@@ -826,9 +842,11 @@ ATHENA_API int athena_cuda_network_train_step(athena_handle_t net, athena_handle
   if (!N || !b) return ATHENA_ERR_HANDLE;
   // the loss read-back (if requested) is deferred until the step is queued,
   // so the host does not stall between backward and update
+  bool stepped = false;
   ATH_TRY(net_loss_grads(N, b, vertex_features, edge_features, target, mem, global_batch,
-                         nullptr));
-  ATH_TRY(launch_update(N->flat_params.as<float>(), N->flat_grads.as<float>(), N->n, N->opt));
+                         nullptr, true, &stepped));
+  if (!stepped)
+    ATH_TRY(launch_update(N->flat_params.as<float>(), N->flat_grads.as<float>(), N->n, N->opt));
   if (loss) return athena_cuda_network_last_loss(net, loss);
   return ATHENA_OK;
 }

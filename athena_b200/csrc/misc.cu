@@ -182,6 +182,30 @@ struct StepArgs {
   float bc1, bc2;
 };
 
+// one parameter of minimise_sgd / minimise_adam (athena_optimiser.f90:649-672, 1043-1088)
+__device__ __forceinline__ void step_one(float* __restrict__ p, float* __restrict__ s1,
+                                         float* __restrict__ s2, long long i, float gr,
+                                         const StepArgs& a) {
+  if (a.kind == ATHENA_OPT_SGD) {
+    gr = -a.lr * gr;
+    if (a.momentum > 1e-8f) {
+      float vel = a.momentum * s1[i] + gr;
+      s1[i] = vel;
+      p[i] = a.nesterov ? p[i] + a.momentum * vel + gr : p[i] + vel;
+    } else {
+      s1[i] = gr;
+      p[i] = p[i] + gr;
+    }
+  } else {
+    float m = a.beta1 * s1[i] + (1.f - a.beta1) * gr;
+    float v = a.beta2 * s2[i] + (1.f - a.beta2) * gr * gr;
+    s1[i] = m;
+    s2[i] = v;
+    float mh = m / a.bc1, vh = v / a.bc2;
+    p[i] = p[i] - a.lr * (mh / (sqrtf(vh) + a.eps));
+  }
+}
+
 __global__ void __launch_bounds__(RED_THREADS)
 k_step(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
        float* __restrict__ s2, long long n, const float* __restrict__ partial, int nb,
@@ -203,25 +227,84 @@ k_step(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
   for (; i < n; i += stride) {
     float gr = g[i];
     if (scale < 1.f) gr = gr * scale;
-    if (a.kind == ATHENA_OPT_SGD) {
-      gr = -a.lr * gr;
-      if (a.momentum > 1e-8f) {
-        float vel = a.momentum * s1[i] + gr;
-        s1[i] = vel;
-        p[i] = a.nesterov ? p[i] + a.momentum * vel + gr : p[i] + vel;
-      } else {
-        s1[i] = gr;
-        p[i] = p[i] + gr;
-      }
-    } else {
-      float m = a.beta1 * s1[i] + (1.f - a.beta1) * gr;
-      float v = a.beta2 * s2[i] + (1.f - a.beta2) * gr * gr;
-      s1[i] = m;
-      s2[i] = v;
-      float mh = m / a.bc1, vh = v / a.bc2;
-      p[i] = p[i] - a.lr * (mh / (sqrtf(vh) + a.eps));
-    }
+    step_one(p, s1, s2, i, gr, a);
     g[i] = 0.f;  // reset_gradients, athena_network_sub.f90:2927
+  }
+}
+
+// ---- end-of-backward finalisation -----------------------------------------------
+// One launch that (1) folds the per-CTA partial weight gradients of the fused dW kernels
+// into the flat gradient vector, (2) folds the per-CTA loss sums into the loss slot and,
+// when no gradient exchange or clipping stands between backward and update (single rank,
+// clip off), (3) applies the optimiser step and zeroes the gradients.  Fixed summation
+// order everywhere: partials are split over FIN_GROUPS lanes in an interleaved, fixed
+// pattern and the group totals are added in group order.
+constexpr int FIN_ELEMS = 32, FIN_GROUPS = 8, FIN_THREADS = FIN_ELEMS * FIN_GROUPS;
+constexpr int FIN_MAX_JOBS = 8;
+struct FinJob {
+  const float* part;  // [nparts][count]
+  int nparts, count;
+  long long dst;      // offset of the block in the flat gradient vector
+};
+struct FinArgs {
+  FinJob job[FIN_MAX_JOBS];
+  int njobs;
+  const float* loss_part;
+  int loss_nparts;
+  float* loss_acc;
+  int do_step;
+};
+
+__global__ void __launch_bounds__(FIN_THREADS)
+k_finalize(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
+           float* __restrict__ s2, long long n, FinArgs f, StepArgs a) {
+  __shared__ float red[FIN_GROUPS][FIN_ELEMS];
+  const int e = threadIdx.x % FIN_ELEMS, grp = threadIdx.x / FIN_ELEMS;
+  const long long i = (long long)blockIdx.x * FIN_ELEMS + e;
+  float sum = 0.f;
+  if (i < n) {
+    for (int jb = 0; jb < f.njobs; ++jb) {
+      const FinJob& J = f.job[jb];
+      const long long off = i - J.dst;
+      if (off >= 0 && off < J.count) {
+        // four independent running sums (fixed pattern) keep four loads in flight
+        const float* src = J.part + off;
+        const size_t st = (size_t)J.count;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        int c = grp;
+        for (; c + 3 * FIN_GROUPS < J.nparts; c += 4 * FIN_GROUPS) {
+          const float v0 = __ldg(src + c * st), v1 = __ldg(src + (c + FIN_GROUPS) * st);
+          const float v2 = __ldg(src + (c + 2 * FIN_GROUPS) * st);
+          const float v3 = __ldg(src + (c + 3 * FIN_GROUPS) * st);
+          acc[0] += v0;
+          acc[1] += v1;
+          acc[2] += v2;
+          acc[3] += v3;
+        }
+        for (int k = 0; c < J.nparts; c += FIN_GROUPS, ++k) acc[k] += __ldg(src + c * st);
+        sum += (acc[0] + acc[1]) + (acc[2] + acc[3]);
+      }
+    }
+  }
+  red[grp][e] = sum;
+  __syncthreads();
+  if (grp == 0 && i < n) {
+    float gr = g[i];
+#pragma unroll
+    for (int k = 0; k < FIN_GROUPS; ++k) gr += red[k][e];
+    if (f.do_step) {
+      step_one(p, s1, s2, i, gr, a);
+      g[i] = 0.f;
+    } else {
+      g[i] = gr;
+    }
+  }
+  if (blockIdx.x == 0 && f.loss_part != nullptr) {
+    __syncthreads();
+    float local = 0.f;
+    for (int k = threadIdx.x; k < f.loss_nparts; k += FIN_THREADS) local += f.loss_part[k];
+    float s = block_sum(local);
+    if (threadIdx.x == 0) f.loss_acc[0] += 0.5f * s;
   }
 }
 
@@ -235,8 +318,7 @@ static float powi(float b, int64_t e) {  // real ** integer
   return r;
 }
 
-int launch_update(float* params, float* grads, int64_t n, OptimState& st) {
-  if (n == 0) return ATHENA_OK;
+static int step_prepare(int64_t n, OptimState& st, StepArgs* a) {
   cudaStream_t s = ctx().stream;
   if (!st.s1.p) {
     ATH_TRY(st.s1.reserve(sizeof(float) * (size_t)n));
@@ -246,6 +328,26 @@ int launch_update(float* params, float* grads, int64_t n, OptimState& st) {
   }
   ATH_TRY(st.scratch.reserve(sizeof(float) * 1024));
   st.iter += 1;  // incremented BEFORE the step, athena_network_sub.f90:2834-2841
+  const athena_optimiser_desc& d = st.d;
+  a->kind = d.kind;
+  a->lr = st.lr;
+  a->beta1 = d.beta1;
+  a->beta2 = d.beta2;
+  a->eps = d.epsilon;
+  a->momentum = d.momentum;
+  a->nesterov = d.nesterov;
+  a->norm_on = d.clip_norm_on;
+  a->clip_norm = d.clip_norm;
+  a->bc1 = 1.f - powi(d.beta1, st.iter);
+  a->bc2 = 1.f - powi(d.beta2, st.iter);
+  return ATHENA_OK;
+}
+
+int launch_update(float* params, float* grads, int64_t n, OptimState& st) {
+  if (n == 0) return ATHENA_OK;
+  cudaStream_t s = ctx().stream;
+  StepArgs a;
+  ATH_TRY(step_prepare(n, st, &a));
   int nb = red_blocks(n);
   const athena_optimiser_desc& d = st.d;
   if (d.clip_min_max || d.clip_norm_on) {
@@ -253,21 +355,48 @@ int launch_update(float* params, float* grads, int64_t n, OptimState& st) {
                                             st.scratch.as<float>());
     ATH_LAUNCHED_T("clip_sumsq");
   }
-  StepArgs a;
-  a.kind = d.kind;
-  a.lr = st.lr;
-  a.beta1 = d.beta1;
-  a.beta2 = d.beta2;
-  a.eps = d.epsilon;
-  a.momentum = d.momentum;
-  a.nesterov = d.nesterov;
-  a.norm_on = d.clip_norm_on;
-  a.clip_norm = d.clip_norm;
-  a.bc1 = 1.f - powi(d.beta1, st.iter);
-  a.bc2 = 1.f - powi(d.beta2, st.iter);
   k_step<<<nb, RED_THREADS, 0, s>>>(params, grads, st.s1.as<float>(), st.s2.as<float>(), n,
                                     st.scratch.as<float>(), nb, a);
   ATH_LAUNCHED_T("optimiser_step");
+  return ATHENA_OK;
+}
+
+bool finalize_can_step(const OptimState& st) {
+  return !st.d.clip_min_max && !st.d.clip_norm_on && comm_world_size() == 1;
+}
+
+// Folds the deferred partial reductions (and the loss partials) into the flat gradient
+// buffer; with `st` != nullptr also performs the optimiser step (caller checked
+// finalize_can_step).  More than FIN_MAX_JOBS reductions are flushed in several launches,
+// the step riding on the last one.
+int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts, float* loss_acc,
+                    float* params, float* grads, int64_t n, OptimState* st) {
+  if (n == 0) return ATHENA_OK;
+  cudaStream_t s = ctx().stream;
+  StepArgs a{};
+  if (st) ATH_TRY(step_prepare(n, *st, &a));
+  size_t done = 0;
+  do {
+    FinArgs f{};
+    f.njobs = (int)std::min<size_t>(FIN_MAX_JOBS, dl.jobs.size() - done);
+    for (int k = 0; k < f.njobs; ++k) {
+      const DeferJob& j = dl.jobs[done + k];
+      f.job[k].part = j.part;
+      f.job[k].nparts = j.nparts;
+      f.job[k].count = j.count;
+      f.job[k].dst = j.dst - grads;
+    }
+    done += f.njobs;
+    const bool last = done == dl.jobs.size();
+    f.loss_part = last ? loss_part : nullptr;
+    f.loss_nparts = loss_nparts;
+    f.loss_acc = loss_acc;
+    f.do_step = (last && st) ? 1 : 0;
+    k_finalize<<<(unsigned)cdiv(n, FIN_ELEMS), FIN_THREADS, 0, s>>>(
+        params, grads, st ? st->s1.as<float>() : nullptr, st ? st->s2.as<float>() : nullptr, n, f,
+        a);
+    ATH_LAUNCHED_T(f.do_step ? "finalize_step" : "finalize");
+  } while (done < dl.jobs.size());
   return ATHENA_OK;
 }
 

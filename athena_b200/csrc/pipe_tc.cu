@@ -349,15 +349,25 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
       }
     };
     if (use_aux && static_cast<int>(blockIdx.x) < a.num_tiles) issue_aux(blockIdx.x);
+    // 1 / (N * nv_s) of this thread's row, fetched one tile ahead (two dependent loads)
+    auto row_scale_of = [&](int t) {
+      float sc = 0.f;
+      if (EPI == EPI_MSE && t < a.num_tiles) {
+        const int4 ti = __ldg(a.tiles + t);
+        if (my_row < ti.y)
+          sc = 1.f / static_cast<float>(N * __ldg(a.nv + __ldg(a.vgraph + ti.x + my_row)));
+      }
+      return sc;
+    };
+    float scale_next = row_scale_of(blockIdx.x);
     int j = 0;
     float lsum = 0.f;
     for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++j) {
       const int b = j & 1;
       const int4 ti = __ldg(a.tiles + t);
       float* out_tile = a.out + static_cast<size_t>(ti.x) * N;
-      float scale = 0.f;
-      if (EPI == EPI_MSE && my_row < ti.y)
-        scale = 1.f / static_cast<float>(N * __ldg(a.nv + __ldg(a.vgraph + ti.x + my_row)));
+      const float scale = scale_next;
+      scale_next = row_scale_of(t + gridDim.x);
       mbar_wait(&acc_full[b], (j >> 1) & 1);
       tc_fence_after();
       if (use_aux) mbar_wait(aux_full, j & 1);
@@ -680,30 +690,27 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // final epilogue: lanes 0..63 hold hi(P)^T.G, lanes 64..127 lo(P)^T.G
-  float* sOut = reinterpret_cast<float*>(smem);
-  if (warp < 4 && my_tiles > 0) {
+  // final epilogue: TMEM lanes 0..63 hold hi(P)^T.G, lanes 64..127 lo(P)^T.G.  Each half is
+  // written as its own [K x N] partial (2 per CTA) straight from registers; the fold over
+  // partials happens in the reduce / finalize kernel, in partial-index order.
+  if (warp < 4) {
     const int q = warp;
+    const int feat = (q & 1) * 32 + lane;
+    float* dst = part + (static_cast<size_t>(blockIdx.x) * 2 + (q >> 1)) * K * N + feat * N;
     float v[32];
-    for (int pass = 0; pass < 2; ++pass) {
-      if ((q >> 1) == pass) {
-        const int feat = (q & 1) * 32 + lane;
-        for (int cg = 0; cg < N / 32; ++cg) {
-          tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + cg * 32, v);
+    for (int cg = 0; cg < N / 32; ++cg) {
+      if (my_tiles > 0) {
+        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + cg * 32, v);
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float* dst = sOut + feat * N + cg * 32 + i;
-            *dst = pass == 0 ? v[i] : *dst + v[i];
-          }
-        }
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(dst + cg * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
   }
   tc_fence_before();
-  __syncthreads();
-  float* dst = part + static_cast<size_t>(blockIdx.x) * K * N;
-  for (int e = tid; e < K * N; e += Cfg::THREADS) dst[e] = my_tiles > 0 ? sOut[e] : 0.f;
   __syncthreads();
   if (warp == Cfg::MMA_WARP) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
 }
@@ -816,7 +823,8 @@ int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const
 }
 
 template <int N>
-static int launch_pipe_tn_t(const float* P, const float* G, float* dW, int64_t M, DevBuf& scratch) {
+static int launch_pipe_tn_t(const float* P, const float* G, float* dW, int64_t M, DevBuf& scratch,
+                            DeferList* defer) {
   using Cfg = Tn2Cfg<N>;
   static bool attr = false;
   if (!attr) {
@@ -826,20 +834,25 @@ static int launch_pipe_tn_t(const float* P, const float* G, float* dW, int64_t M
   }
   const int64_t ntiles = cdiv(M, Cfg::RS);
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx().sm_count);
-  ATH_TRY(scratch.reserve(sizeof(float) * (size_t)grid * Cfg::K * N));
+  ATH_TRY(scratch.reserve(sizeof(float) * (size_t)grid * 2 * Cfg::K * N));
   k_pipe_tn<N><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(P, G, scratch.as<float>(), M);
   ATH_LAUNCHED_T("pipe_tn");
+  if (defer) {
+    defer->jobs.push_back(DeferJob{scratch.as<float>(), 2 * grid, Cfg::K * N, dW});
+    return ATHENA_OK;
+  }
   k_pipe_tn_reduce<<<(unsigned)cdiv((int64_t)Cfg::K * N, 128), 128, 0, ctx().stream>>>(
-      scratch.as<float>(), grid, Cfg::K * N, dW);
+      scratch.as<float>(), 2 * grid, Cfg::K * N, dW);
   ATH_LAUNCHED_T("pipe_tn_reduce");
   return ATHENA_OK;
 }
 
 // dW[64 x N] += P^T . G     (P [M][64], G [M][N], both dense row-major)
-int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int N, DevBuf& scratch) {
+int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int N, DevBuf& scratch,
+                   DeferList* defer) {
   if (M == 0) return ATHENA_OK;
-  if (N == 64) return launch_pipe_tn_t<64>(P, G, dW, M, scratch);
-  if (N == 32) return launch_pipe_tn_t<32>(P, G, dW, M, scratch);
+  if (N == 64) return launch_pipe_tn_t<64>(P, G, dW, M, scratch, defer);
+  if (N == 32) return launch_pipe_tn_t<32>(P, G, dW, M, scratch, defer);
   ATH_REQUIRE(false, ATHENA_ERR_ARG, "pipe_tn: unsupported N=%d", N);
 }
 
