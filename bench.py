@@ -355,14 +355,16 @@ def main():
     # ---- per-kernel durations (same steps, events after every launch) -------------
     roof = None
     kernels = {}
+    # (every rank takes the same steps -- each one contains the gradient all-reduce -- and
+    # rank 0 reports its own per-kernel times)
+    prof_steps = max(3, min(args.steps, 10))
+    ab.check(L.athena_cuda_synchronize())
+    ab.check(L.athena_cuda_profile_begin())
+    for _ in range(prof_steps):
+        dev_step()
+    ntags = C.c_int32()
+    ab.check(L.athena_cuda_profile_end(C.byref(ntags)))
     if rank == 0:
-        prof_steps = max(3, min(args.steps, 10))
-        ab.check(L.athena_cuda_synchronize())
-        ab.check(L.athena_cuda_profile_begin())
-        for _ in range(prof_steps):
-            dev_step()
-        ntags = C.c_int32()
-        ab.check(L.athena_cuda_profile_end(C.byref(ntags)))
         name = C.create_string_buffer(96)
         cnt = C.c_int64(); tms = C.c_float()
         for i in range(ntags.value):
