@@ -546,7 +546,13 @@ struct Tn2Cfg {
   static constexpr int XFORM_THREADS = 256;
   static constexpr int PRODUCER_WARP = 8;
   static constexpr int MMA_WARP = 9;
-  static constexpr int THREADS = 10 * 32;
+  static constexpr int ACC_WARP0 = 10;                       // warps 10..13: warp % 4 = TMEM lane quarter
+  static constexpr int THREADS = 14 * 32;
+  // The tensor core adds into its fp32 accumulator with truncation, so a chain of m
+  // accumulating MMAs carries a bias of ~m * 2^-24.  The accumulator is therefore drained
+  // into registers (IEEE round-to-nearest adds) every FLUSH stages: two TMEM accumulators
+  // alternate, the MMAs of group g+1 overlap the drain of group g.
+  static constexpr int FLUSH = 2;
   static constexpr int P_RAW = RS * K * 4;                   // 16 KB
   static constexpr int G_RAW = RS * N * 4;
   static constexpr int STAGE_BYTES = P_RAW + G_RAW;
@@ -557,7 +563,7 @@ struct Tn2Cfg {
   static constexpr int OFF_RING = 2 * OPS_BYTES;
   static constexpr int OFF_BAR = OFF_RING + NS * STAGE_BYTES;
   static constexpr int SMEM = 1024 + OFF_BAR + 256;
-  static constexpr int TMEM_COLS = (N <= 32 ? 32 : 64);
+  static constexpr int TMEM_COLS = (N <= 32 ? 64 : 128);     // two accumulators of N columns
 };
 
 template <int N>
@@ -574,7 +580,9 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
   uint64_t* empty = bars + Cfg::NS;
   uint64_t* ops_ready = bars + 2 * Cfg::NS;  // [2]
   uint64_t* ops_free = ops_ready + 2;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ops_free + 2);
+  uint64_t* acc_full = ops_free + 2;         // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == Cfg::MMA_WARP) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -586,6 +594,8 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
     for (int ob = 0; ob < 2; ++ob) {
       mbar_init(&ops_ready[ob], Cfg::XFORM_THREADS);
       mbar_init(&ops_free[ob], 1);
+      mbar_init(&acc_full[ob], 1);
+      mbar_init(&acc_empty[ob], 128);
     }
     mbar_fence_init();
   }
@@ -617,21 +627,54 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
       constexpr uint32_t IDESC = make_idesc(128, N, true, true);
       for (int j = 0; j < my_tiles; ++j) {
         const int ob = j & 1;
+        const int g = j / Cfg::FLUSH, first = j - g * Cfg::FLUSH, ab = g & 1;
         const uint32_t a1 = smem_u32(smem + ob * Cfg::OPS_BYTES);
         const uint32_t b_hi = a1 + Cfg::A1_BYTES, b_lo = b_hi + Cfg::A2_HALF;
+        const uint32_t tacc = tmem + ab * N;
         mbar_wait(&ops_ready[ob], (j >> 1) & 1);
+        if (first == 0) mbar_wait(&acc_empty[ab], ((g >> 1) & 1) ^ 1u);  // drained by the acc warps
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < Cfg::RS / 8; ++ks) {
           const uint64_t da = make_desc_mn32(a1 + ks * 1024, Cfg::BLK, 512);
           const uint64_t dbh = make_desc_mn32(b_hi + ks * 1024, Cfg::BLK, 512);
           const uint64_t dbl = make_desc_mn32(b_lo + ks * 1024, Cfg::BLK, 512);
-          umma_tf32(tmem, da, dbh, IDESC, (j | ks) ? 1u : 0u);
-          umma_tf32(tmem, da, dbl, IDESC, 1u);
+          umma_tf32(tacc, da, dbh, IDESC, (first | ks) ? 1u : 0u);
+          umma_tf32(tacc, da, dbl, IDESC, 1u);
         }
         umma_commit(&ops_free[ob]);
+        if (first == Cfg::FLUSH - 1 || j == my_tiles - 1) umma_commit(&acc_full[ab]);
       }
     }
+  } else if (warp >= Cfg::ACC_WARP0) {
+    // accumulate warps: drain the TMEM accumulator of every finished group into registers.
+    // TMEM lanes 0..63 hold hi(P)^T.G, lanes 64..127 lo(P)^T.G; each half becomes its own
+    // [K x N] partial (2 per CTA), written straight from registers at the end; the fold over
+    // partials happens in the reduce / finalize kernel, in partial-index order.
+    const int q = warp & 3;
+    float acc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[i] = 0.f;
+    const int ngroups = (my_tiles + Cfg::FLUSH - 1) / Cfg::FLUSH;
+    for (int g = 0; g < ngroups; ++g) {
+      const int ab = g & 1;
+      mbar_wait(&acc_full[ab], (g >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cg = 0; cg < N / 32; ++cg) {
+        float v[32];
+        tmem_ld32(tmem + ab * N + (static_cast<uint32_t>(q * 32) << 16) + cg * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[cg * 32 + i] += v[i];
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[ab]);
+    }
+    const int feat = (q & 1) * 32 + lane;
+    float* dst = part + (static_cast<size_t>(blockIdx.x) * 2 + (q >> 1)) * K * N + feat * N;
+#pragma unroll
+    for (int i = 0; i < N; i += 4)
+      *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
   } else {
     // transform warps: raw row-major tiles -> hi/lo, MN-major 32B-base swizzle
     // (two operand buffers: the stores of tile j+1 overlap the MMAs of tile j)
@@ -683,31 +726,6 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
       }
       fence_async_smem();
       mbar_arrive(&ops_ready[ob]);
-    }
-    // the last commit covers every MMA (in-order completion)
-    if (my_tiles > 0) mbar_wait(&ops_free[(my_tiles - 1) & 1], ((my_tiles - 1) >> 1) & 1);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  // final epilogue: TMEM lanes 0..63 hold hi(P)^T.G, lanes 64..127 lo(P)^T.G.  Each half is
-  // written as its own [K x N] partial (2 per CTA) straight from registers; the fold over
-  // partials happens in the reduce / finalize kernel, in partial-index order.
-  if (warp < 4) {
-    const int q = warp;
-    const int feat = (q & 1) * 32 + lane;
-    float* dst = part + (static_cast<size_t>(blockIdx.x) * 2 + (q >> 1)) * K * N + feat * N;
-    float v[32];
-    for (int cg = 0; cg < N / 32; ++cg) {
-      if (my_tiles > 0) {
-        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + cg * 32, v);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        *reinterpret_cast<float4*>(dst + cg * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
   }
   tc_fence_before();
