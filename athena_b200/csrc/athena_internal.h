@@ -228,6 +228,11 @@ int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const
 int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int N, DevBuf& scratch,
                    DeferList* defer = nullptr);
 
+// fused SpMM + tcgen05 transform for large graphs, feature width 128 (agg_tc.cu)
+bool agg_tc_supported(int F, int N, const void* X, const void* out);
+int launch_agg_tc_fwd(const Batch* b, const float* X, const float* W, float* P, float* out,
+                      int act);
+
 // elementwise / row-wise helpers
 int launch_act_bwd(int act, const float* Y, const float* G, float* out, int64_t M, int N);
 int launch_softmax_rows(float* Y, int64_t M, int N);

@@ -25,6 +25,7 @@ struct Layer : Object {
   float* params = nullptr;
   float* grads = nullptr;
   bool adopted = false;  // parameters live in a network's flat buffer
+  bool inference = false;  // current forward is network%predict: nothing is saved for backward
   // saved by forward for the reverse sweep
   std::vector<std::unique_ptr<DevBuf>> P, H, S, GZ, TN;  // TN: per-step dW partials (fused path)
   DevBuf Ae, out_buf, g0, g1, g2, tn_scratch, stage_x, stage_e, stage_g, stage_gin;
@@ -118,6 +119,14 @@ static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out,
       // propagate + transform + activation in one fused tcgen05 kernel
       ATH_TRY(launch_pipe_gather_fwd(b, in, L->params + L->poff[t - 1], P.as<float>(),
                                      H.as<float>(), Fi, Fo, L->act));
+      in = H.as<float>();
+      continue;
+    }
+    if (L->act != ATHENA_ACT_SOFTMAX && agg_tc_supported(Fi, Fo, in, H.as<float>())) {
+      // large graph, wide features: SpMM + tcgen05 transform in one pass; the aggregate
+      // is only written when a reverse sweep may follow
+      ATH_TRY(launch_agg_tc_fwd(b, in, L->params + L->poff[t - 1],
+                                L->inference ? nullptr : P.as<float>(), H.as<float>(), L->act));
       in = H.as<float>();
       continue;
     }
@@ -801,7 +810,15 @@ ATHENA_API int athena_cuda_network_forward(athena_handle_t net, athena_handle_t 
   const float *dx, *de, *out;
   ATH_TRY(stage_in(N->stage_x, vertex_features, b->V * first->nvf[0], mem, &dx));
   ATH_TRY(stage_in(N->stage_e, edge_features, b->E * last->nef, mem, &de));
-  ATH_TRY(net_forward_dev(N, b, dx, de, &out));
+  // network%predict runs in inference mode (athena_network_sub.f90:4226-4303): layers keep
+  // nothing for a reverse sweep
+  for (Layer* Lr : N->layers) Lr->inference = true;
+  int frc = net_forward_dev(N, b, dx, de, &out);
+  for (Layer* Lr : N->layers) {
+    Lr->inference = false;
+    Lr->fwd_batch = nullptr;  // a backward call must be preceded by a training forward
+  }
+  ATH_TRY(frc);
   if (output) {
     size_t bytes = sizeof(float) * (size_t)(last->out_rows(b) * last->out_width());
     cudaStream_t st = ctx().stream;

@@ -423,3 +423,32 @@ def test_shard_sum_equals_full_batch_gradient(cuda, oracle32):
         net.update()
     assert abs(loss_sum - loss_full) <= 1e-5 * abs(loss_full)
     assert rel_err(g_sum, g_full) <= RTOL_ACT
+
+
+@pytest.mark.parametrize("act", ["none", "relu", "tanh"])
+def test_kipf_large_graph_width_128_fused_path(cuda, oracle32, oracle64, act):
+    """One graph far larger than a 128-row tile, F = 128: the fused SpMM + tcgen05 kernel of
+    agg_tc.cu (forward, aggregate saved) followed by the generic reverse sweep; and the
+    inference path of network%predict, which does not save the aggregate."""
+    rng = np.random.default_rng(128)
+    p = synth.random_graph(3001, 5, 128, rng)            # last tile is partial (3001 % 128 = 57)
+    spec = kipf_spec([128, 128, 128], 2, act)
+    params = random_params(oracle32.num_params([spec]), rng, 0.1)
+    g_out = rng.standard_normal((p.V, 128)).astype(np.float32)
+    ob = to_oracle_batch(p)
+    r32 = oracle32.layer_fwd_bwd(spec, params, ob, g_out, want_dx=True)
+    r64 = oracle64.layer_fwd_bwd(spec, params, ob, g_out, want_dx=True)
+    L = ab.kipf_msgpass_layer_type([128, 128, 128], 2, activation=act)
+    L.set_params(params)
+    L.set_graph(p)
+    out = L.forward()
+    assert_parity(out, r32[0], r64[0], what="out")
+    L.zero_gradients()
+    dx = L.backward(g_out, want_input_grad=True)
+    assert_parity(L.get_gradients(), r32[1], r64[1], what="dW")
+    assert_parity(dx, r32[2], r64[2], what="dx")
+    net = ab.network_type()
+    net.add(ab.kipf_msgpass_layer_type([128, 128, 128], 2, activation=act))
+    net.compile(ab.sgd_optimiser_type(0.01), batch_size=1)
+    net.set_params(params)
+    assert_parity(net.predict(p), r32[0], r64[0], what="predict")
