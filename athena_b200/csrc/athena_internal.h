@@ -117,7 +117,8 @@ static inline int64_t round_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
 // graph batch (batch.cu)
 // ---------------------------------------------------------------------------
 constexpr int TILE_ROWS = 128;      // vertices per fused-kernel tile (= UMMA M)
-constexpr int TILE_ENTRIES = 3072;  // CSR entries per tile that fit the shared-memory ring
+constexpr int TILE_ENTRIES = 3072;
+constexpr int LONG_ROW = 512;       // CSR rows / CSC columns longer than this are split over a CTA  // CSR entries per tile that fit the shared-memory ring
 
 struct BucketSet {
   int min_deg = 0, max_deg = 0, D = 0;
@@ -166,6 +167,12 @@ struct Batch : Object {
   uint8_t* col8 = nullptr;   // [Z] CSR neighbour - tile first row
   uint8_t* csc8 = nullptr;   // [Z] CSC source    - tile first row
   float* rsdeg = nullptr;    // [V]
+  // rows (CSR) / columns (CSC) with more than LONG_ROW entries: aggregated by a whole CTA
+  // (row split with a fixed-order combine) instead of one lane group
+  DevBuf long_buf;           // int32: [0] #long rows, [1] #long columns, then the two lists
+  const int32_t* long_rows = nullptr;
+  const int32_t* long_cols = nullptr;
+  const int32_t* long_counts = nullptr;
   std::vector<std::unique_ptr<BucketSet>> buckets;
   BucketSet* find_buckets(int min_deg, int max_deg) const;
 };
@@ -179,9 +186,12 @@ struct DeferList;
 // out[v, 0:F] (+)= sum_{w in row v} c_w * X[col[w], 0:F]   (entries with col < 0 skipped)
 // coef == nullptr -> c_w = 1.  accumulate != 0 -> adds to the existing out.
 // tail != nullptr  -> out[v, F:F+tail_n] = tail[v, 0:tail_n]  (plain copy).
+// long_list / long_count (device; may be null): rows with more than LONG_ROW entries, which
+// are then skipped by the row-per-lane-group kernel and split over one CTA each.
 int launch_aggregate(const int32_t* row_ptr, const int32_t* col, const float* coef,
                      const float* X, int ldx, int F, float* out, int ldo, int64_t V,
-                     int accumulate, const float* tail, int tail_n);
+                     int accumulate, const float* tail, int tail_n,
+                     const int32_t* long_list = nullptr, const int32_t* long_count = nullptr);
 
 struct GroupDesc {
   // rows are visited through perm (nullptr = identity) in tiles that never

@@ -305,6 +305,13 @@ __global__ void k_tile_operands(const int4* __restrict__ tiles, const int32_t* _
     rsdeg[ti.x + r] = 1.0f / sqrtf(static_cast<float>(deg[ti.x + r]));
 }
 
+// rows of a CSR/CSC pointer array with more than `limit` entries (order irrelevant)
+__global__ void k_find_long(int V, const int32_t* __restrict__ ptr, int limit,
+                            int32_t* __restrict__ list, int32_t* __restrict__ count) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < V && ptr[v + 1] - ptr[v] > limit) list[atomicAdd(count, 1)] = v;
+}
+
 // ---- degree buckets -----------------------------------------------------------
 constexpr int BKT_THREADS = 1024;
 constexpr int BKT_MAX_D = 256;
@@ -596,6 +603,20 @@ ATHENA_API int athena_cuda_batch_create(athena_handle_t* batch, int32_t num_grap
     }
     k_csc_sort_long<<<ctx().sm_count, 1024, smem, st>>>(b->csc_ptr, b->csc_ent, b->csc_src,
                                                         long_list, status + 1);
+    ATH_LAUNCHED();
+  }
+  if (V > 0 && Z > 0) {
+    const size_t cap = (size_t)(Z / LONG_ROW + 4);
+    ATH_TRY(b->long_buf.reserve(sizeof(int32_t) * (4 + 2 * cap)));
+    int32_t* lb = b->long_buf.as<int32_t>();
+    ATH_CUDA(cudaMemsetAsync(lb, 0, sizeof(int32_t) * 4, st));
+    b->long_counts = lb;
+    b->long_rows = lb + 4;
+    b->long_cols = lb + 4 + cap;
+    k_find_long<<<(int)cdiv(V, 256), 256, 0, st>>>((int)V, b->row_ptr, LONG_ROW, lb + 4, lb);
+    ATH_LAUNCHED();
+    k_find_long<<<(int)cdiv(V, 256), 256, 0, st>>>((int)V, b->csc_ptr, LONG_ROW, lb + 4 + cap,
+                                                  lb + 1);
     ATH_LAUNCHED();
   }
   if (b->num_tiles > 0) {

@@ -132,7 +132,7 @@ static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out,
     }
     // P = D^-1/2 A D^-1/2 . in      (kipf_propagate)
     ATH_TRY(launch_aggregate(b->row_ptr, b->col, b->coef, in, Fi, Fi, P.as<float>(), Fi, V, 0,
-                             nullptr, 0));
+                             nullptr, 0, b->long_rows, b->long_counts));
     // H = act( P . W_t )            (matmul + activation%apply)
     if (L->act != ATHENA_ACT_SOFTMAX &&
         tc_rows_supported(Fi, Fo, Fi, Fo, P.as<float>(), H.as<float>())) {
@@ -172,7 +172,7 @@ static int duvenaud_forward(Layer* L, Batch* b, const float* x, const float* e,
     ATH_TRY(Zt.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fo, 1)));
     // A = [ sum_w in(:,ja(1,w)) ; sum_w E(:,ja(2,w)) ]      (duvenaud_propagate)
     ATH_TRY(launch_aggregate(b->row_ptr, b->col, nullptr, in, Fi, Fi, A.as<float>(), ld, V, 0, tail,
-                             L->nef));
+                             L->nef, b->long_rows, b->long_counts));
     // z = act( W_d(v) . A(:,v)/d(v) )                       (duvenaud_update + activation)
     GroupDesc gd;
     gd.perm = bs->perm.as<int32_t>();
@@ -294,7 +294,7 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
         ATH_TRY(launch_gemm_nt(gy, Fo, Wt, L->g1.as<float>(), Fi, V, Fi, Fo, GroupDesc{}));
       }
       ATH_TRY(launch_aggregate(b->csc_ptr, b->csc_src, nullptr, L->g1.as<float>(), Fi, Fi, dst, Fi,
-                               V, 0, nullptr, 0));
+                               V, 0, nullptr, 0, b->long_cols, b->long_counts ? b->long_counts + 1 : nullptr));
       preact = false;
     }
     g = dst;
@@ -348,10 +348,12 @@ static int duvenaud_backward(Layer* L, Batch* b, const float* gout, float* gin) 
       // d in(:,u) += dA(1:F,v) over the CSC
       if (t > 1)
         ATH_TRY(launch_aggregate(b->csc_ptr, b->csc_src, nullptr, L->g1.as<float>(), ld, Fi,
-                                 L->GZ[t - 2]->as<float>(), Fi, V, 1, nullptr, 0));
+                                 L->GZ[t - 2]->as<float>(), Fi, V, 1, nullptr, 0, b->long_cols,
+                                 b->long_counts ? b->long_counts + 1 : nullptr));
       else
         ATH_TRY(launch_aggregate(b->csc_ptr, b->csc_src, nullptr, L->g1.as<float>(), ld, Fi, gin,
-                                 Fi, V, 0, nullptr, 0));
+                                 Fi, V, 0, nullptr, 0, b->long_cols,
+                                 b->long_counts ? b->long_counts + 1 : nullptr));
     }
   }
   return ATHENA_OK;
