@@ -7,6 +7,7 @@
 // (oracle/athena_oracle.c): counting uses integer atomics (order-independent
 // totals); the CSC fill claims slots in arbitrary order and every column is
 // then sorted by CSR entry index, which yields the unique stable order.
+#include <algorithm>
 #include <climits>
 
 #include "athena_internal.h"
@@ -605,7 +606,10 @@ ATHENA_API int athena_cuda_batch_create(athena_handle_t* batch, int32_t num_grap
                                                         long_list, status + 1);
     ATH_LAUNCHED();
   }
-  if (V > 0 && Z > 0) {
+  // a row / column can only be long if its graph has that many entries (host-known bound)
+  int32_t max_graph_entries = 0;
+  for (int s = 0; s < B; ++s) max_graph_entries = std::max(max_graph_entries, num_entries[s]);
+  if (V > 0 && Z > 0 && max_graph_entries > LONG_ROW) {
     const size_t cap = (size_t)(Z / LONG_ROW + 4);
     ATH_TRY(b->long_buf.reserve(sizeof(int32_t) * (4 + 2 * cap)));
     int32_t* lb = b->long_buf.as<int32_t>();

@@ -260,13 +260,17 @@ k_gemm_tn_partial(const float* __restrict__ A, int lda, const float* __restrict_
   }
 }
 
-// dW[g][e] += sum over the chunks of group g (ascending) of part[chunk][e]
-__global__ void k_gemm_tn_reduce(const float* __restrict__ part, float* __restrict__ dW,
-                                 long long M, int KN, const int32_t* __restrict__ ptr, int D,
-                                 long long wstride) {
-  int g = blockIdx.y;
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= KN) return;
+// dW[g][e] += sum over the chunks of group g of part[chunk][e].  32 elements x 8 lanes per
+// block: lane l adds chunks c0+l, c0+l+8, ... into four running sums (fixed pattern, four
+// loads in flight), the eight lane totals are then added in lane order -- deterministic.
+constexpr int TNR_ELEMS = 32, TNR_LANES = 8;
+__global__ void __launch_bounds__(TNR_ELEMS * TNR_LANES)
+k_gemm_tn_reduce(const float* __restrict__ part, float* __restrict__ dW, long long M, int KN,
+                 const int32_t* __restrict__ ptr, int D, long long wstride) {
+  __shared__ float red[TNR_LANES][TNR_ELEMS];
+  const int g = blockIdx.y;
+  const int el = threadIdx.x % TNR_ELEMS, l = threadIdx.x / TNR_ELEMS;
+  const int e = blockIdx.x * TNR_ELEMS + el;
   int c0 = 0, c1 = 0;
   if (ptr == nullptr) {
     c1 = (int)((M + TN_CHUNK - 1) / TN_CHUNK);
@@ -277,9 +281,29 @@ __global__ void k_gemm_tn_reduce(const float* __restrict__ part, float* __restri
       c1 += nt;
     }
   }
-  float s = 0.f;
-  for (int c = c0; c < c1; ++c) s += part[(size_t)c * KN + e];
-  if (c1 > c0) dW[(size_t)g * wstride + e] += s;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (e < KN) {
+    const float* src = part + e;
+    int c = c0 + l;
+    for (; c + 3 * TNR_LANES < c1; c += 4 * TNR_LANES) {
+      const float v0 = src[(size_t)c * KN], v1 = src[(size_t)(c + TNR_LANES) * KN];
+      const float v2 = src[(size_t)(c + 2 * TNR_LANES) * KN];
+      const float v3 = src[(size_t)(c + 3 * TNR_LANES) * KN];
+      acc[0] += v0;
+      acc[1] += v1;
+      acc[2] += v2;
+      acc[3] += v3;
+    }
+    for (int k = 0; c < c1; c += TNR_LANES, ++k) acc[k] += src[(size_t)c * KN];
+  }
+  red[l][el] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (l == 0 && e < KN && c1 > c0) {
+    float s = red[0][el];
+#pragma unroll
+    for (int k = 1; k < TNR_LANES; ++k) s += red[k][el];
+    dW[(size_t)g * wstride + e] += s;
+  }
 }
 
 int launch_gemm_tn(const float* A, int lda, const float* G, int ldg, float* dW, int64_t M, int N,
@@ -293,8 +317,8 @@ int launch_gemm_tn(const float* A, int lda, const float* G, int ldg, float* dW, 
   k_gemm_tn_partial<<<grid, 256, 0, st>>>(A, lda, G, ldg, scratch.as<float>(), M, N, K, gd.perm,
                                           gd.ptr, D, gd.scale_by_group);
   ATH_LAUNCHED_T("gemm_tn_partial");
-  dim3 rgrid((unsigned)cdiv((int64_t)K * N, 256), (unsigned)D);
-  k_gemm_tn_reduce<<<rgrid, 256, 0, st>>>(scratch.as<float>(), dW, M, K * N, gd.ptr, D,
+  dim3 rgrid((unsigned)cdiv((int64_t)K * N, TNR_ELEMS), (unsigned)D);
+  k_gemm_tn_reduce<<<rgrid, TNR_ELEMS * TNR_LANES, 0, st>>>(scratch.as<float>(), dW, M, K * N, gd.ptr, D,
                                           gd.wstride);
   ATH_LAUNCHED_T("gemm_tn_reduce");
   return ATHENA_OK;
