@@ -20,6 +20,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 ACT = {"none": 0, "linear": 1, "relu": 2, "leaky_relu": 3, "sigmoid": 4, "tanh": 5, "softmax": 6}
 OPT_SGD, OPT_ADAM = 0, 1
 COMM_ID_BYTES = 128
+P2P_HANDLE_BYTES = 128
 
 BATCH_FIELDS = {"row_ptr": 0, "col": 1, "eid": 2, "deg": 3, "vgraph": 4, "csc_ptr": 5,
                 "csc_src": 6, "csc_ent": 7, "bucket": 8, "perm": 9, "bucket_ptr": 10, "coef": 11}
@@ -113,6 +114,8 @@ def lib() -> C.CDLL:
         "athena_cuda_network_last_loss": [H, PF],
         "athena_cuda_comm_unique_id": [P],
         "athena_cuda_comm_init": [I32, I32, P],
+        "athena_cuda_comm_p2p_export": [P],
+        "athena_cuda_comm_p2p_import": [I32, I32, P],
         "athena_cuda_comm_destroy": [],
         "athena_cuda_comm_info": [PI32, PI32],
         "athena_cuda_shard_graphs": [I32, P, I32, P],

@@ -287,11 +287,30 @@ struct DeferList {
   std::vector<DeferJob> jobs;
 };
 bool finalize_can_step(const OptimState& st);
+// xout != nullptr: the finished local gradients (and the loss slot, index n) are also
+// written to xout[0..n] -- the staging buffer of the peer-memory exchange.
 int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts, float* loss_acc,
-                    float* params, float* grads, int64_t n, OptimState* st);
+                    float* params, float* grads, int64_t n, OptimState* st,
+                    float* xout = nullptr);
 
-// comm (comm.cc)
+// comm (comm.cu)
 int comm_allreduce_sum(float* buf, int64_t n);  // no-op when no communicator
 int comm_world_size();
+
+// Peer-memory gradient exchange (comm.cu): every rank exposes a two-slot staging buffer and a
+// flag array through CUDA IPC; k_p2p_sum_step (misc.cu) signals, waits and sums over NVLink.
+constexpr int P2P_MAX_WORLD = 8;
+struct P2PState {
+  bool ready = false;
+  int world = 1, rank = 0;
+  size_t cap = 0;                      // floats per slot
+  uint32_t epoch = 0;                  // exchanges done so far
+  float* xbuf[P2P_MAX_WORLD] = {};     // [2][cap] staging buffer of every rank (own = local)
+  uint32_t* flags[P2P_MAX_WORLD] = {}; // [2][P2P_MAX_WORLD] arrival flags of every rank
+};
+P2PState& p2p();
+// sums the staged gradients of all ranks in rank order (bitwise identical everywhere) into
+// `grads` [0, n] -- or, with st != nullptr, applies the optimiser step and zeroes them
+int launch_p2p_sum_step(float* params, float* grads, int64_t n, OptimState* st);
 
 }  // namespace athena

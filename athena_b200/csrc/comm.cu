@@ -67,7 +67,15 @@ static int nccl_load() {
     }                                                                                    \
   } while (0)
 
-int comm_world_size() { return g_nccl.comm ? g_nccl.world : 1; }
+int comm_world_size() { return (g_nccl.comm || p2p().ready) ? g_nccl.world : 1; }
+
+P2PState& p2p() {
+  static P2PState s;
+  return s;
+}
+static void* g_p2p_local_x = nullptr;
+static void* g_p2p_local_f = nullptr;
+constexpr size_t P2P_CAP_FLOATS = size_t(1) << 20;  // 4 MB per slot: any msgpass network here
 
 int comm_allreduce_sum(float* buf, int64_t n) {
   if (!g_nccl.comm || g_nccl.world == 1 || n == 0) return ATHENA_OK;
@@ -108,7 +116,71 @@ ATHENA_API int athena_cuda_comm_init(int32_t world_size, int32_t rank,
   return ATHENA_OK;
 }
 
+// ---- peer-memory exchange: CUDA IPC set-up ------------------------------------------
+// handle = { cudaIpcMemHandle_t of the staging buffer, cudaIpcMemHandle_t of the flags }
+ATHENA_API int athena_cuda_comm_p2p_export(char handle[ATHENA_P2P_HANDLE_BYTES]) {
+  ATH_REQUIRE(handle, ATHENA_ERR_ARG, "comm_p2p_export: null");
+  ATH_TRY(ensure_init());
+  static_assert(2 * sizeof(cudaIpcMemHandle_t) == ATHENA_P2P_HANDLE_BYTES, "handle size");
+  if (!g_p2p_local_x) {
+    // plain cudaMalloc (not the pool): IPC handles cover whole allocations
+    ATH_CUDA(cudaMalloc(&g_p2p_local_x, 2 * P2P_CAP_FLOATS * sizeof(float)));
+    ATH_CUDA(cudaMalloc(&g_p2p_local_f, 2 * P2P_MAX_WORLD * sizeof(uint32_t)));
+    ATH_CUDA(cudaMemset(g_p2p_local_x, 0, 2 * P2P_CAP_FLOATS * sizeof(float)));
+    ATH_CUDA(cudaMemset(g_p2p_local_f, 0, 2 * P2P_MAX_WORLD * sizeof(uint32_t)));
+  }
+  cudaIpcMemHandle_t hx, hf;
+  ATH_CUDA(cudaIpcGetMemHandle(&hx, g_p2p_local_x));
+  ATH_CUDA(cudaIpcGetMemHandle(&hf, g_p2p_local_f));
+  memcpy(handle, &hx, sizeof(hx));
+  memcpy(handle + sizeof(hx), &hf, sizeof(hf));
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_comm_p2p_import(int32_t world_size, int32_t rank, const char* handles) {
+  ATH_REQUIRE(handles && world_size >= 2 && world_size <= P2P_MAX_WORLD && rank >= 0 &&
+                  rank < world_size,
+              ATHENA_ERR_ARG, "comm_p2p_import: bad argument (world %d, rank %d, max world %d)",
+              world_size, rank, P2P_MAX_WORLD);
+  ATH_REQUIRE(g_p2p_local_x, ATHENA_ERR_STATE, "comm_p2p_import: call comm_p2p_export first");
+  P2PState& P = p2p();
+  ATH_REQUIRE(!P.ready, ATHENA_ERR_STATE, "comm_p2p_import: already initialised");
+  for (int r = 0; r < world_size; ++r) {
+    if (r == rank) {
+      P.xbuf[r] = static_cast<float*>(g_p2p_local_x);
+      P.flags[r] = static_cast<uint32_t*>(g_p2p_local_f);
+      continue;
+    }
+    cudaIpcMemHandle_t hx, hf;
+    memcpy(&hx, handles + (size_t)r * ATHENA_P2P_HANDLE_BYTES, sizeof(hx));
+    memcpy(&hf, handles + (size_t)r * ATHENA_P2P_HANDLE_BYTES + sizeof(hx), sizeof(hf));
+    void *px = nullptr, *pf = nullptr;
+    ATH_CUDA(cudaIpcOpenMemHandle(&px, hx, cudaIpcMemLazyEnablePeerAccess));
+    ATH_CUDA(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+    P.xbuf[r] = static_cast<float*>(px);
+    P.flags[r] = static_cast<uint32_t*>(pf);
+  }
+  P.world = world_size;
+  P.rank = rank;
+  P.cap = P2P_CAP_FLOATS;
+  P.epoch = 0;
+  g_nccl.world = world_size;
+  g_nccl.rank = rank;
+  P.ready = true;
+  return ATHENA_OK;
+}
+
 ATHENA_API int athena_cuda_comm_destroy(void) {
+  P2PState& P = p2p();
+  if (P.ready) {
+    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    for (int r = 0; r < P.world; ++r) {
+      if (r == P.rank) continue;
+      cudaIpcCloseMemHandle(P.xbuf[r]);
+      cudaIpcCloseMemHandle(P.flags[r]);
+    }
+    P = P2PState{};
+  }
   if (g_nccl.comm) {
     if (ctx().ready) cudaStreamSynchronize(ctx().stream);
     g_nccl.CommDestroy(g_nccl.comm);

@@ -481,14 +481,26 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
     g_preact = folded;
     g = gi;
   }
-  if (!defer.jobs.empty() || fo.fused) {
+  // gradient exchange over peer memory when it is set up (comm_p2p_*), else NCCL
+  P2PState& P = p2p();
+  const bool use_p2p = P.ready && P.world > 1 && (size_t)(N->n + 1) <= P.cap;
+  float* xout = use_p2p ? P.xbuf[P.rank] + (size_t)((P.epoch + 1) & 1u) * P.cap : nullptr;
+  if (!defer.jobs.empty() || fo.fused || use_p2p) {
     const bool fuse_step = step_too && finalize_can_step(N->opt);
     ATH_TRY(launch_finalize(defer, fo.fused ? fo.loss_part : nullptr, fo.num_parts, gflat + N->n,
                             N->flat_params.as<float>(), gflat, N->n,
-                            fuse_step ? &N->opt : nullptr));
+                            fuse_step ? &N->opt : nullptr, xout));
     if (stepped) *stepped = fuse_step;
   }
-  ATH_TRY(comm_allreduce_sum(gflat, N->n + 1));
+  if (use_p2p) {
+    // signal + wait + sum over NVLink + (when no clipping intervenes) the step, in one kernel
+    const bool p2p_step = step_too && !N->opt.d.clip_min_max && !N->opt.d.clip_norm_on;
+    ATH_TRY(launch_p2p_sum_step(N->flat_params.as<float>(), gflat, N->n,
+                                p2p_step ? &N->opt : nullptr));
+    if (stepped) *stepped = p2p_step;
+  } else {
+    ATH_TRY(comm_allreduce_sum(gflat, N->n + 1));
+  }
   if (loss) {
     ATH_CUDA(cudaMemcpyAsync(N->pinned_loss, gflat + N->n, sizeof(float), cudaMemcpyDeviceToHost,
                              st));

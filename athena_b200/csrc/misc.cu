@@ -253,6 +253,7 @@ struct FinArgs {
   int loss_nparts;
   float* loss_acc;
   int do_step;
+  float* xout;  // optional copy of the finished gradients + loss slot (peer-memory exchange)
 };
 
 __global__ void __launch_bounds__(FIN_THREADS)
@@ -297,14 +298,76 @@ k_finalize(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
       g[i] = 0.f;
     } else {
       g[i] = gr;
+      if (f.xout) f.xout[i] = gr;
     }
   }
-  if (blockIdx.x == 0 && f.loss_part != nullptr) {
+  if (blockIdx.x == 0 && (f.loss_part != nullptr || f.xout != nullptr)) {
     __syncthreads();
     float local = 0.f;
-    for (int k = threadIdx.x; k < f.loss_nparts; k += FIN_THREADS) local += f.loss_part[k];
+    if (f.loss_part != nullptr)
+      for (int k = threadIdx.x; k < f.loss_nparts; k += FIN_THREADS) local += f.loss_part[k];
     float s = block_sum(local);
-    if (threadIdx.x == 0) f.loss_acc[0] += 0.5f * s;
+    if (threadIdx.x == 0) {
+      const float loss = f.loss_acc[0] + 0.5f * s;
+      f.loss_acc[0] = loss;
+      if (f.xout) f.xout[n] = loss;
+    }
+  }
+}
+
+// ---- peer-memory gradient exchange fused with the step -----------------------------
+// Every rank staged its local gradient vector (+ loss slot) in its own exchange buffer
+// (k_finalize).  This kernel (1) tells every peer "my slot is complete" with a system-scope
+// flag store over NVLink, (2) waits until all peers have said the same, (3) reads the
+// world_size staged vectors straight from peer memory, adds them in rank order -- every
+// rank forms bitwise the same sum -- and (4) applies the optimiser step (or leaves the sums
+// in the gradient buffer).  The all-reduce never exists as a separate pass: the few tens of
+// kB cross NVLink as plain loads issued by the threads that consume them.
+struct P2PArgs {
+  const float* x[P2P_MAX_WORLD];
+  uint32_t* flags[P2P_MAX_WORLD];
+  int world, rank;
+  uint32_t epoch;
+  int slot;
+  int do_step;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_p2p_sum_step(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
+               float* __restrict__ s2, long long n, P2PArgs x, StepArgs a) {
+  if (threadIdx.x < x.world) {
+    const int r = threadIdx.x;
+    if (blockIdx.x == 0) {
+      __threadfence_system();  // the staged vector (written by the previous kernel) first
+      st_release_sys(x.flags[r] + x.slot * P2P_MAX_WORLD + x.rank, x.epoch);
+    }
+    const uint32_t* mine = x.flags[x.rank] + x.slot * P2P_MAX_WORLD + r;
+    while (ld_acquire_sys(mine) != x.epoch) __nanosleep(64);
+  }
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  float sum = 0.f;
+  for (int r = 0; r < x.world; ++r) sum += ld_relaxed_sys(x.x[r] + i);
+  if (i == n || !x.do_step) {
+    g[i] = sum;  // index n: the global batch loss
+  } else {
+    step_one(p, s1, s2, i, sum, a);
+    g[i] = 0.f;
   }
 }
 
@@ -369,8 +432,32 @@ bool finalize_can_step(const OptimState& st) {
 // buffer; with `st` != nullptr also performs the optimiser step (caller checked
 // finalize_can_step).  More than FIN_MAX_JOBS reductions are flushed in several launches,
 // the step riding on the last one.
+int launch_p2p_sum_step(float* params, float* grads, int64_t n, OptimState* st) {
+  P2PState& P = p2p();
+  ATH_REQUIRE(P.ready && (size_t)(n + 1) <= P.cap, ATHENA_ERR_STATE,
+              "p2p exchange: not initialised or gradient vector too long");
+  StepArgs a{};
+  if (st) ATH_TRY(step_prepare(n, *st, &a));
+  P2PArgs x{};
+  P.epoch += 1;
+  x.world = P.world;
+  x.rank = P.rank;
+  x.epoch = P.epoch;
+  x.slot = (int)(P.epoch & 1u);
+  x.do_step = st ? 1 : 0;
+  for (int r = 0; r < P.world; ++r) {
+    x.x[r] = P.xbuf[r] + (size_t)x.slot * P.cap;
+    x.flags[r] = P.flags[r];
+  }
+  k_p2p_sum_step<<<(unsigned)cdiv(n + 1, RED_THREADS), RED_THREADS, 0, ctx().stream>>>(
+      params, grads, st ? st->s1.as<float>() : nullptr, st ? st->s2.as<float>() : nullptr, n, x,
+      a);
+  ATH_LAUNCHED_T(st ? "p2p_sum_step" : "p2p_sum");
+  return ATHENA_OK;
+}
+
 int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts, float* loss_acc,
-                    float* params, float* grads, int64_t n, OptimState* st) {
+                    float* params, float* grads, int64_t n, OptimState* st, float* xout) {
   if (n == 0) return ATHENA_OK;
   cudaStream_t s = ctx().stream;
   StepArgs a{};
@@ -392,6 +479,7 @@ int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts
     f.loss_nparts = loss_nparts;
     f.loss_acc = loss_acc;
     f.do_step = (last && st) ? 1 : 0;
+    f.xout = last ? xout : nullptr;
     k_finalize<<<(unsigned)cdiv(n, FIN_ELEMS), FIN_THREADS, 0, s>>>(
         params, grads, st ? st->s1.as<float>() : nullptr, st ? st->s2.as<float>() : nullptr, n, f,
         a);

@@ -293,6 +293,36 @@ def main():
             idbuf = [raw.raw]
         dist.broadcast_object_list(idbuf, src=0)
         ab.check(L.athena_cuda_comm_init(world, rank, C.create_string_buffer(idbuf[0], 128)))
+        use_p2p = os.environ.get("ATHENA_BENCH_NO_P2P", "0") == "0" and world <= 8
+        if use_p2p:
+            # peer-memory gradient exchange fused with the step.  Every rank must agree: if the
+            # IPC set-up fails anywhere, all ranks fall back to the NCCL all-reduce.
+            ok = 1
+            try:
+                mine = C.create_string_buffer(ab._lib.P2P_HANDLE_BYTES)
+                ab.check(L.athena_cuda_comm_p2p_export(mine))
+                allh = [None] * world
+                dist.all_gather_object(allh, mine.raw)
+                ab.check(L.athena_cuda_comm_p2p_import(world, rank,
+                                                       C.create_string_buffer(b"".join(allh))))
+            except Exception as exc:  # noqa: BLE001
+                print(f"[rank {rank}] peer-memory exchange unavailable: {exc}", file=sys.stderr)
+                ok = 0
+            flag = torch.tensor([ok], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                use_p2p = False
+                ab.check(L.athena_cuda_comm_destroy())
+                idbuf = [None]
+                if rank == 0:
+                    raw = C.create_string_buffer(ab._lib.COMM_ID_BYTES)
+                    ab.check(L.athena_cuda_comm_unique_id(raw))
+                    idbuf = [raw.raw]
+                dist.broadcast_object_list(idbuf, src=0)
+                ab.check(L.athena_cuda_comm_init(world, rank, C.create_string_buffer(idbuf[0], 128)))
+        exchange = "peer-memory sum fused with the step, NVLink" if use_p2p else "NCCL all-reduce"
+    else:
+        exchange = "none"
 
     def barrier():
         ab.check(L.athena_cuda_synchronize())
@@ -469,8 +499,9 @@ def main():
                                    f"{GRAPHS} graphs x {NV} vertices per GPU, 12 neighbours + "
                                    "self loop, F=64, MSE, SGD; fwd+bwd+allreduce+step",
                        "graphs_per_gpu": B, "vertices_per_gpu": V, "entries_per_gpu": Z,
-                       "parallelism": f"dp{world} (graph-sharded, NCCL all-reduce of "
-                                      f"{net.num_params + 1} floats)",
+                       "parallelism": f"dp{world} (graph-sharded; gradient exchange of "
+                                      f"{net.num_params + 1} floats: " +
+                                      exchange + ")",
                        "l2": "working set ~1 GB per step > 126 MB L2 (no flush needed)"},
             "e2e": e2e, "gpu_launches": launches, "launches_per_step": launches / args.steps,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,

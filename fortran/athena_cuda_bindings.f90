@@ -74,6 +74,7 @@ module athena__cuda_bindings
   public :: athena_cuda_network_last_loss
   public :: athena_cuda_comm_unique_id, athena_cuda_comm_init, athena_cuda_comm_destroy
   public :: athena_cuda_comm_info, athena_cuda_shard_graphs
+  public :: athena_cuda_comm_p2p_export, athena_cuda_comm_p2p_import
   public :: athena_cuda_check
 
   interface
@@ -344,6 +345,19 @@ module athena__cuda_bindings
           bind(C, name="athena_cuda_comm_info") result(rc)
        import :: c_int, c_int32_t
        integer(c_int32_t), intent(out) :: world_size, rank
+       integer(c_int) :: rc
+     end function
+     function athena_cuda_comm_p2p_export(handle) &
+          bind(C, name="athena_cuda_comm_p2p_export") result(rc)
+       import :: c_int, c_char
+       character(kind=c_char), intent(out) :: handle(128)
+       integer(c_int) :: rc
+     end function
+     function athena_cuda_comm_p2p_import(world_size, rank, handles) &
+          bind(C, name="athena_cuda_comm_p2p_import") result(rc)
+       import :: c_int, c_int32_t, c_char
+       integer(c_int32_t), value :: world_size, rank
+       character(kind=c_char), intent(in) :: handles(*)   ! world_size x 128 bytes, rank order
        integer(c_int) :: rc
      end function
      function athena_cuda_shard_graphs(num_graphs, entries_per_graph, world_size, first_graph) &

@@ -314,6 +314,18 @@ int athena_cuda_comm_init(int32_t world_size, int32_t rank, const char id[ATHENA
 int athena_cuda_comm_destroy(void);
 int athena_cuda_comm_info(int32_t* world_size, int32_t* rank);
 
+/*
+ * Optional peer-memory gradient exchange (one box, NVLink / NVSwitch): instead of a separate
+ * NCCL all-reduce, every rank exposes a staging buffer through CUDA IPC and ONE kernel on each
+ * rank signals, waits, reads the peers' staged gradients over NVLink, adds them in rank
+ * order and applies the optimiser step.  Every rank calls _export, the 128-byte handles are
+ * all-gathered by any host channel, every rank calls _import with the world_size handles in
+ * rank order.  Falls back to NCCL when not set up (or for gradient vectors > 1 Mi floats).
+ */
+#define ATHENA_P2P_HANDLE_BYTES 128
+int athena_cuda_comm_p2p_export(char handle[ATHENA_P2P_HANDLE_BYTES]);
+int athena_cuda_comm_p2p_import(int32_t world_size, int32_t rank, const char* handles);
+
 /* Host-side helper: contiguous partition of B graphs over world_size ranks,
  * balanced by CSR entries.  first_graph has world_size+1 entries. Pure host code. */
 int athena_cuda_shard_graphs(int32_t num_graphs, const int64_t* entries_per_graph,
