@@ -167,6 +167,7 @@ struct Batch : Object {
   uint8_t* col8 = nullptr;   // [Z] CSR neighbour - tile first row
   uint8_t* csc8 = nullptr;   // [Z] CSC source    - tile first row
   float* rsdeg = nullptr;    // [V]
+  int32_t* vcount = nullptr; // [V] number of vertices of the vertex's graph (MSE cell size)
   // rows (CSR) / columns (CSC) with more than LONG_ROW entries: aggregated by a whole CTA
   // (row split with a fixed-order combine) instead of one lane group
   DevBuf long_buf;           // int32: [0] #long rows, [1] #long columns, then the two lists

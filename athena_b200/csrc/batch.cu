@@ -296,14 +296,18 @@ k_csc_sort_long(const int32_t* __restrict__ csc_ptr, int32_t* __restrict__ csc_e
 __global__ void k_tile_operands(const int4* __restrict__ tiles, const int32_t* __restrict__ col,
                                 const int32_t* __restrict__ csc_src,
                                 const int32_t* __restrict__ deg, uint8_t* __restrict__ col8,
-                                uint8_t* __restrict__ csc8, float* __restrict__ rsdeg) {
+                                uint8_t* __restrict__ csc8, float* __restrict__ rsdeg,
+                                const int32_t* __restrict__ vgraph,
+                                const int32_t* __restrict__ nv, int32_t* __restrict__ vcount) {
   const int4 ti = tiles[blockIdx.x];
   for (int e = threadIdx.x; e < ti.w; e += blockDim.x) {
     col8[ti.z + e] = static_cast<uint8_t>(col[ti.z + e] - ti.x);
     csc8[ti.z + e] = static_cast<uint8_t>(csc_src[ti.z + e] - ti.x);
   }
-  for (int r = threadIdx.x; r < ti.y; r += blockDim.x)
+  for (int r = threadIdx.x; r < ti.y; r += blockDim.x) {
     rsdeg[ti.x + r] = 1.0f / sqrtf(static_cast<float>(deg[ti.x + r]));
+    vcount[ti.x + r] = nv[vgraph[ti.x + r]];
+  }
 }
 
 // rows of a CSR/CSC pointer array with more than `limit` entries (order irrelevant)
@@ -625,12 +629,15 @@ ATHENA_API int athena_cuda_batch_create(athena_handle_t* batch, int32_t num_grap
   }
   if (b->num_tiles > 0) {
     const size_t z16 = (size_t)round_up(Z + 32, 16);
-    ATH_TRY(b->tile_ops.reserve(2 * z16 + sizeof(float) * (size_t)round_up(V + 8, 4)));
+    const size_t v4 = (size_t)round_up(V + 8, 4);
+    ATH_TRY(b->tile_ops.reserve(2 * z16 + 2 * sizeof(float) * v4));
     b->col8 = b->tile_ops.as<uint8_t>();
     b->csc8 = b->col8 + z16;
     b->rsdeg = reinterpret_cast<float*>(b->csc8 + z16);
+    b->vcount = reinterpret_cast<int32_t*>(b->rsdeg + v4);
     k_tile_operands<<<b->num_tiles, 256, 0, st>>>(b->tiles.as<int4>(), b->col, b->csc_src, b->deg,
-                                                 b->col8, b->csc8, b->rsdeg);
+                                                 b->col8, b->csc8, b->rsdeg, b->vgraph, b->nv,
+                                                 b->vcount);
     ATH_LAUNCHED();
   }
   Batch* raw = b.release();

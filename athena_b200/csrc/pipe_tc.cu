@@ -95,14 +95,25 @@ struct GatherArgs {
                            // EPI_MSE: [V][N] target
   int act;
   // EPI_MSE (mse_loss_type%compute for graph outputs, athena_loss.f90:416-427)
-  const int32_t* vgraph;  // [V] graph of a vertex
-  const int32_t* nv;      // [B] vertices per graph
+  const int32_t* vcount;  // [V] vertices of the vertex's graph (Batch::vcount)
   float* loss_part;       // [gridDim.x] sum over this CTA's rows of (p-e)^2 / (N * nv_s)
+  int dbg;                // ATHENA_DEBUG_PIPE bitmask (experiments only): 1 no P store,
+                          // 2 no output store, 4 no gather loop
+  long long* trace;       // ATHENA_DEBUG_TRACE: [role 0..3][tile][8] clock64 stamps of CTA 0
 };
 
-template <int F, int N>
+constexpr int TRACE_TILES = 32;
+#define TRACE(role, slot)                                                                \
+  do {                                                                                   \
+    if (a.trace != nullptr && blockIdx.x == 0 && j < TRACE_TILES)                        \
+      a.trace[((role) * TRACE_TILES + j) * 8 + (slot)] = clock64();                      \
+  } while (0)
+
+template <int F, int N, bool HAS_AUX>
 struct GatherCfg {
-  static constexpr int NS = 2;                                   // ring stages
+  // ring stages: the kernels without a second epilogue operand spend the shared memory of
+  // the operand tile on a third stage (two tiles of prefetch instead of one)
+  static constexpr int NS = HAS_AUX ? 2 : 3;
   static constexpr int GATHER_THREADS = 512;                     // warps 0..15
   static constexpr int EPI_WARP0 = 16;                           // warps 16..19 (warp % 4 = lane quarter)
   static constexpr int PRODUCER_WARP = 20;
@@ -128,7 +139,7 @@ struct GatherCfg {
   static constexpr int OFF_B = 2 * A_BYTES;
   static constexpr int OFF_RING = OFF_B + B_BYTES;
   static constexpr int OFF_AUX = OFF_RING + NS * STAGE_BYTES;    // [128][N + 4] epilogue operand tile
-  static constexpr int AUX_BYTES = TILE_ROWS * (N + 4) * 4;
+  static constexpr int AUX_BYTES = HAS_AUX ? TILE_ROWS * (N + 4) * 4 : 0;
   static constexpr int OFF_BAR = OFF_AUX + AUX_BYTES;
   static constexpr int OFF_EPI = OFF_BAR + 256 + 512;            // 4 epilogue transposition patches
   static constexpr int SMEM = 1024 + OFF_EPI + 4 * (32 * 36) * 4;
@@ -163,7 +174,7 @@ __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, i
                                                float* __restrict__ out_tile,
                                                const float* aux_row /* shared memory */,
                                                float row_scale, float* patch,
-                                               uint64_t* acc_empty) {
+                                               uint64_t* acc_empty, bool no_store = false) {
   float lsum = 0.f;
   float* srow = patch + lane * EPI_PITCH;
 #pragma unroll
@@ -194,7 +205,7 @@ __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, i
           for (int k = 0; k < 4; ++k) {
             const float pk = act_fwd<ACT>(o[k]);
             const float d = pk - t[k];
-            lsum += d * d * row_scale;
+            if (row_scale != 0.f) lsum += d * d * row_scale;
             o[k] = act_bwd<ACT>(pk, d * row_scale);
           }
         } else if (ACT != ATHENA_ACT_NONE) {
@@ -212,7 +223,7 @@ __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, i
       const int idx = it * 32 + lane;
       const int r = idx >> 3, c = idx & 7;
       const int trow = q * 32 + r;
-      if (trow < nrows)
+      if (trow < nrows && !no_store)
         *reinterpret_cast<float4*>(out_tile + static_cast<size_t>(trow) * N + half * 32 + c * 4) =
             *reinterpret_cast<const float4*>(patch + r * EPI_PITCH + c * 4);
     }
@@ -222,8 +233,9 @@ __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, i
 }
 
 template <int F, int N, bool TRANSB, int EPI>
-__global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(GatherArgs a) {
-  using Cfg = GatherCfg<F, N>;
+__global__ void __launch_bounds__(GatherCfg<F, N, EPI != EPI_ACT>::THREADS, 1)
+k_pipe_gather(GatherArgs a) {
+  using Cfg = GatherCfg<F, N, EPI != EPI_ACT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sAhi = smem + Cfg::OFF_OPS;
@@ -238,7 +250,8 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
   uint64_t* acc_full = ops_free + 1;     // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
   uint64_t* aux_full = acc_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 1);
+  uint64_t* aux_empty = aux_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_empty + 1);
   float* loss_red = reinterpret_cast<float*>(smem + Cfg::OFF_BAR + 256);  // [128], EPI_MSE
   float* sAux = reinterpret_cast<float*>(smem + Cfg::OFF_AUX);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -255,7 +268,8 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 128);
     }
-    mbar_init(aux_full, 128);
+    mbar_init(aux_full, 32);
+    mbar_init(aux_empty, 128);
     mbar_fence_init();
   }
   // stacked weight operand [hi(W') ; lo(W')] with W' = op(W) as [N][F] K-major.  One item =
@@ -289,7 +303,9 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
       for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++j) {
         const int s = j % Cfg::NS;
         const uint32_t ph = (j / Cfg::NS) & 1;
+        TRACE(0, 0);
         mbar_wait(&empty[s], ph ^ 1u);
+        TRACE(0, 1);
         const int4 ti = __ldg(a.tiles + t);
         const int r0 = ti.x, nrows = ti.y, e0 = ti.z, nent = ti.w;
         const int ea = e0 & ~15, ebytes = (e0 + nent - ea + 15) & ~15;
@@ -311,8 +327,11 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
       int j = 0;
       for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++j) {
         const int b = j & 1;
+        TRACE(1, 0);
         mbar_wait(ops_ready, j & 1);
+        TRACE(1, 1);
         mbar_wait(&acc_empty[b], ((j >> 1) & 1) ^ 1u);
+        TRACE(1, 2);
         tc_fence_after();
         const uint32_t tacc = tmem + b * Cfg::ACC_COLS;
 #pragma unroll
@@ -328,6 +347,7 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
         }
         umma_commit(ops_free);      // operand tiles may be overwritten
         umma_commit(&acc_full[b]);  // accumulator ready for the epilogue
+        TRACE(1, 3);
       }
     }
   } else if (warp >= Cfg::EPI_WARP0) {
@@ -337,67 +357,93 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
     const bool use_aux = (EPI != EPI_ACT) && a.aux != nullptr;
     const int my_row = q * 32 + lane;
     float* aux_row = sAux + my_row * AUX_PITCH;
-    // every epilogue thread prefetches ITS OWN row of the operand tile (256 B), so no thread
-    // ever waits for another one before re-filling the buffer
-    auto issue_aux = [&](int t) {
-      const int4 ti = __ldg(a.tiles + t);
-      if (my_row < ti.y) {
-        mbar_arrive_expect_tx(aux_full, N * 4);
-        bulk_g2s(aux_row, a.aux + (static_cast<size_t>(ti.x) + my_row) * N, N * 4, aux_full);
-      } else {
-        mbar_arrive(aux_full);
-      }
-    };
-    if (use_aux && static_cast<int>(blockIdx.x) < a.num_tiles) issue_aux(blockIdx.x);
-    // 1 / (N * nv_s) of this thread's row, fetched one tile ahead (two dependent loads)
-    auto row_scale_of = [&](int t) {
-      float sc = 0.f;
+    const int step = gridDim.x;
+    auto tile_at = [&](int t) { return t < a.num_tiles ? __ldg(a.tiles + t) : make_int4(0, 0, 0, 0); };
+    // MSE cell size (vertices of the graph) of this thread's row, fetched one tile ahead
+    auto count_at = [&](int t) {
+      int c = 1;
       if (EPI == EPI_MSE && t < a.num_tiles) {
         const int4 ti = __ldg(a.tiles + t);
-        if (my_row < ti.y)
-          sc = 1.f / static_cast<float>(N * __ldg(a.nv + __ldg(a.vgraph + ti.x + my_row)));
+        if (my_row < ti.y) c = __ldg(a.vcount + ti.x + my_row);
       }
-      return sc;
+      return c;
     };
-    float scale_next = row_scale_of(blockIdx.x);
+    // Second operand of the epilogue (saved activations / target): every epilogue WARP
+    // prefetches its own 32 rows of the next tile with 16-byte cp.async copies (coalesced
+    // global reads) into rows padded to 272 B, so that the row-per-thread reads are
+    // conflict-free and no warp waits for another one before re-filling its rows.
+    // (Measured alternatives: one 256-byte TMA bulk copy per padded row costs ~100+ cycles
+    // of TMA issue each -- 128 per tile is more than a tile period; a single prefetch warp
+    // issuing all 2048 cp.async of a tile is slower than the tile as well.)
+    auto issue_aux = [&](const int4& ti) {
+      const float* src = a.aux + (static_cast<size_t>(ti.x) + q * 32) * N;
+      float* dst = sAux + q * 32 * AUX_PITCH;
+      const int rows = min(32, ti.y - q * 32);
+#pragma unroll
+      for (int it = 0; it < 32 * (N / 4) / 32; ++it) {
+        const int idx = it * 32 + lane;
+        const int r = idx / (N / 4), c = idx - r * (N / 4);
+        if (r < rows)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                           smem_u32(dst + r * AUX_PITCH + c * 4)),
+                       "l"(src + r * N + c * 4)
+                       : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (use_aux && static_cast<int>(blockIdx.x) < a.num_tiles) issue_aux(tile_at(blockIdx.x));
+    int count_next = count_at(blockIdx.x);
     int j = 0;
     float lsum = 0.f;
-    for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++j) {
+    for (int t = blockIdx.x; t < a.num_tiles; t += step, ++j) {
       const int b = j & 1;
       const int4 ti = __ldg(a.tiles + t);
+      const int count = count_next;
+      count_next = count_at(t + step);
       float* out_tile = a.out + static_cast<size_t>(ti.x) * N;
-      const float scale = scale_next;
-      scale_next = row_scale_of(t + gridDim.x);
+      if (q == 0 && lane == 0) TRACE(2, 0);
       mbar_wait(&acc_full[b], (j >> 1) & 1);
       tc_fence_after();
-      if (use_aux) mbar_wait(aux_full, j & 1);
+      if (q == 0 && lane == 0) TRACE(2, 1);
+      if (use_aux) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+      }
+      if (q == 0 && lane == 0) TRACE(2, 2);
       const uint32_t tacc = tmem + b * Cfg::ACC_COLS;
+      // rows past the end of a partial tile carry scale 0 and never touch the loss sum
+      const bool row_valid = my_row < ti.y;
+      const float scale =
+          (EPI == EPI_MSE && row_valid) ? 1.f / static_cast<float>(N * count) : 0.f;
       const int act = use_aux || EPI == EPI_ACT ? a.act : ATHENA_ACT_NONE;
       switch (act) {
         case ATHENA_ACT_RELU:
           lsum += epilogue_tile<ATHENA_ACT_RELU, EPI, N>(tacc, q, lane, ti.y, out_tile, aux_row,
-                                                         scale, patch, &acc_empty[b]);
+                                                         scale, patch, &acc_empty[b], (a.dbg & 2) != 0);
           break;
         case ATHENA_ACT_LEAKY_RELU:
           lsum += epilogue_tile<ATHENA_ACT_LEAKY_RELU, EPI, N>(tacc, q, lane, ti.y, out_tile,
                                                                aux_row, scale, patch,
-                                                               &acc_empty[b]);
+                                                               &acc_empty[b], (a.dbg & 2) != 0);
           break;
         case ATHENA_ACT_SIGMOID:
           lsum += epilogue_tile<ATHENA_ACT_SIGMOID, EPI, N>(tacc, q, lane, ti.y, out_tile, aux_row,
-                                                            scale, patch, &acc_empty[b]);
+                                                            scale, patch, &acc_empty[b], (a.dbg & 2) != 0);
           break;
         case ATHENA_ACT_TANH:
           lsum += epilogue_tile<ATHENA_ACT_TANH, EPI, N>(tacc, q, lane, ti.y, out_tile, aux_row,
-                                                         scale, patch, &acc_empty[b]);
+                                                         scale, patch, &acc_empty[b], (a.dbg & 2) != 0);
           break;
         default:
           lsum += epilogue_tile<ATHENA_ACT_NONE, EPI, N>(tacc, q, lane, ti.y, out_tile, aux_row,
-                                                         scale, patch, &acc_empty[b]);
+                                                         scale, patch, &acc_empty[b], (a.dbg & 2) != 0);
           break;
       }
-      // this thread is done with its operand row: prefetch the next tile's
-      if (use_aux && t + static_cast<int>(gridDim.x) < a.num_tiles) issue_aux(t + gridDim.x);
+      if (q == 0 && lane == 0) TRACE(2, 3);
+      if (use_aux && t + step < a.num_tiles) {  // this warp is done with its operand rows
+        __syncwarp();
+        issue_aux(tile_at(t + step));
+      }
     }
     if (EPI == EPI_MSE) loss_red[my_row] = lsum;
   } else {
@@ -422,7 +468,9 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
       const int32_t* rps = reinterpret_cast<const int32_t*>(st + Cfg::OFF_RP) + (r0 - ra);
       const float* rss = reinterpret_cast<const float*>(st + Cfg::OFF_RS) + (r0 - ra);
       const bool has_coef = a.rs != nullptr;
+      if (tid == 0) TRACE(3, 0);
       mbar_wait(&full[s], ph);
+      if (tid == 0) TRACE(3, 1);
       float4 acc[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -438,7 +486,7 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
         // in ascending order.  The loads of entry k + 1 are issued before the FMAs of
         // entry k.  Coefficient: deg_u^-1/2 per entry, deg_v^-1/2 once per row
         // (athena_diffstruc_extd_sub_kipf.f90:39-44 up to the rounding of the product).
-        while (e4 < end) {
+        while (e4 < end && !(a.dbg & 4)) {
           const int en = e4 + 4;
           uint32_t cn = c4;
           if (en < end) cn = *reinterpret_cast<const uint32_t*>(cols8 + en);  // prefetch
@@ -489,17 +537,20 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
           }
         }
       }
+      if (tid == 0) TRACE(3, 2);
       mbar_arrive(&empty[s]);  // raw stage consumed
       // chunk index of step k: 4 * (k ^ par) + ql
       const int ch0 = 4 * par + ql, ch1 = 4 * (par ^ 1) + ql;
-      if (a.P != nullptr && row < nrows) {
+      if (a.P != nullptr && row < nrows && !(a.dbg & 1)) {
         float* prow = a.P + (static_cast<size_t>(r0) + row) * F;
         *reinterpret_cast<float4*>(prow + ch0 * 4) = acc[0];
         *reinterpret_cast<float4*>(prow + ch1 * 4) = acc[1];
         *reinterpret_cast<float4*>(prow + ch0 * 4 + 32) = acc[2];
         *reinterpret_cast<float4*>(prow + ch1 * 4 + 32) = acc[3];
       }
+      if (tid == 0) TRACE(3, 3);
       mbar_wait(ops_free, (j & 1) ^ 1u);  // MMAs of the previous tile have read the operands
+      if (tid == 0) TRACE(3, 4);
       {
         const uint32_t o0 = sw128_off(row, ch0), o1 = sw128_off(row, ch1);
         float4 hi, lo;
@@ -518,6 +569,7 @@ __global__ void __launch_bounds__(GatherCfg<F, N>::THREADS, 1) k_pipe_gather(Gat
       }
       fence_async_smem();
       mbar_arrive(ops_ready);
+      if (tid == 0) TRACE(3, 5);
     }
   }
   tc_fence_before();
@@ -754,7 +806,7 @@ bool pipe_enabled() {
 
 template <int F, int N, bool TRANSB, int EPI>
 int launch_gather_t(const GatherArgs& a) {
-  using Cfg = GatherCfg<F, N>;
+  using Cfg = GatherCfg<F, N, EPI != EPI_ACT>;
   static bool attr = false;
   if (!attr) {
     ATH_CUDA(cudaFuncSetAttribute(k_pipe_gather<F, N, TRANSB, EPI>,
@@ -762,7 +814,44 @@ int launch_gather_t(const GatherArgs& a) {
     attr = true;
   }
   const int grid = std::min(a.num_tiles, ctx().sm_count);
-  k_pipe_gather<F, N, TRANSB, EPI><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(a);
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("ATHENA_DEBUG_PIPE");
+    dbg = e ? atoi(e) : 0;
+  }
+  GatherArgs b = a;
+  b.dbg = dbg;
+  b.trace = nullptr;
+  static int trace_left = -1;
+  static long long* trace_buf = nullptr;
+  if (trace_left < 0) {
+    const char* e = getenv("ATHENA_DEBUG_TRACE");
+    trace_left = e ? atoi(e) : 0;
+  }
+  const size_t trace_n = (size_t)4 * TRACE_TILES * 8;
+  if (trace_left > 0) {
+    if (!trace_buf) cudaMalloc(&trace_buf, trace_n * sizeof(long long));
+    cudaMemsetAsync(trace_buf, 0, trace_n * sizeof(long long), ctx().stream);
+    b.trace = trace_buf;
+  }
+  k_pipe_gather<F, N, TRANSB, EPI><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(b);
+  if (trace_left > 0) {
+    --trace_left;
+    std::vector<long long> h(trace_n);
+    cudaStreamSynchronize(ctx().stream);
+    cudaMemcpy(h.data(), trace_buf, trace_n * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long t0 = h[(3 * TRACE_TILES + 0) * 8 + 0];
+    fprintf(stderr, "TRACE kernel EPI=%d TRANSB=%d\n", EPI, (int)TRANSB);
+    for (int role = 0; role < 4; ++role)
+      for (int j = 0; j < 16; ++j) {
+        fprintf(stderr, "TRACE role %d tile %2d:", role, j);
+        for (int k = 0; k < 6; ++k) {
+          long long v = h[(role * TRACE_TILES + j) * 8 + k];
+          fprintf(stderr, " %7lld", v ? v - t0 : -1);
+        }
+        fprintf(stderr, "\n");
+      }
+  }
   ATH_LAUNCHED_T(EPI == EPI_ACT ? "pipe_gather_fwd"
                  : EPI == EPI_MSE ? "pipe_gather_fwd_mse" : "pipe_gather_bwd");
   return ATHENA_OK;
@@ -813,8 +902,7 @@ int launch_pipe_gather_fwd_mse(const Batch* b, const float* X, const float* W, f
   a.out = grad;
   a.aux = target;
   a.act = act;
-  a.vgraph = b->vgraph;
-  a.nv = b->nv;
+  a.vcount = b->vcount;
   a.loss_part = loss_part;
   ATH_REQUIRE(F == 64 && N == 64, ATHENA_ERR_ARG, "pipe_gather_fwd_mse: unsupported shape");
   *num_parts = std::min(b->num_tiles, ctx().sm_count);
