@@ -50,6 +50,8 @@ TAGS = [
     (r"k_aggregate<", "aggregate"),
     (r"k_tc_rows", "tc_rows"),
     (r"k_step", "optimiser_step"),
+    (r"k_finalize", "finalize_step"),
+    (r"k_agg_tc128", "agg_tc_fwd"),
 ]
 
 
