@@ -60,10 +60,24 @@ struct Context {
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
   bool profiling = false;
+  // Host->device input copies travel on their own stream so that they overlap the kernels of
+  // the same call (batch build under the feature copy, first layer under the target copy).
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t mark = nullptr;       // main-stream position after the last compute call
+  bool mark_valid = false;
+  cudaEvent_t ev_pool[32] = {};
+  int ev_next = 0;
 };
 Context& ctx();
 int ensure_init();
 void pool_trim();  // return every cached device block to the driver
+
+// side (copy) stream helpers, context.cu
+int side_begin();                                         // copy stream waits for the last mark
+int side_copy(void* dst, const void* src, size_t bytes);  // async H2D on the copy stream
+int side_fence(cudaEvent_t* ev);                          // event after the copies queued so far
+int main_wait(cudaEvent_t ev);                            // main stream waits for `ev` (nullptr: no-op)
+int record_mark();                                        // remember the main-stream position
 
 void prof_mark(const char* tag);  // no-op unless profiling is on
 

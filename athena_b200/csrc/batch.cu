@@ -540,10 +540,14 @@ ATHENA_API int athena_cuda_batch_create(athena_handle_t* batch, int32_t num_grap
     size_t ia_pad = (size_t)round_up((int64_t)ia_ints, 4);
     ATH_TRY(b->raw.reserve(sizeof(int32_t) * (ia_pad + ja_ints + 4)));
     int32_t* r = b->raw.as<int32_t>();
-    ATH_CUDA(cudaMemcpyAsync(r, adj_ia, sizeof(int32_t) * ia_ints, cudaMemcpyHostToDevice, st));
-    if (Z > 0)
-      ATH_CUDA(cudaMemcpyAsync(r + ia_pad, adj_ja, sizeof(int32_t) * ja_ints,
-                               cudaMemcpyHostToDevice, st));
+    // the adjacency (the bulk of the bytes) travels on the copy stream; the build kernels
+    // below wait for it, whatever the caller queues next on the copy stream does not
+    cudaEvent_t ev_adj = nullptr;
+    ATH_TRY(side_begin());
+    ATH_TRY(side_copy(r, adj_ia, sizeof(int32_t) * ia_ints));
+    if (Z > 0) ATH_TRY(side_copy(r + ia_pad, adj_ja, sizeof(int32_t) * ja_ints));
+    ATH_TRY(side_fence(&ev_adj));
+    ATH_TRY(main_wait(ev_adj));
     d_ia = r;
     d_ja = r + ia_pad;
   } else {

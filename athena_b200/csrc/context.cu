@@ -54,7 +54,9 @@ int destroy_object(athena_handle_t h, Kind kind) {
     victim = std::move(it->second);
     g_objects.erase(it);
   }
-  // the object's device buffers return to the stream-ordered pool (no synchronisation)
+  // the object's device buffers return to the stream-ordered pool (no synchronisation);
+  // the copy stream must not touch them before everything queued so far has run
+  if (ctx().ready) record_mark();
   victim.reset();
   return ATHENA_OK;
 }
@@ -148,6 +150,42 @@ void DevBuf::release() {
   }
 }
 
+// ---- copy stream ---------------------------------------------------------------
+// Hazards and how they are closed:
+//  * a destination may still be read by kernels queued by EARLIER calls (staging buffers are
+//    reused, pool blocks are recycled): the copy stream first waits for `mark`, the main-stream
+//    position recorded at the end of every compute call and at every batch destruction;
+//  * consumers on the main stream wait for the event recorded behind the copies;
+//  * athena_cuda_synchronize drains both streams.
+int side_begin() {
+  Context& c = ctx();
+  if (c.mark_valid) ATH_CUDA(cudaStreamWaitEvent(c.copy_stream, c.mark, 0));
+  return ATHENA_OK;
+}
+int side_copy(void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return ATHENA_OK;
+  ATH_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx().copy_stream));
+  return ATHENA_OK;
+}
+int side_fence(cudaEvent_t* ev) {
+  Context& c = ctx();
+  cudaEvent_t e = c.ev_pool[c.ev_next];
+  c.ev_next = (c.ev_next + 1) % 32;
+  ATH_CUDA(cudaEventRecord(e, c.copy_stream));
+  *ev = e;
+  return ATHENA_OK;
+}
+int main_wait(cudaEvent_t ev) {
+  if (ev) ATH_CUDA(cudaStreamWaitEvent(ctx().stream, ev, 0));
+  return ATHENA_OK;
+}
+int record_mark() {
+  Context& c = ctx();
+  ATH_CUDA(cudaEventRecord(c.mark, c.stream));
+  c.mark_valid = true;
+  return ATHENA_OK;
+}
+
 // ---- per-kernel profiling ---------------------------------------------------
 struct ProfRec {
   std::string tag;
@@ -217,6 +255,11 @@ ATHENA_API int athena_cuda_init(int32_t device) {
   c.total_mem = prop.totalGlobalMem;
   c.max_smem_optin = prop.sharedMemPerBlockOptin;
   ATH_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  ATH_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  ATH_CUDA(cudaEventCreateWithFlags(&c.mark, cudaEventDisableTiming));
+  for (int i = 0; i < 32; ++i)
+    ATH_CUDA(cudaEventCreateWithFlags(&c.ev_pool[i], cudaEventDisableTiming));
+  c.mark_valid = false;
   for (int i = 0; i < 16; ++i) {
     ATH_CUDA(cudaEventCreate(&c.ev_start[i]));
     ATH_CUDA(cudaEventCreate(&c.ev_stop[i]));
@@ -241,6 +284,11 @@ ATHENA_API int athena_cuda_shutdown(void) {
     cudaEventDestroy(c.ev_start[i]);
     cudaEventDestroy(c.ev_stop[i]);
   }
+  cudaStreamSynchronize(c.copy_stream);
+  cudaStreamDestroy(c.copy_stream);
+  c.copy_stream = nullptr;
+  cudaEventDestroy(c.mark);
+  for (int i = 0; i < 32; ++i) cudaEventDestroy(c.ev_pool[i]);
   cudaStreamDestroy(c.stream);
   c.stream = nullptr;
   c.ready = false;
@@ -266,6 +314,7 @@ ATHENA_API int athena_cuda_device_info(int32_t* device, int32_t* sm_count,
 
 ATHENA_API int athena_cuda_synchronize(void) {
   ATH_TRY(ensure_init());
+  ATH_CUDA(cudaStreamSynchronize(ctx().copy_stream));
   ATH_CUDA(cudaStreamSynchronize(ctx().stream));
   return ATHENA_OK;
 }

@@ -89,6 +89,7 @@ static int layer_alloc_params(Layer* L) {
 // when the fused kernel applies, the layer output is never materialised; `grad` receives
 // d loss / d pre-activation and `loss_part[0..*num_parts)` the per-CTA loss sums.
 struct FwdOpts {
+  cudaEvent_t target_ready = nullptr;  // the target's H2D copy (copy stream), if any
   const float* mse_target = nullptr;
   float* mse_grad = nullptr;
   float* loss_part = nullptr;
@@ -108,6 +109,8 @@ static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out,
     ATH_TRY(H.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fo, 1)));
     if (fo && fo->mse_target && t == L->T && L->act != ATHENA_ACT_SOFTMAX &&
         pipe_gather_supported(b, Fi, Fo)) {
+      ATH_TRY(main_wait(fo->target_ready));
+      fo->target_ready = nullptr;
       ATH_TRY(launch_pipe_gather_fwd_mse(b, in, L->params + L->poff[t - 1], P.as<float>(),
                                          fo->mse_target, fo->mse_grad, Fi, Fo, L->act,
                                          fo->loss_part, &fo->num_parts));
@@ -401,6 +404,19 @@ static int stage_in(DevBuf& buf, const float* src, int64_t count, int mem, const
   return ATHENA_OK;
 }
 
+// host -> device staging on the copy stream (no-op for device / null inputs)
+static int stage_in_side(DevBuf& buf, const float* src, int64_t count, int mem,
+                         const float** out) {
+  if (src == nullptr || mem == ATHENA_MEM_DEVICE) {
+    *out = src;
+    return ATHENA_OK;
+  }
+  ATH_TRY(buf.reserve(sizeof(float) * (size_t)std::max<int64_t>(count, 1)));
+  if (count > 0) ATH_TRY(side_copy(buf.p, src, sizeof(float) * (size_t)count));
+  *out = buf.as<float>();
+  return ATHENA_OK;
+}
+
 static int net_forward_dev(Network* N, Batch* b, const float* x, const float* e,
                            const float** out, FwdOpts* fo = nullptr) {
   const float* in = x;
@@ -425,22 +441,37 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
   Layer* first = N->layers.front();
   Layer* last = N->layers.back();
   const float *dx, *de, *dt, *out;
-  ATH_TRY(stage_in(N->stage_x, x, b->V * first->nvf[0], mem, &dx));
-  ATH_TRY(stage_in(N->stage_e, e, b->E * last->nef, mem, &de));
+  // inputs on the copy stream: the features first (the first layer waits for them), then the
+  // target, which only the loss needs -- the layers before it run under its copy
+  cudaEvent_t ev_in = nullptr, ev_tgt = nullptr;
   const int64_t out_n = last->out_rows(b) * last->out_width();
-  ATH_TRY(stage_in(N->stage_t, tgt, out_n, mem, &dt));
+  if (mem == ATHENA_MEM_HOST) {
+    ATH_TRY(side_begin());
+    ATH_TRY(stage_in_side(N->stage_x, x, b->V * first->nvf[0], mem, &dx));
+    ATH_TRY(stage_in_side(N->stage_e, e, b->E * last->nef, mem, &de));
+    ATH_TRY(side_fence(&ev_in));
+    ATH_TRY(stage_in_side(N->stage_t, tgt, out_n, mem, &dt));
+    ATH_TRY(side_fence(&ev_tgt));
+    ATH_TRY(main_wait(ev_in));
+  } else {
+    dx = x;
+    de = e;
+    dt = tgt;
+  }
   float* gflat = N->flat_grads.as<float>();
   cudaStream_t st = ctx().stream;
   ATH_CUDA(cudaMemsetAsync(gflat + N->n, 0, sizeof(float), st));
   ATH_TRY(N->gbuf.reserve(sizeof(float) * (size_t)std::max<int64_t>(out_n, 1)));
   ATH_TRY(N->loss_scratch.reserve(sizeof(float) * 1024));
   FwdOpts fo;
+  fo.target_ready = ev_tgt;
   if (last->kind == 0 && b->V > 0) {
     fo.mse_target = dt;
     fo.mse_grad = N->gbuf.as<float>();
     fo.loss_part = N->loss_scratch.as<float>();
   }
   ATH_TRY(net_forward_dev(N, b, dx, de, &out, &fo));
+  ATH_TRY(main_wait(fo.target_ready));  // unfused loss: wait here
   // the activation derivative of the last Kipf layer is folded into the loss gradient
   auto foldable = [](const Layer* L) {
     return L->kind == 0 && L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR &&
@@ -501,6 +532,7 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
   } else {
     ATH_TRY(comm_allreduce_sum(gflat, N->n + 1));
   }
+  ATH_TRY(record_mark());
   if (loss) {
     ATH_CUDA(cudaMemcpyAsync(N->pinned_loss, gflat + N->n, sizeof(float), cudaMemcpyDeviceToHost,
                              st));
@@ -833,6 +865,7 @@ ATHENA_API int athena_cuda_network_forward(athena_handle_t net, athena_handle_t 
     Lr->fwd_batch = nullptr;  // a backward call must be preceded by a training forward
   }
   ATH_TRY(frc);
+  ATH_TRY(record_mark());
   if (output) {
     size_t bytes = sizeof(float) * (size_t)(last->out_rows(b) * last->out_width());
     cudaStream_t st = ctx().stream;
@@ -878,6 +911,7 @@ ATHENA_API int athena_cuda_network_train_step(athena_handle_t net, athena_handle
                          nullptr, true, &stepped));
   if (!stepped)
     ATH_TRY(launch_update(N->flat_params.as<float>(), N->flat_grads.as<float>(), N->n, N->opt));
+  ATH_TRY(record_mark());
   if (loss) return athena_cuda_network_last_loss(net, loss);
   return ATHENA_OK;
 }

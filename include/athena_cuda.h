@@ -18,12 +18,16 @@
  *   - memory order is the reference's: a Fortran val(F,V) column-major array is
  *     passed as-is (== C row-major [V][F]); adj_ja(2,Z) is passed as-is
  *     (interleaved {neighbour, edge id} pairs); indices are 1-based int32.
- *   - the host keeps ownership of every host pointer; nothing is retained
- *     after a call returns.  Device memory is owned by the library.
+ *   - the host keeps ownership of every host pointer; the library keeps no
+ *     reference to it.  Copies from PINNED host buffers are asynchronous: such a
+ *     buffer must stay unchanged until the next call that returns host data (a
+ *     loss, an output, *_get_*) or athena_cuda_synchronize(); pageable buffers
+ *     are consumed before the call returns.  Device memory is owned by the library.
  *   - there is NO CPU fallback: a call that needs the GPU fails with
  *     ATHENA_ERR_CUDA if no device is usable.
- *   - one CUDA stream per process (the library's own); calls are asynchronous
- *     with respect to the host unless they return host data.
+ *   - one compute stream per process (the library's own) plus a copy stream for the
+ *     host->device input copies; calls are asynchronous with respect to the host
+ *     unless they return host data.
  */
 #ifndef ATHENA_CUDA_H
 #define ATHENA_CUDA_H
