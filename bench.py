@@ -277,6 +277,19 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # Bind the process to the CPUs (NUMA node) closest to its GPU before any pinned host
+    # buffer is allocated: with several ranks on one box the host->device copies of the
+    # end-to-end leg otherwise cross the socket interconnect.
+    if world > 1:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[local]) if vis else local
+            nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(idx))
+        except Exception:
+            pass
+
     import athena_b200 as ab
     L = ab.lib()
     ab.check(L.athena_cuda_init(local))
