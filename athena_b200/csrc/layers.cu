@@ -680,6 +680,7 @@ ATHENA_API int athena_cuda_layer_forward(athena_handle_t layer, athena_handle_t 
   ATH_TRY(stage_in(L->stage_x, vertex_features, b->V * L->nvf[0], mem, &dx));
   ATH_TRY(stage_in(L->stage_e, edge_features, b->E * L->nef, mem, &de));
   ATH_TRY(layer_forward_dev(L, b, dx, de, &out));
+  ATH_TRY(record_mark());
   if (output) {
     size_t bytes = sizeof(float) * (size_t)(L->out_rows(b) * L->out_width());
     cudaStream_t st = ctx().stream;
@@ -708,6 +709,7 @@ ATHENA_API int athena_cuda_layer_backward(athena_handle_t layer, athena_handle_t
     dgi = L->stage_gin.as<float>();
   }
   ATH_TRY(layer_backward_dev(L, b, dg, dgi));
+  ATH_TRY(record_mark());
   if (grad_input && mem == ATHENA_MEM_HOST) {
     cudaStream_t st = ctx().stream;
     ATH_CUDA(cudaMemcpyAsync(grad_input, dgi, sizeof(float) * (size_t)gin_n,
@@ -894,7 +896,8 @@ ATHENA_API int athena_cuda_network_update(athena_handle_t net) {
   Network* N = static_cast<Network*>(lookup_object(net, Kind::Network));
   if (!N) return ATHENA_ERR_HANDLE;
   ATH_REQUIRE(N->compiled, ATHENA_ERR_STATE, "network is not compiled");
-  return launch_update(N->flat_params.as<float>(), N->flat_grads.as<float>(), N->n, N->opt);
+  ATH_TRY(launch_update(N->flat_params.as<float>(), N->flat_grads.as<float>(), N->n, N->opt));
+  return record_mark();
 }
 
 ATHENA_API int athena_cuda_network_train_step(athena_handle_t net, athena_handle_t batch,
