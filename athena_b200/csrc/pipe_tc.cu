@@ -7,6 +7,9 @@
 //         kipf_propagate + matmul + activation%apply in ONE pass
 //         (athena_diffstruc_extd_sub_kipf.f90:29-46, athena_kipf_msgpass_layer.f90:943-952);
 //         also stores the propagated tile P for the backward pass.
+//     forward + MSE (last layer of a training step): the epilogue additionally reads the
+//         target tile, writes d loss / d pre-activation instead of the output and reduces
+//         the loss per CTA (mse_loss_type%compute, athena_loss.f90:393-430).
 //     backward (CSC, c = 1,                  W_t^T, epi = .* act'(H_{t-1})):
 //         gY_{t-1} = ( sum_{v->u} gY_t[v] ) W_t^T .* act'(H_{t-1}); the un-normalised
 //         scatter of get_partial_kipf_propagate_left_val (:101-109) commutes with the
@@ -14,22 +17,29 @@
 //   k_pipe_tn<N>
 //       dW[64 x N] += P^T . gY over all vertices (matmul partial w.r.t. W_t)
 //
-// Roles (one CTA per SM, persistent over tiles):
+// Roles of k_pipe_gather (one CTA per SM, persistent over tiles):
 //   producer warp   1 lane issues TMA bulk copies (cp.async.bulk) of the tile's feature
-//                   rows, CSR row pointers, column indices and coefficients into a
+//                   rows, row pointers, tile-local neighbour bytes and deg^-1/2 into a
 //                   shared-memory ring; completion is counted on "full" mbarriers
 //   gather warps    512 threads, FOUR lanes per row, 16 features per lane: walk the row's
-//                   entries in ascending order (the reference's summation order); column
-//                   indices / coefficients are read four entries at a time (one LDS.128
-//                   per array), neighbour rows with four LDS.128 per entry whose 64-byte
-//                   halves alternate between the two rows of a quarter-warp, so every
+//                   entries in ascending order (the reference's summation order); four
+//                   neighbour bytes are one LDS.32, every entry is four LDS.128 whose
+//                   64-byte halves alternate between the two rows of a quarter-warp, so every
 //                   shared-memory access is conflict-free; split the result hi/lo and
 //                   store it as the swizzled K-major A operand; store P
 //   MMA warp        1 lane issues tcgen05.mma.kind::tf32 into a double-buffered TMEM
 //                   accumulator and commits to mbarriers
-//   epilogue warps  128 threads: tcgen05.ld, hi+lo, activation (or act'), row stores
+//   epilogue warps  128 threads: tcgen05.ld (row per thread), hi+lo, activation / act' /
+//                   MSE against the thread's row of a padded operand tile that the warp
+//                   prefetched with cp.async, transposition through a padded patch,
+//                   coalesced row stores
 // so the HBM stream, the shared-memory gather, the tensor pipe and the stores of
 // consecutive tiles overlap.  No float atomics; fixed tile -> CTA mapping.
+//
+// Debug aids (never set in production): ATHENA_DEBUG_PIPE = bitmask that disables the P
+// store (1), the output store (2) or the gather loop (4) for elimination experiments;
+// ATHENA_DEBUG_TRACE = n prints a clock64 timeline of the four roles of CTA 0 for the
+// first n launches.  DESIGN.md section 3.1 quotes what they showed.
 #include <algorithm>
 
 #include "athena_internal.h"
@@ -249,9 +259,7 @@ k_pipe_gather(GatherArgs a) {
   uint64_t* ops_free = ops_ready + 1;
   uint64_t* acc_full = ops_free + 1;     // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
-  uint64_t* aux_full = acc_empty + 2;
-  uint64_t* aux_empty = aux_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_empty + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* loss_red = reinterpret_cast<float*>(smem + Cfg::OFF_BAR + 256);  // [128], EPI_MSE
   float* sAux = reinterpret_cast<float*>(smem + Cfg::OFF_AUX);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -268,8 +276,6 @@ k_pipe_gather(GatherArgs a) {
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 128);
     }
-    mbar_init(aux_full, 32);
-    mbar_init(aux_empty, 128);
     mbar_fence_init();
   }
   // stacked weight operand [hi(W') ; lo(W')] with W' = op(W) as [N][F] K-major.  One item =
