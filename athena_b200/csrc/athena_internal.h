@@ -242,13 +242,15 @@ int launch_tc_tn(const float* A1, int lda1, const float* A2, int lda2, const flo
 // fused warp-specialised tcgen05 kernels for batches of small graphs (pipe_tc.cu)
 bool pipe_gather_supported(const Batch* b, int F, int N);
 bool pipe_tn_supported(int K, int N);
+// mask_out / mask_in: sign bits of the pre-activation, [V][N/32] words (relu, leaky_relu):
+// written by the forward, read by the reverse sweep instead of the saved activations
 int launch_pipe_gather_fwd(const Batch* b, const float* X, const float* W, float* P, float* out,
-                           int F, int N, int act);
+                           int F, int N, int act, uint32_t* mask_out = nullptr);
 int launch_pipe_gather_fwd_mse(const Batch* b, const float* X, const float* W, float* P,
                                const float* target, float* grad, int F, int N, int act,
                                float* loss_part, int* num_parts);
 int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const float* Hin,
-                           float* out, int F, int N, int act);
+                           float* out, int F, int N, int act, const uint32_t* mask_in = nullptr);
 // defer != nullptr: the fold of the per-CTA partials into dW is queued instead of launched
 int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int N, DevBuf& scratch,
                    DeferList* defer = nullptr);

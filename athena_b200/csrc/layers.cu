@@ -28,6 +28,8 @@ struct Layer : Object {
   bool inference = false;  // current forward is network%predict: nothing is saved for backward
   // saved by forward for the reverse sweep
   std::vector<std::unique_ptr<DevBuf>> P, H, S, GZ, TN;  // TN: per-step dW partials (fused path)
+  std::vector<std::unique_ptr<DevBuf>> MK;               // sign bits of step t's pre-activation
+  std::vector<char> mask_valid;                          // MK[t] written by the last forward
   DevBuf Ae, out_buf, g0, g1, g2, tn_scratch, stage_x, stage_e, stage_g, stage_gin;
   Batch* fwd_batch = nullptr;
   int64_t fwd_V = -1;
@@ -63,8 +65,11 @@ static void layer_layout(Layer* L) {
   L->S.clear();
   L->GZ.clear();
   L->TN.clear();
+  L->MK.clear();
+  L->mask_valid.assign(L->T, 0);
   for (int t = 0; t < L->T; ++t) {
     L->TN.emplace_back(new DevBuf);
+    L->MK.emplace_back(new DevBuf);
     L->P.emplace_back(new DevBuf);
     L->H.emplace_back(new DevBuf);
     L->S.emplace_back(new DevBuf);
@@ -107,6 +112,7 @@ static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out,
     DevBuf& H = *L->H[t - 1];
     ATH_TRY(P.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fi, 1)));
     ATH_TRY(H.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fo, 1)));
+    L->mask_valid[t - 1] = 0;
     if (fo && fo->mse_target && t == L->T && L->act != ATHENA_ACT_SOFTMAX &&
         pipe_gather_supported(b, Fi, Fo)) {
       ATH_TRY(main_wait(fo->target_ready));
@@ -119,9 +125,16 @@ static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out,
       continue;
     }
     if (L->act != ATHENA_ACT_SOFTMAX && pipe_gather_supported(b, Fi, Fo)) {
-      // propagate + transform + activation in one fused tcgen05 kernel
+      // propagate + transform + activation in one fused tcgen05 kernel; for relu-type
+      // activations it also records the sign bits the reverse sweep needs
+      uint32_t* mk = nullptr;
+      if (!L->inference && (L->act == ATHENA_ACT_RELU || L->act == ATHENA_ACT_LEAKY_RELU)) {
+        ATH_TRY(L->MK[t - 1]->reserve(sizeof(uint32_t) * (size_t)std::max<int64_t>(V * (Fo / 32), 1)));
+        mk = L->MK[t - 1]->as<uint32_t>();
+        L->mask_valid[t - 1] = 1;
+      }
       ATH_TRY(launch_pipe_gather_fwd(b, in, L->params + L->poff[t - 1], P.as<float>(),
-                                     H.as<float>(), Fi, Fo, L->act));
+                                     H.as<float>(), Fi, Fo, L->act, mk));
       in = H.as<float>();
       continue;
     }
@@ -223,6 +236,7 @@ int layer_forward_dev(Layer* L, Batch* b, const float* x, const float* e, const 
 struct BwdOpts {
   bool gout_is_preact = false;
   int fold_act = ATHENA_ACT_NONE;
+  const uint32_t* fold_mask = nullptr;  // sign bits of the producing layer's output, if recorded
   bool* folded = nullptr;
   DeferList* defer = nullptr;  // queue the dW partial folds for launch_finalize
 };
@@ -276,17 +290,20 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
     if (t > 1) dst = (gy == L->g2.as<float>()) ? L->g0.as<float>() : L->g2.as<float>();
     if (fused_dp) {
       const float* Hin = nullptr;
+      const uint32_t* mk = nullptr;
       int act_e = ATHENA_ACT_NONE;
       if (t > 1 && nonlinear) {
         Hin = L->H[t - 2]->as<float>();
+        if (L->mask_valid[t - 2]) mk = L->MK[t - 2]->as<uint32_t>();
         act_e = L->act;
       } else if (t == 1 && opt.fold_act != ATHENA_ACT_NONE && opt.fold_act != ATHENA_ACT_LINEAR &&
                  opt.fold_act != ATHENA_ACT_SOFTMAX && L->fwd_x != nullptr) {
         Hin = L->fwd_x;  // the producing layer's output
+        mk = opt.fold_mask;
         act_e = opt.fold_act;
         if (opt.folded) *opt.folded = true;
       }
-      ATH_TRY(launch_pipe_gather_bwd(b, gy, Wt, Hin, dst, Fo, Fi, act_e));
+      ATH_TRY(launch_pipe_gather_bwd(b, gy, Wt, Hin, dst, Fo, Fi, act_e, mk));
       preact = t > 1;  // dst already is gY_{t-1}
     } else {
       // dP = W_t^T gY, then dH(:,u) += dP(:,v) for every CSR entry (v,u): CSC gather, NO coefficient
@@ -506,6 +523,11 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
     bool folded = false;
     opt.gout_is_preact = g_preact;
     opt.fold_act = (l > 0 && foldable(N->layers[l - 1])) ? N->layers[l - 1]->act : ATHENA_ACT_NONE;
+    if (l > 0) {
+      const Layer* prev = N->layers[l - 1];
+      if (prev->kind == 0 && prev->mask_valid[prev->T - 1])
+        opt.fold_mask = prev->MK[prev->T - 1]->as<uint32_t>();
+    }
     opt.folded = &folded;
     opt.defer = &defer;
     ATH_TRY(layer_backward_dev(N->layers[l], b, g, gi, opt));

@@ -104,6 +104,11 @@ struct GatherArgs {
   const float* aux;        // EPI_ACTGRAD: [V][N] saved activations (nullptr: act' == 1);
                            // EPI_MSE: [V][N] target
   int act;
+  // relu / leaky_relu: the sign of the pre-activation as one bit per element, [V][N/32]
+  // words.  The forward writes it (mask_out), the reverse sweep of the consuming step reads
+  // it (mask_in) instead of the saved activations: 8 bytes per row instead of 256.
+  uint32_t* mask_out;
+  const uint32_t* mask_in;
   // EPI_MSE (mse_loss_type%compute for graph outputs, athena_loss.f90:416-427)
   const int32_t* vcount;  // [V] vertices of the vertex's graph (Batch::vcount)
   float* loss_part;       // [gridDim.x] sum over this CTA's rows of (p-e)^2 / (N * nv_s)
@@ -184,11 +189,14 @@ __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, i
                                                float* __restrict__ out_tile,
                                                const float* aux_row /* shared memory */,
                                                float row_scale, float* patch,
-                                               uint64_t* acc_empty, bool no_store = false) {
+                                               uint64_t* acc_empty, bool no_store,
+                                               uint32_t* mask_out_row, bool use_mask,
+                                               const uint32_t (&mask_in)[N / 32]) {
   float lsum = 0.f;
   float* srow = patch + lane * EPI_PITCH;
 #pragma unroll
   for (int half = 0; half < N / 32; ++half) {
+    uint32_t mbits = 0;
 #pragma unroll
     for (int cg = 0; cg < 2; ++cg) {
       float vh[16], vl[16];
@@ -207,7 +215,18 @@ __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, i
         for (int k = 0; k < 4; ++k) o[k] = vh[i + k] + vl[i + k];
         if (EPI == EPI_ACT) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) o[k] = act_fwd<ACT>(o[k]);
+          for (int k = 0; k < 4; ++k) {
+            if (ACT == ATHENA_ACT_RELU || ACT == ATHENA_ACT_LEAKY_RELU)
+              mbits |= (o[k] > 0.f ? 1u : 0u) << (cg * 16 + i + k);
+            o[k] = act_fwd<ACT>(o[k]);
+          }
+        } else if (EPI == EPI_ACTGRAD && use_mask) {
+          // act'(H) from the sign bits: relu 1 / 0, leaky_relu 1 / 0.01
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool pos = (mask_in[half] >> (cg * 16 + i + k)) & 1u;
+            o[k] = pos ? o[k] : (ACT == ATHENA_ACT_LEAKY_RELU ? o[k] * 0.01f : 0.f);
+          }
         } else if (EPI == EPI_MSE) {
           const float4 t4 = *reinterpret_cast<const float4*>(aux_row + col0 + i);
           const float t[4] = {t4.x, t4.y, t4.z, t4.w};
@@ -227,6 +246,9 @@ __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, i
         *reinterpret_cast<float4*>(srow + cg * 16 + i) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
+    if (EPI == EPI_ACT && mask_out_row != nullptr &&
+        (ACT == ATHENA_ACT_RELU || ACT == ATHENA_ACT_LEAKY_RELU))
+      mask_out_row[half] = mbits;
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -360,7 +382,8 @@ k_pipe_gather(GatherArgs a) {
     // ===================== epilogue: TMEM -> registers -> global rows ==================
     const int q = warp - Cfg::EPI_WARP0;  // == warp % 4: TMEM lane quarter
     float* patch = reinterpret_cast<float*>(smem + Cfg::OFF_EPI) + q * EPI_PATCH;
-    const bool use_aux = (EPI != EPI_ACT) && a.aux != nullptr;
+    const bool use_mask = (EPI == EPI_ACTGRAD) && a.mask_in != nullptr;
+    const bool use_aux = (EPI != EPI_ACT) && a.aux != nullptr && !use_mask;
     const int my_row = q * 32 + lane;
     float* aux_row = sAux + my_row * AUX_PITCH;
     const int step = gridDim.x;
@@ -407,6 +430,19 @@ k_pipe_gather(GatherArgs a) {
       const int count = count_next;
       count_next = count_at(t + step);
       float* out_tile = a.out + static_cast<size_t>(ti.x) * N;
+      // rows past the end of a partial tile carry scale 0 and never touch the loss sum
+      const bool row_valid = my_row < ti.y;
+      // sign-bit words of this row: loaded before the waits so that their latency hides
+      uint32_t min_w[N / 32] = {};
+      uint32_t* mout = nullptr;
+      if (row_valid) {
+        const size_t grow = static_cast<size_t>(ti.x) + my_row;
+        if (use_mask) {
+#pragma unroll
+          for (int w = 0; w < N / 32; ++w) min_w[w] = __ldg(a.mask_in + grow * (N / 32) + w);
+        }
+        if (EPI == EPI_ACT && a.mask_out != nullptr) mout = a.mask_out + grow * (N / 32);
+      }
       if (q == 0 && lane == 0) TRACE(2, 0);
       mbar_wait(&acc_full[b], (j >> 1) & 1);
       tc_fence_after();
@@ -417,32 +453,30 @@ k_pipe_gather(GatherArgs a) {
       }
       if (q == 0 && lane == 0) TRACE(2, 2);
       const uint32_t tacc = tmem + b * Cfg::ACC_COLS;
-      // rows past the end of a partial tile carry scale 0 and never touch the loss sum
-      const bool row_valid = my_row < ti.y;
       const float scale =
           (EPI == EPI_MSE && row_valid) ? 1.f / static_cast<float>(N * count) : 0.f;
-      const int act = use_aux || EPI == EPI_ACT ? a.act : ATHENA_ACT_NONE;
+      const int act = use_aux || use_mask || EPI == EPI_ACT ? a.act : ATHENA_ACT_NONE;
       switch (act) {
         case ATHENA_ACT_RELU:
           lsum += epilogue_tile<ATHENA_ACT_RELU, EPI, N>(tacc, q, lane, ti.y, out_tile, aux_row,
-                                                         scale, patch, &acc_empty[b], (a.dbg & 2) != 0);
+                                                         scale, patch, &acc_empty[b], (a.dbg & 2) != 0, mout, use_mask, min_w);
           break;
         case ATHENA_ACT_LEAKY_RELU:
           lsum += epilogue_tile<ATHENA_ACT_LEAKY_RELU, EPI, N>(tacc, q, lane, ti.y, out_tile,
                                                                aux_row, scale, patch,
-                                                               &acc_empty[b], (a.dbg & 2) != 0);
+                                                               &acc_empty[b], (a.dbg & 2) != 0, mout, use_mask, min_w);
           break;
         case ATHENA_ACT_SIGMOID:
           lsum += epilogue_tile<ATHENA_ACT_SIGMOID, EPI, N>(tacc, q, lane, ti.y, out_tile, aux_row,
-                                                            scale, patch, &acc_empty[b], (a.dbg & 2) != 0);
+                                                            scale, patch, &acc_empty[b], (a.dbg & 2) != 0, mout, use_mask, min_w);
           break;
         case ATHENA_ACT_TANH:
           lsum += epilogue_tile<ATHENA_ACT_TANH, EPI, N>(tacc, q, lane, ti.y, out_tile, aux_row,
-                                                         scale, patch, &acc_empty[b], (a.dbg & 2) != 0);
+                                                         scale, patch, &acc_empty[b], (a.dbg & 2) != 0, mout, use_mask, min_w);
           break;
         default:
           lsum += epilogue_tile<ATHENA_ACT_NONE, EPI, N>(tacc, q, lane, ti.y, out_tile, aux_row,
-                                                         scale, patch, &acc_empty[b], (a.dbg & 2) != 0);
+                                                         scale, patch, &acc_empty[b], (a.dbg & 2) != 0, mout, use_mask, min_w);
           break;
       }
       if (q == 0 && lane == 0) TRACE(2, 3);
@@ -873,7 +907,7 @@ bool pipe_tn_supported(int K, int N) { return pipe_enabled() && K == 64 && (N ==
 
 // forward: out = act( (A_hat X) W ),  P = A_hat X           (W row-major [F][N])
 int launch_pipe_gather_fwd(const Batch* b, const float* X, const float* W, float* P, float* out,
-                           int F, int N, int act) {
+                           int F, int N, int act, uint32_t* mask_out) {
   GatherArgs a{};
   a.tiles = b->tiles.as<int4>();
   a.num_tiles = b->num_tiles;
@@ -886,6 +920,7 @@ int launch_pipe_gather_fwd(const Batch* b, const float* X, const float* W, float
   a.out = out;
   a.aux = nullptr;
   a.act = act;
+  a.mask_out = mask_out;
   ATH_REQUIRE(F == 64 && N == 64, ATHENA_ERR_ARG, "pipe_gather_fwd: unsupported shape");
   return launch_gather_t<64, 64, false, EPI_ACT>(a);
 }
@@ -917,7 +952,7 @@ int launch_pipe_gather_fwd_mse(const Batch* b, const float* X, const float* W, f
 
 // backward: out = ( (A^T-gather of G) W^T ) .* act'(Hin)      (W row-major [N][F]: W_t as stored)
 int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const float* Hin,
-                           float* out, int F, int N, int act) {
+                           float* out, int F, int N, int act, const uint32_t* mask_in) {
   GatherArgs a{};
   a.tiles = b->tiles.as<int4>();
   a.num_tiles = b->num_tiles;
@@ -929,6 +964,7 @@ int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const
   a.P = nullptr;
   a.out = out;
   a.aux = (act != ATHENA_ACT_NONE && act != ATHENA_ACT_LINEAR) ? Hin : nullptr;
+  a.mask_in = (act == ATHENA_ACT_RELU || act == ATHENA_ACT_LEAKY_RELU) ? mask_in : nullptr;
   a.act = act;
   ATH_REQUIRE(F == 64 && N == 64, ATHENA_ERR_ARG, "pipe_gather_bwd: unsupported shape");
   return launch_gather_t<64, 64, true, EPI_ACTGRAD>(a);

@@ -181,8 +181,9 @@ def kernel_bytes(tag, V, Z):
         "pipe_gather_fwd": idx + 4 * V + vf + 2 * vf + 4 * F * F,
         # fused last layer + MSE: X and target read, P and the loss gradient written
         "pipe_gather_fwd_mse": idx + 4 * V + 2 * vf + 2 * vf + 4 * F * F,
-        # fused dP = gY W^T, CSC gather, .* act'(H): gY and H read, gY_{t-1} written
-        "pipe_gather_bwd": idx + 2 * vf + vf + 4 * F * F,
+        # fused dP = gY W^T, CSC gather, .* relu'(H): gY read, gY_{t-1} written, relu' from the
+        # sign bits the forward recorded (8 B per row instead of the 4VF of saved activations)
+        "pipe_gather_bwd": idx + 2 * vf + 8 * V + 4 * F * F,
         "pipe_tn": 2 * vf + 4 * F * F,
         "pipe_tn_reduce": 4 * F * F,
         "aggregate_v4_g16_c1_coef": idx + 4 * V + 2 * vf,
