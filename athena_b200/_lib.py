@@ -141,7 +141,9 @@ def ptr(a):
         return None
     if isinstance(a, np.ndarray):
         assert a.flags.c_contiguous, "array must be C-contiguous"
-        return C.c_void_p(a.ctypes.data)
+        # data_as keeps a reference to the array, so a temporary passed inline stays alive
+        # until the foreign call has returned
+        return a.ctypes.data_as(C.c_void_p)
     if isinstance(a, DeviceArray):
         return C.c_void_p(a.addr)
     return C.c_void_p(int(a))

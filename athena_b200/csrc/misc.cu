@@ -361,8 +361,14 @@ k_p2p_sum_step(float* __restrict__ p, float* __restrict__ g, float* __restrict__
   __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
+  // issue all peer loads first (independent NVLink round trips overlap), then add in rank order
+  float v[P2P_MAX_WORLD];
+#pragma unroll
+  for (int r = 0; r < P2P_MAX_WORLD; ++r) v[r] = r < x.world ? ld_relaxed_sys(x.x[r] + i) : 0.f;
   float sum = 0.f;
-  for (int r = 0; r < x.world; ++r) sum += ld_relaxed_sys(x.x[r] + i);
+#pragma unroll
+  for (int r = 0; r < P2P_MAX_WORLD; ++r)
+    if (r < x.world) sum += v[r];
   if (i == n || !x.do_step) {
     g[i] = sum;  // index n: the global batch loss
   } else {

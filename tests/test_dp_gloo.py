@@ -54,8 +54,8 @@ def _case(name):
 
 def _shards(p):
     first = np.zeros(WORLD + 1, np.int32)
-    ab.check(ab.lib().athena_cuda_shard_graphs(p.B, ab.ptr(p.nz.astype(np.int64)), WORLD,
-                                               ab.ptr(first)))
+    nz64 = p.nz.astype(np.int64)  # named: the buffer must outlive the call
+    ab.check(ab.lib().athena_cuda_shard_graphs(p.B, ab.ptr(nz64), WORLD, ab.ptr(first)))
     return first
 
 

@@ -403,7 +403,8 @@ def test_shard_sum_equals_full_batch_gradient(cuda, oracle32):
     target = rng.random((64, 8)).astype(np.float32)
     full = ab.GraphBatch(p)
     first = np.zeros(5, np.int32)
-    ab.check(ab.lib().athena_cuda_shard_graphs(64, ab.ptr(p.nz.astype(np.int64)), 4, ab.ptr(first)))
+    nz64 = p.nz.astype(np.int64)  # named: the buffer must outlive the call
+    ab.check(ab.lib().athena_cuda_shard_graphs(64, ab.ptr(nz64), 4, ab.ptr(first)))
     net = ab.network_type()
     for L in (ab.kipf_msgpass_layer_type([32, 32], 1, "relu"),
               ab.duvenaud_msgpass_layer_type([32], [4], 2, 6, 8)):
