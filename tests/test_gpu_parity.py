@@ -453,3 +453,23 @@ def test_kipf_large_graph_width_128_fused_path(cuda, oracle32, oracle64, act):
     net.compile(ab.sgd_optimiser_type(0.01), batch_size=1)
     net.set_params(params)
     assert_parity(net.predict(p), r32[0], r64[0], what="predict")
+
+
+@pytest.mark.parametrize("act2,optim", [("none", "sgd"), ("tanh", "adam_clip"), ("leaky_relu", "sgd")])
+def test_kipf_fused_training_ragged_graphs(cuda, oracle32, act2, optim):
+    """The fused cfg2 path end to end on RAGGED graphs: partial 128-row tiles, the MSE fused
+    into the last layer's epilogue (with and without an activation to fold), sign-bit and
+    saved-activation variants of the backward epilogue, and both the one-launch finalise+step
+    (SGD) and the clip + step path (Adam with clip_norm)."""
+    rng = np.random.default_rng(31)
+    p = synth.molecular_batch(300, 64, 0, rng, nv_range=(2, 50))
+    specs = [kipf_spec([64, 64], 1, "relu"), kipf_spec([64, 64, 64], 2, act2)]
+    layers = [ab.kipf_msgpass_layer_type([64, 64], 1, "relu"),
+              ab.kipf_msgpass_layer_type([64, 64, 64], 2, act2)]
+    target = rng.standard_normal((p.V, 64)).astype(np.float32) * 0.5
+    if optim == "sgd":
+        o, a = OptimSpec("sgd", lr=0.02, momentum=0.5), ab.sgd_optimiser_type(0.02, momentum=0.5)
+    else:
+        o = OptimSpec("adam", lr=2e-3, clip_norm=0.5)
+        a = ab.adam_optimiser_type(2e-3, clip_dict=ab.clip_type(clip_norm=0.5))
+    _train_compare(cuda, oracle32, specs, layers, p, target, o, a, steps=4)
