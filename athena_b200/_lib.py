@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
         "athena_cuda_batch_export": [H, I32, P, I64],
         "athena_cuda_kipf_layer_create": [PH, I32, P, I32],
         "athena_cuda_duvenaud_layer_create": [PH, I32, P, I32, I32, I32, I32, I32, I32],
+        "athena_cuda_full_layer_create": [PH, I32, I32, I32, I32],
         "athena_cuda_layer_destroy": [H],
         "athena_cuda_layer_num_params": [H, PI64],
         "athena_cuda_layer_set_params": [H, P, I64],

@@ -270,6 +270,10 @@ int launch_segment_sum(const float* Y, int N, const int32_t* voff, int32_t B, fl
 int launch_readout_bwd(int act, const float* S, const float* gout, const int32_t* vgraph,
                        float* dY, int64_t V, int N);
 int launch_add_inplace(float* dst, const float* src, int64_t n);
+// Y[m, n] = act( Y[m, n] + bias[n] )   (bias may be null; act may be softmax over n)
+int launch_bias_act(float* Y, const float* bias, int64_t M, int N, int act);
+// dst[n] += sum_m G[m, n]   (ascending m, one thread per column: deterministic)
+int launch_colsum_add(const float* G, int64_t M, int N, float* dst);
 
 // loss (misc.cu)
 // graph output: L = sum_s mean_{F,V_s}((p-e)^2)/2 ; g = (p-e)/(F*V_s).  loss_acc[0] += L.

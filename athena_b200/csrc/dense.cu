@@ -362,6 +362,42 @@ __global__ void k_act_bwd_bcast(int act, const float* __restrict__ Y, const floa
   out[i] = act_grad(act, Y[i], G[(size_t)gidx[row] * N + c]);
 }
 
+__global__ void k_bias_act(float* __restrict__ Y, const float* __restrict__ bias, long long n,
+                           int N, int act) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = Y[i];
+  if (bias) v += __ldg(bias + (int)(i % N));
+  Y[i] = act_apply(act, v);
+}
+
+__global__ void k_colsum_add(const float* __restrict__ G, long long M, int N,
+                             float* __restrict__ dst) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (long long m = 0; m < M; ++m) s += G[m * N + n];
+  dst[n] += s;
+}
+
+int launch_bias_act(float* Y, const float* bias, int64_t M, int N, int act) {
+  if (M == 0) return ATHENA_OK;
+  const int epi = act == ATHENA_ACT_SOFTMAX ? ATHENA_ACT_NONE : act;
+  if (bias != nullptr || (epi != ATHENA_ACT_NONE && epi != ATHENA_ACT_LINEAR)) {
+    k_bias_act<<<(unsigned)cdiv(M * N, 256), 256, 0, ctx().stream>>>(Y, bias, M * N, N, epi);
+    ATH_LAUNCHED_T("bias_act");
+  }
+  if (act == ATHENA_ACT_SOFTMAX) ATH_TRY(launch_softmax_rows(Y, M, N));
+  return ATHENA_OK;
+}
+
+int launch_colsum_add(const float* G, int64_t M, int N, float* dst) {
+  if (M == 0) return ATHENA_OK;
+  k_colsum_add<<<(unsigned)cdiv(N, 128), 128, 0, ctx().stream>>>(G, M, N, dst);
+  ATH_LAUNCHED_T("colsum_add");
+  return ATHENA_OK;
+}
+
 int launch_act_bwd(int act, const float* Y, const float* G, float* out, int64_t M, int N) {
   if (M == 0) return ATHENA_OK;
   cudaStream_t st = ctx().stream;

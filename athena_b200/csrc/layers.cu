@@ -15,7 +15,8 @@ namespace athena {
 
 struct Layer : Object {
   Layer() : Object(Kind::Layer) {}
-  int kind = 0;  // 0 kipf, 1 duvenaud
+  int kind = 0;  // 0 kipf, 1 duvenaud, 2 full (dense head: nvf = {num_inputs, num_outputs})
+  int use_bias = 1;
   int T = 0;
   std::vector<int> nvf;  // (0:T)
   int nef = 0, min_deg = 1, max_deg = 1, n_out = 0, act = 0, ract = 0;
@@ -36,14 +37,21 @@ struct Layer : Object {
   const float* fwd_x = nullptr;  // device input of the last forward (valid until the next one)
 
   int ldA(int t) const { return (int)round_up(nvf[t - 1] + nef, 4); }
-  int out_width() const { return kind == 0 ? nvf[T] : n_out; }
+  int out_width() const { return kind == 1 ? n_out : nvf[T]; }
   int64_t out_rows(const Batch* b) const { return kind == 0 ? b->V : b->B; }
+  int64_t in_rows(const Batch* b) const { return kind == 2 ? b->B : b->V; }
 };
 
 static void layer_layout(Layer* L) {
   L->poff.clear();
   int64_t off = 0;
-  if (L->kind == 0) {
+  if (L->kind == 2) {
+    // W [num_outputs, num_inputs] column-major, then the bias (athena_full_layer.f90:371-396)
+    L->poff.push_back(off);
+    off += (int64_t)L->nvf[1] * L->nvf[0];
+    L->poff.push_back(off);
+    if (L->use_bias) off += L->nvf[1];
+  } else if (L->kind == 0) {
     for (int t = 1; t <= L->T; ++t) {
       L->poff.push_back(off);
       off += (int64_t)L->nvf[t] * L->nvf[t - 1];
@@ -215,12 +223,47 @@ static int duvenaud_forward(Layer* L, Batch* b, const float* x, const float* e,
   return ATHENA_OK;
 }
 
+// full_layer_type%forward (athena_full_layer.f90:839-874) on the [batch][num_inputs] output
+// of a graph-level layer: y = act( x . W + b ).  The dense head of example/msgpass_chemical
+// (main.f90:139-157); tiny, latency-bound work on the generic kernels.
+static int full_forward(Layer* L, Batch* b, const float* x, const float** out) {
+  const int Ni = L->nvf[0], No = L->nvf[1];
+  const int64_t B = b->B;
+  DevBuf& H = *L->H[0];
+  ATH_TRY(H.reserve(sizeof(float) * (size_t)std::max<int64_t>(B * No, 1)));
+  ATH_TRY(launch_gemm_nn(x, Ni, L->params + L->poff[0], H.as<float>(), No, B, No, Ni,
+                         ATHENA_ACT_NONE, GroupDesc{}));
+  ATH_TRY(launch_bias_act(H.as<float>(), L->use_bias ? L->params + L->poff[1] : nullptr, B, No,
+                          L->act));
+  *out = H.as<float>();
+  return ATHENA_OK;
+}
+
+static int full_backward(Layer* L, Batch* b, const float* gout, float* gin) {
+  const int Ni = L->nvf[0], No = L->nvf[1];
+  const int64_t B = b->B;
+  ATH_TRY(L->g0.reserve(sizeof(float) * (size_t)std::max<int64_t>(B * No, 1)));
+  const float* gz = gout;
+  if (L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR) {
+    ATH_TRY(launch_act_bwd(L->act, L->H[0]->as<float>(), gout, L->g0.as<float>(), B, No));
+    gz = L->g0.as<float>();
+  }
+  // dW(o,i) += sum_s gz(o,s) x(i,s) ; db(o) += sum_s gz(o,s) ; dx = W^T gz
+  ATH_TRY(launch_gemm_tn(L->fwd_x, Ni, gz, No, L->grads + L->poff[0], B, No, Ni, GroupDesc{},
+                         L->tn_scratch));
+  if (L->use_bias) ATH_TRY(launch_colsum_add(gz, B, No, L->grads + L->poff[1]));
+  if (gin)
+    ATH_TRY(launch_gemm_nt(gz, No, L->params + L->poff[0], gin, Ni, B, Ni, No, GroupDesc{}));
+  return ATHENA_OK;
+}
+
 int layer_forward_dev(Layer* L, Batch* b, const float* x, const float* e, const float** out,
                       FwdOpts* fo = nullptr) {
   ATH_REQUIRE(x != nullptr || b->V == 0, ATHENA_ERR_ARG, "forward: vertex_features is null");
   L->fwd_batch = b;
   L->fwd_V = b->V;
   L->fwd_x = x;
+  if (L->kind == 2) return full_forward(L, b, x, out);
   if (L->kind == 0) return kipf_forward(L, b, x, out, fo);
   return duvenaud_forward(L, b, x, e, out);
 }
@@ -385,6 +428,7 @@ int layer_backward_dev(Layer* L, Batch* b, const float* gout, float* gin,
               "backward: no forward pass on this batch");
   ATH_REQUIRE(gout != nullptr, ATHENA_ERR_ARG, "backward: grad_output is null");
   if (opt.folded) *opt.folded = false;
+  if (L->kind == 2) return full_backward(L, b, gout, gin);
   if (L->kind == 0) return kipf_backward(L, b, gout, gin, opt);
   ATH_REQUIRE(!opt.gout_is_preact, ATHENA_ERR_STATE, "duvenaud backward: unexpected pre-activation gradient");
   return duvenaud_backward(L, b, gout, gin);
@@ -403,6 +447,11 @@ struct Network : Object {
   DevBuf stage_x, stage_e, stage_t, gbuf, loss_scratch;
   std::vector<std::unique_ptr<DevBuf>> gin;  // input gradient of layer l (l >= 1)
   float* pinned_loss = nullptr;
+  int edge_width() const {  // edge features are consumed by the Duvenaud layer (if any)
+    for (const Layer* L : layers)
+      if (L->kind == 1) return L->nef;
+    return 0;
+  }
   ~Network() {
     if (pinned_loss) cudaFreeHost(pinned_loss);
   }
@@ -465,7 +514,7 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
   if (mem == ATHENA_MEM_HOST) {
     ATH_TRY(side_begin());
     ATH_TRY(stage_in_side(N->stage_x, x, b->V * first->nvf[0], mem, &dx));
-    ATH_TRY(stage_in_side(N->stage_e, e, b->E * last->nef, mem, &de));
+    ATH_TRY(stage_in_side(N->stage_e, e, b->E * N->edge_width(), mem, &de));
     ATH_TRY(side_fence(&ev_in));
     ATH_TRY(stage_in_side(N->stage_t, tgt, out_n, mem, &dt));
     ATH_TRY(side_fence(&ev_tgt));
@@ -507,7 +556,7 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
                              gflat + N->n, N->loss_scratch));
   } else {
     int gb = global_batch > 0 ? global_batch : b->B;
-    ATH_TRY(launch_mse_array(out, dt, out_n, (float)((int64_t)last->n_out * gb),
+    ATH_TRY(launch_mse_array(out, dt, out_n, (float)((int64_t)last->out_width() * gb),
                              N->gbuf.as<float>(), gflat + N->n, N->loss_scratch));
   }
   const float* g = N->gbuf.as<float>();
@@ -515,8 +564,8 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
     float* gi = nullptr;
     if (l > 0) {
       DevBuf& buf = *N->gin[l];
-      ATH_TRY(buf.reserve(sizeof(float) *
-                          (size_t)std::max<int64_t>(b->V * N->layers[l]->nvf[0], 1)));
+      ATH_TRY(buf.reserve(sizeof(float) * (size_t)std::max<int64_t>(
+                                                N->layers[l]->in_rows(b) * N->layers[l]->nvf[0], 1)));
       gi = buf.as<float>();
     }
     BwdOpts opt;
@@ -635,6 +684,27 @@ ATHENA_API int athena_cuda_duvenaud_layer_create(athena_handle_t* layer, int32_t
   return ATHENA_OK;
 }
 
+ATHENA_API int athena_cuda_full_layer_create(athena_handle_t* layer, int32_t num_inputs,
+                                             int32_t num_outputs, int32_t activation,
+                                             int32_t use_bias) {
+  ATH_TRY(ensure_init());
+  ATH_REQUIRE(layer, ATHENA_ERR_ARG, "full_layer_create: null argument");
+  ATH_REQUIRE(num_inputs >= 1 && num_outputs >= 1, ATHENA_ERR_ARG,
+              "full_layer_create: num_inputs = %d, num_outputs = %d", num_inputs, num_outputs);
+  ATH_REQUIRE(check_act(activation), ATHENA_ERR_ARG, "full_layer_create: unknown activation %d",
+              activation);
+  std::unique_ptr<Layer> L(new Layer);
+  L->kind = 2;
+  L->T = 1;
+  L->act = activation;
+  L->use_bias = use_bias ? 1 : 0;
+  L->nvf = {num_inputs, num_outputs};
+  layer_layout(L.get());
+  ATH_TRY(layer_alloc_params(L.get()));
+  *layer = register_object(L.release());
+  return ATHENA_OK;
+}
+
 ATHENA_API int athena_cuda_layer_destroy(athena_handle_t layer) {
   Layer* L = static_cast<Layer*>(lookup_object(layer, Kind::Layer));
   if (!L) return ATHENA_ERR_HANDLE;
@@ -699,7 +769,7 @@ ATHENA_API int athena_cuda_layer_forward(athena_handle_t layer, athena_handle_t 
   Batch* b = static_cast<Batch*>(lookup_object(batch, Kind::Batch));
   if (!L || !b) return ATHENA_ERR_HANDLE;
   const float *dx, *de, *out;
-  ATH_TRY(stage_in(L->stage_x, vertex_features, b->V * L->nvf[0], mem, &dx));
+  ATH_TRY(stage_in(L->stage_x, vertex_features, L->in_rows(b) * L->nvf[0], mem, &dx));
   ATH_TRY(stage_in(L->stage_e, edge_features, b->E * L->nef, mem, &de));
   ATH_TRY(layer_forward_dev(L, b, dx, de, &out));
   ATH_TRY(record_mark());
@@ -725,7 +795,7 @@ ATHENA_API int athena_cuda_layer_backward(athena_handle_t layer, athena_handle_t
   const float* dg;
   ATH_TRY(stage_in(L->stage_g, grad_output, L->out_rows(b) * L->out_width(), mem, &dg));
   float* dgi = grad_input;
-  int64_t gin_n = b->V * L->nvf[0];
+  int64_t gin_n = L->in_rows(b) * L->nvf[0];
   if (grad_input && mem == ATHENA_MEM_HOST) {
     ATH_TRY(L->stage_gin.reserve(sizeof(float) * (size_t)std::max<int64_t>(gin_n, 1)));
     dgi = L->stage_gin.as<float>();
@@ -767,11 +837,23 @@ ATHENA_API int athena_cuda_network_add(athena_handle_t net, athena_handle_t laye
   ATH_REQUIRE(!L->adopted, ATHENA_ERR_STATE, "network_add: layer already belongs to a network");
   if (!N->layers.empty()) {
     Layer* prev = N->layers.back();
-    ATH_REQUIRE(prev->kind == 0, ATHENA_ERR_ARG,
-                "network_add: a Duvenaud layer emits a graph-level output and must be last");
-    ATH_REQUIRE(prev->nvf[prev->T] == L->nvf[0], ATHENA_ERR_ARG,
-                "network_add: layer expects %d vertex features, previous layer emits %d",
-                L->nvf[0], prev->nvf[prev->T]);
+    if (L->kind == 2) {
+      // dense head: consumes the [num_outputs, batch] output of a graph-level layer
+      ATH_REQUIRE(prev->kind != 0, ATHENA_ERR_ARG,
+                  "network_add: a full layer must follow a Duvenaud or another full layer");
+      ATH_REQUIRE(prev->out_width() == L->nvf[0], ATHENA_ERR_ARG,
+                  "network_add: full layer expects %d inputs, previous layer emits %d", L->nvf[0],
+                  prev->out_width());
+    } else {
+      ATH_REQUIRE(prev->kind == 0, ATHENA_ERR_ARG,
+                  "network_add: only full layers may follow a graph-level (Duvenaud) output");
+      ATH_REQUIRE(prev->nvf[prev->T] == L->nvf[0], ATHENA_ERR_ARG,
+                  "network_add: layer expects %d vertex features, previous layer emits %d",
+                  L->nvf[0], prev->nvf[prev->T]);
+    }
+  } else {
+    ATH_REQUIRE(L->kind != 2, ATHENA_ERR_ARG,
+                "network_add: the first layer must be a message-passing layer");
   }
   L->adopted = true;
   N->layers.push_back(L);
@@ -879,7 +961,7 @@ ATHENA_API int athena_cuda_network_forward(athena_handle_t net, athena_handle_t 
   Layer* last = N->layers.back();
   const float *dx, *de, *out;
   ATH_TRY(stage_in(N->stage_x, vertex_features, b->V * first->nvf[0], mem, &dx));
-  ATH_TRY(stage_in(N->stage_e, edge_features, b->E * last->nef, mem, &de));
+  ATH_TRY(stage_in(N->stage_e, edge_features, b->E * N->edge_width(), mem, &de));
   // network%predict runs in inference mode (athena_network_sub.f90:4226-4303): layers keep
   // nothing for a reverse sweep
   for (Layer* Lr : N->layers) Lr->inference = true;

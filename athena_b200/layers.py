@@ -238,6 +238,67 @@ class duvenaud_msgpass_layer_type(msgpass_layer_type):
         return (self.graph.B, self.num_outputs)
 
 
+class full_layer_type(msgpass_layer_type):
+    """full_layer_type(num_outputs, num_inputs, use_bias=True, activation="none") -- the dense
+    head that follows the Duvenaud readout in example/msgpass_chemical (main.f90:139-157);
+    athena_full_layer.f90:147-160 (constructor), :839-874 (forward: act(matmul(W, x) + b)).
+    Parameters: W [num_outputs, num_inputs] column-major, then the bias (:371-396).  It takes
+    the graph-level [batch, num_inputs] array of the previous layer, not vertex features."""
+    name = "full"
+
+    def __init__(self, num_outputs: int, num_inputs: Optional[int] = None, use_bias: bool = True,
+                 activation="none", kernel_initialiser: Optional[str] = None,
+                 bias_initialiser: Optional[str] = None, verbose: int = 0):
+        super().__init__()
+        self.num_outputs = int(num_outputs)
+        self.use_bias = bool(use_bias)
+        self.activation = "none" if activation is None else str(activation)
+        self._init = (kernel_initialiser, bias_initialiser)
+        _act_id(self.activation)
+        # without num_inputs the layer is initialised when it is added to a network, from the
+        # previous layer's output shape (athena_full_layer.f90:212-215, network%compile)
+        if num_inputs is not None:
+            self._create(num_inputs)
+
+    def _create(self, num_inputs: int):
+        kernel_initialiser, bias_initialiser = self._init
+        if num_inputs < 1 or self.num_outputs < 1:
+            raise AthenaCudaError(-2, "full_layer: num_inputs and num_outputs must be positive")
+        self.num_inputs = int(num_inputs)
+        self.num_vertex_features = [self.num_inputs, self.num_outputs]
+        h = C.c_int64()
+        check(lib().athena_cuda_full_layer_create(C.byref(h), self.num_inputs, self.num_outputs,
+                                                  _act_id(self.activation), int(self.use_bias)))
+        self.handle = h.value
+        _initialise(self, kernel_initialiser)
+        if self.use_bias:  # bias_initialiser defaults to zeros (athena_full_layer.f90:281-284)
+            prm = self.get_params()
+            prm[self.num_inputs * self.num_outputs:] = 1.0 if bias_initialiser == "ones" else 0.0
+            self.set_params(prm)
+
+    def _out_shape(self):
+        return (self.graph.B, self.num_outputs)
+
+    def forward(self, input=None, edge_features=None) -> np.ndarray:
+        """layer%forward(input) with input [batch, num_inputs] (Fortran val(num_inputs, batch))."""
+        if self.graph is None:
+            raise AthenaCudaError(-5, "forward: set_graph has not been called")
+        x = np.ascontiguousarray(input, np.float32)
+        assert x.shape == (self.graph.B, self.num_inputs), "full_layer: input shape mismatch"
+        out = np.empty(self._out_shape(), np.float32)
+        check(lib().athena_cuda_layer_forward(self.handle, self.graph.handle, ptr(x), None,
+                                              ptr(out), _lib.MEM_HOST))
+        self.output = out
+        return out
+
+    def backward(self, grad_output, want_input_grad: bool = False):
+        g = np.ascontiguousarray(grad_output, np.float32)
+        gin = np.empty((self.graph.B, self.num_inputs), np.float32) if want_input_grad else None
+        check(lib().athena_cuda_layer_backward(self.handle, self.graph.handle, ptr(g), ptr(gin),
+                                               _lib.MEM_HOST))
+        return gin
+
+
 def _initialise(layer: msgpass_layer_type, kernel_initialiser: Optional[str]):
     """Host-side initialisers stay host-side (athena_initialiser*.f90 use the
     compiler RNG and are out of scope; parity tests inject parameters with

@@ -95,6 +95,11 @@ class network_type:
 
     # -- construction -------------------------------------------------------
     def add(self, layer: msgpass_layer_type):
+        if not layer.handle and hasattr(layer, "_create"):
+            if not self.model:
+                raise AthenaCudaError(-2, "network_add: the first layer must be a message-passing layer")
+            layer._create(self.model[-1].num_outputs if self.model[-1].name != "kipf"
+                          else self.model[-1].num_vertex_features[-1])
         check(lib().athena_cuda_network_add(self.handle, layer.handle))
         layer._owned = False  # the network owns the device object now
         self.model.append(layer)
@@ -144,7 +149,7 @@ class network_type:
         last = self.model[-1]
         if last.name == "kipf":
             return (batch.V, last.num_vertex_features[-1])
-        return (batch.B, last.num_outputs)
+        return (batch.B, last.num_outputs)  # duvenaud / full: graph-level output
 
     def forward(self, graphs: Union[Sequence[graph_type], PackedGraphs, GraphBatch],
                 vertex_features=None, edge_features=None) -> np.ndarray:

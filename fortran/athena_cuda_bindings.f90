@@ -60,6 +60,7 @@ module athena__cuda_bindings
   public :: athena_cuda_batch_create, athena_cuda_batch_destroy, athena_cuda_batch_status
   public :: athena_cuda_batch_bucketize
   public :: athena_cuda_kipf_layer_create, athena_cuda_duvenaud_layer_create
+  public :: athena_cuda_full_layer_create
   public :: athena_cuda_layer_destroy, athena_cuda_layer_num_params
   public :: athena_cuda_layer_set_params, athena_cuda_layer_get_params
   public :: athena_cuda_layer_set_gradients, athena_cuda_layer_get_gradients
@@ -156,6 +157,13 @@ module athena__cuda_bindings
        integer(c_int32_t), intent(in) :: num_vertex_features(*)  ! (0:T)
        integer(c_int32_t), value :: num_edge_features, min_vertex_degree, max_vertex_degree
        integer(c_int32_t), value :: num_outputs, message_activation, readout_activation
+       integer(c_int) :: rc
+     end function
+     function athena_cuda_full_layer_create(layer, num_inputs, num_outputs, activation, &
+          use_bias) bind(C, name="athena_cuda_full_layer_create") result(rc)
+       import :: c_int, c_int32_t, c_int64_t
+       integer(c_int64_t), intent(out) :: layer
+       integer(c_int32_t), value :: num_inputs, num_outputs, activation, use_bias
        integer(c_int) :: rc
      end function
      function athena_cuda_layer_destroy(layer) bind(C, name="athena_cuda_layer_destroy") result(rc)

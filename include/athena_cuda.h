@@ -193,6 +193,16 @@ int athena_cuda_duvenaud_layer_create(athena_handle_t* layer, int32_t num_time_s
                                       int32_t num_edge_features, int32_t min_vertex_degree,
                                       int32_t max_vertex_degree, int32_t num_outputs,
                                       int32_t message_activation, int32_t readout_activation);
+/* full_layer_type(num_inputs, num_outputs, use_bias, activation) -- the dense head that
+ * follows the Duvenaud readout in example/msgpass_chemical (main.f90:139-157).
+ * athena_full_layer.f90:147-160 (constructor), :839-874 (forward: act(matmul(W, x) + b));
+ * parameters W [num_outputs, num_inputs] column-major, then the bias [num_outputs]
+ * (:371-396); num_params = (num_inputs + 1) * num_outputs (:122-138) with a bias.
+ * In a network it consumes the [num_outputs, batch] output of a Duvenaud (or another
+ * full) layer; forward/backward through athena_cuda_layer_forward/_backward take
+ * vertex_features = [B][num_inputs] and return [B][num_outputs]. */
+int athena_cuda_full_layer_create(athena_handle_t* layer, int32_t num_inputs,
+                                  int32_t num_outputs, int32_t activation, int32_t use_bias);
 int athena_cuda_layer_destroy(athena_handle_t layer);
 int athena_cuda_layer_num_params(athena_handle_t layer, int64_t* n);
 
@@ -245,9 +255,10 @@ int athena_cuda_layer_backward(athena_handle_t layer, athena_handle_t batch,
 int athena_cuda_network_create(athena_handle_t* net);
 int athena_cuda_network_destroy(athena_handle_t net);
 /* network%add(layer): layers run in order; each layer's vertex input is the
- * previous layer's node-level output.  A Duvenaud layer must be last and
- * reads the ORIGINAL edge features (SURVEY finding 7).  The network takes
- * ownership of the layer's parameters (re-homed into one flat buffer). */
+ * previous layer's node-level output.  A Duvenaud layer reads the ORIGINAL edge
+ * features (SURVEY finding 7) and emits a graph-level [num_outputs, batch] array, after
+ * which only full layers may follow.  The network takes ownership of the layer's
+ * parameters (re-homed into one flat buffer, layer order x params order). */
 int athena_cuda_network_add(athena_handle_t net, athena_handle_t layer);
 
 typedef struct athena_optimiser_desc {

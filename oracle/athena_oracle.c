@@ -569,16 +569,26 @@ API void oracle_bucketize(int V, const int *deg, int min_deg, int max_deg,
 /* ------------------------------------------------------------------------- */
 
 typedef struct {
-  int kind;      /* 0 = kipf, 1 = duvenaud */
+  int kind;      /* 0 = kipf, 1 = duvenaud, 2 = full (dense head, T = 1) */
   int T;         /* num_time_steps */
-  int nvf[17];   /* num_vertex_features(0:T), T <= 16 */
+  int nvf[17];   /* num_vertex_features(0:T), T <= 16; full: {num_inputs, num_outputs} */
   int nef;       /* num_edge_features(0) (duvenaud) */
   int min_deg, max_deg, n_out;
   int act, ract; /* message activation, readout activation */
+  int use_bias;  /* full_layer_type%use_bias */
 } oracle_layer_t;
+
+/* width of a graph-level ([n, batch]) layer output */
+static int graph_level_width(const oracle_layer_t *L) {
+  return L->kind == 1 ? L->n_out : L->nvf[1];
+}
 
 API int oracle_layer_num_params(const oracle_layer_t *L) {
   int n = 0;
+  if (L->kind == 2) {
+    /* athena_full_layer.f90:122-138, 371-396: W [num_outputs, num_inputs] then bias */
+    return L->nvf[1] * L->nvf[0] + (L->use_bias ? L->nvf[1] : 0);
+  }
   if (L->kind == 0) {
     /* athena_kipf_msgpass_layer.f90:347-351 : W_t [F_t, F_{t-1}] */
     for (int t = 1; t <= L->T; ++t) n += L->nvf[t] * L->nvf[t - 1];
@@ -659,6 +669,47 @@ static void kipf_backward_sample(const oracle_layer_t *L, const real *params,
     free(gy);
   }
   free(g);
+}
+
+/* full_layer_type%forward for ONE sample (column) of the [num_inputs, batch] input:
+ * y = act( matmul(W, x) + b ).  athena_full_layer.f90:839-874.  Saves x and y.   */
+static const real *full_forward_sample(const oracle_layer_t *L, const real *params,
+                                       const real *x, saved_t *sv) {
+  int Ni = L->nvf[0], No = L->nvf[1];
+  sv->P = (real **)calloc(1, sizeof(real *));
+  sv->H = (real **)calloc(1, sizeof(real *));
+  real *xs = (real *)malloc(sizeof(real) * (size_t)Ni + 8);
+  real *z = (real *)malloc(sizeof(real) * (size_t)No + 8);
+  real *y = (real *)malloc(sizeof(real) * (size_t)No + 8);
+  memcpy(xs, x, sizeof(real) * (size_t)Ni);
+  oracle_matmul(No, Ni, 1, params, x, z);
+  if (L->use_bias) {
+    const real *b = params + (size_t)No * Ni;
+    for (int o = 0; o < No; ++o) z[o] = z[o] + b[o];
+  }
+  oracle_activation(L->act, No, 1, z, y);
+  free(z);
+  sv->P[0] = xs;
+  sv->H[0] = y;
+  return y;
+}
+
+/* reverse sweep of one sample through a full layer: dW += gz x^T, db += gz,
+ * dx = W^T gz with gz = act'(y) . g  (diffstruc matmul / add partials; shared operands
+ * summed over samples, test/test_diffstruc_extd.f90:41-45).                          */
+static void full_backward_sample(const oracle_layer_t *L, const real *params,
+                                 const saved_t *sv, const real *g_out, real *dparams,
+                                 real *dx) {
+  int Ni = L->nvf[0], No = L->nvf[1];
+  real *gz = (real *)malloc(sizeof(real) * (size_t)No + 8);
+  oracle_activation_bwd(L->act, No, 1, sv->H[0], g_out, gz);
+  oracle_matmul_bwd_left(No, Ni, 1, gz, sv->P[0], dparams);
+  if (L->use_bias) {
+    real *db = dparams + (size_t)No * Ni;
+    for (int o = 0; o < No; ++o) db[o] = db[o] + gz[o];
+  }
+  if (dx) oracle_matmul_bwd_right(No, Ni, 1, params, gz, dx);
+  free(gz);
 }
 
 /* update_message_duvenaud for ONE sample (athena_duvenaud_msgpass_layer.f90:
@@ -807,7 +858,10 @@ API real oracle_stack_fwd_bwd(int n_layers, const oracle_layer_t *layers,
   }
   if (dparams) memset(dparams, 0, sizeof(real) * np_total);
   int F0 = layers[0].nvf[0];
-  int Fe = last->kind == 1 ? last->nef : 0;
+  int Fe = 0;
+  for (int l = 0; l < n_layers; ++l)
+    if (layers[l].kind == 1) Fe = layers[l].nef;
+  const int n_last = last->kind == 0 ? 0 : graph_level_width(last);
   real loss = 0;
   const int *ia = ia_cat;
   const int *ja = ja_cat;
@@ -818,15 +872,28 @@ API real oracle_stack_fwd_bwd(int n_layers, const oracle_layer_t *layers,
     int nz = ia[V] - 1;
     const real *in = x_cat + voff * F0;
     const real *es = e_cat ? e_cat + eoff * Fe : NULL;
-    real *dout = NULL; /* duvenaud per-sample output */
+    real *dout = NULL;      /* graph-level output of this sample (final layer) */
+    real *duv_tmp = NULL;   /* Duvenaud output when dense layers follow it */
+    const real *vec = NULL; /* current graph-level vector */
     for (int l = 0; l < n_layers; ++l) {
       const oracle_layer_t *L = &layers[l];
       if (L->kind == 0) {
         in = kipf_forward_sample(L, params + poff[l], V, ia, ja, in, &sv[l]);
+      } else if (L->kind == 1) {
+        real *dst = out + (size_t)s * L->n_out;
+        if (l != n_layers - 1) {
+          duv_tmp = (real *)malloc(sizeof(real) * (size_t)L->n_out + 8);
+          dst = duv_tmp;
+        }
+        duvenaud_forward_sample(L, params + poff[l], V, ia, ja, in, es, &sv[l], dst);
+        vec = dst;
       } else {
-        dout = out + (size_t)s * L->n_out;
-        duvenaud_forward_sample(L, params + poff[l], V, ia, ja, in, es, &sv[l], dout);
+        vec = full_forward_sample(L, params + poff[l], vec, &sv[l]);
       }
+    }
+    if (last->kind != 0) {
+      dout = out + (size_t)s * n_last;
+      if (last->kind == 2) memcpy(dout, vec, sizeof(real) * (size_t)n_last);
     }
     int FT = last->nvf[last->T];
     size_t out_off = 0;
@@ -843,9 +910,9 @@ API real oracle_stack_fwd_bwd(int n_layers, const oracle_layer_t *layers,
         g = (real *)malloc(sizeof(real) * n + 8);
         oracle_mse_cell_bwd(n, out + out_off, target + out_off, g, (real)n);
       } else {
-        size_t n = (size_t)last->n_out;
+        size_t n = (size_t)n_last;
         const real *ts = target + (size_t)s * n;
-        real denom = (real)((size_t)last->n_out * (size_t)global_B);
+        real denom = (real)((size_t)n_last * (size_t)global_B);
         real sq = 0;
         for (size_t i = 0; i < n; ++i) {
           real d = dout[i] - ts[i];
@@ -859,13 +926,16 @@ API real oracle_stack_fwd_bwd(int n_layers, const oracle_layer_t *layers,
         for (int l = n_layers - 1; l >= 0; --l) {
           const oracle_layer_t *L = &layers[l];
           int Fi = L->nvf[0];
-          real *dx = (l > 0) ? (real *)malloc(sizeof(real) * (size_t)Fi * V + 8) : NULL;
+          size_t dx_n = L->kind == 2 ? (size_t)Fi : (size_t)Fi * V;
+          real *dx = (l > 0) ? (real *)malloc(sizeof(real) * dx_n + 8) : NULL;
           if (L->kind == 0)
             kipf_backward_sample(L, params + poff[l], V, ia, ja, &sv[l], g,
                                  dparams + poff[l], dx);
-          else
+          else if (L->kind == 1)
             duvenaud_backward_sample(L, params + poff[l], V, ia, ja, &sv[l], g,
                                      dparams + poff[l], dx);
+          else
+            full_backward_sample(L, params + poff[l], &sv[l], g, dparams + poff[l], dx);
           free(g);
           g = dx;
         }
@@ -873,6 +943,7 @@ API real oracle_stack_fwd_bwd(int n_layers, const oracle_layer_t *layers,
       free(g);
     }
     for (int l = 0; l < n_layers; ++l) saved_free(&sv[l], layers[l].T);
+    free(duv_tmp);
     ia += V + 1;
     ja += 2 * (size_t)nz;
     voff += (size_t)V;
@@ -902,7 +973,14 @@ API void oracle_layer_fwd_bwd(const oracle_layer_t *L, const real *params, int B
     int nz = ia[V] - 1;
     saved_t sv;
     const real *xs = x_cat + voff * F0;
-    if (L->kind == 0) {
+    if (L->kind == 2) {
+      /* dense head on its own: x_cat is the graph-level [B][num_inputs] array */
+      const real *o = full_forward_sample(L, params, x_cat + (size_t)s * F0, &sv);
+      if (out) memcpy(out + (size_t)s * FT, o, sizeof(real) * (size_t)FT);
+      if (g_out)
+        full_backward_sample(L, params, &sv, g_out + (size_t)s * FT, dparams,
+                             dx_cat ? dx_cat + (size_t)s * F0 : NULL);
+    } else if (L->kind == 0) {
       const real *o = kipf_forward_sample(L, params, V, ia, ja, xs, &sv);
       if (out) memcpy(out + voff * FT, o, sizeof(real) * (size_t)FT * V);
       if (g_out)

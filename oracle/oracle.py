@@ -39,7 +39,7 @@ def build(force: bool = False) -> None:
 class _LayerT(C.Structure):
     _fields_ = [("kind", C.c_int), ("T", C.c_int), ("nvf", C.c_int * 17),
                 ("nef", C.c_int), ("min_deg", C.c_int), ("max_deg", C.c_int),
-                ("n_out", C.c_int), ("act", C.c_int), ("ract", C.c_int)]
+                ("n_out", C.c_int), ("act", C.c_int), ("ract", C.c_int), ("use_bias", C.c_int)]
 
 
 @dataclass
@@ -47,7 +47,7 @@ class LayerSpec:
     """Mirror of the constructor arguments of kipf_msgpass_layer_type
     (athena_kipf_msgpass_layer.f90:80-97) / duvenaud_msgpass_layer_type
     (athena_duvenaud_msgpass_layer.f90:88-120)."""
-    kind: str                      # "kipf" | "duvenaud"
+    kind: str                      # "kipf" | "duvenaud" | "full" (num_vertex_features = [n_in, n_out])
     num_vertex_features: Sequence[int]  # (0:T)
     num_time_steps: int
     num_edge_features: int = 0
@@ -56,10 +56,12 @@ class LayerSpec:
     num_outputs: int = 0
     activation: str = "none"
     readout_activation: str = "softmax"
+    use_bias: bool = True
 
     def to_c(self) -> _LayerT:
         L = _LayerT()
-        L.kind = 0 if self.kind == "kipf" else 1
+        L.kind = {"kipf": 0, "duvenaud": 1, "full": 2}[self.kind]
+        L.use_bias = int(self.use_bias)
         L.T = self.num_time_steps
         nvf = list(self.num_vertex_features)
         if len(nvf) == 1:
@@ -299,6 +301,8 @@ class Oracle:
         if last.kind == "kipf":
             nvf = list(last.num_vertex_features)
             return (b.V, nvf[-1])
+        if last.kind == "full":
+            return (b.B, list(last.num_vertex_features)[1])
         return (b.B, last.num_outputs)
 
     def stack_fwd_bwd(self, layers: List[LayerSpec], params, b: Batch, target=None,
@@ -315,10 +319,12 @@ class Oracle:
             self.rp(x), self.rp(e), self.rp(tgt), int(global_B or b.B), self.rp(out), self.rp(dparams))
         return float(loss), out, dparams
 
-    def layer_fwd_bwd(self, layer: LayerSpec, params, b: Batch, g_out=None, want_dx=False):
-        """-> (out, dparams, dx)"""
+    def layer_fwd_bwd(self, layer: LayerSpec, params, b: Batch, g_out=None, want_dx=False,
+                      x=None):
+        """-> (out, dparams, dx).  `x` overrides the batch's vertex features (a full layer
+        takes the graph-level [B, num_inputs] array)."""
         params = self.r(params)
-        x = self.r(b.x); e = self.r(b.e) if b.e is not None else None
+        x = self.r(b.x if x is None else x); e = self.r(b.e) if b.e is not None else None
         out = np.zeros(self.out_shape([layer], b), self.dtype)
         g = self.r(g_out) if g_out is not None else None
         dparams = np.zeros(params.size, self.dtype) if g is not None else None

@@ -32,6 +32,10 @@ def duvenaud_spec(nvf, nef, T, min_deg, max_deg, n_out, act="sigmoid", ract="sof
     return LayerSpec("duvenaud", list(nvf), T, nef, min_deg, max_deg, n_out, act, ract)
 
 
+def full_spec(n_in, n_out, act="none", use_bias=True) -> LayerSpec:
+    return LayerSpec("full", [n_in, n_out], 1, activation=act, use_bias=use_bias)
+
+
 def random_params(n, rng, scale=0.5):
     return (rng.standard_normal(n) * scale).astype(np.float32)
 

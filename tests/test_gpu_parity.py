@@ -14,7 +14,7 @@ import pytest
 
 import athena_b200 as ab
 from athena_b200 import synth
-from helpers import (RTOL_ACT, RTOL_PARAM, assert_parity, duvenaud_spec, kipf_spec,
+from helpers import (RTOL_ACT, RTOL_PARAM, assert_parity, duvenaud_spec, full_spec, kipf_spec,
                      random_params, rel_err, to_oracle_batch)
 from oracle.oracle import Batch, OptimSpec
 
@@ -381,6 +381,70 @@ def test_kipf_duvenaud_stack_training_parity(cuda, oracle32):
     _train_compare(cuda, oracle32, specs, layers, p, target,
                    OptimSpec("adam", lr=5e-3, clip_min=-0.05, clip_max=0.05),
                    ab.adam_optimiser_type(5e-3, clip_dict=ab.clip_type(-0.05, 0.05)))
+
+
+def test_chemical_example_network_training_parity(cuda, oracle32):
+    """The whole network of example/msgpass_chemical (main.f90:129-192): Duvenaud(T=4, Fv=6,
+    Fe=1, D=10, n_out=10) -> full 10->128 -> 64 -> 1, leaky_relu, Adam lr 1e-2, clip_norm 0.1,
+    batch 8.  The full layers take num_inputs from the previous layer, as in the example."""
+    rng = np.random.default_rng(17)
+    p = synth.chemical_batch(8, rng)
+    specs = [duvenaud_spec([6] * 5, 1, 4, 1, 10, 10), full_spec(10, 128, "leaky_relu"),
+             full_spec(128, 64, "leaky_relu"), full_spec(64, 1, "leaky_relu")]
+    layers = [ab.duvenaud_msgpass_layer_type([6], [1], 4, 10, 10),
+              ab.full_layer_type(128, activation="leaky_relu"),
+              ab.full_layer_type(64, activation="leaky_relu"),
+              ab.full_layer_type(1, activation="leaky_relu")]
+    target = rng.random((8, 1)).astype(np.float32)
+    _train_compare(cuda, oracle32, specs, layers, p, target,
+                   OptimSpec("adam", lr=1e-2, clip_norm=0.1),
+                   ab.adam_optimiser_type(1e-2, clip_dict=ab.clip_type(clip_norm=0.1)), steps=8)
+
+
+@pytest.mark.parametrize("act,bias", [("none", True), ("tanh", False), ("softmax", True),
+                                      ("sigmoid", True)])
+def test_full_layer_forward_backward_parity(cuda, oracle32, act, bias):
+    """full_layer_type forward / reverse sweep on its own (athena_full_layer.f90:839-874):
+    y = act(W x + b), dW = gz x^T, db = sum gz, dx = W^T gz."""
+    rng = np.random.default_rng(zlib.crc32(f"{act}{bias}".encode()))
+    p = synth.chemical_batch(37, rng)
+    spec = full_spec(19, 23, act, bias)
+    L = ab.full_layer_type(23, 19, use_bias=bias, activation=act)
+    n = oracle32.num_params([spec])
+    assert L.num_params == n == 19 * 23 + (23 if bias else 0)
+    params = random_params(n, rng, 0.4)
+    L.set_params(params)
+    L.set_graph(p)
+    x = rng.standard_normal((37, 19)).astype(np.float32)
+    g = rng.standard_normal((37, 23)).astype(np.float32)
+    ob = to_oracle_batch(p)
+    out_ref, grad_ref, dx_ref = oracle32.layer_fwd_bwd(spec, params, ob, g_out=g, want_dx=True,
+                                                       x=x)
+    assert rel_err(L.forward(x), out_ref) <= RTOL_ACT
+    L.zero_gradients()
+    dx = L.backward(g, want_input_grad=True)
+    assert rel_err(L.get_gradients(), grad_ref) <= RTOL_ACT
+    assert rel_err(dx, dx_ref) <= RTOL_ACT
+    L.destroy()
+
+
+def test_full_layer_placement_rules(cuda):
+    """A full layer consumes a graph-level array: it may only follow a Duvenaud or full layer,
+    and nothing but full layers may follow a graph-level output."""
+    net = ab.network_type()
+    with pytest.raises(ab.AthenaCudaError):
+        net.add(ab.full_layer_type(4, 4))
+    net.add(ab.kipf_msgpass_layer_type([4, 4], 1))
+    with pytest.raises(ab.AthenaCudaError):
+        net.add(ab.full_layer_type(4, 4))
+    net.add(ab.duvenaud_msgpass_layer_type([4], [0], 1, 3, 5))
+    with pytest.raises(ab.AthenaCudaError):
+        net.add(ab.full_layer_type(4, 7))          # width mismatch
+    with pytest.raises(ab.AthenaCudaError):
+        net.add(ab.kipf_msgpass_layer_type([5, 5], 1))
+    net.add(ab.full_layer_type(4))
+    assert net.model[-1].num_inputs == 5
+    net.destroy()
 
 
 def test_network_train_loop_runs_epochs(cuda):

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import duvenaud_spec, kipf_spec, rel_err
+from helpers import duvenaud_spec, full_spec, kipf_spec, rel_err
 from oracle.oracle import Batch, LayerSpec, OptimSpec
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -139,6 +139,42 @@ def test_duvenaud_gradients_are_true_gradients(oracle64):
     params = rng.standard_normal(n) * 0.5
     target = rng.random((b.B, 5))
     _fd_check(oracle64, [L], params, b, target, rng.choice(n, 12, replace=False))
+
+
+def test_duvenaud_full_head_gradients_are_true_gradients(oracle64):
+    """Duvenaud -> full -> full (the wiring of example/msgpass_chemical, main.f90:129-157):
+    the reverse sweep through the dense head (athena_full_layer.f90:839-874) is exact."""
+    rng = np.random.default_rng(13)
+    b = _toy_batch(rng)
+    Ls = [duvenaud_spec([4, 4, 4], 2, 2, 1, 3, 5), full_spec(5, 7, "tanh"),
+          full_spec(7, 2, "leaky_relu", use_bias=False)]
+    n = oracle64.num_params(Ls)
+    assert n == oracle64.num_params(Ls[:1]) + (5 + 1) * 7 + 7 * 2
+    params = rng.standard_normal(n) * 0.5
+    target = rng.random((b.B, 2))
+    _fd_check(oracle64, Ls, params, b, target, rng.choice(n, 24, replace=False))
+
+
+def test_full_layer_reference_training_case(oracle32):
+    """test/test_full_network.f90:22-66: full(1 -> 1), kernel 'ones', zero bias, SGD lr 1,
+    x = 0.124, y = 0.765, loss mse: converges to |predict - y| < 1e-3 (the reference allows 1000
+    iterations; with loss = (p-y)^2 / 2 the error shrinks by -x^2 per step, so 2 suffice)."""
+    b = Batch(np.array([1], np.int32), np.array([0], np.int32), np.array([1, 1], np.int32),
+              np.zeros((2, 0), np.int32), np.zeros((1, 1), np.float32), None)
+    L = full_spec(1, 1)
+    params = np.array([1.0, 0.0], np.float32)
+    x = np.array([[0.124]], np.float32)
+    y = 0.765
+    errs = []
+    for it in range(1000):
+        out, _, _ = oracle32.layer_fwd_bwd(L, params, b, x=x)
+        errs.append(float(out[0, 0]) - y)
+        if abs(errs[-1]) < 1e-3:
+            break
+        _, g, _ = oracle32.layer_fwd_bwd(L, params, b, g_out=np.array([[errs[-1]]], np.float32), x=x)
+        params = params - 1.0 * g
+    assert len(errs) <= 3 and abs(errs[-1]) < 1e-3
+    assert abs(errs[1] / errs[0] + 0.124 ** 2) < 1e-5
 
 
 def test_kipf_single_step_weight_gradient_is_true_gradient(oracle64):
