@@ -180,6 +180,12 @@ struct Batch : Object {
   DevBuf tile_ops;
   uint8_t* col8 = nullptr;   // [Z] CSR neighbour - tile first row
   uint8_t* csc8 = nullptr;   // [Z] CSC source    - tile first row
+  // adjacency rows as 128-bit masks over the tile's vertices (CSR / CSC direction) for the
+  // tensor-core gather; multi_edges: -1 unknown (status not read yet), 0 none, 1 some pair
+  // repeats (bits cannot carry a multiplicity: the list kernels are used)
+  uint4* abits = nullptr;
+  uint4* atbits = nullptr;
+  int multi_edges = -1;
   float* rsdeg = nullptr;    // [V]
   int32_t* vcount = nullptr; // [V] number of vertices of the vertex's graph (MSE cell size)
   // rows (CSR) / columns (CSC) with more than LONG_ROW entries: aggregated by a whole CTA

@@ -298,8 +298,29 @@ __global__ void k_tile_operands(const int4* __restrict__ tiles, const int32_t* _
                                 const int32_t* __restrict__ deg, uint8_t* __restrict__ col8,
                                 uint8_t* __restrict__ csc8, float* __restrict__ rsdeg,
                                 const int32_t* __restrict__ vgraph,
-                                const int32_t* __restrict__ nv, int32_t* __restrict__ vcount) {
+                                const int32_t* __restrict__ nv, int32_t* __restrict__ vcount,
+                                const int32_t* __restrict__ row_ptr,
+                                const int32_t* __restrict__ csc_ptr, uint4* __restrict__ abits,
+                                uint4* __restrict__ atbits, int32_t* __restrict__ multi) {
   const int4 ti = tiles[blockIdx.x];
+  // adjacency rows of the tile as 128-bit masks (bit c = an entry to tile-local vertex c),
+  // CSR and CSC direction: the operand of the tensor-core gather (pipe_tcg.cu).  A repeated
+  // (row, column) pair cannot be a bit; *multi reports it and the batch keeps the list path.
+  for (int i = threadIdx.x; i < 2 * ti.y; i += blockDim.x) {
+    const int r = i >> 1, dir = i & 1;
+    const int32_t* ptr = dir ? csc_ptr : row_ptr;
+    const int32_t* idx = dir ? csc_src : col;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    bool dup = false;
+    for (int e = ptr[ti.x + r]; e < ptr[ti.x + r + 1]; ++e) {
+      const int c = idx[e] - ti.x;
+      const uint32_t bit = 1u << (c & 31);
+      dup |= (w[(c >> 5) & 3] & bit) != 0u;
+      w[(c >> 5) & 3] |= bit;
+    }
+    (dir ? atbits : abits)[ti.x + r] = make_uint4(w[0], w[1], w[2], w[3]);
+    if (dup) atomicOr(multi, 1);
+  }
   for (int e = threadIdx.x; e < ti.w; e += blockDim.x) {
     col8[ti.z + e] = static_cast<uint8_t>(col[ti.z + e] - ti.x);
     csc8[ti.z + e] = static_cast<uint8_t>(csc_src[ti.z + e] - ti.x);
@@ -634,14 +655,17 @@ ATHENA_API int athena_cuda_batch_create(athena_handle_t* batch, int32_t num_grap
   if (b->num_tiles > 0) {
     const size_t z16 = (size_t)round_up(Z + 32, 16);
     const size_t v4 = (size_t)round_up(V + 8, 4);
-    ATH_TRY(b->tile_ops.reserve(2 * z16 + 2 * sizeof(float) * v4));
+    ATH_TRY(b->tile_ops.reserve(2 * z16 + 2 * sizeof(float) * v4 + 2 * sizeof(uint4) * v4));
     b->col8 = b->tile_ops.as<uint8_t>();
     b->csc8 = b->col8 + z16;
     b->rsdeg = reinterpret_cast<float*>(b->csc8 + z16);
     b->vcount = reinterpret_cast<int32_t*>(b->rsdeg + v4);
+    b->abits = reinterpret_cast<uint4*>(b->vcount + v4);
+    b->atbits = b->abits + v4;
     k_tile_operands<<<b->num_tiles, 256, 0, st>>>(b->tiles.as<int4>(), b->col, b->csc_src, b->deg,
                                                  b->col8, b->csc8, b->rsdeg, b->vgraph, b->nv,
-                                                 b->vcount);
+                                                 b->vcount, b->row_ptr, b->csc_ptr, b->abits,
+                                                 b->atbits, status + 2);
     ATH_LAUNCHED();
   }
   Batch* raw = b.release();
@@ -668,6 +692,7 @@ ATHENA_API int athena_cuda_batch_status(athena_handle_t batch) {
   int32_t st[4];
   ATH_CUDA(cudaMemcpyAsync(st, b->status.p, sizeof(st), cudaMemcpyDeviceToHost, ctx().stream));
   ATH_CUDA(cudaStreamSynchronize(ctx().stream));
+  b->multi_edges = st[2] != 0 ? 1 : 0;
   ATH_REQUIRE(st[0] == INT_MAX, ATHENA_ERR_GRAPH,
               "graph adjacency matrix has indices greater than the number of vertices "
               "(or inconsistent adj_ia) in sample %d",
