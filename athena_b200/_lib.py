@@ -13,7 +13,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libathena_cuda.so")
+# ATHENA_CUDA_LIB: load another build of the library (A/B experiments on the GPU box)
+LIB_PATH = os.environ.get("ATHENA_CUDA_LIB") or os.path.join(_HERE, "lib", "libathena_cuda.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -76,7 +76,8 @@ constexpr int EPI_PITCH = 36;                 // floats per staged row (32 + 4 p
 constexpr int EPI_PATCH = 32 * EPI_PITCH;
 constexpr int AUX_PITCH = 68;                 // floats per operand row (64 + 4 pad)
 // STACKED: the accumulator holds hi | lo partial products side by side (N columns each).
-template <int ACT, int EPI, int N, bool STACKED = true>
+// [HB, HE): the 32-column halves this call handles (pipe_tcg.cu gives each half its own warp).
+template <int ACT, int EPI, int N, bool STACKED = true, int HB = 0, int HE = N / 32>
 __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, int nrows,
                                                float* __restrict__ out_tile,
                                                const float* aux_row /* shared memory */,
@@ -87,7 +88,7 @@ __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, i
   float lsum = 0.f;
   float* srow = patch + lane * EPI_PITCH;
 #pragma unroll
-  for (int half = 0; half < N / 32; ++half) {
+  for (int half = HB; half < HE; ++half) {
     uint32_t mbits = 0;
 #pragma unroll
     for (int cg = 0; cg < 2; ++cg) {
@@ -96,7 +97,7 @@ __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, i
       const uint32_t taddr = tacc + (static_cast<uint32_t>(q * 32) << 16) + col0;
       tmem_ld16(taddr, vh);
       if (STACKED) tmem_ld16(taddr + N, vl);
-      if (half == N / 32 - 1 && cg == 1) {
+      if (half == HE - 1 && cg == 1) {
         tc_fence_before();
         mbar_arrive(acc_empty);  // the accumulator buffer may be overwritten now
       }

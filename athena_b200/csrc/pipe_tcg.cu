@@ -35,6 +35,7 @@
 // Batches in which some (row, column) pair repeats (multi-edges) keep the list kernels.
 #include <algorithm>
 #include <cstdio>
+#include <vector>
 
 #include "athena_internal.h"
 #include "pipe_common.cuh"
@@ -73,19 +74,42 @@ __device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity, int 
   }
 }
 
+constexpr int TCG_TRACE_TILES = 16;
+#define TCG_TRACE(role, slot)                                                            \
+  do {                                                                                   \
+    if (a.trace != nullptr && blockIdx.x == a.dbg && j >= 0 && j < TCG_TRACE_TILES)      \
+      a.trace[((role) * TCG_TRACE_TILES + j) * 8 + (slot)] = clock64();                  \
+  } while (0)
+
 template <int EPI>
 struct TcgCfg {
   static constexpr int F = 64, N = 64;
-  static constexpr int NS = EPI == EPI_MSE ? 1 : 2;             // ring stages (shared memory budget)
-  static constexpr int SPLIT_WARP0 = 0;                          // warps 0..3
-  static constexpr int BUILD_WARP0 = 4;                          // warps 4..7   (warp % 4 = TMEM lane quarter)
-  static constexpr int FIX_WARP0 = 8;                            // warps 8..11
-  static constexpr int EPI_WARP0 = 12;                           // warps 12..15
-  static constexpr int PRODUCER_WARP = 16;
-  static constexpr int MMA_WARP = 17;
-  static constexpr int THREADS = 18 * 32;
+  // Ring stages.  The split warps pull a stage into registers as soon as it lands, so the
+  // next copy is issued almost immediately; deeper rings measured the same or slower (fwd
+  // 60.1 / 61.6 / 62.0 us for 1 / 2 / 3 stages), so the shared memory is left to the L1.
+  static constexpr int NS = 1;
+  // Operand tiles of the epilogue (saved activations / target).  Two tiles (copy for tile
+  // j + 2 issued when tile j is done) measured slower than one with this epilogue (96 vs 83 us
+  // for the fused MSE step): the kernel is bound by its HBM stream, not by this latency.
+  static constexpr int NAUX = 1;
+  static constexpr int SPLIT_WARP0 = 0;                          // warps 0..7
+  static constexpr int SPLIT_THREADS = 256;
+  static constexpr int BUILD_WARP0 = 8;                          // warps 8..11  (warp % 4 = TMEM lane quarter)
+  // fix and epilogue: TWO warps per TMEM lane quarter, one per 32-column half of the tile
+  // (their per-tile work is a chain of TMEM / shared-memory round trips; more warps = more
+  // of those latencies in flight)
+  // (Tried: two fix and two epilogue warps per TMEM lane quarter, one per 32-column half.
+  // No gain -- 31 warps leave 64 registers per thread and the roles wait for memory anyway.)
+  static constexpr int FIX_WARP0 = 12;                           // warps 12..15
+  static constexpr int EPI_WARP0 = 16;                           // warps 16..19
+  static constexpr int PRODUCER_WARP = 20;
+  static constexpr int MMA_WARP = PRODUCER_WARP + 1;             // issues G (and owns the TMEM allocation)
+  static constexpr int MMA_T_WARP = PRODUCER_WARP + 2;           // issues T
+  static constexpr int THREADS = (PRODUCER_WARP + 3) * 32;
+  static constexpr int STAGE_W_THREADS = 8 * 32;                 // fix + epilogue warps
   static constexpr int X_BYTES = TILE_ROWS * F * 4;              // 32 KB of raw feature rows
   static constexpr int RS_BYTES = (TILE_ROWS + 8) * 4;
+  static constexpr int AUX_TILE = TILE_ROWS * AUX_PITCH * 4;
   static constexpr int STAGE_BYTES = (X_BYTES + RS_BYTES + 127) / 128 * 128;
   static constexpr int OP_BLK = TILE_ROWS * 128;                 // [128 vertices x 32 features]
   static constexpr int OP_BYTES = (F / 32) * OP_BLK;             // hi (or lo) feature operand
@@ -95,16 +119,24 @@ struct TcgCfg {
   static constexpr int OFF_W = 2 * OP_BYTES;
   static constexpr int OFF_RING = OFF_W + (F / 32) * W_BLK;
   static constexpr int OFF_AUX = OFF_RING + NS * STAGE_BYTES;
-  static constexpr int AUX_BYTES = EPI != EPI_ACT ? TILE_ROWS * AUX_PITCH * 4 : 0;
-  static constexpr int OFF_BAR = OFF_AUX + AUX_BYTES;
+  static constexpr int AUX_BYTES = EPI != EPI_ACT ? NAUX * AUX_TILE : 0;
+  static constexpr int OFF_BAR = OFF_RING + NS * STAGE_BYTES + AUX_BYTES;
   static constexpr int OFF_EPI = OFF_BAR + 256 + 512;
-  static constexpr int OFF_FIX = OFF_EPI + 4 * EPI_PATCH * 4;
-  static constexpr int FIX_BYTES = EPI != EPI_ACTGRAD ? 4 * EPI_PATCH * 4 : 0;  // P is stored forward only
+  static constexpr int FIX_PATCH = 32 * 16;                      // floats per fix / epilogue warp patch
+  static constexpr int EPI_PATCH_FLOATS = EPI_PATCH;             // pipe::epilogue_tile: 32-column groups
+  static constexpr int OFF_FIX = OFF_EPI + 4 * EPI_PATCH_FLOATS * 4;
+  static constexpr int FIX_BYTES = EPI != EPI_ACTGRAD ? 4 * FIX_PATCH * 4 : 0;  // P is stored forward only
   static constexpr int SMEM = 1024 + OFF_FIX + FIX_BYTES;
   static_assert(SMEM <= 232448, "shared memory budget");
   static constexpr uint32_t T_ADJ = 0, T_P = 128, T_O = 384;     // TMEM columns
 };
 
+// Every role runs its loop body once "dry" (iteration -1: an empty tile, no barrier traffic,
+// scratch TMEM buffers) before the first real tile.  A CTA only owns ~14 tiles, and the
+// first pass of each role through its code misses the instruction cache (measured: 4-9
+// thousand clocks per role, serialised along the tile-0 dependency chain = a third of the
+// kernel).  The dry pass takes those misses in all roles AT ONCE while the first TMA copy
+// is in flight; it must execute the same instructions, hence one loop, not a copy.
 template <bool TRANSB, int EPI>
 __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs a) {
   using Cfg = TcgCfg<EPI>;
@@ -116,28 +148,40 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
   uint8_t* sW = smem + Cfg::OFF_W;
   uint8_t* ring = smem + Cfg::OFF_RING;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint64_t* full = bars;                  // [NS]  TMA landed
-  uint64_t* empty = bars + 2;             // [NS]  split warps hold the stage in registers
-  uint64_t* ops_ready = bars + 4;         // feature operand (hi/lo) of tile j staged
-  uint64_t* adj_ready = bars + 5;         // adjacency of tile j in TMEM
-  uint64_t* g_done = bars + 6;            // G(j) finished: operand buffers + ADJ reusable
-  uint64_t* p_full = bars + 7;            // [2] P accumulator of tile j complete
-  uint64_t* p_fixed = bars + 9;           // [2] scaled hi/lo P back in TMEM
-  uint64_t* o_full = bars + 11;           // [2]
-  uint64_t* o_empty = bars + 13;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
-  float* loss_red = reinterpret_cast<float*>(smem + Cfg::OFF_BAR + 256);  // [128], EPI_MSE
+  uint64_t* full = bars;                  // [NS <= 3]  TMA landed
+  uint64_t* empty = bars + 3;             // [NS]  split warps hold the stage in registers
+  uint64_t* ops_ready = bars + 6;         // feature operand (hi/lo) of tile j staged
+  uint64_t* adj_ready = bars + 7;         // adjacency of tile j in TMEM
+  uint64_t* g_done = bars + 8;            // G(j) finished: operand buffers + ADJ reusable
+  uint64_t* p_full = bars + 9;            // [2] P accumulator of tile j complete
+  uint64_t* p_fixed = bars + 11;          // [2] scaled hi/lo P back in TMEM
+  uint64_t* o_full = bars + 13;           // [2]
+  uint64_t* o_empty = bars + 15;          // [2]
+  uint64_t* warm = bars + 17;             // W staged + dry passes of the fix / epilogue warps done
+  uint64_t* dummy = bars + 18;            // sink for the arrivals of the dry epilogue pass
+  uint64_t* t_done = bars + 19;           // [2] T(j) has read P[j & 1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  float* loss_red = reinterpret_cast<float*>(smem + Cfg::OFF_BAR + 256);  // [256], EPI_MSE
   float* sAux = reinterpret_cast<float*>(smem + Cfg::OFF_AUX);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int step = gridDim.x;
+  if (a.trace != nullptr && tid == 0) {
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.trace[6 * TCG_TRACE_TILES * 8 + 2 * blockIdx.x] = gt;
+    if (blockIdx.x == a.dbg) {
+      a.trace[(5 * TCG_TRACE_TILES + 14) * 8 + 0] = clock64();
+      a.trace[(5 * TCG_TRACE_TILES + 14) * 8 + 1] = gt;
+    }
+  }
 
   if (warp == Cfg::MMA_WARP) tmem_alloc<512>(tmem_slot);
   if (tid == 0) {
     for (int s = 0; s < Cfg::NS; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 128);
+      mbar_init(&empty[s], Cfg::SPLIT_THREADS);
     }
-    mbar_init(ops_ready, 128);
+    mbar_init(ops_ready, Cfg::SPLIT_THREADS);
     mbar_init(adj_ready, 128);
     mbar_init(g_done, 1);
     for (int b = 0; b < 2; ++b) {
@@ -145,40 +189,52 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
       mbar_init(&p_fixed[b], 128);
       mbar_init(&o_full[b], 1);
       mbar_init(&o_empty[b], 128);
+      mbar_init(&t_done[b], 1);
     }
+    mbar_init(warm, Cfg::STAGE_W_THREADS);
+    mbar_init(dummy, 1u << 19);
     mbar_fence_init();
   }
-  // stacked weight operand [hi(W') ; lo(W')], W' = op(W) as [N][F] K-major (as k_pipe_gather)
-  for (int item = tid; item < N * (F / 4); item += Cfg::THREADS) {
-    const int n = item / (F / 4), kc = item - n * (F / 4);
-    float4 w;
-    if (!TRANSB) {  // W row-major [F][N]: W'[n][k] = W[k][n]
-      const float* src = a.W + (kc * 4) * N + n;
-      w = make_float4(__ldg(src), __ldg(src + N), __ldg(src + 2 * N), __ldg(src + 3 * N));
-    } else {        // W row-major [N][F] used as is
-      w = __ldg(reinterpret_cast<const float4*>(a.W + n * F + kc * 4));
-    }
-    float4 hi, lo;
-    split_tf32(w, hi, lo);
-    uint8_t* blk = sW + (kc >> 3) * Cfg::W_BLK;
-    *reinterpret_cast<float4*>(blk + sw128_off(n, kc & 7)) = hi;
-    *reinterpret_cast<float4*>(blk + sw128_off(N + n, kc & 7)) = lo;
-  }
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const bool has_coef = a.rs != nullptr;
+  constexpr int ns = Cfg::NS;
+  int my_tiles = 0;
+  for (int t = blockIdx.x; t < a.num_tiles; t += step) ++my_tiles;
+
+  // stacked weight operand [hi(W') ; lo(W')], W' = op(W) as [N][F] K-major (as k_pipe_gather);
+  // staged by the fix + epilogue warps, which have nothing to do until the first G finishes
+  if (warp >= Cfg::FIX_WARP0 && warp < Cfg::PRODUCER_WARP) {
+    for (int item = tid - Cfg::FIX_WARP0 * 32; item < N * (F / 4); item += Cfg::STAGE_W_THREADS) {
+      const int n = item / (F / 4), kc = item - n * (F / 4);
+      float4 w;
+      if (!TRANSB) {  // W row-major [F][N]: W'[n][k] = W[k][n]
+        const float* src = a.W + (kc * 4) * N + n;
+        w = make_float4(__ldg(src), __ldg(src + N), __ldg(src + 2 * N), __ldg(src + 3 * N));
+      } else {        // W row-major [N][F] used as is
+        w = __ldg(reinterpret_cast<const float4*>(a.W + n * F + kc * 4));
+      }
+      float4 hi, lo;
+      split_tf32(w, hi, lo);
+      uint8_t* blk = sW + (kc >> 3) * Cfg::W_BLK;
+      *reinterpret_cast<float4*>(blk + sw128_off(n, kc & 7)) = hi;
+      *reinterpret_cast<float4*>(blk + sw128_off(N + n, kc & 7)) = lo;
+    }
+    fence_async_smem();
+  }
 
   if (warp == Cfg::PRODUCER_WARP) {
     // ===================== producer: TMA bulk copies into the ring =====================
     if (lane == 0) {
       int j = 0;
       for (int t = blockIdx.x; t < a.num_tiles; t += step, ++j) {
-        const int s = j % Cfg::NS;
-        const uint32_t ph = (j / Cfg::NS) & 1;
+        const int s = j % ns;
+        const uint32_t ph = (j / ns) & 1;
+        TCG_TRACE(0, 0);
         mbar_wait_g(&empty[s], ph ^ 1u, 0);
+        TCG_TRACE(0, 1);
         const int4 ti = __ldg(a.tiles + t);
         const int r0 = ti.x, nrows = ti.y;
         const int ra = r0 & ~3, rcnt = (r0 + nrows - ra + 3) & ~3;
@@ -190,69 +246,89 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
       }
     }
   } else if (warp == Cfg::MMA_WARP) {
-    // ===================== MMA issuer ==================================================
-    if (lane == 0) {
-      const uint32_t bHi = smem_u32(sBhi), bLo = smem_u32(sBlo), wAddr = smem_u32(sW);
-      constexpr uint32_t IDESC_G = make_idesc(128, F, false, true);   // B = features, MN-major
-      constexpr uint32_t IDESC_T = make_idesc(128, N, false, false);  // B = W', K-major
-      int my_tiles = 0;
-      for (int t = blockIdx.x; t < a.num_tiles; t += step) ++my_tiles;
-      for (int j = 0; j <= my_tiles; ++j) {
-        if (j < my_tiles) {
-          // ---- G(j): P[j&1] = ADJ . (Xhi + Xlo)
+    // ===================== MMA issuer, G: [P(hi) | P(lo)] = ADJ . [Xhi | Xlo] ==========
+    // Every tcgen05.mma costs tens of clocks of issue latency in the issuing thread whatever
+    // its N.  Hence (a) the hi and lo halves of the feature operand are stacked along N (one
+    // N = 128 instruction per k-step), (b) G and T are issued by two different warps; the
+    // order between the two streams is carried by mbarriers (p_fixed, t_done), and (c) the
+    // warp stays converged with the instruction predicated on one elected lane.
+    {
+      const uint32_t leader = elect_one();
+      const uint32_t bHi = smem_u32(sBhi);
+      constexpr uint32_t IDESC_G = make_idesc(128, 2 * F, false, true);  // B MN-major
+      for (int j = -1; j < my_tiles; ++j) {
+        const bool dry = j < 0;
+        if (!dry) {
+          if (lane == 0) TCG_TRACE(1, 0);
           mbar_wait_g(ops_ready, j & 1, 1);
           mbar_wait_g(adj_ready, j & 1, 2);
-          tc_fence_after();
-          const uint32_t tp = tmem + Cfg::T_P + (j & 1) * 128;
-          // The tensor core adds into its fp32 accumulator with truncation: the small (lo)
-          // terms go first, while the accumulator is small, so that only the hi terms (one
-          // per neighbour block) contribute a full-size truncation step.
-#pragma unroll
-          for (int ks = 0; ks < TILE_ROWS / 8; ++ks) {
-            const uint64_t dl = make_desc_mn32(bLo + ks * 1024, Cfg::OP_BLK, 512);
-            umma_tf32_ts(tp, tmem + Cfg::T_ADJ + ks * 8, dl, IDESC_G, ks ? 1u : 0u);
-          }
-#pragma unroll
-          for (int ks = 0; ks < TILE_ROWS / 8; ++ks) {
-            const uint64_t dh = make_desc_mn32(bHi + ks * 1024, Cfg::OP_BLK, 512);
-            umma_tf32_ts(tp, tmem + Cfg::T_ADJ + ks * 8, dh, IDESC_G, 1u);
-          }
-          umma_commit(g_done);
-          umma_commit(&p_full[j & 1]);
+          if (j >= 2) mbar_wait_g(&t_done[j & 1], ((j - 2) >> 1) & 1, 11);  // T(j-2) has read P[j & 1]
+          if (lane == 0) TCG_TRACE(1, 1);
         }
-        if (j >= 1) {
-          // ---- T(j-1): O = P . Whi + P . Wlo + Plo . Whi
-          const int jj = j - 1, b = jj & 1;
-          mbar_wait_g(&p_fixed[b], (jj >> 1) & 1, 3);
-          mbar_wait_g(&o_empty[b], ((jj >> 1) & 1) ^ 1u, 4);
-          tc_fence_after();
-          const uint32_t tp = tmem + Cfg::T_P + b * 128, to = tmem + Cfg::T_O + b * N;
-          // cross terms first (see G): P . Wlo, Plo . Whi, then P . Whi
+        tc_fence_after();
+        const uint32_t tp = tmem + Cfg::T_P + (dry ? 128u : (j & 1) * 128u);
 #pragma unroll
-          for (int k8 = 0; k8 < F / 8; ++k8) {
-            const uint32_t wk = wAddr + (k8 >> 2) * Cfg::W_BLK + (k8 & 3) * 32;
-            const uint64_t dwh = make_desc(wk, 16, 1024);
-            const uint64_t dwl = make_desc(wk + N * 128, 16, 1024);
-            umma_tf32_ts(to, tp + k8 * 8, dwl, IDESC_T, k8 ? 1u : 0u);
-            umma_tf32_ts(to, tp + 64 + k8 * 8, dwh, IDESC_T, 1u);
-          }
-#pragma unroll
-          for (int k8 = 0; k8 < F / 8; ++k8) {
-            const uint32_t wk = wAddr + (k8 >> 2) * Cfg::W_BLK + (k8 & 3) * 32;
-            umma_tf32_ts(to, tp + k8 * 8, make_desc(wk, 16, 1024), IDESC_T, 1u);
-          }
-          umma_commit(&o_full[b]);
+        for (int ks = 0; ks < TILE_ROWS / 8; ++ks)
+          umma_tf32_ts_w(leader, tp, tmem + Cfg::T_ADJ + ks * 8,
+                         make_desc_mn32(bHi + ks * 1024, Cfg::OP_BLK, 512), IDESC_G,
+                         ks ? 1u : 0u);
+        if (!dry) {
+          umma_commit_w(leader, g_done);
+          umma_commit_w(leader, &p_full[j & 1]);
+          if (lane == 0) TCG_TRACE(1, 2);
+        } else {
+          mbar_wait_g(warm, 0, 10);  // the dry pass of the fix warps (it writes P[1]) is over
         }
+        __syncwarp();
+      }
+    }
+  } else if (warp == Cfg::MMA_T_WARP) {
+    // ===================== MMA issuer, T: O = Plo . Whi + P . Wlo + P . Whi ==============
+    // (small terms first: the tensor core adds into its fp32 accumulator with truncation)
+    {
+      const uint32_t leader = elect_one();
+      const uint32_t wAddr = smem_u32(sW);
+      constexpr uint32_t IDESC_T = make_idesc(128, N, false, false);  // B = W', K-major
+      for (int j = -1; j < my_tiles; ++j) {
+        const bool dry = j < 0;
+        const int b = dry ? 1 : (j & 1);
+        if (!dry) {
+          if (lane == 0) TCG_TRACE(1, 3);
+          mbar_wait_g(&p_fixed[b], (j >> 1) & 1, 3);
+          mbar_wait_g(&o_empty[b], ((j >> 1) & 1) ^ 1u, 4);
+          if (lane == 0) TCG_TRACE(1, 4);
+        }
+        tc_fence_after();
+        const uint32_t tp = tmem + Cfg::T_P + b * 128, to = tmem + Cfg::T_O + b * N;
+#pragma unroll
+        for (int k8 = 0; k8 < F / 8; ++k8) {
+          const uint32_t wk = wAddr + (k8 >> 2) * Cfg::W_BLK + (k8 & 3) * 32;
+          umma_tf32_ts_w(leader, to, tp + 64 + k8 * 8, make_desc(wk, 16, 1024), IDESC_T,
+                         k8 ? 1u : 0u);
+          umma_tf32_ts_w(leader, to, tp + k8 * 8, make_desc(wk + N * 128, 16, 1024), IDESC_T, 1u);
+        }
+#pragma unroll
+        for (int k8 = 0; k8 < F / 8; ++k8) {
+          const uint32_t wk = wAddr + (k8 >> 2) * Cfg::W_BLK + (k8 & 3) * 32;
+          umma_tf32_ts_w(leader, to, tp + k8 * 8, make_desc(wk, 16, 1024), IDESC_T, 1u);
+        }
+        if (!dry) {
+          umma_commit_w(leader, &o_full[b]);
+          umma_commit_w(leader, &t_done[b]);
+          if (lane == 0) TCG_TRACE(1, 5);
+        } else {
+          mbar_wait_g(warm, 0, 12);  // the weights are staged
+        }
+        __syncwarp();
       }
     }
   } else if (warp >= Cfg::EPI_WARP0) {
     // ===================== epilogue: TMEM -> registers -> global rows ==================
     const int q = warp - Cfg::EPI_WARP0;
-    float* patch = reinterpret_cast<float*>(smem + Cfg::OFF_EPI) + q * EPI_PATCH;
+    float* patch = reinterpret_cast<float*>(smem + Cfg::OFF_EPI) + q * Cfg::EPI_PATCH_FLOATS;
     const bool use_mask = (EPI == EPI_ACTGRAD) && a.mask_in != nullptr;
     const bool use_aux = (EPI != EPI_ACT) && a.aux != nullptr && !use_mask;
     const int my_row = q * 32 + lane;
-    float* aux_row = sAux + my_row * AUX_PITCH;
     auto tile_at = [&](int t) { return t < a.num_tiles ? __ldg(a.tiles + t) : make_int4(0, 0, 0, 0); };
     auto count_at = [&](int t) {
       int c = 1;
@@ -262,14 +338,18 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
       }
       return c;
     };
-    // second operand (saved activations / target): each warp prefetches its own 32 rows of
-    // the next tile with cp.async into rows padded to 272 B (see pipe_tc.cu)
-    auto issue_aux = [&](const int4& ti) {
+    // Second operand (saved activations / target): each warp prefetches its own 32 rows with
+    // cp.async into rows padded to 272 B (conflict-free row-per-thread reads).  One cp.async
+    // group per tile, possibly empty.  With two operand tiles (MSE) the copy for tile j + 2
+    // is issued when tile j is done, i.e. a whole tile period before it is needed; with one
+    // tile (backward with saved activations) only the rest of the period hides it.
+    auto issue_aux = [&](int t, int buf) {
+      const int4 ti = tile_at(t);
       const float* src = a.aux + (static_cast<size_t>(ti.x) + q * 32) * N;
-      float* dst = sAux + q * 32 * AUX_PITCH;
+      float* dst = sAux + buf * (TILE_ROWS * AUX_PITCH) + q * 32 * AUX_PITCH;
       const int rows = min(32, ti.y - q * 32);
 #pragma unroll
-      for (int it = 0; it < 32 * (N / 4) / 32; ++it) {
+      for (int it = 0; it < N / 4; ++it) {
         const int idx = it * 32 + lane;
         const int r = idx / (N / 4), c = idx - r * (N / 4);
         if (r < rows)
@@ -280,67 +360,78 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (use_aux && static_cast<int>(blockIdx.x) < a.num_tiles) issue_aux(tile_at(blockIdx.x));
     int count_next = count_at(blockIdx.x);
-    int j = 0;
     float lsum = 0.f;
-    for (int t = blockIdx.x; t < a.num_tiles; t += step, ++j) {
-      const int b = j & 1;
-      const int4 ti = __ldg(a.tiles + t);
+    for (int j = -1; j < my_tiles; ++j) {
+      const bool dry = j < 0;
+      const int t = blockIdx.x + j * step;
+      const int b = dry ? 1 : (j & 1);
+      const int4 ti = dry ? make_int4(0, 0, 0, 0) : __ldg(a.tiles + t);
       const int count = count_next;
-      count_next = count_at(t + step);
+      if (!dry) count_next = count_at(t + step);
       float* out_tile = a.out + static_cast<size_t>(ti.x) * N;
       const bool row_valid = my_row < ti.y;
-      uint32_t min_w[N / 32] = {};
+      uint32_t m0 = 0, m1 = 0;
       uint32_t* mout = nullptr;
       if (row_valid) {
         const size_t grow = static_cast<size_t>(ti.x) + my_row;
         if (use_mask) {
-#pragma unroll
-          for (int w = 0; w < N / 32; ++w) min_w[w] = __ldg(a.mask_in + grow * (N / 32) + w);
+          m0 = __ldg(a.mask_in + grow * 2);
+          m1 = __ldg(a.mask_in + grow * 2 + 1);
         }
-        if (EPI == EPI_ACT && a.mask_out != nullptr) mout = a.mask_out + grow * (N / 32);
+        if (EPI == EPI_ACT && a.mask_out != nullptr) mout = a.mask_out + grow * 2;
       }
-      mbar_wait_g(&o_full[b], (j >> 1) & 1, 5);
+      if (!dry) {
+        if (q == 0 && lane == 0) TCG_TRACE(5, 0);
+        mbar_wait_g(&o_full[b], (j >> 1) & 1, 5);
+        if (q == 0 && lane == 0) TCG_TRACE(5, 1);
+      }
       tc_fence_after();
-      if (use_aux) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (use_aux && !dry) {
+        if (Cfg::NAUX == 2)
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
       }
+      const float* aux_row =
+          sAux + (Cfg::NAUX == 2 ? (j & 1) : 0) * (TILE_ROWS * AUX_PITCH) + my_row * AUX_PITCH;
       const uint32_t tacc = tmem + Cfg::T_O + b * N;
+      uint64_t* release = dry ? dummy : &o_empty[b];
       const float scale =
           (EPI == EPI_MSE && row_valid) ? 1.f / static_cast<float>(N * count) : 0.f;
       const int act = use_aux || use_mask || EPI == EPI_ACT ? a.act : ATHENA_ACT_NONE;
+      const uint32_t min_w[2] = {m0, m1};
+#define TCG_EPI(ACT)                                                                          \
+  lsum += epilogue_tile<ACT, EPI, N, false>(tacc, q, lane, ti.y, out_tile, aux_row, scale,      \
+                                            patch, release, false, mout, use_mask, min_w)
       switch (act) {
-        case ATHENA_ACT_RELU:
-          lsum += epilogue_tile<ATHENA_ACT_RELU, EPI, N, false>(
-              tacc, q, lane, ti.y, out_tile, aux_row, scale, patch, &o_empty[b], false, mout,
-              use_mask, min_w);
-          break;
-        case ATHENA_ACT_LEAKY_RELU:
-          lsum += epilogue_tile<ATHENA_ACT_LEAKY_RELU, EPI, N, false>(
-              tacc, q, lane, ti.y, out_tile, aux_row, scale, patch, &o_empty[b], false, mout,
-              use_mask, min_w);
-          break;
-        case ATHENA_ACT_SIGMOID:
-          lsum += epilogue_tile<ATHENA_ACT_SIGMOID, EPI, N, false>(
-              tacc, q, lane, ti.y, out_tile, aux_row, scale, patch, &o_empty[b], false, mout,
-              use_mask, min_w);
-          break;
-        case ATHENA_ACT_TANH:
-          lsum += epilogue_tile<ATHENA_ACT_TANH, EPI, N, false>(
-              tacc, q, lane, ti.y, out_tile, aux_row, scale, patch, &o_empty[b], false, mout,
-              use_mask, min_w);
-          break;
-        default:
-          lsum += epilogue_tile<ATHENA_ACT_NONE, EPI, N, false>(
-              tacc, q, lane, ti.y, out_tile, aux_row, scale, patch, &o_empty[b], false, mout,
-              use_mask, min_w);
-          break;
+        case ATHENA_ACT_RELU: TCG_EPI(ATHENA_ACT_RELU); break;
+        case ATHENA_ACT_LEAKY_RELU: TCG_EPI(ATHENA_ACT_LEAKY_RELU); break;
+        case ATHENA_ACT_SIGMOID: TCG_EPI(ATHENA_ACT_SIGMOID); break;
+        case ATHENA_ACT_TANH: TCG_EPI(ATHENA_ACT_TANH); break;
+        default: TCG_EPI(ATHENA_ACT_NONE); break;
       }
-      if (use_aux && t + step < a.num_tiles) {
+#undef TCG_EPI
+      if (dry) {
+        lsum = 0.f;  // whatever the scratch accumulator held
+        mbar_arrive(warm);
+      } else if (q == 0 && lane == 0) {
+        TCG_TRACE(5, 2);
+      }
+      if (use_aux) {
         __syncwarp();
-        issue_aux(tile_at(t + step));
+        if (Cfg::NAUX == 2) {
+          // after the dry pass: tiles 0 and 1; after tile j: tile j + 2 into the buffer it frees
+          if (dry) {
+            issue_aux(blockIdx.x, 0);
+            issue_aux(blockIdx.x + step, 1);
+          } else {
+            issue_aux(t + 2 * step, j & 1);
+          }
+        } else {
+          issue_aux(t + step, 0);
+        }
       }
     }
     if (EPI == EPI_MSE) loss_red[my_row] = lsum;
@@ -348,7 +439,7 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
     // ===================== fix warps: P * deg_v^-1/2 -> hi / lo back into TMEM, P -> global ====
     const int q = warp - Cfg::FIX_WARP0;
     const int my_row = q * 32 + lane;
-    float* patch = reinterpret_cast<float*>(smem + Cfg::OFF_FIX) + q * EPI_PATCH;
+    float* patch = reinterpret_cast<float*>(smem + Cfg::OFF_FIX) + q * Cfg::FIX_PATCH;
     auto rs_at = [&](int t) {
       float w = 1.f;
       if (has_coef && t < a.num_tiles) {
@@ -358,53 +449,72 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
       return w;
     };
     float w_next = rs_at(blockIdx.x);
-    int j = 0;
-    for (int t = blockIdx.x; t < a.num_tiles; t += step, ++j) {
-      const int b = j & 1;
-      const int4 ti = __ldg(a.tiles + t);
+    for (int j = -1; j < my_tiles; ++j) {
+      const bool dry = j < 0;
+      const int t = blockIdx.x + j * step;
+      const int b = dry ? 1 : (j & 1);
+      const int4 ti = dry ? make_int4(0, 0, 0, 0) : __ldg(a.tiles + t);
       const float wv = w_next;
-      w_next = rs_at(t + step);
-      mbar_wait_g(&p_full[b], (j >> 1) & 1, 6);
+      if (!dry) {
+        w_next = rs_at(t + step);
+        if (q == 0 && lane == 0) TCG_TRACE(4, 0);
+        mbar_wait_g(&p_full[b], (j >> 1) & 1, 6);
+        if (q == 0 && lane == 0) TCG_TRACE(4, 1);
+      }
       tc_fence_after();
       const uint32_t tp = tmem + Cfg::T_P + b * 128 + (static_cast<uint32_t>(q * 32) << 16);
       const bool store_p = EPI != EPI_ACTGRAD && a.P != nullptr;
       float* p_tile = a.P + static_cast<size_t>(ti.x) * F;
-      float* srow = patch + lane * EPI_PITCH;
+#pragma unroll 1
+      for (int g = 0; g < F / 16; ++g) {
+        // P = (A . Xhi + A . Xlo) * deg_v^-1/2 ; hi -> columns 0..63, lo -> columns 64..127
+        float v[16], vl[16];
+        tmem_ld16_nowait(tp + g * 16, v);
+        tmem_ld16_nowait(tp + 64 + g * 16, vl);
+        tmem_ld_wait();
+        if (!dry && g == 0 && q == 0 && lane == 0) TCG_TRACE(4, 3);
+        uint32_t hi[16];
 #pragma unroll
-      for (int h = 0; h < F / 32; ++h) {
-        float v[32];
-        tmem_ld32(tp + h * 32, v);
-        uint32_t hi[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] *= wv;
+        for (int i = 0; i < 16; ++i) {
+          v[i] = (v[i] + vl[i]) * wv;
           hi[i] = __float_as_uint(v[i]) & 0xffffe000u;
         }
-        tmem_st32(tp + h * 32, hi);
+        tmem_st16(tp + g * 16, hi);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) hi[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
-        tmem_st32(tp + 64 + h * 32, hi);
+        for (int i = 0; i < 16; ++i) hi[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+        tmem_st16(tp + 64 + g * 16, hi);
+        if (!dry && g == 0 && q == 0 && lane == 0) TCG_TRACE(4, 4);
         if (store_p) {
-          // coalesced store of the propagated tile (the operand of dW = P^T gY)
+          // coalesced store of the propagated tile (the operand of dW = P^T gY) through a
+          // [32 rows][16 floats] patch whose 16-byte chunks are XOR-permuted with (row / 2) % 4:
+          // row-per-thread STS.128 and the two-rows-per-quarter-warp LDS.128 are conflict-free
+          const int sw = (lane >> 1) & 3;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(srow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(patch + lane * 16 + ((k ^ sw) << 2)) =
+                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
           __syncwarp();
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
+          for (int it = 0; it < 4; ++it) {
             const int idx = it * 32 + lane;
-            const int r = idx >> 3, c = idx & 7;
+            const int r = idx >> 2, c = idx & 3;
             const int trow = q * 32 + r;
             if (trow < ti.y)
-              *reinterpret_cast<float4*>(p_tile + static_cast<size_t>(trow) * F + h * 32 + c * 4) =
-                  *reinterpret_cast<const float4*>(patch + r * EPI_PITCH + c * 4);
+              *reinterpret_cast<float4*>(p_tile + static_cast<size_t>(trow) * F + g * 16 + c * 4) =
+                  *reinterpret_cast<const float4*>(patch + r * 16 + ((c ^ ((r >> 1) & 3)) << 2));
           }
           __syncwarp();
         }
+        if (!dry && g == 0 && q == 0 && lane == 0) TCG_TRACE(4, 5);
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_fixed[b]);
+      if (dry) {
+        mbar_arrive(warm);
+      } else {
+        mbar_arrive(&p_fixed[b]);
+        if (q == 0 && lane == 0) TCG_TRACE(4, 2);
+      }
     }
   } else if (warp >= Cfg::BUILD_WARP0) {
     // ===================== build warps: adjacency bits -> TMEM A operand ================
@@ -419,41 +529,63 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
       return w;
     };
     uint4 b_next = bits_at(blockIdx.x);
-    int j = 0;
-    for (int t = blockIdx.x; t < a.num_tiles; t += step, ++j) {
+    for (int j = -1; j < my_tiles; ++j) {
+      const bool dry = j < 0;  // the dry pass expands tile 0 as well (and is overwritten by it)
+      const int t = blockIdx.x + j * step;
       const uint4 bits = b_next;
-      b_next = bits_at(t + step);
-      mbar_wait_g(g_done, (j & 1) ^ 1u, 7);  // G(j-1) has read the previous adjacency
+      if (!dry) {
+        b_next = bits_at(t + step);
+        if (q == 0 && lane == 0) TCG_TRACE(3, 0);
+        mbar_wait_g(g_done, (j & 1) ^ 1u, 7);  // G(j-1) has read the previous adjacency
+        if (q == 0 && lane == 0) TCG_TRACE(3, 1);
+      }
       tc_fence_after();
       const uint32_t ta = tmem + Cfg::T_ADJ + (static_cast<uint32_t>(q * 32) << 16);
-      const uint32_t words[4] = {bits.x, bits.y, bits.z, bits.w};
-#pragma unroll
+      uint4 rot = bits;
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
+        const uint32_t w = rot.x;
+        rot = make_uint4(rot.y, rot.z, rot.w, 0u);
         uint32_t v[32];
+        if (__any_sync(0xffffffffu, w != 0u)) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = ((words[c] >> k) & 1u) ? 0x3f800000u : 0u;
+          for (int k = 0; k < 32; ++k) v[k] = ((w >> k) & 1u) ? 0x3f800000u : 0u;
+        } else {
+          // block diagonal: no row of this warp reaches these 32 vertices
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = 0u;
+        }
         tmem_st32(ta + c * 32, v);
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(adj_ready);
+      if (!dry) {
+        mbar_arrive(adj_ready);
+        if (q == 0 && lane == 0) TCG_TRACE(3, 2);
+      }
     }
   } else {
     // ===================== split warps: ring -> scaled hi / lo B operand ================
-    constexpr int LOADS = TILE_ROWS * (F / 4) / 128;  // 16-byte chunks per thread
-    int j = 0;
-    for (int t = blockIdx.x; t < a.num_tiles; t += step, ++j) {
-      const int s = j % Cfg::NS;
-      const uint32_t ph = (j / Cfg::NS) & 1;
-      const int4 ti = __ldg(a.tiles + t);
+    constexpr int LOADS = TILE_ROWS * (F / 4) / Cfg::SPLIT_THREADS;  // 16-byte chunks per thread
+    for (int j = -1; j < my_tiles; ++j) {
+      const bool dry = j < 0;
+      const int t = blockIdx.x + j * step;
+      const int jr = dry ? 0 : j;
+      const int s = jr % ns;
+      const uint32_t ph = (jr / ns) & 1;
+      const int4 ti = dry ? make_int4(0, 0, 0, 0) : __ldg(a.tiles + t);
       const int r0 = ti.x, nrows = ti.y;
       const uint8_t* st = ring + s * Cfg::STAGE_BYTES;
       const float* rss = reinterpret_cast<const float*>(st + Cfg::X_BYTES) + (r0 - (r0 & ~3));
-      mbar_wait_g(&full[s], ph, 8);
+      if (!dry) {
+        if (tid == 0) TCG_TRACE(2, 0);
+        mbar_wait_g(&full[s], ph, 8);
+        if (tid == 0) TCG_TRACE(2, 1);
+      }
       float4 x[LOADS];
 #pragma unroll
       for (int i = 0; i < LOADS; ++i) {
-        const int idx = tid + 128 * i;
+        const int idx = tid + Cfg::SPLIT_THREADS * i;
         const int row = idx >> 4;
         x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < nrows) {
@@ -467,11 +599,15 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
           }
         }
       }
-      mbar_arrive(&empty[s]);                // the stage lives in registers now
-      mbar_wait_g(g_done, (j & 1) ^ 1u, 9);  // G(j-1) has read the operand buffers
+      if (!dry) {
+        mbar_arrive(&empty[s]);                // the stage lives in registers now
+        if (tid == 0) TCG_TRACE(2, 2);
+        mbar_wait_g(g_done, (j & 1) ^ 1u, 9);  // G(j-1) has read the operand buffers
+        if (tid == 0) TCG_TRACE(2, 3);
+      }
 #pragma unroll
       for (int i = 0; i < LOADS; ++i) {
-        const int idx = tid + 128 * i;
+        const int idx = tid + Cfg::SPLIT_THREADS * i;
         const int row = idx >> 4, ch = idx & 15;
         float4 hi, lo;
         split_tf32(x[i], hi, lo);
@@ -480,7 +616,10 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
         *reinterpret_cast<float4*>(sBlo + off) = lo;
       }
       fence_async_smem();
-      mbar_arrive(ops_ready);
+      if (!dry) {
+        mbar_arrive(ops_ready);
+        if (tid == 0) TCG_TRACE(2, 4);
+      }
     }
   }
   tc_fence_before();
@@ -490,6 +629,15 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
       float tot = 0.f;
       for (int i = 0; i < 128; ++i) tot += loss_red[i];
       a.loss_part[blockIdx.x] = tot;
+    }
+  }
+  if (a.trace != nullptr && tid == 0) {
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.trace[6 * TCG_TRACE_TILES * 8 + 2 * blockIdx.x + 1] = gt;
+    if (blockIdx.x == a.dbg) {
+      a.trace[(5 * TCG_TRACE_TILES + 15) * 8 + 0] = clock64();
+      a.trace[(5 * TCG_TRACE_TILES + 15) * 8 + 1] = gt;
     }
   }
   tc_fence_before();
@@ -507,7 +655,50 @@ int launch_tcg_t(const GatherArgs& a) {
     attr = true;
   }
   const int grid = std::min(a.num_tiles, ctx().sm_count);
-  k_pipe_tcg<TRANSB, EPI><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(a);
+  GatherArgs b = a;
+  b.trace = nullptr;
+  static int trace_left = -1;
+  static long long* trace_buf = nullptr;
+  if (trace_left < 0) {
+    const char* e = getenv("ATHENA_DEBUG_TRACE");
+    trace_left = e ? atoi(e) : 0;
+  }
+  const size_t trace_n = (size_t)6 * TCG_TRACE_TILES * 8 + 2 * 256;
+  if (trace_left > 0) {
+    if (!trace_buf) cudaMalloc(&trace_buf, trace_n * sizeof(long long));
+    cudaMemsetAsync(trace_buf, 0, trace_n * sizeof(long long), ctx().stream);
+    b.trace = trace_buf;
+    const char* e = getenv("ATHENA_DEBUG_TRACE_BLOCK");
+    b.dbg = e ? atoi(e) : 0;
+  }
+  k_pipe_tcg<TRANSB, EPI><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(b);
+  if (trace_left > 0) {
+    --trace_left;
+    std::vector<long long> h(trace_n);
+    cudaStreamSynchronize(ctx().stream);
+    cudaMemcpy(h.data(), trace_buf, trace_n * sizeof(long long), cudaMemcpyDeviceToHost);
+    const long long t0 = h[(2 * TCG_TRACE_TILES + 0) * 8 + 0];
+    static const char* names[6] = {"producer", "mma", "split", "build", "fix", "epilogue"};
+    fprintf(stderr, "TRACE k_pipe_tcg EPI=%d\n", EPI);
+    {
+      const long long* se = h.data() + 6 * TCG_TRACE_TILES * 8;
+      long long s0 = se[0];
+      for (int c = 0; c < grid; ++c) s0 = std::min(s0, se[2 * c]);
+      fprintf(stderr, "TRACE cta start/end (ns after first start), tiles:");
+      for (int c = 0; c < grid; ++c)
+        fprintf(stderr, " %d:%lld/%lld", c, se[2 * c] - s0, se[2 * c + 1] - s0);
+      fprintf(stderr, "\n");
+    }
+    for (int role = 0; role < 6; ++role)
+      for (int j = 0; j < 16; ++j) {
+        fprintf(stderr, "TRACE %-8s tile %2d:", names[role], j);
+        for (int k = 0; k < 6; ++k) {
+          const long long v = h[(role * TCG_TRACE_TILES + j) * 8 + k];
+          fprintf(stderr, " %7lld", v ? (role == 5 && j >= 14 && k == 1 ? v % 100000000ll : v - t0) : -1);
+        }
+        fprintf(stderr, "\n");
+      }
+  }
   ATH_LAUNCHED_T(EPI == EPI_ACT ? "pipe_gather_fwd"
                  : EPI == EPI_MSE ? "pipe_gather_fwd_mse" : "pipe_gather_bwd");
   return ATHENA_OK;
