@@ -239,7 +239,7 @@ k_step(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
 // clip off), (3) applies the optimiser step and zeroes the gradients.  Fixed summation
 // order everywhere: partials are split over FIN_GROUPS lanes in an interleaved, fixed
 // pattern and the group totals are added in group order.
-constexpr int FIN_ELEMS = 32, FIN_GROUPS = 8, FIN_THREADS = FIN_ELEMS * FIN_GROUPS;
+constexpr int FIN_ELEMS = 32, FIN_GROUPS = 32, FIN_THREADS = FIN_ELEMS * FIN_GROUPS;
 constexpr int FIN_MAX_JOBS = 8;
 struct FinJob {
   const float* part;  // [nparts][count]

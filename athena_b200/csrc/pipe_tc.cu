@@ -516,7 +516,7 @@ struct Tn2Cfg {
   static constexpr int OFF_RING = 2 * OPS_BYTES;
   static constexpr int OFF_BAR = OFF_RING + NS * STAGE_BYTES;
   static constexpr int SMEM = 1024 + OFF_BAR + 256;
-  static constexpr int TMEM_COLS = (N <= 32 ? 64 : 128);     // two accumulators of N columns
+  static constexpr int TMEM_COLS = (N <= 32 ? 128 : 256);    // two accumulators of 2N columns
 };
 
 template <int N>
@@ -576,28 +576,27 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
       }
     }
   } else if (warp == Cfg::MMA_WARP) {
-    if (lane == 0) {
-      constexpr uint32_t IDESC = make_idesc(128, N, true, true);
-      for (int j = 0; j < my_tiles; ++j) {
-        const int ob = j & 1;
-        const int g = j / Cfg::FLUSH, first = j - g * Cfg::FLUSH, ab = g & 1;
-        const uint32_t a1 = smem_u32(smem + ob * Cfg::OPS_BYTES);
-        const uint32_t b_hi = a1 + Cfg::A1_BYTES, b_lo = b_hi + Cfg::A2_HALF;
-        const uint32_t tacc = tmem + ab * N;
-        mbar_wait(&ops_ready[ob], (j >> 1) & 1);
-        if (first == 0) mbar_wait(&acc_empty[ab], ((g >> 1) & 1) ^ 1u);  // drained by the acc warps
-        tc_fence_after();
+    // One instruction per k-step: A = [hi(P)^T ; lo(P)^T] (M = 128), B = [hi(G) | lo(G)]
+    // (N = 2N) -> all four partial products at once.  The warp stays converged and the
+    // instruction is predicated on one elected lane (see tc_common.cuh).
+    const uint32_t leader = elect_one();
+    constexpr uint32_t IDESC = make_idesc(128, 2 * N, true, true);
+    for (int j = 0; j < my_tiles; ++j) {
+      const int ob = j & 1;
+      const int g = j / Cfg::FLUSH, first = j - g * Cfg::FLUSH, ab = g & 1;
+      const uint32_t a1 = smem_u32(smem + ob * Cfg::OPS_BYTES);
+      const uint32_t b_hi = a1 + Cfg::A1_BYTES;
+      const uint32_t tacc = tmem + ab * 2 * N;
+      mbar_wait(&ops_ready[ob], (j >> 1) & 1);
+      if (first == 0) mbar_wait(&acc_empty[ab], ((g >> 1) & 1) ^ 1u);  // drained by the acc warps
+      tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < Cfg::RS / 8; ++ks) {
-          const uint64_t da = make_desc_mn32(a1 + ks * 1024, Cfg::BLK, 512);
-          const uint64_t dbh = make_desc_mn32(b_hi + ks * 1024, Cfg::BLK, 512);
-          const uint64_t dbl = make_desc_mn32(b_lo + ks * 1024, Cfg::BLK, 512);
-          umma_tf32(tacc, da, dbh, IDESC, (first | ks) ? 1u : 0u);
-          umma_tf32(tacc, da, dbl, IDESC, 1u);
-        }
-        umma_commit(&ops_free[ob]);
-        if (first == Cfg::FLUSH - 1 || j == my_tiles - 1) umma_commit(&acc_full[ab]);
-      }
+      for (int ks = 0; ks < Cfg::RS / 8; ++ks)
+        umma_tf32_w(leader, tacc, make_desc_mn32(a1 + ks * 1024, Cfg::BLK, 512),
+                    make_desc_mn32(b_hi + ks * 1024, Cfg::BLK, 512), IDESC, (first | ks) ? 1u : 0u);
+      umma_commit_w(leader, &ops_free[ob]);
+      if (first == Cfg::FLUSH - 1 || j == my_tiles - 1) umma_commit_w(leader, &acc_full[ab]);
+      __syncwarp();
     }
   } else if (warp >= Cfg::ACC_WARP0) {
     // accumulate warps: drain the TMEM accumulator of every finished group into registers.
@@ -613,12 +612,16 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
       const int ab = g & 1;
       mbar_wait(&acc_full[ab], (g >> 1) & 1);
       tc_fence_after();
+      // columns n and N + n of a lane are the  . hi(G)  and  . lo(G)  products
 #pragma unroll
-      for (int cg = 0; cg < N / 32; ++cg) {
-        float v[32];
-        tmem_ld32(tmem + ab * N + (static_cast<uint32_t>(q * 32) << 16) + cg * 32, v);
+      for (int cg = 0; cg < N / 16; ++cg) {
+        float v[16], w[16];
+        const uint32_t ta = tmem + ab * 2 * N + (static_cast<uint32_t>(q * 32) << 16) + cg * 16;
+        tmem_ld16_nowait(ta, v);
+        tmem_ld16_nowait(ta + N, w);
+        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[cg * 32 + i] += v[i];
+        for (int i = 0; i < 16; ++i) acc[cg * 16 + i] += v[i] + w[i];
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);

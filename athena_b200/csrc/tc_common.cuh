@@ -201,6 +201,18 @@ __device__ __forceinline__ void umma_tf32_ts_w(uint32_t leader, uint32_t tmem_d,
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32_w(uint32_t leader, uint32_t tmem_d, uint64_t desc_a,
+                                            uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_w(uint32_t leader, uint64_t* bar) {
   asm volatile(
       "{\n\t"
