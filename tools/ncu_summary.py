@@ -41,6 +41,9 @@ RAW_KEYS = [
 ]
 
 TAGS = [
+    (r"k_pipe_tcg<(0|false), 0>", "pipe_gather_fwd"),
+    (r"k_pipe_tcg<(0|false), 2>", "pipe_gather_fwd_mse"),
+    (r"k_pipe_tcg<(1|true), 1>", "pipe_gather_bwd"),
     (r"k_pipe_gather<64, 64, (0|false), 0>", "pipe_gather_fwd"),
     (r"k_pipe_gather<64, 64, (0|false), 2>", "pipe_gather_fwd_mse"),
     (r"k_pipe_gather<64, 64, (1|true), 1>", "pipe_gather_bwd"),
