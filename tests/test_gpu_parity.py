@@ -490,6 +490,34 @@ def test_shard_sum_equals_full_batch_gradient(cuda, oracle32):
     assert rel_err(g_sum, g_full) <= RTOL_ACT
 
 
+def test_kipf_fused_training_multi_edge_batch_uses_list_gather(cuda, oracle32):
+    """Repeated (row, column) pairs cannot be adjacency BITS: such a batch must take the
+    list-gather kernels (k_pipe_gather) and still match the reference, which sums a repeated
+    neighbour as often as it is listed (athena_diffstruc_extd_sub_kipf.f90:36-44)."""
+    rng = np.random.default_rng(64)
+    nv = rng.integers(20, 70, 24).astype(np.int64)
+    voff = np.concatenate([[0], np.cumsum(nv)])
+    src, dst = [], []
+    for g, n in enumerate(nv):
+        m = 3 * int(n)
+        a = voff[g] + rng.integers(0, n, m)
+        b = voff[g] + rng.integers(0, n, m)
+        src += [a, a[: m // 4]]                    # a quarter of the edges is listed twice
+        dst += [b, b[: m // 4]]
+    p, _ = synth.packed_from_edges(nv, np.concatenate(src), np.concatenate(dst))
+    ref = oracle32.batch_build(p.nv, p.ne, p.ia, p.ja)
+    rows = np.repeat(np.arange(p.V), ref["deg"])
+    pairs = rows.astype(np.int64) * p.V + ref["col"]
+    assert np.unique(pairs).size < pairs.size      # the batch really has multi-edges
+    p.x = rng.standard_normal((p.V, 64)).astype(np.float32)
+    specs = [kipf_spec([64, 64], 1, "relu"), kipf_spec([64, 64], 1, "none")]
+    layers = [ab.kipf_msgpass_layer_type([64, 64], 1, "relu"),
+              ab.kipf_msgpass_layer_type([64, 64], 1, "none")]
+    target = rng.standard_normal((p.V, 64)).astype(np.float32)
+    _train_compare(cuda, oracle32, specs, layers, p, target, OptimSpec("sgd", lr=0.05),
+                   ab.sgd_optimiser_type(0.05))
+
+
 @pytest.mark.parametrize("act", ["none", "relu", "tanh"])
 def test_kipf_large_graph_width_128_fused_path(cuda, oracle32, oracle64, act):
     """One graph far larger than a 128-row tile, F = 128: the fused SpMM + tcgen05 kernel of
