@@ -259,7 +259,7 @@ int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const
                            float* out, int F, int N, int act, const uint32_t* mask_in = nullptr);
 // defer != nullptr: the fold of the per-CTA partials into dW is queued instead of launched
 int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int N, DevBuf& scratch,
-                   DeferList* defer = nullptr);
+                   DeferList* defer = nullptr, bool queue = false);
 
 // fused SpMM + tcgen05 transform for large graphs, feature width 128 (agg_tc.cu)
 bool agg_tc_supported(int F, int N, const void* X, const void* out);
@@ -310,9 +310,20 @@ struct DeferJob {
   int nparts, count;
   float* dst;         // += into this block of the flat gradient vector
 };
+// dW = P^T . G products (k_pipe_tn) queued during the reverse sweep and run in one launch
+struct TnPending {
+  const float* P;
+  const float* G;
+  float* dW;
+  int64_t M;
+  int N;
+  DevBuf* scratch;  // per-CTA partials of this product
+};
 struct DeferList {
   std::vector<DeferJob> jobs;
+  std::vector<TnPending> tn;
 };
+int launch_pipe_tn_pending(DeferList* defer);
 bool finalize_can_step(const OptimState& st);
 // xout != nullptr: the finished local gradients (and the loss slot, index n) are also
 // written to xout[0..n] -- the staging buffer of the peer-memory exchange.

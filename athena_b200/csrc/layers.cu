@@ -322,7 +322,9 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
     }
     // dW_t(o,i) += sum_v gY(o,v) P(i,v)
     if (fused_tn) {
-      ATH_TRY(launch_pipe_tn(Pt, gy, dWt, V, Fo, *L->TN[t - 1], opt.defer));
+      // a one-step layer never reuses its gradient buffers inside the sweep: the product can
+      // join the batched launch at the end of the sweep
+      ATH_TRY(launch_pipe_tn(Pt, gy, dWt, V, Fo, *L->TN[t - 1], opt.defer, L->T == 1));
     } else if (tn_tc) {
       ATH_TRY(launch_tc_tn(Pt, Fi, gy, Fo, Hact, L->act, dWt, V, Fo, Fi, L->tn_scratch));
     } else {
@@ -583,6 +585,7 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
     g_preact = folded;
     g = gi;
   }
+  ATH_TRY(launch_pipe_tn_pending(&defer));  // all queued dW products in one launch
   // gradient exchange over peer memory when it is set up (comm_p2p_*), else NCCL
   P2PState& P = p2p();
   const bool use_p2p = P.ready && P.world > 1 && (size_t)(N->n + 1) <= P.cap;

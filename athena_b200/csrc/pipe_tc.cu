@@ -491,6 +491,18 @@ k_pipe_gather(GatherArgs a) {
 // ---------------------------------------------------------------------------
 // dW = P^T . G, pipelined: bulk-copied raw row tiles -> split/swizzle -> MMA
 // ---------------------------------------------------------------------------
+// Up to TN_MAX_JOBS products dW = P^T . G of one reverse sweep (one per layer-step) run in ONE
+// launch, back to back on the same pipeline: set-up, instruction-cache warm-up and tail are
+// paid once.
+constexpr int TN_MAX_JOBS = 4;
+struct TnJobs {
+  int n;
+  const float* P[TN_MAX_JOBS];
+  const float* G[TN_MAX_JOBS];
+  float* part[TN_MAX_JOBS];   // [gridDim.x * 2][K * N] per job
+  long long M[TN_MAX_JOBS];
+};
+
 template <int N>
 struct Tn2Cfg {
   static constexpr int K = 64;
@@ -519,10 +531,20 @@ struct Tn2Cfg {
   static constexpr int TMEM_COLS = (N <= 32 ? 128 : 256);    // two accumulators of 2N columns
 };
 
+// All threads of the CTA meet here at the end of every product, from whatever role branch
+// they are in: no role starts product q + 1 before the accumulate warps have written the
+// partials of product q.  (Letting the roles run ahead across the boundary -- which the
+// mbarrier protocol should allow -- gave run-to-run differences in the SECOND product of a
+// launch in about half of the runs; tools/check_determinism.py.  The pipeline drain costs
+// ~1 us per boundary against ~8 us for a second launch.)
+template <int THREADS>
+__device__ __forceinline__ void job_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+}
+
 template <int N>
 __global__ void __launch_bounds__(Tn2Cfg<N>::THREADS, 1)
-k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __restrict__ part,
-          long long M) {
+k_pipe_tn(TnJobs jobs) {
   using Cfg = Tn2Cfg<N>;
   constexpr int K = Cfg::K;
   extern __shared__ uint8_t smem_raw[];
@@ -556,14 +578,22 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const long long ntiles = (M + Cfg::RS - 1) / Cfg::RS;
-  int my_tiles = 0;
-  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) ++my_tiles;
+  // stages of job q owned by this CTA; every role walks the jobs in order with running
+  // counters: j over stages (ring / operand-buffer phases), gcount over accumulator groups
+  auto tiles_of = [&](int q) { return (jobs.M[q] + Cfg::RS - 1) / Cfg::RS; };
+  auto mine_of = [&](int q) {
+    const long long nt = tiles_of(q);
+    return nt > blockIdx.x ? static_cast<int>((nt - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  };
 
   if (warp == Cfg::PRODUCER_WARP) {
-    if (lane == 0) {
-      int j = 0;
+    int j = 0;
+    for (int q = 0; q < jobs.n; ++q) {
+      const float* P = jobs.P[q];
+      const float* G = jobs.G[q];
+      const long long M = jobs.M[q], ntiles = tiles_of(q);
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+        if (lane != 0) continue;
         const int s = j % Cfg::NS;
         const uint32_t ph = (j / Cfg::NS) & 1;
         mbar_wait(&empty[s], ph ^ 1u);
@@ -574,6 +604,8 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
         bulk_g2s(st, P + r0 * K, rows * K * 4, &full[s]);
         bulk_g2s(st + Cfg::P_RAW, G + r0 * N, rows * N * 4, &full[s]);
       }
+      __syncwarp();
+      job_sync<Cfg::THREADS>();
     }
   } else if (warp == Cfg::MMA_WARP) {
     // One instruction per k-step: A = [hi(P)^T ; lo(P)^T] (M = 128), B = [hi(G) | lo(G)]
@@ -581,56 +613,70 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
     // instruction is predicated on one elected lane (see tc_common.cuh).
     const uint32_t leader = elect_one();
     constexpr uint32_t IDESC = make_idesc(128, 2 * N, true, true);
-    for (int j = 0; j < my_tiles; ++j) {
-      const int ob = j & 1;
-      const int g = j / Cfg::FLUSH, first = j - g * Cfg::FLUSH, ab = g & 1;
-      const uint32_t a1 = smem_u32(smem + ob * Cfg::OPS_BYTES);
-      const uint32_t b_hi = a1 + Cfg::A1_BYTES;
-      const uint32_t tacc = tmem + ab * 2 * N;
-      mbar_wait(&ops_ready[ob], (j >> 1) & 1);
-      if (first == 0) mbar_wait(&acc_empty[ab], ((g >> 1) & 1) ^ 1u);  // drained by the acc warps
-      tc_fence_after();
+    int j = 0, gcount = 0;
+    for (int q = 0; q < jobs.n; ++q) {
+      const int my_tiles = mine_of(q);
+      for (int jl = 0; jl < my_tiles; ++jl, ++j) {
+        const int ob = j & 1;
+        const int gl = jl / Cfg::FLUSH, first = jl - gl * Cfg::FLUSH;
+        const int g = gcount + gl, ab = g & 1;
+        const uint32_t a1 = smem_u32(smem + ob * Cfg::OPS_BYTES);
+        const uint32_t b_hi = a1 + Cfg::A1_BYTES;
+        const uint32_t tacc = tmem + ab * 2 * N;
+        mbar_wait(&ops_ready[ob], (j >> 1) & 1);
+        if (first == 0) mbar_wait(&acc_empty[ab], ((g >> 1) & 1) ^ 1u);  // drained by the acc warps
+        tc_fence_after();
 #pragma unroll
-      for (int ks = 0; ks < Cfg::RS / 8; ++ks)
-        umma_tf32_w(leader, tacc, make_desc_mn32(a1 + ks * 1024, Cfg::BLK, 512),
-                    make_desc_mn32(b_hi + ks * 1024, Cfg::BLK, 512), IDESC, (first | ks) ? 1u : 0u);
-      umma_commit_w(leader, &ops_free[ob]);
-      if (first == Cfg::FLUSH - 1 || j == my_tiles - 1) umma_commit_w(leader, &acc_full[ab]);
-      __syncwarp();
+        for (int ks = 0; ks < Cfg::RS / 8; ++ks)
+          umma_tf32_w(leader, tacc, make_desc_mn32(a1 + ks * 1024, Cfg::BLK, 512),
+                      make_desc_mn32(b_hi + ks * 1024, Cfg::BLK, 512), IDESC,
+                      (first | ks) ? 1u : 0u);
+        umma_commit_w(leader, &ops_free[ob]);
+        if (first == Cfg::FLUSH - 1 || jl == my_tiles - 1) umma_commit_w(leader, &acc_full[ab]);
+        __syncwarp();
+      }
+      gcount += (my_tiles + Cfg::FLUSH - 1) / Cfg::FLUSH;
+      job_sync<Cfg::THREADS>();
     }
   } else if (warp >= Cfg::ACC_WARP0) {
     // accumulate warps: drain the TMEM accumulator of every finished group into registers.
     // TMEM lanes 0..63 hold hi(P)^T.G, lanes 64..127 lo(P)^T.G; each half becomes its own
     // [K x N] partial (2 per CTA), written straight from registers at the end; the fold over
     // partials happens in the reduce / finalize kernel, in partial-index order.
-    const int q = warp & 3;
-    float acc[N];
+    const int lq = warp & 3;
+    int gcount = 0;
+    for (int q = 0; q < jobs.n; ++q) {
+      float acc[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) acc[i] = 0.f;
-    const int ngroups = (my_tiles + Cfg::FLUSH - 1) / Cfg::FLUSH;
-    for (int g = 0; g < ngroups; ++g) {
-      const int ab = g & 1;
-      mbar_wait(&acc_full[ab], (g >> 1) & 1);
-      tc_fence_after();
-      // columns n and N + n of a lane are the  . hi(G)  and  . lo(G)  products
+      for (int i = 0; i < N; ++i) acc[i] = 0.f;
+      const int ngroups = (mine_of(q) + Cfg::FLUSH - 1) / Cfg::FLUSH;
+      for (int gl = 0; gl < ngroups; ++gl) {
+        const int g = gcount + gl, ab = g & 1;
+        mbar_wait(&acc_full[ab], (g >> 1) & 1);
+        tc_fence_after();
+        // columns n and N + n of a lane are the  . hi(G)  and  . lo(G)  products
 #pragma unroll
-      for (int cg = 0; cg < N / 16; ++cg) {
-        float v[16], w[16];
-        const uint32_t ta = tmem + ab * 2 * N + (static_cast<uint32_t>(q * 32) << 16) + cg * 16;
-        tmem_ld16_nowait(ta, v);
-        tmem_ld16_nowait(ta + N, w);
-        tmem_ld_wait();
+        for (int cg = 0; cg < N / 16; ++cg) {
+          float v[16], w[16];
+          const uint32_t ta = tmem + ab * 2 * N + (static_cast<uint32_t>(lq * 32) << 16) + cg * 16;
+          tmem_ld16_nowait(ta, v);
+          tmem_ld16_nowait(ta + N, w);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[cg * 16 + i] += v[i] + w[i];
+          for (int i = 0; i < 16; ++i) acc[cg * 16 + i] += v[i] + w[i];
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[ab]);
       }
-      tc_fence_before();
-      mbar_arrive(&acc_empty[ab]);
-    }
-    const int feat = (q & 1) * 32 + lane;
-    float* dst = part + (static_cast<size_t>(blockIdx.x) * 2 + (q >> 1)) * K * N + feat * N;
+      gcount += ngroups;
+      const int feat = (lq & 1) * 32 + lane;
+      float* dst =
+          jobs.part[q] + (static_cast<size_t>(blockIdx.x) * 2 + (lq >> 1)) * K * N + feat * N;
 #pragma unroll
-    for (int i = 0; i < N; i += 4)
-      *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+      for (int i = 0; i < N; i += 4)
+        *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+      job_sync<Cfg::THREADS>();
+    }
   } else {
     // transform warps: raw row-major tiles -> hi/lo, MN-major 32B-base swizzle
     // (two operand buffers: the stores of tile j+1 overlap the MMAs of tile j)
@@ -638,6 +684,8 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
     constexpr int LOADS = Cfg::RS * CHT / Cfg::XFORM_THREADS;
     static_assert(Cfg::RS * CHT % Cfg::XFORM_THREADS == 0, "loader mapping");
     int j = 0;
+    for (int q = 0; q < jobs.n; ++q) {
+    const long long M = jobs.M[q], ntiles = tiles_of(q);
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
       const int s = j % Cfg::NS;
       const uint32_t ph = (j / Cfg::NS) & 1;
@@ -682,6 +730,8 @@ k_pipe_tn(const float* __restrict__ P, const float* __restrict__ G, float* __res
       }
       fence_async_smem();
       mbar_arrive(&ops_ready[ob]);
+    }
+    job_sync<Cfg::THREADS>();
     }
   }
   tc_fence_before();
@@ -847,8 +897,7 @@ int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const
 }
 
 template <int N>
-static int launch_pipe_tn_t(const float* P, const float* G, float* dW, int64_t M, DevBuf& scratch,
-                            DeferList* defer) {
+static int launch_pipe_tn_t(const TnPending* jobs, int njobs, DeferList* defer) {
   using Cfg = Tn2Cfg<N>;
   static bool attr = false;
   if (!attr) {
@@ -856,28 +905,70 @@ static int launch_pipe_tn_t(const float* P, const float* G, float* dW, int64_t M
                                   Cfg::SMEM));
     attr = true;
   }
-  const int64_t ntiles = cdiv(M, Cfg::RS);
-  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx().sm_count);
-  ATH_TRY(scratch.reserve(sizeof(float) * (size_t)grid * 2 * Cfg::K * N));
-  k_pipe_tn<N><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(P, G, scratch.as<float>(), M);
-  ATH_LAUNCHED_T("pipe_tn");
-  if (defer) {
-    defer->jobs.push_back(DeferJob{scratch.as<float>(), 2 * grid, Cfg::K * N, dW});
-    return ATHENA_OK;
+  int64_t max_tiles = 0;
+  for (int q = 0; q < njobs; ++q) max_tiles = std::max(max_tiles, cdiv(jobs[q].M, Cfg::RS));
+  const int grid = (int)std::min<int64_t>(max_tiles, (int64_t)ctx().sm_count);
+  TnJobs tj{};
+  tj.n = njobs;
+  for (int q = 0; q < njobs; ++q) {
+    ATH_TRY(jobs[q].scratch->reserve(sizeof(float) * (size_t)grid * 2 * Cfg::K * N));
+    tj.P[q] = jobs[q].P;
+    tj.G[q] = jobs[q].G;
+    tj.part[q] = jobs[q].scratch->template as<float>();
+    tj.M[q] = jobs[q].M;
   }
-  k_pipe_tn_reduce<<<(unsigned)cdiv((int64_t)Cfg::K * N, 128), 128, 0, ctx().stream>>>(
-      scratch.as<float>(), 2 * grid, Cfg::K * N, dW);
-  ATH_LAUNCHED_T("pipe_tn_reduce");
+  k_pipe_tn<N><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(tj);
+  ATH_LAUNCHED_T("pipe_tn");
+  for (int q = 0; q < njobs; ++q) {
+    float* part = jobs[q].scratch->template as<float>();
+    if (defer) {
+      defer->jobs.push_back(DeferJob{part, 2 * grid, Cfg::K * N, jobs[q].dW});
+      continue;
+    }
+    k_pipe_tn_reduce<<<(unsigned)cdiv((int64_t)Cfg::K * N, 128), 128, 0, ctx().stream>>>(
+        part, 2 * grid, Cfg::K * N, jobs[q].dW);
+    ATH_LAUNCHED_T("pipe_tn_reduce");
+  }
   return ATHENA_OK;
 }
 
 // dW[64 x N] += P^T . G     (P [M][64], G [M][N], both dense row-major)
+// With a DeferList the product is only queued: launch_pipe_tn_pending runs every queued product
+// of the reverse sweep in one launch per width (before launch_finalize folds the partials).
+// queue: P and G stay untouched until the end of the sweep, so the product itself may wait;
+// otherwise only the fold of its partials is deferred.
 int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int N, DevBuf& scratch,
-                   DeferList* defer) {
+                   DeferList* defer, bool queue) {
   if (M == 0) return ATHENA_OK;
-  if (N == 64) return launch_pipe_tn_t<64>(P, G, dW, M, scratch, defer);
-  if (N == 32) return launch_pipe_tn_t<32>(P, G, dW, M, scratch, defer);
-  ATH_REQUIRE(false, ATHENA_ERR_ARG, "pipe_tn: unsupported N=%d", N);
+  ATH_REQUIRE(N == 64 || N == 32, ATHENA_ERR_ARG, "pipe_tn: unsupported N=%d", N);
+  const TnPending job{P, G, dW, M, N, &scratch};
+  static int nobatch = -1;
+  if (nobatch < 0) {
+    const char* e = getenv("ATHENA_DEBUG_TN_NOBATCH");  // A/B switch: one launch per product
+    nobatch = e ? atoi(e) : 0;  // 1: launch at once; 2: queue, but one launch per product
+  }
+  if (defer && queue && nobatch != 1) {
+    defer->tn.push_back(job);
+    return ATHENA_OK;
+  }
+  return N == 64 ? launch_pipe_tn_t<64>(&job, 1, defer) : launch_pipe_tn_t<32>(&job, 1, defer);
+}
+
+int launch_pipe_tn_pending(DeferList* defer) {
+  for (int width : {64, 32}) {
+    std::vector<TnPending> batch;
+    for (const TnPending& j : defer->tn)
+      if (j.N == width) batch.push_back(j);
+    const char* e = getenv("ATHENA_DEBUG_TN_NOBATCH");
+    const size_t per_launch = (e && atoi(e) == 2) ? 1 : TN_MAX_JOBS;
+    for (size_t i = 0; i < batch.size(); i += per_launch) {
+      const int n = (int)std::min<size_t>(per_launch, batch.size() - i);
+      ATH_TRY(width == 64 ? launch_pipe_tn_t<64>(batch.data() + i, n, defer)
+                          : launch_pipe_tn_t<32>(batch.data() + i, n, defer));
+    }
+  }
+  defer->tn.clear();
+  return ATHENA_OK;
 }
 
 }  // namespace athena

@@ -184,7 +184,8 @@ def kernel_bytes(tag, V, Z):
         # fused dP = gY W^T, CSC gather, .* relu'(H): gY read, gY_{t-1} written, relu' from the
         # sign bits the forward recorded (8 B per row instead of the 4VF of saved activations)
         "pipe_gather_bwd": idx + 2 * vf + 8 * V + 4 * F * F,
-        "pipe_tn": 2 * vf + 4 * F * F,
+        # the dW products of both layers run in ONE launch (P and gY read, per layer)
+        "pipe_tn": 2 * (2 * vf + 4 * F * F),
         "pipe_tn_reduce": 4 * F * F,
         "aggregate_v4_g16_c1_coef": idx + 4 * V + 2 * vf,
         "aggregate_v4_g16_c1": idx + 2 * vf,

@@ -96,10 +96,14 @@ def test_cfg2_full_size_train_steps_match_oracle(cuda, oracle32, oracle64):
         lref, _ = oracle32.train_step(specs, ref, ob, target, OptimSpec("sgd", lr=0.01), s1, s2, it)
         assert abs(losses[-1] - lref) <= 2 * RTOL_ACT * abs(lref)
     assert rel_err(net.get_params(), ref) <= RTOL_PARAM
-    # bitwise determinism of the whole step
-    net.set_params(params0)
-    again = [net.train_step(batch, target) for _ in range(3)]
-    assert again == losses
+    # bitwise determinism of the whole step (several repeats: a race between the batched dW
+    # products of one launch once showed up in about half of the runs)
+    prm = net.get_params()
+    for _ in range(6):
+        net.set_params(params0)
+        again = [net.train_step(batch, target) for _ in range(3)]
+        assert again == losses
+        assert np.array_equal(net.get_params(), prm)
 
 
 def test_cfg3_large_graph_inference_sampled_rows(cuda, oracle32):
