@@ -508,7 +508,8 @@ struct Tn2Cfg {
   static constexpr int K = 64;
   static constexpr int RS = 64;                              // rows per stage
   static constexpr int NS = 3;
-  static constexpr int XFORM_THREADS = 256;
+  static constexpr int G_THREADS = 128;                      // warps 0..3: gY -> hi/lo B operand
+  static constexpr int A_WARP0 = 4;                          // warps 4..7: P^T -> TMEM A operand
   static constexpr int PRODUCER_WARP = 8;
   static constexpr int MMA_WARP = 9;
   static constexpr int ACC_WARP0 = 10;                       // warps 10..13: warp % 4 = TMEM lane quarter
@@ -522,13 +523,14 @@ struct Tn2Cfg {
   static constexpr int G_RAW = RS * N * 4;
   static constexpr int STAGE_BYTES = P_RAW + G_RAW;
   static constexpr int BLK = RS * 128;                       // [64 rows x 32 feats]
-  static constexpr int A1_BYTES = 2 * (K / 32) * BLK;
-  static constexpr int A2_HALF = (N / 32) * BLK;
-  static constexpr int OPS_BYTES = A1_BYTES + 2 * A2_HALF;   // one operand buffer (two exist)
+  static constexpr int B_HALF = (N / 32) * BLK;              // hi (or lo) of gY
+  static constexpr int OPS_BYTES = 2 * B_HALF;               // one B operand buffer (two exist)
   static constexpr int OFF_RING = 2 * OPS_BYTES;
   static constexpr int OFF_BAR = OFF_RING + NS * STAGE_BYTES;
   static constexpr int SMEM = 1024 + OFF_BAR + 256;
-  static constexpr int TMEM_COLS = (N <= 32 ? 128 : 256);    // two accumulators of 2N columns
+  // TMEM: two A operand buffers [hi(P)^T ; lo(P)^T] x 64 vertices, two accumulators of 2N columns
+  static constexpr uint32_t T_A = 0, T_ACC = 2 * RS;
+  static constexpr int TMEM_COLS = (2 * RS + 4 * N <= 256) ? 256 : 512;
 };
 
 // All threads of the CTA meet here at the end of every product, from whatever role branch
@@ -553,8 +555,9 @@ k_pipe_tn(TnJobs jobs) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::NS;
-  uint64_t* ops_ready = bars + 2 * Cfg::NS;  // [2]
-  uint64_t* ops_free = ops_ready + 2;        // [2]
+  uint64_t* ops_ready = bars + 2 * Cfg::NS;  // [2] B operand (gY hi/lo) staged in shared memory
+  uint64_t* a_ready = ops_ready + 2;         // [2] A operand (P^T hi/lo) stored in TMEM
+  uint64_t* ops_free = a_ready + 2;          // [2] MMAs of the stage have read both operands
   uint64_t* acc_full = ops_free + 2;         // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
@@ -564,10 +567,11 @@ k_pipe_tn(TnJobs jobs) {
   if (tid == 0) {
     for (int s = 0; s < Cfg::NS; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], Cfg::XFORM_THREADS);
+      mbar_init(&empty[s], Cfg::G_THREADS + 128);
     }
     for (int ob = 0; ob < 2; ++ob) {
-      mbar_init(&ops_ready[ob], Cfg::XFORM_THREADS);
+      mbar_init(&ops_ready[ob], Cfg::G_THREADS);
+      mbar_init(&a_ready[ob], 128);
       mbar_init(&ops_free[ob], 1);
       mbar_init(&acc_full[ob], 1);
       mbar_init(&acc_empty[ob], 128);
@@ -608,11 +612,12 @@ k_pipe_tn(TnJobs jobs) {
       job_sync<Cfg::THREADS>();
     }
   } else if (warp == Cfg::MMA_WARP) {
-    // One instruction per k-step: A = [hi(P)^T ; lo(P)^T] (M = 128), B = [hi(G) | lo(G)]
-    // (N = 2N) -> all four partial products at once.  The warp stays converged and the
-    // instruction is predicated on one elected lane (see tc_common.cuh).
+    // One instruction per k-step (8 vertices): A = [hi(P)^T ; lo(P)^T] (M = 128) read from
+    // TENSOR MEMORY, B = [hi(gY) | lo(gY)] (N = 2N) from shared memory -> all four partial
+    // products at once.  The warp stays converged and the instruction is predicated on one
+    // elected lane (see tc_common.cuh).
     const uint32_t leader = elect_one();
-    constexpr uint32_t IDESC = make_idesc(128, 2 * N, true, true);
+    constexpr uint32_t IDESC = make_idesc(128, 2 * N, false, true);
     int j = 0, gcount = 0;
     for (int q = 0; q < jobs.n; ++q) {
       const int my_tiles = mine_of(q);
@@ -620,17 +625,18 @@ k_pipe_tn(TnJobs jobs) {
         const int ob = j & 1;
         const int gl = jl / Cfg::FLUSH, first = jl - gl * Cfg::FLUSH;
         const int g = gcount + gl, ab = g & 1;
-        const uint32_t a1 = smem_u32(smem + ob * Cfg::OPS_BYTES);
-        const uint32_t b_hi = a1 + Cfg::A1_BYTES;
-        const uint32_t tacc = tmem + ab * 2 * N;
+        const uint32_t b_hi = smem_u32(smem + ob * Cfg::OPS_BYTES);
+        const uint32_t ta = tmem + Cfg::T_A + ob * Cfg::RS;
+        const uint32_t tacc = tmem + Cfg::T_ACC + ab * 2 * N;
         mbar_wait(&ops_ready[ob], (j >> 1) & 1);
+        mbar_wait(&a_ready[ob], (j >> 1) & 1);
         if (first == 0) mbar_wait(&acc_empty[ab], ((g >> 1) & 1) ^ 1u);  // drained by the acc warps
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < Cfg::RS / 8; ++ks)
-          umma_tf32_w(leader, tacc, make_desc_mn32(a1 + ks * 1024, Cfg::BLK, 512),
-                      make_desc_mn32(b_hi + ks * 1024, Cfg::BLK, 512), IDESC,
-                      (first | ks) ? 1u : 0u);
+          umma_tf32_ts_w(leader, tacc, ta + ks * 8,
+                         make_desc_mn32(b_hi + ks * 1024, Cfg::BLK, 512), IDESC,
+                         (first | ks) ? 1u : 0u);
         umma_commit_w(leader, &ops_free[ob]);
         if (first == Cfg::FLUSH - 1 || jl == my_tiles - 1) umma_commit_w(leader, &acc_full[ab]);
         __syncwarp();
@@ -658,7 +664,8 @@ k_pipe_tn(TnJobs jobs) {
 #pragma unroll
         for (int cg = 0; cg < N / 16; ++cg) {
           float v[16], w[16];
-          const uint32_t ta = tmem + ab * 2 * N + (static_cast<uint32_t>(lq * 32) << 16) + cg * 16;
+          const uint32_t ta = tmem + Cfg::T_ACC + ab * 2 * N +
+                              (static_cast<uint32_t>(lq * 32) << 16) + cg * 16;
           tmem_ld16_nowait(ta, v);
           tmem_ld16_nowait(ta + N, w);
           tmem_ld_wait();
@@ -677,61 +684,94 @@ k_pipe_tn(TnJobs jobs) {
         *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
       job_sync<Cfg::THREADS>();
     }
-  } else {
-    // transform warps: raw row-major tiles -> hi/lo, MN-major 32B-base swizzle
-    // (two operand buffers: the stores of tile j+1 overlap the MMAs of tile j)
-    constexpr int CH1 = K / 4, CH2 = N / 4, CHT = CH1 + CH2;
-    constexpr int LOADS = Cfg::RS * CHT / Cfg::XFORM_THREADS;
-    static_assert(Cfg::RS * CHT % Cfg::XFORM_THREADS == 0, "loader mapping");
+  } else if (warp >= Cfg::A_WARP0) {
+    // A-operand warps: thread = TMEM lane = one feature of hi(P)^T (lanes 0..63) or lo(P)^T
+    // (lanes 64..127).  It reads its feature of the stage's 64 vertices with LDS.32 (a warp
+    // reads 32 consecutive floats of one row: conflict-free) -- the transposition is free --
+    // and stores them as 64 TMEM columns: the A operand never touches shared memory again
+    // (no operand stores, no operand reads by the MMA: -25 % shared-memory traffic per stage).
+    const int lq = warp & 3;
+    const int f = (lq & 1) * 32 + lane;
+    const bool lo_part = lq >= 2;
     int j = 0;
     for (int q = 0; q < jobs.n; ++q) {
-    const long long M = jobs.M[q], ntiles = tiles_of(q);
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
-      const int s = j % Cfg::NS;
-      const uint32_t ph = (j / Cfg::NS) & 1;
-      const long long r0 = t * Cfg::RS;
-      const int rows = static_cast<int>(min(static_cast<long long>(Cfg::RS), M - r0));
-      const uint8_t* st = ring + s * Cfg::STAGE_BYTES;
-      mbar_wait(&full[s], ph);
-      float4 x[LOADS];
+      const long long M = jobs.M[q], ntiles = tiles_of(q);
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+        const int s = j % Cfg::NS;
+        const uint32_t ph = (j / Cfg::NS) & 1;
+        const long long r0 = t * Cfg::RS;
+        const int rows = static_cast<int>(min(static_cast<long long>(Cfg::RS), M - r0));
+        const float* raw = reinterpret_cast<const float*>(ring + s * Cfg::STAGE_BYTES);
+        mbar_wait(&full[s], ph);
+        float x[Cfg::RS];
 #pragma unroll
-      for (int i = 0; i < LOADS; ++i) {
-        const int idx = tid + Cfg::XFORM_THREADS * i;
-        const int row = idx / CHT, ch = idx - row * CHT;
-        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < rows) {
-          x[i] = ch < CH1
-                     ? *reinterpret_cast<const float4*>(st + (row * CH1 + ch) * 16)
-                     : *reinterpret_cast<const float4*>(st + Cfg::P_RAW + (row * CH2 + ch - CH1) * 16);
-        }
-      }
-      mbar_arrive(&empty[s]);
-      const int ob = j & 1;
-      uint8_t* sA1 = smem + ob * Cfg::OPS_BYTES;
-      uint8_t* sA2hi = sA1 + Cfg::A1_BYTES;
-      uint8_t* sA2lo = sA2hi + Cfg::A2_HALF;
-      mbar_wait(&ops_free[ob], ((j >> 1) & 1) ^ 1u);  // MMAs of tile j-2 have read this buffer
+        for (int r = 0; r < Cfg::RS; ++r) x[r] = r < rows ? raw[r * K + f] : 0.f;
+        mbar_arrive(&empty[s]);
+        const int ob = j & 1;
+        mbar_wait(&ops_free[ob], ((j >> 1) & 1) ^ 1u);  // MMAs of stage j-2 have read this buffer
+        tc_fence_after();
+        const uint32_t ta =
+            tmem + Cfg::T_A + ob * Cfg::RS + (static_cast<uint32_t>(lq * 32) << 16);
 #pragma unroll
-      for (int i = 0; i < LOADS; ++i) {
-        const int idx = tid + Cfg::XFORM_THREADS * i;
-        const int row = idx / CHT, ch = idx - row * CHT;
-        float4 hi, lo;
-        split_tf32(x[i], hi, lo);
-        if (ch < CH1) {
-          const uint32_t off = (ch >> 3) * Cfg::BLK + sw128b32_off(row, ch & 7);
-          *reinterpret_cast<float4*>(sA1 + off) = hi;
-          *reinterpret_cast<float4*>(sA1 + (K / 32) * Cfg::BLK + off) = lo;
-        } else {
-          const int c2 = ch - CH1;
-          const uint32_t off = (c2 >> 3) * Cfg::BLK + sw128b32_off(row, c2 & 7);
-          *reinterpret_cast<float4*>(sA2hi + off) = hi;
-          *reinterpret_cast<float4*>(sA2lo + off) = lo;
+        for (int h = 0; h < Cfg::RS / 32; ++h) {
+          uint32_t v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float xx = x[h * 32 + i];
+            const uint32_t hi = __float_as_uint(xx) & 0xffffe000u;
+            v[i] = lo_part ? __float_as_uint(xx - __uint_as_float(hi)) : hi;
+          }
+          tmem_st32(ta + h * 32, v);
         }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&a_ready[ob]);
       }
-      fence_async_smem();
-      mbar_arrive(&ops_ready[ob]);
+      job_sync<Cfg::THREADS>();
     }
-    job_sync<Cfg::THREADS>();
+  } else {
+    // B-operand warps: raw row-major gY -> hi/lo, MN-major 32B-base swizzle
+    // (two operand buffers: the stores of stage j+1 overlap the MMAs of stage j)
+    constexpr int CH2 = N / 4;
+    constexpr int LOADS = Cfg::RS * CH2 / Cfg::G_THREADS;
+    static_assert(Cfg::RS * CH2 % Cfg::G_THREADS == 0, "loader mapping");
+    int j = 0;
+    for (int q = 0; q < jobs.n; ++q) {
+      const long long M = jobs.M[q], ntiles = tiles_of(q);
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+        const int s = j % Cfg::NS;
+        const uint32_t ph = (j / Cfg::NS) & 1;
+        const long long r0 = t * Cfg::RS;
+        const int rows = static_cast<int>(min(static_cast<long long>(Cfg::RS), M - r0));
+        const uint8_t* st = ring + s * Cfg::STAGE_BYTES + Cfg::P_RAW;
+        mbar_wait(&full[s], ph);
+        float4 x[LOADS];
+#pragma unroll
+        for (int i = 0; i < LOADS; ++i) {
+          const int idx = tid + Cfg::G_THREADS * i;
+          const int row = idx / CH2;
+          x[i] = row < rows ? *reinterpret_cast<const float4*>(st + idx * 16)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        mbar_arrive(&empty[s]);
+        const int ob = j & 1;
+        uint8_t* sBhi = smem + ob * Cfg::OPS_BYTES;
+        uint8_t* sBlo = sBhi + Cfg::B_HALF;
+        mbar_wait(&ops_free[ob], ((j >> 1) & 1) ^ 1u);  // MMAs of stage j-2 have read this buffer
+#pragma unroll
+        for (int i = 0; i < LOADS; ++i) {
+          const int idx = tid + Cfg::G_THREADS * i;
+          const int row = idx / CH2, ch = idx - row * CH2;
+          float4 hi, lo;
+          split_tf32(x[i], hi, lo);
+          const uint32_t off = (ch >> 3) * Cfg::BLK + sw128b32_off(row, ch & 7);
+          *reinterpret_cast<float4*>(sBhi + off) = hi;
+          *reinterpret_cast<float4*>(sBlo + off) = lo;
+        }
+        fence_async_smem();
+        mbar_arrive(&ops_ready[ob]);
+      }
+      job_sync<Cfg::THREADS>();
     }
   }
   tc_fence_before();
