@@ -50,6 +50,8 @@ struct GatherArgs {
   uint32_t* mask_out;
   const uint32_t* mask_in;
   const uint4* abits;     // pipe_tcg: adjacency rows as bit masks (Batch::abits / atbits)
+  long long num_rows;     // pipe_tcg: V (extent of the TMA tensor map of `aux`)
+  int aux_tma;            // pipe_tcg fwd+MSE: the target tile arrives by TMA tensor copies
   // EPI_MSE (mse_loss_type%compute for graph outputs, athena_loss.f90:416-427)
   const int32_t* vcount;  // [V] vertices of the vertex's graph (Batch::vcount)
   float* loss_part;       // [gridDim.x] sum over this CTA's rows of (p-e)^2 / (N * nv_s)
@@ -77,7 +79,11 @@ constexpr int EPI_PATCH = 32 * EPI_PITCH;
 constexpr int AUX_PITCH = 68;                 // floats per operand row (64 + 4 pad)
 // STACKED: the accumulator holds hi | lo partial products side by side (N columns each).
 // [HB, HE): the 32-column halves this call handles (pipe_tcg.cu gives each half its own warp).
-template <int ACT, int EPI, int N, bool STACKED = true, int HB = 0, int HE = N / 32>
+// AUX_SWZ: `aux_row` is the BASE of an operand tile that TMA wrote as two [128 rows x 32
+// floats] boxes with the 128-byte swizzle (16-byte chunk c of row r at chunk c ^ (r % 8)): the
+// row-per-thread reads are conflict-free without padding.
+template <int ACT, int EPI, int N, bool STACKED = true, int HB = 0, int HE = N / 32,
+          bool AUX_SWZ = false>
 __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, int nrows,
                                                float* __restrict__ out_tile,
                                                const float* aux_row /* shared memory */,
@@ -87,6 +93,15 @@ __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, i
                                                const uint32_t (&mask_in)[N / 32]) {
   float lsum = 0.f;
   float* srow = patch + lane * EPI_PITCH;
+  auto aux4 = [&](int col) {
+    if (AUX_SWZ) {
+      const int r = q * 32 + lane;
+      return *reinterpret_cast<const float4*>(
+          reinterpret_cast<const uint8_t*>(aux_row) + (col >> 5) * (TILE_ROWS * 128) + r * 128 +
+          ((((col & 31) >> 2) ^ (r & 7)) << 4));
+    }
+    return *reinterpret_cast<const float4*>(aux_row + col);
+  };
 #pragma unroll
   for (int half = HB; half < HE; ++half) {
     uint32_t mbits = 0;
@@ -121,7 +136,7 @@ __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, i
             o[k] = pos ? o[k] : (ACT == ATHENA_ACT_LEAKY_RELU ? o[k] * 0.01f : 0.f);
           }
         } else if (EPI == EPI_MSE) {
-          const float4 t4 = *reinterpret_cast<const float4*>(aux_row + col0 + i);
+          const float4 t4 = aux4(col0 + i);
           const float t[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -131,7 +146,7 @@ __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, i
             o[k] = act_bwd<ACT>(pk, d * row_scale);
           }
         } else if (ACT != ATHENA_ACT_NONE) {
-          const float4 h4 = *reinterpret_cast<const float4*>(aux_row + col0 + i);
+          const float4 h4 = aux4(col0 + i);
           const float h[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) o[k] = act_bwd<ACT>(h[k], o[k]);

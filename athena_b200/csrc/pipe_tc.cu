@@ -907,6 +907,7 @@ int launch_pipe_gather_fwd_mse(const Batch* b, const float* X, const float* W, f
   *num_parts = std::min(b->num_tiles, ctx().sm_count);
   if (pipe_tcg_supported(const_cast<Batch*>(b), F, N)) {
     a.abits = b->abits;
+    a.num_rows = b->V;
     return launch_pipe_tcg(a, false, EPI_MSE);
   }
   return launch_gather_t<64, 64, false, EPI_MSE>(a);

@@ -33,8 +33,11 @@
 // (truncating) accumulation, not in the reference's entry order; with <= 128 terms the
 // difference is ~1e-7 relative, inside the 1e-5 parity tolerance.
 // Batches in which some (row, column) pair repeats (multi-edges) keep the list kernels.
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 
 #include "athena_internal.h"
@@ -105,7 +108,8 @@ struct TcgCfg {
   static constexpr int PRODUCER_WARP = 20;
   static constexpr int MMA_WARP = PRODUCER_WARP + 1;             // issues G (and owns the TMEM allocation)
   static constexpr int MMA_T_WARP = PRODUCER_WARP + 2;           // issues T
-  static constexpr int THREADS = (PRODUCER_WARP + 3) * 32;
+  static constexpr int AUX_WARP = PRODUCER_WARP + 3;             // second producer (fwd + MSE)
+  static constexpr int THREADS = (PRODUCER_WARP + 4) * 32;
   static constexpr int STAGE_W_THREADS = 8 * 32;                 // fix + epilogue warps
   static constexpr int X_BYTES = TILE_ROWS * F * 4;              // 32 KB of raw feature rows
   static constexpr int RS_BYTES = (TILE_ROWS + 8) * 4;
@@ -118,9 +122,15 @@ struct TcgCfg {
   static constexpr int OFF_BLO = OP_BYTES;
   static constexpr int OFF_W = 2 * OP_BYTES;
   static constexpr int OFF_RING = OFF_W + (F / 32) * W_BLK;
-  static constexpr int OFF_AUX = OFF_RING + NS * STAGE_BYTES;
-  static constexpr int AUX_BYTES = EPI != EPI_ACT ? NAUX * AUX_TILE : 0;
-  static constexpr int OFF_BAR = OFF_RING + NS * STAGE_BYTES + AUX_BYTES;
+  // fwd + MSE: the target tile is fetched by the producer with TMA tensor copies (128-byte
+  // swizzle, two [128 x 32] boxes per tile, double-buffered) instead of cp.async from the
+  // epilogue warps: no LSU traffic for the copy and a whole tile period of prefetch distance.
+  // The cp.async path (padded tile in the same region) remains for unaligned targets.
+  static constexpr bool AUX_TMA = EPI == EPI_MSE;
+  static constexpr int AUX_TMA_TILE = TILE_ROWS * N * 4;
+  static constexpr int OFF_AUX = (OFF_RING + NS * STAGE_BYTES + 1023) / 1024 * 1024;
+  static constexpr int AUX_BYTES = AUX_TMA ? 2 * AUX_TMA_TILE : EPI != EPI_ACT ? NAUX * AUX_TILE : 0;
+  static constexpr int OFF_BAR = OFF_AUX + AUX_BYTES;
   static constexpr int OFF_EPI = OFF_BAR + 256 + 512;
   static constexpr int FIX_PATCH = 32 * 16;                      // floats per fix / epilogue warp patch
   static constexpr int EPI_PATCH_FLOATS = EPI_PATCH;             // pipe::epilogue_tile: 32-column groups
@@ -138,7 +148,8 @@ struct TcgCfg {
 // kernel).  The dry pass takes those misses in all roles AT ONCE while the first TMA copy
 // is in flight; it must execute the same instructions, hence one loop, not a copy.
 template <bool TRANSB, int EPI>
-__global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs a) {
+__global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1)
+k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
   using Cfg = TcgCfg<EPI>;
   constexpr int F = Cfg::F, N = Cfg::N;
   extern __shared__ uint8_t smem_raw[];
@@ -160,7 +171,9 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
   uint64_t* warm = bars + 17;             // W staged + dry passes of the fix / epilogue warps done
   uint64_t* dummy = bars + 18;            // sink for the arrivals of the dry epilogue pass
   uint64_t* t_done = bars + 19;           // [2] T(j) has read P[j & 1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* aux_full = bars + 21;         // [2] target tile landed (TMA)
+  uint64_t* aux_empty = bars + 23;        // [2] epilogue warps are done with it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
   float* loss_red = reinterpret_cast<float*>(smem + Cfg::OFF_BAR + 256);  // [256], EPI_MSE
   float* sAux = reinterpret_cast<float*>(smem + Cfg::OFF_AUX);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -190,6 +203,8 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
       mbar_init(&o_full[b], 1);
       mbar_init(&o_empty[b], 128);
       mbar_init(&t_done[b], 1);
+      mbar_init(&aux_full[b], 1);
+      mbar_init(&aux_empty[b], 128);
     }
     mbar_init(warm, Cfg::STAGE_W_THREADS);
     mbar_init(dummy, 1u << 19);
@@ -225,6 +240,7 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
     fence_async_smem();
   }
 
+  const bool aux_tma = Cfg::AUX_TMA && a.aux_tma != 0 && a.aux != nullptr;
   if (warp == Cfg::PRODUCER_WARP) {
     // ===================== producer: TMA bulk copies into the ring =====================
     if (lane == 0) {
@@ -243,6 +259,22 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
         mbar_arrive_expect_tx(&full[s], xb + (has_coef ? rb : 0u));
         bulk_g2s(st, a.X + static_cast<size_t>(r0) * F, xb, &full[s]);
         if (has_coef) bulk_g2s(st + Cfg::X_BYTES, a.rs + ra, rb, &full[s]);
+      }
+    }
+  } else if (warp == Cfg::AUX_WARP) {
+    // ===================== second producer: the epilogue's operand tile (target) =======
+    // two [128 rows x 32 floats] TMA tensor copies per tile, at most two tiles ahead
+    if (lane == 0 && aux_tma) {
+      uint8_t* sAuxT = smem + Cfg::OFF_AUX;
+      int j = 0;
+      for (int t = blockIdx.x; t < a.num_tiles; t += step, ++j) {
+        const int b = j & 1;
+        mbar_wait_g(&aux_empty[b], ((j >> 1) & 1) ^ 1u, 13);
+        const int4 ti = __ldg(a.tiles + t);
+        mbar_arrive_expect_tx(&aux_full[b], Cfg::AUX_TMA_TILE);
+        tma_load_2d(sAuxT + b * Cfg::AUX_TMA_TILE, &aux_map, 0, ti.x, &aux_full[b]);
+        tma_load_2d(sAuxT + b * Cfg::AUX_TMA_TILE + TILE_ROWS * 128, &aux_map, 32, ti.x,
+                    &aux_full[b]);
       }
     }
   } else if (warp == Cfg::MMA_WARP) {
@@ -387,7 +419,9 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
         if (q == 0 && lane == 0) TCG_TRACE(5, 1);
       }
       tc_fence_after();
-      if (use_aux && !dry) {
+      if (aux_tma) {
+        if (!dry) mbar_wait_g(&aux_full[j & 1], (j >> 1) & 1, 14);
+      } else if (use_aux && !dry) {
         if (Cfg::NAUX == 2)
           asm volatile("cp.async.wait_group 1;" ::: "memory");
         else
@@ -395,7 +429,10 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
         __syncwarp();
       }
       const float* aux_row =
-          sAux + (Cfg::NAUX == 2 ? (j & 1) : 0) * (TILE_ROWS * AUX_PITCH) + my_row * AUX_PITCH;
+          aux_tma ? reinterpret_cast<const float*>(smem + Cfg::OFF_AUX +
+                                                   (j & 1) * Cfg::AUX_TMA_TILE)
+                  : sAux + (Cfg::NAUX == 2 ? (j & 1) : 0) * (TILE_ROWS * AUX_PITCH) +
+                        my_row * AUX_PITCH;
       const uint32_t tacc = tmem + Cfg::T_O + b * N;
       uint64_t* release = dry ? dummy : &o_empty[b];
       const float scale =
@@ -403,8 +440,12 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
       const int act = use_aux || use_mask || EPI == EPI_ACT ? a.act : ATHENA_ACT_NONE;
       const uint32_t min_w[2] = {m0, m1};
 #define TCG_EPI(ACT)                                                                          \
-  lsum += epilogue_tile<ACT, EPI, N, false>(tacc, q, lane, ti.y, out_tile, aux_row, scale,      \
-                                            patch, release, false, mout, use_mask, min_w)
+  lsum += (Cfg::AUX_TMA && aux_tma)                                                            \
+              ? epilogue_tile<ACT, EPI, N, false, 0, N / 32, Cfg::AUX_TMA>(                     \
+                    tacc, q, lane, ti.y, out_tile, aux_row, scale, patch, release, false, mout, \
+                    use_mask, min_w)                                                            \
+              : epilogue_tile<ACT, EPI, N, false>(tacc, q, lane, ti.y, out_tile, aux_row, scale, \
+                                                  patch, release, false, mout, use_mask, min_w)
       switch (act) {
         case ATHENA_ACT_RELU: TCG_EPI(ATHENA_ACT_RELU); break;
         case ATHENA_ACT_LEAKY_RELU: TCG_EPI(ATHENA_ACT_LEAKY_RELU); break;
@@ -416,10 +457,11 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
       if (dry) {
         lsum = 0.f;  // whatever the scratch accumulator held
         mbar_arrive(warm);
-      } else if (q == 0 && lane == 0) {
-        TCG_TRACE(5, 2);
+      } else {
+        if (aux_tma) mbar_arrive(&aux_empty[j & 1]);
+        if (q == 0 && lane == 0) TCG_TRACE(5, 2);
       }
-      if (use_aux) {
+      if (use_aux && !aux_tma) {
         __syncwarp();
         if (Cfg::NAUX == 2) {
           // after the dry pass: tiles 0 and 1; after tile j: tile j + 2 into the buffer it frees
@@ -645,6 +687,33 @@ __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1) k_pipe_tcg(GatherArgs
   if (warp == Cfg::MMA_WARP) tmem_dealloc<512>(tmem);
 }
 
+// 2-D tensor map of a dense [rows][64] fp32 array, box = [128 rows][32 floats], 128-byte
+// swizzle.  The driver entry point is resolved at run time (no link-time libcuda dependency).
+static bool make_row_tile_map(const float* base, long long rows, CUtensorMap* out) {
+  using Fn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                          const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                          CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                          CUtensorMapFloatOOBfill);
+  static Fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<Fn>(p);
+  }
+  if (!fn || rows <= 0 || (reinterpret_cast<uintptr_t>(base) & 15u) != 0) return false;
+  const cuuint64_t gdim[2] = {64, static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstr[1] = {64 * sizeof(float)};
+  const cuuint32_t box[2] = {32, TILE_ROWS};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box,
+            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <bool TRANSB, int EPI>
 int launch_tcg_t(const GatherArgs& a) {
   using Cfg = TcgCfg<EPI>;
@@ -657,6 +726,17 @@ int launch_tcg_t(const GatherArgs& a) {
   const int grid = std::min(a.num_tiles, ctx().sm_count);
   GatherArgs b = a;
   b.trace = nullptr;
+  alignas(64) CUtensorMap aux_map;
+  memset(&aux_map, 0, sizeof(aux_map));
+  static int no_tma = -1;
+  if (no_tma < 0) {
+    const char* e = getenv("ATHENA_DEBUG_NO_AUX_TMA");  // A/B switch: cp.async operand prefetch
+    no_tma = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  b.aux_tma = (Cfg::AUX_TMA && !no_tma && a.aux != nullptr &&
+               make_row_tile_map(a.aux, a.num_rows, &aux_map))
+                  ? 1
+                  : 0;
   static int trace_left = -1;
   static long long* trace_buf = nullptr;
   if (trace_left < 0) {
@@ -671,7 +751,7 @@ int launch_tcg_t(const GatherArgs& a) {
     const char* e = getenv("ATHENA_DEBUG_TRACE_BLOCK");
     b.dbg = e ? atoi(e) : 0;
   }
-  k_pipe_tcg<TRANSB, EPI><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(b);
+  k_pipe_tcg<TRANSB, EPI><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(b, aux_map);
   if (trace_left > 0) {
     --trace_left;
     std::vector<long long> h(trace_n);

@@ -71,6 +71,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
       : "memory");
 }
 
+// TMA tensor copy (2-D tiled tensor map): global -> shared, completion counted on `bar`.
+// `tmap` is the generic address of a CUtensorMap in kernel-parameter (__grid_constant__) space.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int x, int y,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // generic-proxy shared-memory writes -> visible to the async proxy (UMMA reads)
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
