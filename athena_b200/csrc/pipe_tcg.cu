@@ -16,17 +16,21 @@
 // memory wavefronts per tile) a tile costs ~2900 wavefronts, which moves the kernel from
 // the shared-memory bandwidth wall to the HBM stream.
 //
-// Roles (one persistent CTA per SM, 18 warps):
+// Roles (one persistent CTA per SM, 24 warps):
 //   producer (1 lane)   TMA bulk copies: feature rows + deg^-1/2 into a shared-memory ring
-//   split warps (4)     ring -> registers (scaled by deg_u^-1/2), hi/lo split, MN-major
-//                       swizzled B operand (the layout k_pipe_tn uses)
+//   split warps (8)     ring -> registers (scaled by deg_u^-1/2), hi/lo split, MN-major
+//                       swizzled B operand [Xhi | Xlo] (the layout k_pipe_tn uses)
 //   build warps (4)     adjacency bits -> 1.0f / 0.0f -> tcgen05.st into TMEM (A operand)
-//   MMA (1 lane)        G(j):  P  = ADJ . [Xhi ; Xlo]            32 x (128 x 64 x 8)
-//                       T(j):  O  = P . Whi + P . Wlo + Plo . Whi 24 x (128 x 64 x 8)
-//                       issued G(j+1) before T(j) so the pipe never waits for the fix warps
-//   fix warps (4)       tcgen05.ld P, * deg_v^-1/2, hi -> P, lo -> Plo (tcgen05.st), and the
-//                       coalesced global store of P (saved for dW) through a padded patch
+//   MMA warp G          G(j):  [P(hi part) | P(lo part)] = ADJ . [Xhi | Xlo]   16 x (128 x 128 x 8)
+//   fix warps (4)       tcgen05.ld P, add the halves, * deg_v^-1/2, hi -> P, lo -> Plo
+//                       (tcgen05.st, in place), and the coalesced global store of P (saved
+//                       for dW) through a swizzled patch
+//   MMA warp T          T(j):  O = Plo . Whi + P . Wlo + P . Whi                24 x (128 x 64 x 8)
+//                       G and T are issued by different warps (issue cost, not the tensor
+//                       pipe, limits one issuer); both stay converged and predicate the
+//                       instruction on one elected lane
 //   epilogue warps (4)  the epilogue of pipe_tc.cu (activation / act' / fused MSE)
+//   2nd producer (1 lane, fwd + MSE)  the target tile as two TMA TENSOR copies (128B swizzle)
 // TMEM (512 columns): ADJ 0..127 | P0,Plo0 128..255 | P1,Plo1 256..383 | O0 384..447 | O1 448..511
 //
 // Summation order: the tensor core adds the row's terms in column order with fp32
