@@ -181,8 +181,10 @@ struct Batch : Object {
   uint8_t* col8 = nullptr;   // [Z] CSR neighbour - tile first row
   uint8_t* csc8 = nullptr;   // [Z] CSC source    - tile first row
   // adjacency rows as 128-bit masks over the tile's vertices (CSR / CSC direction) for the
-  // tensor-core gather; multi_edges: -1 unknown (status not read yet), 0 none, 1 some pair
-  // repeats (bits cannot carry a multiplicity: the list kernels are used)
+  // tensor-core gather; multi_edges: -1 unknown (status not read yet), 0 the bit masks are a
+  // faithful adjacency, != 0 not (bit 0: some pair repeats -- bits cannot carry a multiplicity;
+  // bit 1: some vertex has degree 0, i.e. deg^-1/2 = Infinity, and 0 * Infinity = NaN): the list
+  // kernels are used
   uint4* abits = nullptr;
   uint4* atbits = nullptr;
   int multi_edges = -1;

@@ -320,6 +320,10 @@ __global__ void k_tile_operands(const int4* __restrict__ tiles, const int32_t* _
     }
     (dir ? atbits : abits)[ti.x + r] = make_uint4(w[0], w[1], w[2], w[3]);
     if (dup) atomicOr(multi, 1);
+    // a vertex without CSR entries has deg^-1/2 = Infinity (as in the reference, where it only
+    // matters to the rows that list the vertex): in the dense adjacency product 0 * Infinity =
+    // NaN would reach every row of the tile -- such batches keep the list kernels
+    if (dir == 1 && deg[ti.x + r] == 0) atomicOr(multi, 2);
   }
   for (int e = threadIdx.x; e < ti.w; e += blockDim.x) {
     col8[ti.z + e] = static_cast<uint8_t>(col[ti.z + e] - ti.x);

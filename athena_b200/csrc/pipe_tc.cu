@@ -427,7 +427,7 @@ k_pipe_gather(GatherArgs a) {
           c4 = cn;
           e4 = en;
         }
-        if (has_coef) {
+        if (has_coef && end > beg) {  // an empty row sums to 0 (its deg^-1/2 is Infinity)
           const float wv = rss[row];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {

@@ -95,10 +95,6 @@ struct TcgCfg {
   // next copy is issued almost immediately; deeper rings measured the same or slower (fwd
   // 60.1 / 61.6 / 62.0 us for 1 / 2 / 3 stages), so the shared memory is left to the L1.
   static constexpr int NS = 1;
-  // Operand tiles of the epilogue (saved activations / target).  Two tiles (copy for tile
-  // j + 2 issued when tile j is done) measured slower than one with this epilogue (96 vs 83 us
-  // for the fused MSE step): the kernel is bound by its HBM stream, not by this latency.
-  static constexpr int NAUX = 1;
   static constexpr int SPLIT_WARP0 = 0;                          // warps 0..7
   static constexpr int SPLIT_THREADS = 256;
   static constexpr int BUILD_WARP0 = 8;                          // warps 8..11  (warp % 4 = TMEM lane quarter)
@@ -133,7 +129,7 @@ struct TcgCfg {
   static constexpr bool AUX_TMA = EPI == EPI_MSE;
   static constexpr int AUX_TMA_TILE = TILE_ROWS * N * 4;
   static constexpr int OFF_AUX = (OFF_RING + NS * STAGE_BYTES + 1023) / 1024 * 1024;
-  static constexpr int AUX_BYTES = AUX_TMA ? 2 * AUX_TMA_TILE : EPI != EPI_ACT ? NAUX * AUX_TILE : 0;
+  static constexpr int AUX_BYTES = AUX_TMA ? 2 * AUX_TMA_TILE : EPI != EPI_ACT ? AUX_TILE : 0;
   static constexpr int OFF_BAR = OFF_AUX + AUX_BYTES;
   static constexpr int OFF_EPI = OFF_BAR + 256 + 512;
   static constexpr int FIX_PATCH = 32 * 16;                      // floats per fix / epilogue warp patch
@@ -374,15 +370,14 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
       }
       return c;
     };
-    // Second operand (saved activations / target): each warp prefetches its own 32 rows with
-    // cp.async into rows padded to 272 B (conflict-free row-per-thread reads).  One cp.async
-    // group per tile, possibly empty.  With two operand tiles (MSE) the copy for tile j + 2
-    // is issued when tile j is done, i.e. a whole tile period before it is needed; with one
-    // tile (backward with saved activations) only the rest of the period hides it.
-    auto issue_aux = [&](int t, int buf) {
+    // Second operand without TMA (saved activations of the backward pass; unaligned targets):
+    // each warp prefetches its own 32 rows of the next tile with cp.async into rows padded to
+    // 272 B (conflict-free row-per-thread reads) when it is done with the current one.
+    // (Two such tiles, copy for tile j + 2 issued when tile j is done, measured slower.)
+    auto issue_aux = [&](int t) {
       const int4 ti = tile_at(t);
       const float* src = a.aux + (static_cast<size_t>(ti.x) + q * 32) * N;
-      float* dst = sAux + buf * (TILE_ROWS * AUX_PITCH) + q * 32 * AUX_PITCH;
+      float* dst = sAux + q * 32 * AUX_PITCH;
       const int rows = min(32, ti.y - q * 32);
 #pragma unroll
       for (int it = 0; it < N / 4; ++it) {
@@ -426,17 +421,13 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
       if (aux_tma) {
         if (!dry) mbar_wait_g(&aux_full[j & 1], (j >> 1) & 1, 14);
       } else if (use_aux && !dry) {
-        if (Cfg::NAUX == 2)
-          asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
       }
       const float* aux_row =
           aux_tma ? reinterpret_cast<const float*>(smem + Cfg::OFF_AUX +
                                                    (j & 1) * Cfg::AUX_TMA_TILE)
-                  : sAux + (Cfg::NAUX == 2 ? (j & 1) : 0) * (TILE_ROWS * AUX_PITCH) +
-                        my_row * AUX_PITCH;
+                  : sAux + my_row * AUX_PITCH;
       const uint32_t tacc = tmem + Cfg::T_O + b * N;
       uint64_t* release = dry ? dummy : &o_empty[b];
       const float scale =
@@ -467,17 +458,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
       }
       if (use_aux && !aux_tma) {
         __syncwarp();
-        if (Cfg::NAUX == 2) {
-          // after the dry pass: tiles 0 and 1; after tile j: tile j + 2 into the buffer it frees
-          if (dry) {
-            issue_aux(blockIdx.x, 0);
-            issue_aux(blockIdx.x + step, 1);
-          } else {
-            issue_aux(t + 2 * step, j & 1);
-          }
-        } else {
-          issue_aux(t + step, 0);
-        }
+        issue_aux(t + step);  // the first tile right after the dry pass
       }
     }
     if (EPI == EPI_MSE) loss_red[my_row] = lsum;

@@ -518,6 +518,41 @@ def test_kipf_fused_training_multi_edge_batch_uses_list_gather(cuda, oracle32):
                    ab.sgd_optimiser_type(0.05))
 
 
+def test_kipf_fused_directed_graph_with_sinks(cuda, oracle32):
+    """Directed graphs with vertices that have no outgoing entry (degree 0, deg^-1/2 =
+    Infinity as in the reference) but are somebody's neighbour: only the rows that list such a
+    vertex may become non-finite; every other row must match.  (In a dense adjacency product
+    0 * Infinity would poison the whole tile: these batches take the list kernels.)"""
+    rng = np.random.default_rng(77)
+    nv = np.array([60, 68, 50], np.int64)
+    voff = np.concatenate([[0], np.cumsum(nv)])
+    src, dst = [], []
+    for g, n in enumerate(nv):
+        n = int(n)
+        s_ = np.repeat(np.arange(n - 2), 3)              # the last two vertices are sinks
+        d_ = rng.integers(0, n - 2, s_.size)
+        d_[rng.random(s_.size) < 0.02] = n - 1           # a few edges point at a sink
+        keep = np.unique(s_ * n + d_, return_index=True)[1]
+        src.append(voff[g] + s_[keep]); dst.append(voff[g] + d_[keep])
+    p, _ = synth.packed_from_edges(nv, np.concatenate(src), np.concatenate(dst), directed=True,
+                                   add_self_loops=False)
+    p.x = rng.standard_normal((p.V, 64)).astype(np.float32)
+    spec = kipf_spec([64, 64], 1, "none")
+    params = random_params(oracle32.num_params([spec]), rng, 0.3)
+    with np.errstate(all="ignore"):
+        out_ref, _, _ = oracle32.layer_fwd_bwd(spec, params, to_oracle_batch(p))
+    L = ab.kipf_msgpass_layer_type([64, 64], 1)
+    L.set_params(params)
+    L.set_graph(p)
+    out = L.forward()
+    finite = np.isfinite(out_ref).all(axis=1)
+    assert 0 < (~finite).sum() < p.V // 2                # some rows list a sink, most do not
+    assert np.isfinite(out[finite]).all()
+    assert rel_err(out[finite], out_ref[finite]) <= RTOL_ACT
+    assert not np.isfinite(out[~finite]).all(axis=1).any()
+    L.destroy()
+
+
 @pytest.mark.parametrize("act", ["none", "relu", "tanh"])
 def test_kipf_large_graph_width_128_fused_path(cuda, oracle32, oracle64, act):
     """One graph far larger than a 128-row tile, F = 128: the fused SpMM + tcgen05 kernel of
