@@ -55,8 +55,11 @@ using namespace pipe;
 
 namespace {
 
-// mbarrier wait that traps (instead of hanging the GPU) when a barrier never completes
+// mbarrier wait.  Development builds (-DATHENA_TCG_WATCHDOG) trap with the barrier's tag
+// instead of hanging the GPU when a barrier never completes; production builds wait without a
+// deadline (a time-sliced or profiled context may legitimately stall for seconds).
 __device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity, int tag) {
+#ifdef ATHENA_TCG_WATCHDOG
   const uint32_t addr = smem_u32(bar);
   long long t0 = 0;
   for (;;) {
@@ -79,6 +82,10 @@ __device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity, int 
       __trap();
     }
   }
+#else
+  (void)tag;
+  mbar_wait(bar, parity);
+#endif
 }
 
 constexpr int TCG_TRACE_TILES = 16;
