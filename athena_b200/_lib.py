@@ -19,7 +19,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 MEM_HOST, MEM_DEVICE = 0, 1
 ACT = {"none": 0, "linear": 1, "relu": 2, "leaky_relu": 3, "sigmoid": 4, "tanh": 5, "softmax": 6}
-OPT_SGD, OPT_ADAM = 0, 1
+OPT_SGD, OPT_ADAM, OPT_RMSPROP, OPT_ADAGRAD = 0, 1, 2, 3
 COMM_ID_BYTES = 128
 P2P_HANDLE_BYTES = 128
 

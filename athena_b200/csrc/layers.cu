@@ -871,7 +871,7 @@ ATHENA_API int athena_cuda_network_compile(athena_handle_t net,
   ATH_REQUIRE(optimiser, ATHENA_ERR_ARG, "network_compile: null optimiser");
   ATH_REQUIRE(!N->layers.empty(), ATHENA_ERR_STATE, "network_compile: no layers");
   ATH_REQUIRE(!N->compiled, ATHENA_ERR_STATE, "network_compile: already compiled");
-  ATH_REQUIRE(optimiser->kind == ATHENA_OPT_SGD || optimiser->kind == ATHENA_OPT_ADAM,
+  ATH_REQUIRE(optimiser->kind >= ATHENA_OPT_SGD && optimiser->kind <= ATHENA_OPT_ADAGRAD,
               ATHENA_ERR_ARG, "network_compile: unknown optimiser kind %d", optimiser->kind);
   int64_t n = 0;
   for (Layer* L : N->layers) n += L->num_params;

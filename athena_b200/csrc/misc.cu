@@ -182,7 +182,8 @@ struct StepArgs {
   float bc1, bc2;
 };
 
-// one parameter of minimise_sgd / minimise_adam (athena_optimiser.f90:649-672, 1043-1088)
+// one parameter of minimise_sgd / _adam / _rmsprop / _adagrad
+// (athena_optimiser.f90:649-672, 1043-1088, 795-803, 919-924)
 __device__ __forceinline__ void step_one(float* __restrict__ p, float* __restrict__ s1,
                                          float* __restrict__ s2, long long i, float gr,
                                          const StepArgs& a) {
@@ -196,13 +197,23 @@ __device__ __forceinline__ void step_one(float* __restrict__ p, float* __restric
       s1[i] = gr;
       p[i] = p[i] + gr;
     }
-  } else {
+  } else if (a.kind == ATHENA_OPT_ADAM) {
     float m = a.beta1 * s1[i] + (1.f - a.beta1) * gr;
     float v = a.beta2 * s2[i] + (1.f - a.beta2) * gr * gr;
     s1[i] = m;
     s2[i] = v;
     float mh = m / a.bc1, vh = v / a.bc2;
     p[i] = p[i] - a.lr * (mh / (sqrtf(vh) + a.eps));
+  } else if (a.kind == ATHENA_OPT_RMSPROP) {
+    // minimise_rmsprop (athena_optimiser.f90:795-803): the moving average lives in s1
+    const float avg = a.beta1 * s1[i] + (1.f - a.beta1) * (gr * gr);
+    s1[i] = avg;
+    p[i] = p[i] - a.lr * gr / sqrtf(avg + a.eps);
+  } else {
+    // minimise_adagrad (athena_optimiser.f90:919-924): the sum of squares lives in s1
+    const float ss = s1[i] + gr * gr;
+    s1[i] = ss;
+    p[i] = p[i] - a.lr * gr / sqrtf(ss + a.eps);
   }
 }
 

@@ -81,6 +81,38 @@ class adam_optimiser_type(base_optimiser_type):
         return d
 
 
+class rmsprop_optimiser_type(base_optimiser_type):
+    """rmsprop_optimiser_type(learning_rate, beta, epsilon) -- athena_optimiser.f90:160-166
+    (defaults beta = 0, epsilon = 1e-8), minimise_rmsprop :771-803."""
+    kind = _lib.OPT_RMSPROP
+
+    def __init__(self, learning_rate: float = 0.01, beta: float = 0.0, epsilon: float = 1e-8,
+                 clip_dict: Optional[clip_type] = None):
+        super().__init__(learning_rate, clip_dict)
+        self.beta, self.epsilon = float(beta), float(epsilon)
+
+    def desc(self):
+        d = super().desc()
+        d.beta1, d.epsilon = self.beta, self.epsilon
+        return d
+
+
+class adagrad_optimiser_type(base_optimiser_type):
+    """adagrad_optimiser_type(learning_rate, epsilon) -- athena_optimiser.f90:199-203,
+    minimise_adagrad :898-925."""
+    kind = _lib.OPT_ADAGRAD
+
+    def __init__(self, learning_rate: float = 0.01, epsilon: float = 1e-8,
+                 clip_dict: Optional[clip_type] = None):
+        super().__init__(learning_rate, clip_dict)
+        self.epsilon = float(epsilon)
+
+    def desc(self):
+        d = super().desc()
+        d.epsilon = self.epsilon
+        return d
+
+
 class network_type:
     def __init__(self):
         h = C.c_int64()

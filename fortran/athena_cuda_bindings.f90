@@ -38,6 +38,8 @@ module athena__cuda_bindings
 
   integer(c_int32_t), parameter, public :: ATHENA_OPT_SGD = 0
   integer(c_int32_t), parameter, public :: ATHENA_OPT_ADAM = 1
+  integer(c_int32_t), parameter, public :: ATHENA_OPT_RMSPROP = 2
+  integer(c_int32_t), parameter, public :: ATHENA_OPT_ADAGRAD = 3
   integer(c_int32_t), parameter, public :: ATHENA_MEM_HOST = 0
   integer(c_int32_t), parameter, public :: ATHENA_MEM_DEVICE = 1
   integer, parameter, public :: ATHENA_COMM_ID_BYTES = 128

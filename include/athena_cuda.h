@@ -64,6 +64,8 @@ typedef int64_t athena_handle_t;
 /* optimiser kinds: athena_optimiser.f90:634-673 (sgd), :1027-1091 (adam) */
 #define ATHENA_OPT_SGD 0
 #define ATHENA_OPT_ADAM 1
+#define ATHENA_OPT_RMSPROP 2 /* athena_optimiser.f90:771-803; beta in `beta1`, epsilon */
+#define ATHENA_OPT_ADAGRAD 3 /* athena_optimiser.f90:898-925; epsilon */
 
 /* memory space of data pointers handed to *_forward/_backward/_train_step */
 #define ATHENA_MEM_HOST 0
@@ -264,7 +266,7 @@ int athena_cuda_network_add(athena_handle_t net, athena_handle_t layer);
 typedef struct athena_optimiser_desc {
   int32_t kind;          /* ATHENA_OPT_* */
   float learning_rate;
-  float beta1, beta2, epsilon; /* adam */
+  float beta1, beta2, epsilon; /* adam; rmsprop: beta1 = beta; adagrad: epsilon */
   float momentum;        /* sgd */
   int32_t nesterov;      /* sgd */
   int32_t clip_min_max;  /* clip_type%l_min_max, athena_clipper.f90:190-193 */

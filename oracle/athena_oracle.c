@@ -1006,12 +1006,31 @@ API void oracle_layer_fwd_bwd(const oracle_layer_t *L, const real *params, int B
 }
 
 typedef struct {
-  int kind; /* 0 = sgd, 1 = adam */
+  int kind; /* 0 = sgd, 1 = adam, 2 = rmsprop (beta in beta1), 3 = adagrad */
   real lr, beta1, beta2, eps, momentum;
   int nesterov;
   int clip_flags;
   real clip_min, clip_max, clip_norm;
 } oracle_optim_t;
+
+/* minimise_rmsprop: moving_avg = beta*moving_avg + (1-beta)*g^2 ;
+ * param -= lr * g / sqrt(moving_avg + eps).  src/athena/athena_optimiser.f90:771-803  */
+API void oracle_rmsprop(int n, real *p, const real *g, real *avg, real lr, real beta,
+                        real eps) {
+  for (int i = 0; i < n; ++i) {
+    avg[i] = beta * avg[i] + ((real)1 - beta) * (g[i] * g[i]);
+    p[i] = p[i] - lr * g[i] / R_SQRT(avg[i] + eps);
+  }
+}
+
+/* minimise_adagrad: sum_squares += g^2 ; param -= lr * g / sqrt(sum_squares + eps).
+ * src/athena/athena_optimiser.f90:898-925                                              */
+API void oracle_adagrad(int n, real *p, const real *g, real *ss, real lr, real eps) {
+  for (int i = 0; i < n; ++i) {
+    ss[i] = ss[i] + g[i] * g[i];
+    p[i] = p[i] - lr * g[i] / R_SQRT(ss[i] + eps);
+  }
+}
 
 /* network%update: iter already incremented by the caller; grads are summed
  * over samples (single column) so no column mean applies.
@@ -1021,8 +1040,12 @@ API void oracle_update(int n, real *params, real *grads, const oracle_optim_t *o
   oracle_clip(n, grads, o->clip_flags, o->clip_min, o->clip_max, o->clip_norm);
   if (o->kind == 0)
     oracle_sgd(n, params, grads, state1, o->lr, o->momentum, o->nesterov);
-  else
+  else if (o->kind == 1)
     oracle_adam(n, params, grads, state1, state2, o->lr, o->beta1, o->beta2, o->eps, iter);
+  else if (o->kind == 2)
+    oracle_rmsprop(n, params, grads, state1, o->lr, o->beta1, o->eps);
+  else
+    oracle_adagrad(n, params, grads, state1, o->lr, o->eps);
 }
 
 /* one full train step of the batch loop (athena_network_sub.f90:3611-3670):

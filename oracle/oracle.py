@@ -166,7 +166,7 @@ class Oracle:
 
     def optim_c(self, o: OptimSpec):
         s = self._OptimT()
-        s.kind = 0 if o.kind == "sgd" else 1
+        s.kind = {"sgd": 0, "adam": 1, "rmsprop": 2, "adagrad": 3}[o.kind]  # rmsprop: beta in beta1
         s.lr, s.beta1, s.beta2, s.eps, s.momentum = o.lr, o.beta1, o.beta2, o.eps, o.momentum
         s.nesterov = int(o.nesterov)
         flags = 0

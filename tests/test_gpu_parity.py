@@ -447,6 +447,26 @@ def test_full_layer_placement_rules(cuda):
     net.destroy()
 
 
+@pytest.mark.parametrize("kind", ["rmsprop", "rmsprop_beta", "adagrad"])
+def test_rmsprop_adagrad_training_parity(cuda, oracle32, kind):
+    """minimise_rmsprop / minimise_adagrad on the flat parameter vector
+    (athena_optimiser.f90:771-803, 898-925), fused Kipf steps underneath, with clipping."""
+    rng = np.random.default_rng(31)
+    p = synth.regular_batch(12, 64, 4, 64, rng)
+    specs = [kipf_spec([64, 64], 1, "relu"), kipf_spec([64, 64], 1, "none")]
+    layers = [ab.kipf_msgpass_layer_type([64, 64], 1, "relu"),
+              ab.kipf_msgpass_layer_type([64, 64], 1, "none")]
+    target = rng.standard_normal((p.V, 64)).astype(np.float32)
+    clip = ab.clip_type(clip_norm=5.0)
+    if kind == "adagrad":
+        spec_o, opt = OptimSpec("adagrad", lr=0.01, clip_norm=5.0), ab.adagrad_optimiser_type(0.01, clip_dict=clip)
+    else:
+        beta = 0.9 if kind == "rmsprop_beta" else 0.0
+        spec_o = OptimSpec("rmsprop", lr=0.002, beta1=beta, clip_norm=5.0)
+        opt = ab.rmsprop_optimiser_type(0.002, beta=beta, clip_dict=clip)
+    _train_compare(cuda, oracle32, specs, layers, p, target, spec_o, opt)
+
+
 def test_network_train_loop_runs_epochs(cuda):
     """network%train batch loop with a ragged last batch (athena_network_sub.f90:3575-3670)."""
     rng = np.random.default_rng(9)

@@ -141,6 +141,23 @@ def test_duvenaud_gradients_are_true_gradients(oracle64):
     _fd_check(oracle64, [L], params, b, target, rng.choice(n, 12, replace=False))
 
 
+def test_rmsprop_and_adagrad_match_their_definitions(oracle64):
+    """minimise_rmsprop / minimise_adagrad (athena_optimiser.f90:795-803, 919-924) against the
+    formulas evaluated with numpy over three steps (the reference has no test for them)."""
+    rng = np.random.default_rng(21)
+    p0 = rng.standard_normal(17)
+    gs = [rng.standard_normal(17) for _ in range(3)]
+    for kind, beta in (("rmsprop", 0.0), ("rmsprop", 0.9), ("adagrad", 0.0)):
+        o = OptimSpec(kind, lr=0.05, beta1=beta, eps=1e-8)
+        p, s1, s2 = p0.copy(), np.zeros(17), np.zeros(17)
+        q, acc = p0.copy(), np.zeros(17)
+        for it, g in enumerate(gs, 1):
+            p, s1, s2 = oracle64.update(p, g, o, s1, s2, it)
+            acc = beta * acc + (1 - beta) * g * g if kind == "rmsprop" else acc + g * g
+            q = q - 0.05 * g / np.sqrt(acc + 1e-8)
+        assert np.allclose(p, q, rtol=1e-12, atol=0) and np.allclose(s1, acc, rtol=1e-12)
+
+
 def test_duvenaud_full_head_gradients_are_true_gradients(oracle64):
     """Duvenaud -> full -> full (the wiring of example/msgpass_chemical, main.f90:129-157):
     the reverse sweep through the dense head (athena_full_layer.f90:839-874) is exact."""
