@@ -20,6 +20,7 @@ CSRC = os.path.join(_HERE, "csrc")
 MEM_HOST, MEM_DEVICE = 0, 1
 ACT = {"none": 0, "linear": 1, "relu": 2, "leaky_relu": 3, "sigmoid": 4, "tanh": 5, "softmax": 6}
 OPT_SGD, OPT_ADAM, OPT_RMSPROP, OPT_ADAGRAD = 0, 1, 2, 3
+REG_NONE, REG_L1, REG_L2, REG_L1L2 = 0, 1, 2, 3
 COMM_ID_BYTES = 128
 P2P_HANDLE_BYTES = 128
 
@@ -37,7 +38,9 @@ class OptimiserDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("learning_rate", C.c_float), ("beta1", C.c_float),
                 ("beta2", C.c_float), ("epsilon", C.c_float), ("momentum", C.c_float),
                 ("nesterov", C.c_int32), ("clip_min_max", C.c_int32), ("clip_min", C.c_float),
-                ("clip_max", C.c_float), ("clip_norm_on", C.c_int32), ("clip_norm", C.c_float)]
+                ("clip_max", C.c_float), ("clip_norm_on", C.c_int32), ("clip_norm", C.c_float),
+                ("regulariser", C.c_int32), ("l1", C.c_float), ("l2", C.c_float),
+                ("l2_decoupled", C.c_int32)]
 
 
 def build(force: bool = False) -> str:

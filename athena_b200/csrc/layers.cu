@@ -873,6 +873,8 @@ ATHENA_API int athena_cuda_network_compile(athena_handle_t net,
   ATH_REQUIRE(!N->compiled, ATHENA_ERR_STATE, "network_compile: already compiled");
   ATH_REQUIRE(optimiser->kind >= ATHENA_OPT_SGD && optimiser->kind <= ATHENA_OPT_ADAGRAD,
               ATHENA_ERR_ARG, "network_compile: unknown optimiser kind %d", optimiser->kind);
+  ATH_REQUIRE(optimiser->regulariser >= ATHENA_REG_NONE && optimiser->regulariser <= ATHENA_REG_L1L2,
+              ATHENA_ERR_ARG, "network_compile: unknown regulariser %d", optimiser->regulariser);
   int64_t n = 0;
   for (Layer* L : N->layers) n += L->num_params;
   N->n = n;

@@ -180,6 +180,9 @@ struct StepArgs {
   int norm_on;
   float clip_norm;
   float bc1, bc2;
+  int reg;          // ATHENA_REG_*
+  float l1, l2;
+  int l2_decoupled;
 };
 
 // one parameter of minimise_sgd / _adam / _rmsprop / _adagrad
@@ -187,6 +190,17 @@ struct StepArgs {
 __device__ __forceinline__ void step_one(float* __restrict__ p, float* __restrict__ s1,
                                          float* __restrict__ s2, long long i, float gr,
                                          const StepArgs& a) {
+  if (a.reg != ATHENA_REG_NONE) {
+    // regulariser%regularise inside minimise_* (athena_regulariser.f90:99, 117, 135-136),
+    // in the reference's order of operations
+    const float pv = p[i], sgn = copysignf(1.f, pv);
+    if (a.reg == ATHENA_REG_L1)
+      gr = gr + a.lr * a.l1 * sgn;
+    else if (a.reg == ATHENA_REG_L2)
+      gr = gr + a.lr * 2.f * a.l2 * pv;
+    else
+      gr = gr + a.lr * (a.l1 * sgn + 2.f * a.l2 * pv);
+  }
   if (a.kind == ATHENA_OPT_SGD) {
     gr = -a.lr * gr;
     if (a.momentum > 1e-8f) {
@@ -203,7 +217,18 @@ __device__ __forceinline__ void step_one(float* __restrict__ p, float* __restric
     s1[i] = m;
     s2[i] = v;
     float mh = m / a.bc1, vh = v / a.bc2;
-    p[i] = p[i] - a.lr * (mh / (sqrtf(vh) + a.eps));
+    if (a.reg == ATHENA_REG_L2) {
+      // athena_optimiser.f90:1064-1078: AdamW (decoupled decay) or L2 inside the quotient
+      float pv = p[i];
+      if (a.l2_decoupled) {
+        pv = pv - a.lr * a.l2 * pv;
+        p[i] = pv - a.lr * (mh / (sqrtf(vh) + a.eps));
+      } else {
+        p[i] = pv - a.lr * ((mh + a.l2 * pv) / (sqrtf(vh) + a.eps));
+      }
+    } else {
+      p[i] = p[i] - a.lr * (mh / (sqrtf(vh) + a.eps));
+    }
   } else if (a.kind == ATHENA_OPT_RMSPROP) {
     // minimise_rmsprop (athena_optimiser.f90:795-803): the moving average lives in s1
     const float avg = a.beta1 * s1[i] + (1.f - a.beta1) * (gr * gr);
@@ -418,6 +443,10 @@ static int step_prepare(int64_t n, OptimState& st, StepArgs* a) {
   a->nesterov = d.nesterov;
   a->norm_on = d.clip_norm_on;
   a->clip_norm = d.clip_norm;
+  a->reg = d.regulariser;
+  a->l1 = d.l1;
+  a->l2 = d.l2;
+  a->l2_decoupled = d.l2_decoupled;
   a->bc1 = 1.f - powi(d.beta1, st.iter);
   a->bc2 = 1.f - powi(d.beta2, st.iter);
   return ATHENA_OK;

@@ -31,12 +31,39 @@ class clip_type:
         self.norm = 0.0 if clip_norm is None else float(clip_norm)
 
 
+class l1_regulariser_type:
+    """l1_regulariser_type(l1=0.01) -- athena_regulariser.f90:40-49, 85-101."""
+    kind = _lib.REG_L1
+
+    def __init__(self, l1: float = 0.01):
+        self.l1, self.l2, self.decoupled = float(l1), 0.0, True
+
+
+class l2_regulariser_type:
+    """l2_regulariser_type(l2=0.01, decoupled=.true.) -- athena_regulariser.f90:51-66, 103-119;
+    `decoupled` selects AdamW in minimise_adam (athena_optimiser.f90:1064-1084)."""
+    kind = _lib.REG_L2
+
+    def __init__(self, l2: float = 0.01, decoupled: bool = True):
+        self.l1, self.l2, self.decoupled = 0.0, float(l2), bool(decoupled)
+
+
+class l1l2_regulariser_type:
+    """l1l2_regulariser_type(l1=0.01, l2=0.01) -- athena_regulariser.f90:121-137."""
+    kind = _lib.REG_L1L2
+
+    def __init__(self, l1: float = 0.01, l2: float = 0.01):
+        self.l1, self.l2, self.decoupled = float(l1), float(l2), True
+
+
 class base_optimiser_type:
     kind = _lib.OPT_SGD
 
-    def __init__(self, learning_rate: float = 0.01, clip_dict: Optional[clip_type] = None):
+    def __init__(self, learning_rate: float = 0.01, clip_dict: Optional[clip_type] = None,
+                 regulariser=None):
         self.learning_rate = float(learning_rate)
         self.clip_dict = clip_dict or clip_type()
+        self.regulariser = regulariser
         self.iter = 0
 
     def desc(self) -> OptimiserDesc:
@@ -48,6 +75,10 @@ class base_optimiser_type:
         c = self.clip_dict
         d.clip_min_max, d.clip_min, d.clip_max = int(c.l_min_max), c.min, c.max
         d.clip_norm_on, d.clip_norm = int(c.l_norm), c.norm
+        r = self.regulariser
+        d.regulariser = _lib.REG_NONE if r is None else r.kind
+        d.l1, d.l2 = (0.0, 0.0) if r is None else (r.l1, r.l2)
+        d.l2_decoupled = 1 if r is None else int(r.decoupled)
         return d
 
 
@@ -56,8 +87,8 @@ class sgd_optimiser_type(base_optimiser_type):
     kind = _lib.OPT_SGD
 
     def __init__(self, learning_rate: float = 0.01, momentum: float = 0.0, nesterov: bool = False,
-                 clip_dict: Optional[clip_type] = None):
-        super().__init__(learning_rate, clip_dict)
+                 clip_dict: Optional[clip_type] = None, regulariser=None):
+        super().__init__(learning_rate, clip_dict, regulariser)
         self.momentum, self.nesterov = float(momentum), bool(nesterov)
 
     def desc(self):
@@ -71,8 +102,8 @@ class adam_optimiser_type(base_optimiser_type):
     kind = _lib.OPT_ADAM
 
     def __init__(self, learning_rate: float = 0.01, beta1: float = 0.9, beta2: float = 0.999,
-                 epsilon: float = 1e-8, clip_dict: Optional[clip_type] = None):
-        super().__init__(learning_rate, clip_dict)
+                 epsilon: float = 1e-8, clip_dict: Optional[clip_type] = None, regulariser=None):
+        super().__init__(learning_rate, clip_dict, regulariser)
         self.beta1, self.beta2, self.epsilon = float(beta1), float(beta2), float(epsilon)
 
     def desc(self):
@@ -87,8 +118,8 @@ class rmsprop_optimiser_type(base_optimiser_type):
     kind = _lib.OPT_RMSPROP
 
     def __init__(self, learning_rate: float = 0.01, beta: float = 0.0, epsilon: float = 1e-8,
-                 clip_dict: Optional[clip_type] = None):
-        super().__init__(learning_rate, clip_dict)
+                 clip_dict: Optional[clip_type] = None, regulariser=None):
+        super().__init__(learning_rate, clip_dict, regulariser)
         self.beta, self.epsilon = float(beta), float(epsilon)
 
     def desc(self):
@@ -103,8 +134,8 @@ class adagrad_optimiser_type(base_optimiser_type):
     kind = _lib.OPT_ADAGRAD
 
     def __init__(self, learning_rate: float = 0.01, epsilon: float = 1e-8,
-                 clip_dict: Optional[clip_type] = None):
-        super().__init__(learning_rate, clip_dict)
+                 clip_dict: Optional[clip_type] = None, regulariser=None):
+        super().__init__(learning_rate, clip_dict, regulariser)
         self.epsilon = float(epsilon)
 
     def desc(self):

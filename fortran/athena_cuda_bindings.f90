@@ -40,6 +40,8 @@ module athena__cuda_bindings
   integer(c_int32_t), parameter, public :: ATHENA_OPT_ADAM = 1
   integer(c_int32_t), parameter, public :: ATHENA_OPT_RMSPROP = 2
   integer(c_int32_t), parameter, public :: ATHENA_OPT_ADAGRAD = 3
+  integer(c_int32_t), parameter, public :: ATHENA_REG_NONE = 0, ATHENA_REG_L1 = 1
+  integer(c_int32_t), parameter, public :: ATHENA_REG_L2 = 2, ATHENA_REG_L1L2 = 3
   integer(c_int32_t), parameter, public :: ATHENA_MEM_HOST = 0
   integer(c_int32_t), parameter, public :: ATHENA_MEM_DEVICE = 1
   integer, parameter, public :: ATHENA_COMM_ID_BYTES = 128
@@ -55,6 +57,9 @@ module athena__cuda_bindings
      real(c_float) :: clip_min, clip_max
      integer(c_int32_t) :: clip_norm_on
      real(c_float) :: clip_norm
+     integer(c_int32_t) :: regulariser
+     real(c_float) :: l1, l2
+     integer(c_int32_t) :: l2_decoupled
   end type athena_optimiser_desc
 
   public :: athena_cuda_init, athena_cuda_shutdown, athena_cuda_last_error

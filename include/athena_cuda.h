@@ -67,6 +67,11 @@ typedef int64_t athena_handle_t;
 #define ATHENA_OPT_RMSPROP 2 /* athena_optimiser.f90:771-803; beta in `beta1`, epsilon */
 #define ATHENA_OPT_ADAGRAD 3 /* athena_optimiser.f90:898-925; epsilon */
 
+#define ATHENA_REG_NONE 0
+#define ATHENA_REG_L1 1
+#define ATHENA_REG_L2 2
+#define ATHENA_REG_L1L2 3
+
 /* memory space of data pointers handed to *_forward/_backward/_train_step */
 #define ATHENA_MEM_HOST 0
 #define ATHENA_MEM_DEVICE 1
@@ -273,6 +278,13 @@ typedef struct athena_optimiser_desc {
   float clip_min, clip_max;
   int32_t clip_norm_on;  /* clip_type%l_norm, :196-203 */
   float clip_norm;
+  /* regulariser%regularise(param, gradient, learning_rate), applied inside minimise_* before
+   * the step (athena_regulariser.f90:85-137): gradient += lr * (l1 sign(1,p) + 2 l2 p).
+   * With an l2 regulariser minimise_adam additionally decays the parameter, decoupled
+   * (AdamW) or inside the quotient (athena_optimiser.f90:1064-1084). */
+  int32_t regulariser;   /* ATHENA_REG_* */
+  float l1, l2;
+  int32_t l2_decoupled;  /* l2_regulariser_type%decoupled (default .true.) */
 } athena_optimiser_desc;
 
 /* network%compile(optimiser, loss_method="mse").  Loss: athena_loss.f90:393-430. */

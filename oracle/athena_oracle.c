@@ -40,12 +40,14 @@
 typedef double real;
 #define R_EXP exp
 #define R_SQRT sqrt
+#define R_COPYSIGN copysign
 #define R_POW pow
 #define R_TANH tanh
 #else
 typedef float real;
 #define R_EXP expf
 #define R_SQRT sqrtf
+#define R_COPYSIGN copysignf
 #define R_POW powf
 #define R_TANH tanhf
 #endif
@@ -1011,7 +1013,42 @@ typedef struct {
   int nesterov;
   int clip_flags;
   real clip_min, clip_max, clip_norm;
+  int reg; /* 0 none, 1 l1, 2 l2, 3 l1l2 (athena_regulariser.f90) */
+  real l1, l2;
+  int l2_decoupled;
 } oracle_optim_t;
+
+/* regulariser%regularise(param, gradient, learning_rate), called at the top of every
+ * minimise_* (athena_regulariser.f90:99, 117, 135-136).                              */
+API void oracle_regularise(int n, const real *p, real *g, int reg, real lr, real l1, real l2) {
+  for (int i = 0; i < n; ++i) {
+    real sgn = R_COPYSIGN((real)1, p[i]);
+    if (reg == 1)
+      g[i] = g[i] + lr * l1 * sgn;
+    else if (reg == 2)
+      g[i] = g[i] + lr * (real)2 * l2 * p[i];
+    else if (reg == 3)
+      g[i] = g[i] + lr * (l1 * sgn + (real)2 * l2 * p[i]);
+  }
+}
+
+/* minimise_adam with an l2 regulariser: AdamW (decoupled) or L2 inside the quotient.
+ * src/athena/athena_optimiser.f90:1049-1078                                          */
+API void oracle_adam_l2(int n, real *p, const real *g, real *m, real *v, real lr, real b1,
+                        real b2, real eps, int iter, real l2, int decoupled) {
+  real bc1 = (real)1 - powi(b1, iter), bc2 = (real)1 - powi(b2, iter);
+  for (int i = 0; i < n; ++i) {
+    m[i] = b1 * m[i] + ((real)1 - b1) * g[i];
+    v[i] = b2 * v[i] + ((real)1 - b2) * g[i] * g[i];
+    real mh = m[i] / bc1, vh = v[i] / bc2;
+    if (decoupled) {
+      p[i] = p[i] - lr * l2 * p[i];
+      p[i] = p[i] - lr * (mh / (R_SQRT(vh) + eps));
+    } else {
+      p[i] = p[i] - lr * ((mh + l2 * p[i]) / (R_SQRT(vh) + eps));
+    }
+  }
+}
 
 /* minimise_rmsprop: moving_avg = beta*moving_avg + (1-beta)*g^2 ;
  * param -= lr * g / sqrt(moving_avg + eps).  src/athena/athena_optimiser.f90:771-803  */
@@ -1038,7 +1075,11 @@ API void oracle_adagrad(int n, real *p, const real *g, real *ss, real lr, real e
 API void oracle_update(int n, real *params, real *grads, const oracle_optim_t *o,
                        real *state1, real *state2, int iter) {
   oracle_clip(n, grads, o->clip_flags, o->clip_min, o->clip_max, o->clip_norm);
-  if (o->kind == 0)
+  if (o->reg) oracle_regularise(n, params, grads, o->reg, o->lr, o->l1, o->l2);
+  if (o->kind == 1 && o->reg == 2)
+    oracle_adam_l2(n, params, grads, state1, state2, o->lr, o->beta1, o->beta2, o->eps, iter,
+                   o->l2, o->l2_decoupled);
+  else if (o->kind == 0)
     oracle_sgd(n, params, grads, state1, o->lr, o->momentum, o->nesterov);
   else if (o->kind == 1)
     oracle_adam(n, params, grads, state1, state2, o->lr, o->beta1, o->beta2, o->eps, iter);

@@ -94,6 +94,10 @@ class OptimSpec:
     clip_min: Optional[float] = None
     clip_max: Optional[float] = None
     clip_norm: Optional[float] = None
+    regulariser: Optional[str] = None   # "l1" | "l2" | "l1l2" (athena_regulariser.f90)
+    l1: float = 0.01
+    l2: float = 0.01
+    l2_decoupled: bool = True
 
 
 @dataclass
@@ -142,7 +146,9 @@ class Oracle:
                           ("beta2", self.creal), ("eps", self.creal),
                           ("momentum", self.creal), ("nesterov", C.c_int),
                           ("clip_flags", C.c_int), ("clip_min", self.creal),
-                          ("clip_max", self.creal), ("clip_norm", self.creal)]
+                          ("clip_max", self.creal), ("clip_norm", self.creal),
+                          ("reg", C.c_int), ("l1", self.creal), ("l2", self.creal),
+                          ("l2_decoupled", C.c_int)]
         self._OptimT = type("_OptimT_" + precision, (C.Structure,), {"_fields_": _OptimT_fields})
         R, I, RP = self.creal, C.c_int, C.POINTER(self.creal)
         self.lib.oracle_mse_cell.restype = self.creal
@@ -178,6 +184,8 @@ class Oracle:
             flags |= 2
             s.clip_norm = o.clip_norm
         s.clip_flags = flags
+        s.reg = {None: 0, "l1": 1, "l2": 2, "l1l2": 3}[o.regulariser]
+        s.l1, s.l2, s.l2_decoupled = o.l1, o.l2, int(o.l2_decoupled)
         return s
 
     # -- primitive ops (single graph) -------------------------------------

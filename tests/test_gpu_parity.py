@@ -467,6 +467,30 @@ def test_rmsprop_adagrad_training_parity(cuda, oracle32, kind):
     _train_compare(cuda, oracle32, specs, layers, p, target, spec_o, opt)
 
 
+@pytest.mark.parametrize("case", ["sgd_l1", "rmsprop_l1l2", "adamw", "adam_l2"])
+def test_regulariser_training_parity(cuda, oracle32, case):
+    """regulariser%regularise in front of the step and the AdamW / L2 branches of
+    minimise_adam (athena_regulariser.f90:85-137, athena_optimiser.f90:1064-1078)."""
+    rng = np.random.default_rng(41)
+    p = synth.molecular_batch(24, 32, 0, rng)
+    specs = [kipf_spec([32, 32], 1, "tanh"), kipf_spec([32, 32], 1, "none")]
+    layers = [ab.kipf_msgpass_layer_type([32, 32], 1, "tanh"),
+              ab.kipf_msgpass_layer_type([32, 32], 1, "none")]
+    target = rng.standard_normal((p.V, 32)).astype(np.float32)
+    if case == "sgd_l1":
+        so = OptimSpec("sgd", lr=0.05, momentum=0.9, regulariser="l1", l1=0.02)
+        opt = ab.sgd_optimiser_type(0.05, momentum=0.9, regulariser=ab.l1_regulariser_type(0.02))
+    elif case == "rmsprop_l1l2":
+        so = OptimSpec("rmsprop", lr=0.002, beta1=0.9, regulariser="l1l2", l1=0.01, l2=0.03)
+        opt = ab.rmsprop_optimiser_type(0.002, beta=0.9,
+                                        regulariser=ab.l1l2_regulariser_type(0.01, 0.03))
+    else:
+        dec = case == "adamw"
+        so = OptimSpec("adam", lr=0.01, regulariser="l2", l2=0.05, l2_decoupled=dec)
+        opt = ab.adam_optimiser_type(0.01, regulariser=ab.l2_regulariser_type(0.05, decoupled=dec))
+    _train_compare(cuda, oracle32, specs, layers, p, target, so, opt)
+
+
 def test_network_train_loop_runs_epochs(cuda):
     """network%train batch loop with a ragged last batch (athena_network_sub.f90:3575-3670)."""
     rng = np.random.default_rng(9)

@@ -158,6 +158,29 @@ def test_rmsprop_and_adagrad_match_their_definitions(oracle64):
         assert np.allclose(p, q, rtol=1e-12, atol=0) and np.allclose(s1, acc, rtol=1e-12)
 
 
+def test_regularisers_match_their_definitions(oracle64):
+    """regularise_l1 / _l2 / _l1l2 (athena_regulariser.f90:99, 117, 135-136) in front of an SGD
+    step, and the two l2 branches of minimise_adam (athena_optimiser.f90:1064-1078)."""
+    rng = np.random.default_rng(22)
+    p0, g = rng.standard_normal(13), rng.standard_normal(13)
+    z = np.zeros(13)
+    lr, l1, l2 = 0.1, 0.03, 0.02
+    for reg, add in (("l1", l1 * np.sign(p0)), ("l2", 2 * l2 * p0),
+                     ("l1l2", l1 * np.sign(p0) + 2 * l2 * p0)):
+        o = OptimSpec("sgd", lr=lr, regulariser=reg, l1=l1, l2=l2)
+        p, _, _ = oracle64.update(p0, g, o, z, z, 1)
+        assert np.allclose(p, p0 - lr * (g + lr * add), rtol=1e-12)
+    gr = g + lr * 2 * l2 * p0                       # regularise_l2 runs first in both branches
+    m, v = 0.1 * gr, 0.001 * gr * gr
+    q = (m / 0.1) / (np.sqrt(v / 0.001) + 1e-8)
+    o = OptimSpec("adam", lr=lr, regulariser="l2", l2=l2, l2_decoupled=True)
+    p, _, _ = oracle64.update(p0, g, o, z, z, 1)
+    assert np.allclose(p, (p0 - lr * l2 * p0) - lr * q, rtol=1e-10)
+    o = OptimSpec("adam", lr=lr, regulariser="l2", l2=l2, l2_decoupled=False)
+    p, _, _ = oracle64.update(p0, g, o, z, z, 1)
+    assert np.allclose(p, p0 - lr * ((m / 0.1 + l2 * p0) / (np.sqrt(v / 0.001) + 1e-8)), rtol=1e-10)
+
+
 def test_duvenaud_full_head_gradients_are_true_gradients(oracle64):
     """Duvenaud -> full -> full (the wiring of example/msgpass_chemical, main.f90:129-157):
     the reverse sweep through the dense head (athena_full_layer.f90:839-874) is exact."""
