@@ -32,6 +32,31 @@ def test_python_binding_covers_every_declared_symbol():
         assert getattr(L, n).restype is not None
 
 
+def test_optimiser_descriptor_layout_matches_the_header(tmp_path):
+    """The ctypes mirror of struct athena_optimiser_desc (and the constants it carries) must be
+    the struct the C compiler sees: size and the offset of every field."""
+    import subprocess
+    from athena_b200 import _lib
+    fields = [f for f, _ in _lib.OptimiserDesc._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "athena_cuda.h"\n'
+                   "int main(void) {\n"
+                   '  printf("%zu", sizeof(athena_optimiser_desc));\n'
+                   + "".join(f'  printf(" %zu", offsetof(athena_optimiser_desc, {f}));\n'
+                             for f in fields)
+                   + '  printf(" %d %d %d %d", ATHENA_OPT_SGD, ATHENA_OPT_ADAM, ATHENA_OPT_RMSPROP,'
+                     " ATHENA_OPT_ADAGRAD);\n"
+                   '  printf(" %d %d %d %d", ATHENA_REG_NONE, ATHENA_REG_L1, ATHENA_REG_L2,'
+                     " ATHENA_REG_L1L2);\n  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(_lib.OptimiserDesc)] + [getattr(_lib.OptimiserDesc, f).offset for f in fields]
+    want += [_lib.OPT_SGD, _lib.OPT_ADAM, _lib.OPT_RMSPROP, _lib.OPT_ADAGRAD,
+             _lib.REG_NONE, _lib.REG_L1, _lib.REG_L2, _lib.REG_L1L2]
+    assert got == want
+
+
 def test_header_cites_the_reference_interfaces():
     hdr = open(os.path.join(ROOT, "include", "athena_cuda.h")).read()
     for cite in ("athena_msgpass_layer_sub.f90:144-174", "athena_kipf_msgpass_layer.f90:915-959",
