@@ -6,6 +6,7 @@
 !>   update_message_kipf      athena_kipf_msgpass_layer.f90:915-959
 !>   update_message_duvenaud  athena_duvenaud_msgpass_layer.f90:755-817
 !>   update_readout_duvenaud  athena_duvenaud_msgpass_layer.f90:822-859
+!>   network%compile          optimiser object -> athena_optimiser_desc (cuda_optimiser_desc)
 !>   network%update           athena_network_sub.f90:2816-2929
 !>   train batch loop         athena_network_sub.f90:3611-3670
 !>
@@ -23,6 +24,7 @@ module athena__cuda_msgpass
 
   public :: cuda_graph_batch_type
   public :: cuda_msgpass_forward, cuda_msgpass_backward
+  public :: cuda_optimiser_desc
 
   !> Device twin of graph(:) -- built once per mini-batch and shared by every
   !> message-passing layer of the network (replaces the per-layer deep copies
@@ -142,5 +144,61 @@ contains
     call athena_cuda_check(athena_cuda_layer_backward(layer_handle, batch%handle, &
          c_loc(upstream_grad), gi, ATHENA_MEM_HOST))
   end subroutine cuda_msgpass_backward
+
+  !> network%compile: describe athena's optimiser object to athena_cuda_network_compile.
+  !> The decayed learning rate is passed per update with
+  !> athena_cuda_network_set_learning_rate (lr_decay%get_lr stays on the host).
+  !> Optimisers / regularisers outside the device path stop the program, as an unknown
+  !> option does in the reference.
+  function cuda_optimiser_desc(optimiser) result(d)
+    use athena__optimiser, only: base_optimiser_type, sgd_optimiser_type, &
+         adam_optimiser_type, rmsprop_optimiser_type, adagrad_optimiser_type
+    use athena__regulariser, only: l1_regulariser_type, l2_regulariser_type, &
+         l1l2_regulariser_type
+    use athena__misc_types, only: stop_program
+    class(base_optimiser_type), intent(in) :: optimiser
+    type(athena_optimiser_desc) :: d
+
+    d%kind = ATHENA_OPT_SGD
+    d%learning_rate = optimiser%learning_rate
+    d%beta1 = 0.9_c_float;  d%beta2 = 0.999_c_float;  d%epsilon = 1.e-8_c_float
+    d%momentum = 0._c_float;  d%nesterov = 0
+    select type(optimiser)
+    type is (sgd_optimiser_type)          ! athena_optimiser.f90:119-132
+       d%momentum = optimiser%momentum
+       d%nesterov = merge(1, 0, optimiser%nesterov)
+    type is (adam_optimiser_type)         ! :236-250
+       d%kind = ATHENA_OPT_ADAM
+       d%beta1 = optimiser%beta1;  d%beta2 = optimiser%beta2;  d%epsilon = optimiser%epsilon
+    type is (rmsprop_optimiser_type)      ! :160-173
+       d%kind = ATHENA_OPT_RMSPROP
+       d%beta1 = optimiser%beta;  d%epsilon = optimiser%epsilon
+    type is (adagrad_optimiser_type)      ! :199-210
+       d%kind = ATHENA_OPT_ADAGRAD
+       d%epsilon = optimiser%epsilon
+    class default
+       call stop_program("optimiser type has no device implementation")
+    end select
+    ! clip_type (athena_clipper.f90:20-30)
+    d%clip_min_max = merge(1, 0, optimiser%clip_dict%l_min_max)
+    d%clip_min = optimiser%clip_dict%min;  d%clip_max = optimiser%clip_dict%max
+    d%clip_norm_on = merge(1, 0, optimiser%clip_dict%l_norm)
+    d%clip_norm = optimiser%clip_dict%norm
+    ! regulariser (athena_regulariser.f90:40-76)
+    d%regulariser = ATHENA_REG_NONE;  d%l1 = 0._c_float;  d%l2 = 0._c_float;  d%l2_decoupled = 1
+    if (optimiser%regularisation .and. allocated(optimiser%regulariser)) then
+       select type(r => optimiser%regulariser)
+       type is (l1_regulariser_type)
+          d%regulariser = ATHENA_REG_L1;  d%l1 = r%l1
+       type is (l2_regulariser_type)
+          d%regulariser = ATHENA_REG_L2;  d%l2 = r%l2
+          d%l2_decoupled = merge(1, 0, r%decoupled)
+       type is (l1l2_regulariser_type)
+          d%regulariser = ATHENA_REG_L1L2;  d%l1 = r%l1;  d%l2 = r%l2
+       class default
+          call stop_program("regulariser type has no device implementation")
+       end select
+    end if
+  end function cuda_optimiser_desc
 
 end module athena__cuda_msgpass
