@@ -155,7 +155,7 @@ contains
          adam_optimiser_type, rmsprop_optimiser_type, adagrad_optimiser_type
     use athena__regulariser, only: l1_regulariser_type, l2_regulariser_type, &
          l1l2_regulariser_type
-    use athena__misc_types, only: stop_program
+    use coreutils, only: stop_program
     class(base_optimiser_type), intent(in) :: optimiser
     type(athena_optimiser_desc) :: d
 
