@@ -499,7 +499,7 @@ struct TnJobs {
   int n;
   const float* P[TN_MAX_JOBS];
   const float* G[TN_MAX_JOBS];
-  float* part[TN_MAX_JOBS];   // [gridDim.x * 2][K * N] per job
+  float* part[TN_MAX_JOBS];   // [gridDim.x][K * N] per job
   long long M[TN_MAX_JOBS];
 };
 
@@ -527,7 +527,11 @@ struct Tn2Cfg {
   static constexpr int OPS_BYTES = 2 * B_HALF;               // one B operand buffer (two exist)
   static constexpr int OFF_RING = 2 * OPS_BYTES;
   static constexpr int OFF_BAR = OFF_RING + NS * STAGE_BYTES;
-  static constexpr int SMEM = 1024 + OFF_BAR + 256;
+  // hand-over of the lo(P)^T . G half to the warps that own the hi(P)^T . G half (one
+  // partial per CTA instead of two): [K features][N + 4] floats, padded against bank conflicts
+  static constexpr int COMB_PITCH = N + 4;
+  static constexpr int OFF_COMB = OFF_BAR + 256;
+  static constexpr int SMEM = 1024 + OFF_COMB + K * COMB_PITCH * 4;
   // TMEM: two A operand buffers [hi(P)^T ; lo(P)^T] x 64 vertices, two accumulators of 2N columns
   static constexpr uint32_t T_A = 0, T_ACC = 2 * RS;
   static constexpr int TMEM_COLS = (2 * RS + 4 * N <= 256) ? 256 : 512;
@@ -646,9 +650,9 @@ k_pipe_tn(TnJobs jobs) {
     }
   } else if (warp >= Cfg::ACC_WARP0) {
     // accumulate warps: drain the TMEM accumulator of every finished group into registers.
-    // TMEM lanes 0..63 hold hi(P)^T.G, lanes 64..127 lo(P)^T.G; each half becomes its own
-    // [K x N] partial (2 per CTA), written straight from registers at the end; the fold over
-    // partials happens in the reduce / finalize kernel, in partial-index order.
+    // TMEM lanes 0..63 hold hi(P)^T.G, lanes 64..127 lo(P)^T.G; the halves are added at the
+    // end of the product and leave as ONE [K x N] partial per CTA; the fold over the CTAs
+    // happens in the reduce / finalize kernel, in partial-index order.
     const int lq = warp & 3;
     int gcount = 0;
     for (int q = 0; q < jobs.n; ++q) {
@@ -676,12 +680,25 @@ k_pipe_tn(TnJobs jobs) {
         mbar_arrive(&acc_empty[ab]);
       }
       gcount += ngroups;
+      // the two halves (TMEM lanes 0..63: hi(P)^T . G, lanes 64..127: lo(P)^T . G) are added
+      // here, in a fixed order, so that the CTA writes ONE partial
       const int feat = (lq & 1) * 32 + lane;
-      float* dst =
-          jobs.part[q] + (static_cast<size_t>(blockIdx.x) * 2 + (lq >> 1)) * K * N + feat * N;
+      float* comb = reinterpret_cast<float*>(smem + Cfg::OFF_COMB) + feat * Cfg::COMB_PITCH;
+      if (lq >= 2) {
 #pragma unroll
-      for (int i = 0; i < N; i += 4)
-        *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+        for (int i = 0; i < N; i += 4)
+          *reinterpret_cast<float4*>(comb + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");  // the four accumulate warps
+      if (lq < 2) {
+        float* dst = jobs.part[q] + static_cast<size_t>(blockIdx.x) * K * N + feat * N;
+#pragma unroll
+        for (int i = 0; i < N; i += 4) {
+          const float4 lo = *reinterpret_cast<const float4*>(comb + i);
+          *reinterpret_cast<float4*>(dst + i) =
+              make_float4(acc[i] + lo.x, acc[i + 1] + lo.y, acc[i + 2] + lo.z, acc[i + 3] + lo.w);
+        }
+      }
       job_sync<Cfg::THREADS>();
     }
   } else if (warp >= Cfg::A_WARP0) {
@@ -952,7 +969,7 @@ static int launch_pipe_tn_t(const TnPending* jobs, int njobs, DeferList* defer) 
   TnJobs tj{};
   tj.n = njobs;
   for (int q = 0; q < njobs; ++q) {
-    ATH_TRY(jobs[q].scratch->reserve(sizeof(float) * (size_t)grid * 2 * Cfg::K * N));
+    ATH_TRY(jobs[q].scratch->reserve(sizeof(float) * (size_t)grid * Cfg::K * N));
     tj.P[q] = jobs[q].P;
     tj.G[q] = jobs[q].G;
     tj.part[q] = jobs[q].scratch->template as<float>();
@@ -963,11 +980,11 @@ static int launch_pipe_tn_t(const TnPending* jobs, int njobs, DeferList* defer) 
   for (int q = 0; q < njobs; ++q) {
     float* part = jobs[q].scratch->template as<float>();
     if (defer) {
-      defer->jobs.push_back(DeferJob{part, 2 * grid, Cfg::K * N, jobs[q].dW});
+      defer->jobs.push_back(DeferJob{part, grid, Cfg::K * N, jobs[q].dW});
       continue;
     }
     k_pipe_tn_reduce<<<(unsigned)cdiv((int64_t)Cfg::K * N, 128), 128, 0, ctx().stream>>>(
-        part, 2 * grid, Cfg::K * N, jobs[q].dW);
+        part, grid, Cfg::K * N, jobs[q].dW);
     ATH_LAUNCHED_T("pipe_tn_reduce");
   }
   return ATHENA_OK;
