@@ -105,11 +105,9 @@ struct TcgCfg {
   static constexpr int SPLIT_WARP0 = 0;                          // warps 0..7
   static constexpr int SPLIT_THREADS = 256;
   static constexpr int BUILD_WARP0 = 8;                          // warps 8..11  (warp % 4 = TMEM lane quarter)
-  // fix and epilogue: TWO warps per TMEM lane quarter, one per 32-column half of the tile
-  // (their per-tile work is a chain of TMEM / shared-memory round trips; more warps = more
-  // of those latencies in flight)
-  // (Tried: two fix and two epilogue warps per TMEM lane quarter, one per 32-column half.
-  // No gain -- 31 warps leave 64 registers per thread and the roles wait for memory anyway.)
+  // fix and epilogue: one warp per TMEM lane quarter.  (Tried: two of each per quarter, one
+  // per 32-column half.  No gain -- 31 warps leave 64 registers per thread and the roles
+  // wait for the L1 / shared-memory data path anyway.)
   static constexpr int FIX_WARP0 = 12;                           // warps 12..15
   static constexpr int EPI_WARP0 = 16;                           // warps 16..19
   static constexpr int PRODUCER_WARP = 20;
@@ -139,7 +137,7 @@ struct TcgCfg {
   static constexpr int AUX_BYTES = AUX_TMA ? 2 * AUX_TMA_TILE : EPI != EPI_ACT ? AUX_TILE : 0;
   static constexpr int OFF_BAR = OFF_AUX + AUX_BYTES;
   static constexpr int OFF_EPI = OFF_BAR + 256 + 512;
-  static constexpr int FIX_PATCH = 32 * 16;                      // floats per fix / epilogue warp patch
+  static constexpr int FIX_PATCH = 32 * 16;                      // floats per fix-warp patch (16-column groups)
   static constexpr int EPI_PATCH_FLOATS = EPI_PATCH;             // pipe::epilogue_tile: 32-column groups
   static constexpr int OFF_FIX = OFF_EPI + 4 * EPI_PATCH_FLOATS * 4;
   static constexpr int FIX_BYTES = EPI != EPI_ACTGRAD ? 4 * FIX_PATCH * 4 : 0;  // P is stored forward only
