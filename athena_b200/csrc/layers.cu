@@ -508,7 +508,7 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
   ATH_REQUIRE(tgt != nullptr, ATHENA_ERR_ARG, "train: target is null");
   Layer* first = N->layers.front();
   Layer* last = N->layers.back();
-  const float *dx, *de, *dt, *out;
+  const float *dx = nullptr, *de = nullptr, *dt = nullptr, *out = nullptr;
   // inputs on the copy stream: the features first (the first layer waits for them), then the
   // target, which only the loss needs -- the layers before it run under its copy
   cudaEvent_t ev_in = nullptr, ev_tgt = nullptr;
@@ -771,7 +771,7 @@ ATHENA_API int athena_cuda_layer_forward(athena_handle_t layer, athena_handle_t 
   Layer* L = static_cast<Layer*>(lookup_object(layer, Kind::Layer));
   Batch* b = static_cast<Batch*>(lookup_object(batch, Kind::Batch));
   if (!L || !b) return ATHENA_ERR_HANDLE;
-  const float *dx, *de, *out;
+  const float *dx = nullptr, *de = nullptr, *out = nullptr;
   ATH_TRY(stage_in(L->stage_x, vertex_features, L->in_rows(b) * L->nvf[0], mem, &dx));
   ATH_TRY(stage_in(L->stage_e, edge_features, b->E * L->nef, mem, &de));
   ATH_TRY(layer_forward_dev(L, b, dx, de, &out));
@@ -964,7 +964,7 @@ ATHENA_API int athena_cuda_network_forward(athena_handle_t net, athena_handle_t 
   ATH_REQUIRE(!N->layers.empty(), ATHENA_ERR_STATE, "network_forward: no layers");
   Layer* first = N->layers.front();
   Layer* last = N->layers.back();
-  const float *dx, *de, *out;
+  const float *dx = nullptr, *de = nullptr, *out = nullptr;
   ATH_TRY(stage_in(N->stage_x, vertex_features, b->V * first->nvf[0], mem, &dx));
   ATH_TRY(stage_in(N->stage_e, edge_features, b->E * N->edge_width(), mem, &de));
   // network%predict runs in inference mode (athena_network_sub.f90:4226-4303): layers keep
