@@ -57,6 +57,27 @@ def test_optimiser_descriptor_layout_matches_the_header(tmp_path):
     assert got == want
 
 
+def test_optimiser_mirror_fills_the_descriptor_like_the_reference_defaults():
+    """Host logic of the Python mirror: constructor defaults are the reference's
+    (athena_optimiser.f90:119-250, athena_regulariser.f90:40-76, athena_clipper.f90:14-30)."""
+    from athena_b200 import _lib
+    d = ab.sgd_optimiser_type().desc()
+    assert (d.kind, d.momentum, d.nesterov, d.regulariser) == (_lib.OPT_SGD, 0.0, 0, _lib.REG_NONE)
+    assert abs(d.learning_rate - 0.01) < 1e-7 and d.clip_min_max == 0 and d.clip_norm_on == 0
+    d = ab.adam_optimiser_type(1e-3, regulariser=ab.l2_regulariser_type()).desc()
+    assert d.kind == _lib.OPT_ADAM and abs(d.beta1 - 0.9) < 1e-7 and abs(d.beta2 - 0.999) < 1e-7
+    assert abs(d.epsilon - 1e-8) < 1e-12
+    assert (d.regulariser, d.l2_decoupled) == (_lib.REG_L2, 1) and abs(d.l2 - 0.01) < 1e-7
+    d = ab.rmsprop_optimiser_type(clip_dict=ab.clip_type(clip_norm=0.5)).desc()
+    assert d.kind == _lib.OPT_RMSPROP and d.beta1 == 0.0 and d.clip_norm_on == 1
+    assert abs(d.clip_norm - 0.5) < 1e-7
+    d = ab.adagrad_optimiser_type(regulariser=ab.l1l2_regulariser_type(0.02, 0.03)).desc()
+    assert d.kind == _lib.OPT_ADAGRAD and d.regulariser == _lib.REG_L1L2
+    assert abs(d.l1 - 0.02) < 1e-7 and abs(d.l2 - 0.03) < 1e-7
+    d = ab.sgd_optimiser_type(clip_dict=ab.clip_type(-0.1, 0.2)).desc()
+    assert d.clip_min_max == 1 and abs(d.clip_min + 0.1) < 1e-7 and abs(d.clip_max - 0.2) < 1e-7
+
+
 def test_header_cites_the_reference_interfaces():
     hdr = open(os.path.join(ROOT, "include", "athena_cuda.h")).read()
     for cite in ("athena_msgpass_layer_sub.f90:144-174", "athena_kipf_msgpass_layer.f90:915-959",
