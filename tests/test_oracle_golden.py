@@ -141,6 +141,21 @@ def test_duvenaud_gradients_are_true_gradients(oracle64):
     _fd_check(oracle64, [L], params, b, target, rng.choice(n, 12, replace=False))
 
 
+def test_kipf_vertex_without_entries(oracle32):
+    """Restated semantics the device path has to keep (athena_diffstruc_extd_sub_kipf.f90:36-44):
+    a vertex with no CSR entry sums nothing (its row is 0), and its degree 0 makes the
+    coefficient of every row that LISTS it infinite -- only those rows, not the whole graph."""
+    # directed 4-vertex graph: 0 -> 1, 1 -> 0, 2 -> 3 (vertex 3 has no outgoing entry)
+    ia = np.array([1, 2, 3, 4, 4], np.int32)
+    ja = np.array([[2, 1], [1, 2], [4, 3]], np.int32)
+    x = np.arange(1, 9, dtype=np.float32).reshape(4, 2)
+    with np.errstate(all="ignore"):
+        P = oracle32.kipf_propagate(x, ia, ja)
+    assert np.array_equal(P[3], [0.0, 0.0])                 # empty row
+    assert np.isinf(P[2]).all()                             # lists the degree-0 vertex
+    assert np.allclose(P[0], x[1]) and np.allclose(P[1], x[0])   # (1 * 1) ** -0.5 = 1
+
+
 def test_rmsprop_and_adagrad_match_their_definitions(oracle64):
     """minimise_rmsprop / minimise_adagrad (athena_optimiser.f90:795-803, 919-924) against the
     formulas evaluated with numpy over three steps (the reference has no test for them)."""
