@@ -263,6 +263,34 @@ int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const
 int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int N, DevBuf& scratch,
                    DeferList* defer = nullptr, bool queue = false);
 
+// fused FP32 (FFMA2) tile kernels for batches of small graphs (tile_fma.cu): one Kipf step of
+// any width up to 128, and the whole Duvenaud layer (all time steps + readout) per launch
+bool tile_kipf_supported(const Batch* b, int Fi, int Fo);
+int launch_tile_kipf_fwd(const Batch* b, const float* X, const float* W, float* P, float* out,
+                         int Fi, int Fo, int act);
+// G: gradient w.r.t. the step output (H != nullptr: act'(H) is applied) or w.r.t. the
+// pre-activation (H == nullptr); part receives [*nparts][Fi*Fo] CTA partials of dW
+int launch_tile_kipf_bwd(const Batch* b, const float* G, const float* H, const float* P,
+                         const float* W, float* gin, int Fi, int Fo, int act, DevBuf& part,
+                         int* nparts);
+struct TileDuvDesc {
+  int T, nef, min_deg, max_deg, no, act, ract;
+  const int* nvf;         // (0:T)
+  const int64_t* poff;    // offsets of W_1..W_T, R_1..R_T inside the layer's parameter block
+  const float* params;
+  const float* X;         // [V][F_0]
+  const float* E;         // [E][F_e]
+  float* const* Z;        // z_t, t = 1..T (written by the forward, read by the backward)
+};
+bool tile_duv_supported(const Batch* b, int T, const int* nvf, int nef, int D, int no);
+// target != nullptr: also the [num_outputs, batch] MSE cell -- mse_grad = (out - target) /
+// mse_denom and loss_part[0..*num_parts) = per-CTA sums of (out - target)^2 / mse_denom
+int launch_tile_duv_fwd(const Batch* b, const TileDuvDesc& d, float* out, const float* target,
+                        float* mse_grad, float mse_denom, float* loss_part, int* num_parts);
+// part receives [*nparts][num_params] CTA partials of the layer's parameter gradients
+int launch_tile_duv_bwd(const Batch* b, const TileDuvDesc& d, const float* gout, float* gin,
+                        int64_t num_params, DevBuf& part, int* nparts);
+
 // fused SpMM + tcgen05 transform for large graphs, feature width 128 (agg_tc.cu)
 bool agg_tc_supported(int F, int N, const void* X, const void* out);
 int launch_agg_tc_fwd(const Batch* b, const float* X, const float* W, float* P, float* out,

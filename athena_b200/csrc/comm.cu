@@ -220,6 +220,21 @@ ATHENA_API int athena_cuda_shard_graphs(int32_t num_graphs, const int64_t* entri
       run += entries_per_graph[s] + 1;
       ++s;
     }
+    // When there are at least as many graphs as ranks every rank gets one: boundary r is
+    // kept inside [r, num_graphs - (world - r)].  (A skewed batch -- one graph holding most
+    // of the entries -- would otherwise leave ranks without work, and athena_cuda_batch_create
+    // rejects an empty batch while the peers wait in the gradient exchange.)
+    if (num_graphs >= world_size) {
+      const int32_t lo = r, hi = num_graphs - (world_size - r);
+      while (s < lo) {
+        run += entries_per_graph[s] + 1;
+        ++s;
+      }
+      while (s > hi) {
+        --s;
+        run -= entries_per_graph[s] + 1;
+      }
+    }
     first_graph[r] = s;
   }
   first_graph[world_size] = num_graphs;

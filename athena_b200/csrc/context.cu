@@ -89,7 +89,12 @@ void pool_trim() {
   DevPool& P = pool();
   std::lock_guard<std::mutex> lk(P.mu);
   if (P.free_blocks.empty()) return;
-  if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+  if (ctx().ready) {
+    // both streams: a host->device copy queued by a call that failed before its consumer was
+    // launched may still be writing into a cached block
+    cudaStreamSynchronize(ctx().copy_stream);
+    cudaStreamSynchronize(ctx().stream);
+  }
   for (auto& kv : P.free_blocks) cudaFree(kv.second);
   P.free_blocks.clear();
   P.cached = 0;
@@ -271,6 +276,7 @@ ATHENA_API int athena_cuda_init(int32_t device) {
 ATHENA_API int athena_cuda_shutdown(void) {
   Context& c = ctx();
   if (!c.ready) return ATHENA_OK;
+  cudaStreamSynchronize(c.copy_stream);
   cudaStreamSynchronize(c.stream);
   {
     std::lock_guard<std::mutex> lk(g_mu);

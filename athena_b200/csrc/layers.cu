@@ -32,6 +32,9 @@ struct Layer : Object {
   std::vector<std::unique_ptr<DevBuf>> MK;               // sign bits of step t's pre-activation
   std::vector<char> mask_valid;                          // MK[t] written by the last forward
   DevBuf Ae, out_buf, g0, g1, g2, tn_scratch, stage_x, stage_e, stage_g, stage_gin;
+  DevBuf tile_part;          // CTA partials of the fused Duvenaud reverse sweep (tile_fma.cu)
+  bool tile_fwd = false;     // the last forward ran on the fused tile kernel (saved: z_t only)
+  const float* fwd_e = nullptr;  // device edge features of the last forward
   Batch* fwd_batch = nullptr;
   int64_t fwd_V = -1;
   const float* fwd_x = nullptr;  // device input of the last forward (valid until the next one)
@@ -108,6 +111,7 @@ struct FwdOpts {
   float* loss_part = nullptr;
   int num_parts = 0;
   bool fused = false;
+  float mse_denom = 0.f;  // Duvenaud-last: num_outputs * global batch (one [no, batch] cell)
 };
 
 static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out,
@@ -146,6 +150,14 @@ static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out,
       in = H.as<float>();
       continue;
     }
+    if (tile_kipf_supported(b, Fi, Fo)) {
+      // small graphs, narrow features: propagate + transform + activation in one FP32 tile kernel
+      ATH_TRY(launch_tile_kipf_fwd(b, in, L->params + L->poff[t - 1],
+                                   L->inference ? nullptr : P.as<float>(), H.as<float>(), Fi, Fo,
+                                   L->act));
+      in = H.as<float>();
+      continue;
+    }
     if (L->act != ATHENA_ACT_SOFTMAX && agg_tc_supported(Fi, Fo, in, H.as<float>())) {
       // large graph, wide features: SpMM + tcgen05 transform in one pass; the aggregate
       // is only written when a reverse sweep may follow
@@ -172,9 +184,55 @@ static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out,
   return ATHENA_OK;
 }
 
+static void duv_desc(const Layer* L, const float* x, const float* e, float* const* Z,
+                     TileDuvDesc* d) {
+  d->T = L->T;
+  d->nef = L->nef;
+  d->min_deg = L->min_deg;
+  d->max_deg = L->max_deg;
+  d->no = L->n_out;
+  d->act = L->act;
+  d->ract = L->ract;
+  d->nvf = L->nvf.data();
+  d->poff = L->poff.data();
+  d->params = L->params;
+  d->X = x;
+  d->E = e;
+  d->Z = Z;
+}
+
 static int duvenaud_forward(Layer* L, Batch* b, const float* x, const float* e,
-                            const float** out) {
+                            const float** out, FwdOpts* fo = nullptr) {
   const int64_t V = b->V;
+  L->tile_fwd = false;
+  L->fwd_e = e;
+  if (tile_duv_supported(b, L->T, L->nvf.data(), L->nef, L->max_deg - L->min_deg + 1, L->n_out)) {
+    // every time step and the readout of the whole layer in ONE launch (tile_fma.cu); only
+    // z_t is kept for the reverse sweep
+    ATH_REQUIRE(L->nef == 0 || e != nullptr, ATHENA_ERR_ARG,
+                "duvenaud forward: edge_features is null");
+    float* Z[16];
+    for (int t = 1; t <= L->T; ++t) {
+      DevBuf& Zt = *L->H[t - 1];
+      ATH_TRY(Zt.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * L->nvf[t], 1)));
+      Z[t - 1] = Zt.as<float>();
+    }
+    ATH_TRY(L->out_buf.reserve(sizeof(float) * (size_t)b->B * L->n_out));
+    TileDuvDesc d;
+    duv_desc(L, x, e, Z, &d);
+    const bool mse = fo != nullptr && fo->mse_target != nullptr;
+    if (mse) {
+      ATH_TRY(main_wait(fo->target_ready));
+      fo->target_ready = nullptr;
+    }
+    ATH_TRY(launch_tile_duv_fwd(b, d, L->out_buf.as<float>(), mse ? fo->mse_target : nullptr,
+                                mse ? fo->mse_grad : nullptr, mse ? fo->mse_denom : 1.f,
+                                mse ? fo->loss_part : nullptr, mse ? &fo->num_parts : nullptr));
+    if (mse) fo->fused = true;
+    L->tile_fwd = true;
+    *out = L->out_buf.as<float>();
+    return ATHENA_OK;
+  }
   BucketSet* bs = nullptr;
   ATH_TRY(batch_bucketize(b, L->min_deg, L->max_deg, &bs));
   const int D = bs->D;
@@ -265,7 +323,7 @@ int layer_forward_dev(Layer* L, Batch* b, const float* x, const float* e, const 
   L->fwd_x = x;
   if (L->kind == 2) return full_forward(L, b, x, out);
   if (L->kind == 0) return kipf_forward(L, b, x, out, fo);
-  return duvenaud_forward(L, b, x, e, out);
+  return duvenaud_forward(L, b, x, e, out, fo);
 }
 
 // ---- backward --------------------------------------------------------------------
@@ -304,6 +362,25 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
     float* dWt = L->grads + L->poff[t - 1];
     const bool need_dp = (t > 1 || gin);
     const bool need_act = nonlinear && !preact;
+    if (tile_kipf_supported(b, Fi, Fo) && !pipe_gather_supported(b, Fo, Fi)) {
+      // act', dW partials, dP = gY W^T and the un-normalised CSC scatter in one FP32 tile kernel
+      float* dst = gin;
+      if (t > 1) dst = (g == L->g2.as<float>()) ? L->g0.as<float>() : L->g2.as<float>();
+      int nparts = 0;
+      ATH_TRY(launch_tile_kipf_bwd(b, g, need_act ? Ht : nullptr, Pt, Wt, need_dp ? dst : nullptr,
+                                   Fi, Fo, L->act, *L->TN[t - 1], &nparts));
+      DeferJob job{L->TN[t - 1]->as<float>(), nparts, Fi * Fo, dWt};
+      if (opt.defer) {
+        opt.defer->jobs.push_back(job);
+      } else {
+        DeferList dl;
+        dl.jobs.push_back(job);
+        ATH_TRY(launch_finalize(dl, nullptr, 0, nullptr, nullptr, dWt, (int64_t)Fi * Fo, nullptr));
+      }
+      g = dst;
+      preact = false;
+      continue;
+    }
     // fused path: one tcgen05 kernel gathers gY_t over the CSC, multiplies by W_t^T and applies
     // act'(H_{t-1}); the un-normalised scatter commutes with the linear map
     const bool fused_dp = need_dp && L->act != ATHENA_ACT_SOFTMAX && pipe_gather_supported(b, Fo, Fi);
@@ -367,8 +444,27 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
   return ATHENA_OK;
 }
 
-static int duvenaud_backward(Layer* L, Batch* b, const float* gout, float* gin) {
+static int duvenaud_backward(Layer* L, Batch* b, const float* gout, float* gin,
+                             DeferList* defer = nullptr) {
   const int64_t V = b->V;
+  if (L->tile_fwd) {
+    // the whole reverse sweep of the layer in ONE launch; A_t and S_t are recomputed from z_t
+    float* Z[16];
+    for (int t = 1; t <= L->T; ++t) Z[t - 1] = L->H[t - 1]->as<float>();
+    TileDuvDesc d;
+    duv_desc(L, L->fwd_x, L->fwd_e, Z, &d);
+    int nparts = 0;
+    ATH_TRY(launch_tile_duv_bwd(b, d, gout, gin, L->num_params, L->tile_part, &nparts));
+    DeferJob job{L->tile_part.as<float>(), nparts, (int)L->num_params, L->grads};
+    if (defer) {
+      defer->jobs.push_back(job);
+    } else {
+      DeferList dl;
+      dl.jobs.push_back(job);
+      ATH_TRY(launch_finalize(dl, nullptr, 0, nullptr, nullptr, L->grads, L->num_params, nullptr));
+    }
+    return ATHENA_OK;
+  }
   BucketSet* bs = nullptr;
   ATH_TRY(batch_bucketize(b, L->min_deg, L->max_deg, &bs));
   const int no = L->n_out, T = L->T;
@@ -433,7 +529,7 @@ int layer_backward_dev(Layer* L, Batch* b, const float* gout, float* gin,
   if (L->kind == 2) return full_backward(L, b, gout, gin);
   if (L->kind == 0) return kipf_backward(L, b, gout, gin, opt);
   ATH_REQUIRE(!opt.gout_is_preact, ATHENA_ERR_STATE, "duvenaud backward: unexpected pre-activation gradient");
-  return duvenaud_backward(L, b, gout, gin);
+  return duvenaud_backward(L, b, gout, gin, opt.defer);
 }
 
 // ---- network ---------------------------------------------------------------------
@@ -533,10 +629,12 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
   ATH_TRY(N->loss_scratch.reserve(sizeof(float) * 1024));
   FwdOpts fo;
   fo.target_ready = ev_tgt;
-  if (last->kind == 0 && b->V > 0) {
+  if ((last->kind == 0 || last->kind == 1) && b->V > 0) {
     fo.mse_target = dt;
     fo.mse_grad = N->gbuf.as<float>();
     fo.loss_part = N->loss_scratch.as<float>();
+    const int gb = global_batch > 0 ? global_batch : b->B;
+    fo.mse_denom = (float)((int64_t)last->out_width() * gb);
   }
   ATH_TRY(net_forward_dev(N, b, dx, de, &out, &fo));
   ATH_TRY(main_wait(fo.target_ready));  // unfused loss: wait here
@@ -548,9 +646,10 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
   bool g_preact = false;
   DeferList defer;
   if (fo.fused) {
-    // the last layer's kernel already produced d loss / d pre-activation and the per-CTA
-    // loss sums, which launch_finalize folds into the loss slot
-    g_preact = true;
+    // the last layer's kernel already produced the loss gradient (Kipf: w.r.t. the
+    // pre-activation; Duvenaud: w.r.t. the [num_outputs, batch] output) and the per-CTA loss
+    // sums, which launch_finalize folds into the loss slot
+    g_preact = last->kind == 0;
   } else if (last->kind == 0) {
     g_preact = foldable(last);
     ATH_TRY(launch_mse_graph(out, dt, b->vgraph, b->nv, last->nvf[last->T], b->V,

@@ -16,8 +16,12 @@ namespace athena {
 
 constexpr int RED_THREADS = 256;
 
+// Sum over a block of THREADS threads (the launch must use exactly that many); fixed
+// combine pattern, result valid in warp 0.
+template <int THREADS = RED_THREADS>
 __device__ __forceinline__ float block_sum(float v) {
-  __shared__ float ws[RED_THREADS / 32];
+  static_assert(THREADS % 32 == 0 && THREADS <= 1024, "block_sum: whole warps, one block");
+  __shared__ float ws[THREADS / 32];
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -25,7 +29,7 @@ __device__ __forceinline__ float block_sum(float v) {
   __syncthreads();
   float r = 0.f;
   if (warp == 0) {
-    r = lane < RED_THREADS / 32 ? ws[lane] : 0.f;
+    r = lane < THREADS / 32 ? ws[lane] : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
   }
@@ -342,7 +346,7 @@ k_finalize(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
     float local = 0.f;
     if (f.loss_part != nullptr)
       for (int k = threadIdx.x; k < f.loss_nparts; k += FIN_THREADS) local += f.loss_part[k];
-    float s = block_sum(local);
+    float s = block_sum<FIN_THREADS>(local);
     if (threadIdx.x == 0) {
       const float loss = f.loss_acc[0] + 0.5f * s;
       f.loss_acc[0] = loss;

@@ -114,7 +114,21 @@ def test_shard_graphs_balances_entries():
     assert first[0] == 0 and first[2] == 8 and 4 <= first[1] <= 5
     first = np.zeros(9, np.int32)
     ab.check(ab.lib().athena_cuda_shard_graphs(w.size, ab.ptr(w), 8, ab.ptr(first)))
-    assert first[0] == 0 and first[8] == 8 and np.all(np.diff(first) >= 0)
+    # as many graphs as ranks: every rank owns exactly one graph, however skewed the weights
+    assert first.tolist() == list(range(9))
+    # skewed batches never leave a rank empty while num_graphs >= world_size
+    # (an empty rank cannot build a batch and its peers would wait in the gradient exchange)
+    for w, world in ((np.array([1, 100], np.int64), 2),
+                     (np.array([1000, 1, 1, 1, 1, 1, 1, 1, 1, 1], np.int64), 4),
+                     (np.array([1, 1, 1, 1, 1, 1, 1, 1, 1, 1000], np.int64), 8)):
+        first = np.zeros(world + 1, np.int32)
+        ab.check(ab.lib().athena_cuda_shard_graphs(w.size, ab.ptr(w), world, ab.ptr(first)))
+        assert first[0] == 0 and first[world] == w.size and np.all(np.diff(first) >= 1), first
+    # fewer graphs than ranks: trailing ranks are empty by necessity, boundaries stay ordered
+    w = np.array([5, 5], np.int64)
+    first = np.zeros(5, np.int32)
+    ab.check(ab.lib().athena_cuda_shard_graphs(w.size, ab.ptr(w), 4, ab.ptr(first)))
+    assert first[0] == 0 and first[4] == 2 and np.all(np.diff(first) >= 0)
     # uniform weights -> equal contiguous shards
     w = np.full(4096, 832, np.int64)
     first = np.zeros(5, np.int32)
