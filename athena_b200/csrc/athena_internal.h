@@ -280,6 +280,7 @@ struct TileDuvDesc {
   const float* params;
   const float* X;         // [V][F_0]
   const float* E;         // [E][F_e]
+  float* Ae;              // [V][F_e] per-vertex edge-feature sums (forward writes, backward reads)
   float* const* Z;        // z_t, t = 1..T (written by the forward, read by the backward)
 };
 bool tile_duv_supported(const Batch* b, int T, const int* nvf, int nef, int D, int no);

@@ -184,7 +184,7 @@ static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out,
   return ATHENA_OK;
 }
 
-static void duv_desc(const Layer* L, const float* x, const float* e, float* const* Z,
+static void duv_desc(Layer* L, const float* x, const float* e, float* const* Z,
                      TileDuvDesc* d) {
   d->T = L->T;
   d->nef = L->nef;
@@ -198,6 +198,7 @@ static void duv_desc(const Layer* L, const float* x, const float* e, float* cons
   d->params = L->params;
   d->X = x;
   d->E = e;
+  d->Ae = L->nef > 0 ? L->Ae.as<float>() : nullptr;
   d->Z = Z;
 }
 
@@ -218,6 +219,8 @@ static int duvenaud_forward(Layer* L, Batch* b, const float* x, const float* e,
       Z[t - 1] = Zt.as<float>();
     }
     ATH_TRY(L->out_buf.reserve(sizeof(float) * (size_t)b->B * L->n_out));
+    if (L->nef > 0)
+      ATH_TRY(L->Ae.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * L->nef, 1)));
     TileDuvDesc d;
     duv_desc(L, x, e, Z, &d);
     const bool mse = fo != nullptr && fo->mse_target != nullptr;
