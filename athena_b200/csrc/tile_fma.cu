@@ -378,59 +378,180 @@ __device__ __forceinline__ void tf_gemm_nt(int tid, float* C, int pc, const floa
   }
 }
 
+// Ungrouped products with TWO vertex rows per lane (v and v + 32 of a 64-row group) and four
+// outputs: every weight LDS.128 feeds four FFMA2 instead of two.
+//   C[v][n] = epi(v, n, sum_k A[v][k] * W[k][n])
+template <class Epi>
+__device__ __forceinline__ void tf_gemm2(int tid, float* C, int pc, const float* A, int pa, int K,
+                                         const float* W, int pw, int rows, int N, Epi epi) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int nrg = (rows + 63) >> 6, nnb = (N + 3) >> 2;
+  const int K4 = K >> 2;
+  for (int it = warp; it < nrg * nnb; it += TF_GWARPS) {
+    const int nb = it / nrg, rg = it - nb * nrg;
+    const int v0 = rg * 64 + lane, v1 = v0 + 32;
+    const bool live0 = v0 < rows, live1 = v1 < rows;
+    const float* A0 = A + (live0 ? v0 : rows - 1) * pa;
+    const float* A1 = A + (live1 ? v1 : rows - 1) * pa;
+    const float* w = W + nb * 4;
+    float2 acc[2][2];
+    acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = make_float2(0.f, 0.f);
+#pragma unroll 2
+    for (int k4 = 0; k4 < K4; ++k4) {
+      const float4 x0 = *reinterpret_cast<const float4*>(A0 + 4 * k4);
+      const float4 x1 = *reinterpret_cast<const float4*>(A1 + 4 * k4);
+      const float a0[4] = {x0.x, x0.y, x0.z, x0.w};
+      const float a1[4] = {x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w);
+        w += pw;
+        const float2 wlo = make_float2(w4.x, w4.y), whi = make_float2(w4.z, w4.w);
+        fma2s(acc[0][0], a0[i], wlo);
+        fma2s(acc[0][1], a0[i], whi);
+        fma2s(acc[1][0], a1[i], wlo);
+        fma2s(acc[1][1], a1[i], whi);
+      }
+    }
+    for (int k = K4 * 4; k < K; ++k) {
+      const float4 w4 = *reinterpret_cast<const float4*>(w);
+      w += pw;
+      const float2 wlo = make_float2(w4.x, w4.y), whi = make_float2(w4.z, w4.w);
+      fma2s(acc[0][0], A0[k], wlo);
+      fma2s(acc[0][1], A0[k], whi);
+      fma2s(acc[1][0], A1[k], wlo);
+      fma2s(acc[1][1], A1[k], whi);
+    }
+    const int n0 = nb * 4;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int v = rr ? v1 : v0;
+      if (rr ? live1 : live0) {
+        const float r4[4] = {acc[rr][0].x, acc[rr][0].y, acc[rr][1].x, acc[rr][1].y};
+        float o4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o4[j] = n0 + j < N ? epi(v, n0 + j, r4[j]) : 0.f;
+        *reinterpret_cast<float4*>(C + v * pc + n0) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+  }
+}
+
+//   C[v][n] = epi(v, n, sum_k A[v][k] * W[n][k])      (weights used transposed)
+template <class Epi>
+__device__ __forceinline__ void tf_gemm_nt2(int tid, float* C, int pc, const float* A, int pa,
+                                            int K, const float* W, int pw, int rows, int N,
+                                            Epi epi) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int nrg = (rows + 63) >> 6, nnb = (N + 3) >> 2;
+  const int K4 = K >> 2;
+  for (int it = warp; it < nrg * nnb; it += TF_GWARPS) {
+    const int nb = it / nrg, rg = it - nb * nrg;
+    const int v0 = rg * 64 + lane, v1 = v0 + 32;
+    const bool live0 = v0 < rows, live1 = v1 < rows;
+    const float* A0 = A + (live0 ? v0 : rows - 1) * pa;
+    const float* A1 = A + (live1 ? v1 : rows - 1) * pa;
+    const float* w = W + nb * 4 * pw;
+    float2 acc[2][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[0][j] = acc[1][j] = make_float2(0.f, 0.f);
+#pragma unroll 2
+    for (int k4 = 0; k4 < K4; ++k4) {
+      const float4 x0 = *reinterpret_cast<const float4*>(A0 + 4 * k4);
+      const float4 x1 = *reinterpret_cast<const float4*>(A1 + 4 * k4);
+      const float2 x0lo = make_float2(x0.x, x0.y), x0hi = make_float2(x0.z, x0.w);
+      const float2 x1lo = make_float2(x1.x, x1.y), x1hi = make_float2(x1.z, x1.w);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w + j * pw + 4 * k4);
+        const float2 wlo = make_float2(w4.x, w4.y), whi = make_float2(w4.z, w4.w);
+        fma2p(acc[0][j], x0lo, wlo);
+        fma2p(acc[0][j], x0hi, whi);
+        fma2p(acc[1][j], x1lo, wlo);
+        fma2p(acc[1][j], x1hi, whi);
+      }
+    }
+    for (int k = K4 * 4; k < K; ++k) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float wk = w[j * pw + k];
+        acc[0][j].x = fmaf(A0[k], wk, acc[0][j].x);
+        acc[1][j].x = fmaf(A1[k], wk, acc[1][j].x);
+      }
+    }
+    const int n0 = nb * 4;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int v = rr ? v1 : v0;
+      if (rr ? live1 : live0) {
+        float o4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          o4[j] = n0 + j < N ? epi(v, n0 + j, acc[rr][j].x + acc[rr][j].y) : 0.f;
+        *reinterpret_cast<float4*>(C + v * pc + n0) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+  }
+}
+
 // part[(g*K + k)*N + n] += sum_{p in segment g, ascending} A[list[p]][k] * G[list[p]][n]
 // (the layout of a column-major [N, K] parameter block per group: n + N*k + N*K*g).
-// One warp owns four k of one group: A arrives as a broadcast LDS.128, G as one conflict-free
-// LDS.32 per lane; the group-private partial is read before the loop and written after it.
-// list_s == nullptr: identity (one segment with all rows).  Handles 64 columns per pass.
+// One warp owns 8 k x 32 n of one group: lane = (k pair, n quad), i.e. a 2 x 4 register tile
+// fed by one LDS.64 of A (4 distinct addresses per warp) and one LDS.128 of G (one contiguous
+// 128-byte row piece per warp) per vertex -- 4 FFMA2 per 2 loads.  The group-private partial
+// is read before the loop and written after it.  list_s == nullptr: identity (one segment
+// with all rows).  G must be zero in columns N .. 4*ceil(N/4).
+// (Measured and dropped: cutting the rows of an ungrouped product into slices for otherwise
+// idle warps -- the extra barrier and the combine through shared memory cost more.)
 __device__ __forceinline__ void tf_outer(int tid, float* __restrict__ part, const float* A, int pa,
                                          int K, const float* G, int pg, int N,
                                          const uint8_t* list_s, const int* seg_s, int ngroups,
                                          int rows) {
   const int warp = tid >> 5, lane = tid & 31;
-  const int K4 = (K + 3) >> 2;
-  const int NP = (N + 63) >> 6;  // passes of 64 columns
-  for (int it = warp; it < ngroups * K4 * NP; it += TF_GWARPS) {
+  const int kp = lane >> 3, nq = lane & 7;
+  const int K8 = (K + 7) >> 3;
+  const int NP = (N + 31) >> 5;  // passes of 32 columns
+  const int N4 = ((N + 3) >> 2) << 2;
+  for (int it = warp; it < ngroups * K8 * NP; it += TF_GWARPS) {
     const int np = it % NP, r = it / NP;
-    const int g = r / K4, kb = r - g * K4;
+    const int g = r / K8, kb = r - g * K8;
     const int p0 = seg_s != nullptr ? seg_s[g] : 0;
     const int p1 = seg_s != nullptr ? seg_s[g + 1] : rows;
     if (p0 >= p1) continue;
-    const int n0 = np * 64 + lane, n1 = n0 + 32;
-    const bool h0 = n0 < N, h1 = n1 < N;
-    float old[4][2], acc[4][2];
+    const int k0 = 8 * kb + 2 * kp, n0 = 32 * np + 4 * nq;
+    const bool active = k0 < K && n0 < N4;
+    float old[2][4];
+    float2 acc[2][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = 4 * kb + i;
-      float* row = part + (static_cast<size_t>(g) * K + k) * N;
-      acc[i][0] = acc[i][1] = 0.f;
-      old[i][0] = (k < K && h0) ? row[n0] : 0.f;
-      old[i][1] = (k < K && h1) ? row[n1] : 0.f;
+    for (int i = 0; i < 2; ++i) {
+      const float* row = part + (static_cast<size_t>(g) * K + k0 + i) * N + n0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        old[i][j] = (active && k0 + i < K && n0 + j < N) ? row[j] : 0.f;
+      acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
     }
-    const float* Ak = A + 4 * kb;
+    const float* Ak = A + (active ? k0 : 0);
+    const float* Gn = G + (active ? n0 : 0);
 #pragma unroll 4
     for (int p = p0; p < p1; ++p) {
       const int v = list_s != nullptr ? list_s[p] : p;
-      const float4 a4 = *reinterpret_cast<const float4*>(Ak + v * pa);
-      const float g0 = h0 ? G[v * pg + n0] : 0.f;
-      acc[0][0] = fmaf(a4.x, g0, acc[0][0]);
-      acc[1][0] = fmaf(a4.y, g0, acc[1][0]);
-      acc[2][0] = fmaf(a4.z, g0, acc[2][0]);
-      acc[3][0] = fmaf(a4.w, g0, acc[3][0]);
-      if (N > 32) {
-        const float g1 = h1 ? G[v * pg + n1] : 0.f;
-        acc[0][1] = fmaf(a4.x, g1, acc[0][1]);
-        acc[1][1] = fmaf(a4.y, g1, acc[1][1]);
-        acc[2][1] = fmaf(a4.z, g1, acc[2][1]);
-        acc[3][1] = fmaf(a4.w, g1, acc[3][1]);
-      }
+      const float2 a2 = *reinterpret_cast<const float2*>(Ak + v * pa);
+      const float4 g4 = *reinterpret_cast<const float4*>(Gn + v * pg);
+      const float2 glo = make_float2(g4.x, g4.y), ghi = make_float2(g4.z, g4.w);
+      fma2s(acc[0][0], a2.x, glo);
+      fma2s(acc[0][1], a2.x, ghi);
+      fma2s(acc[1][0], a2.y, glo);
+      fma2s(acc[1][1], a2.y, ghi);
     }
+    if (active) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = 4 * kb + i;
-      float* row = part + (static_cast<size_t>(g) * K + k) * N;
-      if (k < K && h0) row[n0] = old[i][0] + acc[i][0];
-      if (k < K && h1) row[n1] = old[i][1] + acc[i][1];
+      for (int i = 0; i < 2; ++i) {
+        float* row = part + (static_cast<size_t>(g) * K + k0 + i) * N + n0;
+        const float r4[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (k0 + i < K && n0 + j < N) row[j] = old[i][j] + r4[j];
+      }
     }
   }
 }
@@ -713,9 +834,14 @@ __device__ __forceinline__ void duv_stage_weights(float* sm, const DuvArgs& a) {
 __device__ __forceinline__ void duv_update(int tid, int act, float* Z, const float* A, int P, int K,
                                            const float* W, int pw, int gs, const uint8_t* bkt_s,
                                            int rows, int Fo) {
-#define TF_UPD(ACT)                                                        \
-  tf_gemm(tid, Z, P, A, P, K, W, pw, gs, bkt_s, rows, Fo,                  \
-          [](int, int, float s) { return ACT{}(s); })
+#define TF_UPD(ACT)                                                                          \
+  do {                                                                                       \
+    if (bkt_s != nullptr)                                                                    \
+      tf_gemm(tid, Z, P, A, P, K, W, pw, gs, bkt_s, rows, Fo,                                \
+              [](int, int, float s) { return ACT{}(s); });                                   \
+    else                                                                                     \
+      tf_gemm2(tid, Z, P, A, P, K, W, pw, rows, Fo, [](int, int, float s) { return ACT{}(s); }); \
+  } while (0)
   switch (act) {
     case ATHENA_ACT_RELU: TF_UPD(ActRelu); break;
     case ATHENA_ACT_LEAKY_RELU: TF_UPD(ActLeaky); break;
@@ -915,11 +1041,11 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
         const bool has_carry = t < T;
         const float* zt = X;
         const float* cc = Z;
-        tf_gemm_nt(tid, Z, P, Y, P, no, sm + L.r[i], L.pr[i], 0, nullptr, tv.rows, Fo,
-                   [act, has_carry, zt, cc, P](int v, int n, float s) {
-                     const float dz = has_carry ? s + cc[v * P + n] : s;
-                     return tf_act_grad(act, zt[v * P + n], dz);
-                   });
+        tf_gemm_nt2(tid, Z, P, Y, P, no, sm + L.r[i], L.pr[i], tv.rows, Fo,
+                    [act, has_carry, zt, cc, P](int v, int n, float s) {
+                      const float dz = has_carry ? s + cc[v * P + n] : s;
+                      return tf_act_grad(act, zt[v * P + n], dz);
+                    });
       }
       tf_sync(grp);
       // 4. z_{t-1} replaces z_t; A = [gather(z_{t-1}) ; Ae] / d is recomputed into Y (dY is dead)
@@ -1069,8 +1195,7 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_kipf_bwd(const KipfAr
       // dP = W_t^T gY, then the un-normalised scatter dX(:,u) += dP(:,v) as a gather over the
       // CSC (entries ascending)
       float* dP = need_act ? Gb : Hb;
-      tf_gemm_nt(tid, dP, P, gy, P, Fo, Ws, a.pw, 0, nullptr, rows, Fi,
-                 [](int, int, float s) { return s; });
+      tf_gemm_nt2(tid, dP, P, gy, P, Fo, Ws, a.pw, rows, Fi, [](int, int, float s) { return s; });
       tf_sync(grp);  // also orders the outer product's reads of Pb before the gather's writes
       tf_gather<false>(tid, Pb, P, dP, P, (Fi + 3) >> 2, ptr_s, idx_s, nullptr, rows, nullptr);
       tf_sync(grp);
