@@ -101,6 +101,31 @@ def regular_batch(B: int, n: int, half_degree: int, F: int, rng: np.random.Gener
     return packed
 
 
+def ragged_batch(B: int, n_min: int, n_max: int, half_degree: int, F: int,
+                 rng: np.random.Generator) -> PackedGraphs:
+    """cfg2 with ragged graph sizes: graph s has n_s ~ U[n_min, n_max] vertices, every vertex
+    2*half_degree distinct neighbours inside its graph (randomly relabelled circulant) + a
+    self-loop.  Graph-aligned 128-row tiles are then partially filled and unequal."""
+    assert 2 * half_degree < n_min <= n_max
+    nv = rng.integers(n_min, n_max + 1, B)
+    voff = np.concatenate([[0], np.cumsum(nv)])
+    srcs, dsts = [], []
+    for n in np.unique(nv):
+        gs = np.nonzero(nv == n)[0]
+        k = gs.size
+        offs = np.stack([rng.permutation((n - 1) // 2)[:half_degree] + 1 for _ in range(k)])
+        perm = np.stack([rng.permutation(n) for _ in range(k)])
+        base = np.arange(n)[None, :, None]
+        a = np.broadcast_to(base, (k, n, half_degree))
+        b = (base + offs[:, None, :]) % n
+        gi = np.arange(k)[:, None, None]
+        srcs.append((perm[gi, a] + voff[gs][:, None, None]).ravel())
+        dsts.append((perm[gi, b] + voff[gs][:, None, None]).ravel())
+    packed, _ = packed_from_edges(nv, np.concatenate(srcs), np.concatenate(dsts))
+    packed.x = rng.standard_normal((int(voff[-1]), F), dtype=np.float32)
+    return packed
+
+
 def random_graph(V: int, out_degree: int, F: int, rng: np.random.Generator) -> PackedGraphs:
     """cfg3: one large graph; `out_degree` random out-neighbours per vertex, symmetrised,
     duplicates removed, + self-loops."""

@@ -12,6 +12,14 @@ fixed: weak scaling).  `value` is timed with CUDA events on the library stream
 with inputs resident in HBM; `e2e` goes through the public API with pinned HOST
 buffers (batch build + H2D copies + loss read-back inside the timed region).
 An edge is one CSR entry, self-loops included.
+
+The other BASELINE.json configs are measured in the same run and reported under
+`extra.configs` (device-resident, CUDA events, max over ranks): cfg4 -- the
+multi-GPU config, Duvenaud + Kipf stack on molecular graphs, at every N both
+with the global batch of 8192 graphs sharded over the ranks (strong) and with
+8192 graphs per rank (weak) -- and, at N = 1, cfg1 (chemical Duvenaud), cfg3
+(2 M-vertex inference), cfg5 (power law) and a ragged variant of cfg2.
+`--extras none|cfg4|all` selects them (default: all at N = 1, cfg4 at N > 1).
 """
 import argparse
 import ctypes as C
@@ -172,23 +180,26 @@ class ClockSampler:
 
 # algorithmic (compulsory) bytes per launch, SURVEY 8(d) / DESIGN.md "Roofline accounting":
 # every tensor a kernel must touch counted once, int32 indices, fp32 values.
-def kernel_bytes(tag, V, Z):
+def kernel_bytes(tag, V, Z, tcg=True):
+    """Bytes a launch has to move (what the kernel reads and writes, each tensor once).
+    The tensor-core gather kernels read the adjacency as 16-byte bit masks per vertex
+    (tcg=True); the list kernels read row_ptr + one neighbour byte per entry."""
     vf = 4 * V * F
-    idx = 4 * (V + 1) + 4 * Z
+    idx = 16 * V if tcg else 4 * (V + 1) + Z
     table = {
-        # fused propagate + transform + activation (SURVEY B_f with the saved aggregate P):
-        # row_ptr + col + degree/coefficient vector + X read, P and H written
-        "pipe_gather_fwd": idx + 4 * V + vf + 2 * vf + 4 * F * F,
+        # fused propagate + transform + activation: adjacency + deg^-1/2 + X read, the saved
+        # aggregate P and H written, 8 B of sign bits per row
+        "pipe_gather_fwd": idx + 4 * V + vf + 2 * vf + 8 * V + 4 * F * F,
         # fused last layer + MSE: X and target read, P and the loss gradient written
-        "pipe_gather_fwd_mse": idx + 4 * V + 2 * vf + 2 * vf + 4 * F * F,
+        "pipe_gather_fwd_mse": idx + 4 * V + 2 * vf + 2 * vf + 4 * V + 4 * F * F,
         # fused dP = gY W^T, CSC gather, .* relu'(H): gY read, gY_{t-1} written, relu' from the
         # sign bits the forward recorded (8 B per row instead of the 4VF of saved activations)
         "pipe_gather_bwd": idx + 2 * vf + 8 * V + 4 * F * F,
         # the dW products of both layers run in ONE launch (P and gY read, per layer)
         "pipe_tn": 2 * (2 * vf + 4 * F * F),
         "pipe_tn_reduce": 4 * F * F,
-        "aggregate_v4_g16_c1_coef": idx + 4 * V + 2 * vf,
-        "aggregate_v4_g16_c1": idx + 2 * vf,
+        "aggregate_v4_g16_c1_coef": 4 * (V + 1) + 8 * Z + 2 * vf,
+        "aggregate_v4_g16_c1": 4 * (V + 1) + 4 * Z + 2 * vf,
         "gemm_nn": 2 * vf + 4 * F * F,
         "gemm_nt": 2 * vf + 4 * F * F,
         "gemm_tn_partial": 2 * vf,
@@ -209,12 +220,196 @@ def measured_traffic(tag):
         return None
 
 
+def survey_kernel_bytes(tag, V, Z):
+    """The SURVEY 8(d) contract figure (int32 index lists) for the same launches, reported
+    beside the tighter count above."""
+    vf = 4 * V * F
+    idx = 4 * (V + 1) + 4 * Z
+    return {"pipe_gather_fwd": idx + 4 * V + 3 * vf + 4 * F * F,
+            "pipe_gather_fwd_mse": idx + 4 * V + 4 * vf + 4 * F * F,
+            "pipe_gather_bwd": idx + 2 * vf + 8 * V + 4 * F * F}.get(tag)
+
+
 def step_bytes(V, Z):
     """Compulsory bytes of one cfg2 train step (BASELINE.md section 3 formulas)."""
     fwd = 4 * (V + 1) + 4 * Z + 4 * V + 4 * V * F + 4 * V * F + 4 * V * F   # incl. saving P
     bwd_dense = 8 * V * F + 4 * V * F + 8 * F * F
     bwd_scatter = 4 * (V + 1) + 4 * Z + 8 * V * F
     return 2 * fwd + 2 * bwd_dense + bwd_scatter
+
+
+def run_extra_configs(which, ab, L, rank, world, barrier, max_over_ranks):
+    """Device-resident timings of the other BASELINE.json configs (CUDA events on the library
+    stream, barrier on both sides, max over ranks).  Returns {name: {...}} (rank 0 keeps it)."""
+    from athena_b200 import synth
+    out = {}
+
+    def timed(step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        barrier()
+        ms = C.c_float()
+        ab.check(L.athena_cuda_timer_start(1))
+        for _ in range(steps):
+            step()
+        ab.check(L.athena_cuda_timer_stop(1, C.byref(ms)))
+        barrier()
+        return max_over_ranks(float(ms.value)) / steps
+
+    def launches_and_kernels(step, n=3):
+        n0 = np.zeros(1, np.int64); n1 = np.zeros(1, np.int64)
+        ab.check(L.athena_cuda_synchronize())
+        L.athena_cuda_launch_count(ab.ptr(n0))
+        ab.check(L.athena_cuda_profile_begin())
+        for _ in range(n):
+            step()
+        nt = C.c_int32()
+        ab.check(L.athena_cuda_profile_end(C.byref(nt)))
+        L.athena_cuda_launch_count(ab.ptr(n1))
+        ks = {}
+        name = C.create_string_buffer(96)
+        cnt = C.c_int64(); tms = C.c_float()
+        for i in range(nt.value):
+            ab.check(L.athena_cuda_profile_get(i, name, 96, C.byref(cnt), C.byref(tms)))
+            ks[name.value.decode()] = {"launches_per_step": cnt.value / n,
+                                       "us_per_launch": round(tms.value / cnt.value * 1e3, 2)}
+        return int(n1[0] - n0[0]) / n, ks
+
+    def cfg4(mode):
+        # Kipf(32->32) x 2 + Duvenaud(T=2, 6 degree buckets, 32 outputs), Adam; the Duvenaud
+        # layer reads the ORIGINAL edge features (SURVEY finding 7)
+        G = 8192
+        if mode == "strong":     # one global batch of 8192 graphs sharded by graph
+            rng = np.random.default_rng(2)
+            p_all = synth.molecular_batch(G, 32, 4, rng)
+            tgt_all = rng.random((G, 32)).astype(np.float32)
+            first = np.zeros(world + 1, np.int32)
+            nz64 = p_all.nz.astype(np.int64)
+            ab.check(L.athena_cuda_shard_graphs(p_all.B, ab.ptr(nz64), world, ab.ptr(first)))
+            g0, g1 = int(first[rank]), int(first[rank + 1])
+            q, tgt, global_B = p_all.slice(g0, g1), np.ascontiguousarray(tgt_all[g0:g1]), G
+            Zg, Vg = p_all.Z, p_all.V
+        else:                    # 8192 graphs per rank
+            rng = np.random.default_rng(200 + rank)
+            q = synth.molecular_batch(G, 32, 4, rng)
+            tgt = rng.random((G, 32)).astype(np.float32)
+            global_B = G * world
+            Zg = Vg = None           # summed over the ranks below
+        net = ab.network_type()
+        net.add(ab.kipf_msgpass_layer_type([32, 32], 1, "relu"))
+        net.add(ab.kipf_msgpass_layer_type([32, 32], 1, "relu"))
+        net.add(ab.duvenaud_msgpass_layer_type([32], [4], 2, 6, 32))
+        net.compile(ab.adam_optimiser_type(0.001), batch_size=q.B)
+        net.set_params((np.random.default_rng(7).standard_normal(net.num_params) * 0.1)
+                       .astype(np.float32))
+        batch = ab.GraphBatch(q)
+        x = ab.DeviceArray.from_host(q.x)
+        e = ab.DeviceArray.from_host(q.e)
+        t = ab.DeviceArray.from_host(tgt)
+
+        def step():
+            ab.check(L.athena_cuda_network_train_step(net.handle, batch.handle, ab.ptr(x), ab.ptr(e),
+                                                      ab.ptr(t), ab.MEM_DEVICE, global_B, None))
+        ms = timed(step, 30, 5)
+        lps, ks = launches_and_kernels(step)
+        if mode != "strong":
+            Zg, Vg = int(_sum_over_ranks(q.Z)), int(_sum_over_ranks(q.V))
+        loss = C.c_float()
+        ab.check(L.athena_cuda_network_last_loss(net.handle, C.byref(loss)))
+        return {"workload": "cfg4: Kipf(32->32, relu) x 2 + Duvenaud(T=2, D=6, 32 outputs, sigmoid / "
+                            "softmax) train, molecular graphs (V~U[10,50], degree<=4+self, Fv=32, "
+                            "Fe=4), MSE, Adam; fwd+bwd+exchange+step",
+                "scaling": mode, "global_graphs": global_B, "graphs_this_rank": q.B,
+                "global_vertices": Vg, "global_entries": Zg, "ms_per_step": ms,
+                "graphs_per_s": global_B / ms * 1e3, "edges_per_s": Zg / ms * 1e3,
+                "launches_per_step": lps, "kernels": ks, "final_loss": float(loss.value)}
+
+    def cfg1():
+        rng = np.random.default_rng(42)
+        q = synth.chemical_batch(8, rng)
+        net = ab.network_type()
+        net.add(ab.duvenaud_msgpass_layer_type([6], [1], 4, 10, 10))
+        net.compile(ab.adam_optimiser_type(0.01, clip_dict=ab.clip_type(clip_norm=0.1)),
+                    batch_size=8)
+        net.set_params((rng.standard_normal(net.num_params) * 0.3).astype(np.float32))
+        batch = ab.GraphBatch(q)
+        x = ab.DeviceArray.from_host(q.x)
+        e = ab.DeviceArray.from_host(q.e)
+        t = ab.DeviceArray.from_host(rng.random((q.B, 10)).astype(np.float32))
+
+        def step():
+            ab.check(L.athena_cuda_network_train_step(net.handle, batch.handle, ab.ptr(x), ab.ptr(e),
+                                                      ab.ptr(t), ab.MEM_DEVICE, q.B, None))
+        ms = timed(step, 200, 20)
+        lps, ks = launches_and_kernels(step, 10)
+        return {"workload": "cfg1: example/msgpass_chemical dims -- Duvenaud (T=4, 10 degree "
+                            "buckets, 10 outputs), 8 graphs x 8 atoms per batch (synthetic "
+                            "stand-in), Adam + clip_norm 0.1; one train step",
+                "vertices": q.V, "entries": q.Z, "us_per_step": ms * 1e3,
+                "graphs_per_s": q.B / ms * 1e3, "edges_per_s": q.Z / ms * 1e3,
+                "launches_per_step": lps, "kernels": ks, "roofline": "n/a (latency-bound)"}
+
+    def kipf2(q, Fw, what, train=True, steps=20):
+        rng = np.random.default_rng(5)
+        net = ab.network_type()
+        net.add(ab.kipf_msgpass_layer_type([Fw, Fw], 1, "relu"))
+        net.add(ab.kipf_msgpass_layer_type([Fw, Fw], 1, "none"))
+        net.compile(ab.sgd_optimiser_type(LR), batch_size=q.B)
+        net.set_params((rng.standard_normal(net.num_params) / np.sqrt(Fw)).astype(np.float32))
+        batch = ab.GraphBatch(q)
+        x = ab.DeviceArray.from_host(q.x)
+        if train:
+            t = ab.DeviceArray.from_host(rng.standard_normal((q.V, Fw)).astype(np.float32))
+
+            def step():
+                ab.check(L.athena_cuda_network_train_step(net.handle, batch.handle, ab.ptr(x), None,
+                                                          ab.ptr(t), ab.MEM_DEVICE, q.B, None))
+        else:
+            o = ab.DeviceArray((q.V, Fw))
+
+            def step():
+                ab.check(L.athena_cuda_network_forward(net.handle, batch.handle, ab.ptr(x), None,
+                                                       ab.ptr(o), ab.MEM_DEVICE))
+        ms = timed(step, steps, 5)
+        lps, ks = launches_and_kernels(step)
+        return {"workload": what, "vertices": q.V, "entries": q.Z, "graphs": q.B,
+                "ms_per_step": ms, "edges_per_s": q.Z / ms * 1e3, "launches_per_step": lps,
+                "kernels": ks}
+
+    for name in which:
+        try:
+            if name == "cfg4":
+                out["cfg4"] = cfg4("strong")
+                out["cfg4_weak"] = cfg4("weak")
+            elif name == "cfg1":
+                out["cfg1"] = cfg1()
+            elif name == "cfg2_ragged":
+                q = synth.ragged_batch(GRAPHS, 33, 64, HALF_DEG, F, np.random.default_rng(11))
+                out[name] = kipf2(q, F, "cfg2 with ragged graphs: Kipf 2 x (64->64) train, "
+                                  f"{GRAPHS} graphs of 33..64 vertices, 12 neighbours + self loop "
+                                  "(graph-aligned tiles partially filled, unequal)")
+            elif name == "cfg3":
+                q = synth.random_graph(2_000_000, 8, 128, np.random.default_rng(1))
+                r = kipf2(q, 128, "cfg3: Kipf 2 x (128->128) inference, one graph, V = 2e6, "
+                          "16 neighbours + self loop", train=False)
+                V, Z = q.V, q.Z
+                comp = 2 * (4 * (V + 1) + 4 * Z + 4 * V + 8 * V * 128)
+                gath = 2 * (Z * (4 + 4 * 128) + V * (8 + 4 * 128))
+                peak, _ = peaks()
+                r["roofline"] = {"bound": "hbm", "compulsory_bytes": comp, "gather_model_bytes": gath,
+                                 "compulsory_frac": comp / (r["ms_per_step"] * 1e-3) / 1e9 / peak,
+                                 "gather_model_frac": gath / (r["ms_per_step"] * 1e-3) / 1e9 / peak}
+                out[name] = r
+            elif name == "cfg5":
+                q = synth.powerlaw_batch(64, 16384, 64, np.random.default_rng(3), max_degree=10000)
+                out[name] = kipf2(q, 64, "cfg5: Kipf 2 x (64->64) train, 64 power-law graphs x "
+                                  "16384 vertices (Zipf 2.1, max degree 10000)")
+        except Exception as exc:  # noqa: BLE001  (an extra must never take the headline down)
+            out[name] = {"error": str(exc)[:300]}
+    return out
+
+
+_sum_over_ranks = None
 
 
 def run_reference(args, rank, world):
@@ -246,14 +441,18 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = p.Z * args.steps / dt
     sample = (f"{sample_graphs} of the {GRAPHS} graphs of the cfg2 batch per step "
-              f"({p.Z} CSR entries), full train step")
+              f"({p.Z} CSR entries), full train step; C restatement of the reference at -O3 on "
+              "one core (the reference is single-threaded)")
     print(json.dumps({
         "impl": "reference", "metric": "msgpass train edges/sec (fwd+bwd)", "value": value,
         "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: Kipf GCN 2-layer (64->64 relu, 64->64), 64-vertex graphs, "
-                               "12 neighbours + self loop, F=64, MSE, SGD", "sample": sample},
+        "config": {"workload": "cfg2: Kipf GCN 2-layer (64->64 relu, 64->64), "
+                               f"{GRAPHS} graphs x {NV} vertices per GPU, 12 neighbours + "
+                               "self loop, F=64, MSE, SGD; fwd+bwd+allreduce+step",
+                   "graphs_per_gpu": sample_graphs, "vertices_per_gpu": p.V,
+                   "entries_per_gpu": p.Z, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": 1, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0,
@@ -268,10 +467,11 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-graphs", type=int, default=128)
+    ap.add_argument("--ref-graphs", type=int, default=GRAPHS)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--extras", default="auto", choices=["auto", "none", "cfg4", "all"])
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
 
@@ -431,6 +631,7 @@ def main():
                 "frac": (ach / peak) if ach else None, "traffic": measured_traffic(top),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": nb,
+                "survey_formula_bytes_per_launch": survey_kernel_bytes(top, V, Z),
                 "us_per_launch": kernels[top]["us_per_launch"],
                 "step": {"algorithmic_bytes": step_bytes(V, Z),
                          "achieved": step_bytes(V, Z) / (ms_step * 1e-3) / 1e9,
@@ -478,6 +679,23 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                "ms_per_step": dt / args.steps * 1e3}
 
+    # ---- the other BASELINE.json configs ----------------------------------------------
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+    global _sum_over_ranks
+    _sum_over_ranks = sum_over_ranks
+    sel = args.extras
+    if sel == "auto":
+        sel = "all" if world == 1 else "cfg4"
+    which = {"none": [], "cfg4": ["cfg4"],
+             "all": ["cfg4", "cfg1", "cfg2_ragged", "cfg5", "cfg3"]}[sel]
+    extra_cfgs = run_extra_configs(which, ab, L, rank, world, barrier, max_over_ranks) if which else {}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -521,6 +739,7 @@ def main():
             "e2e": e2e, "gpu_launches": launches, "launches_per_step": launches / args.steps,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
             "final_loss": float(loss.value),
+            "extra": {"configs": extra_cfgs},
         }
         print(json.dumps(out))
     if dist is not None:
