@@ -103,6 +103,8 @@ def lib() -> C.CDLL:
         "athena_cuda_layer_zero_gradients": [H],
         "athena_cuda_layer_forward": [H, H, P, P, P, I32],
         "athena_cuda_layer_backward": [H, H, P, P, I32],
+        "athena_cuda_layer_backward_stage": [H, H, I32, P, I64],
+        "athena_cuda_layer_backward_flush": [H, H],
         "athena_cuda_network_create": [PH],
         "athena_cuda_network_destroy": [H],
         "athena_cuda_network_add": [H, H],

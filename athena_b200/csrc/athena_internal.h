@@ -146,6 +146,7 @@ struct Batch : Object {
   Batch() : Object(Kind::Batch) {}
   int32_t B = 0;
   int64_t V = 0, Z = 0, E = 0;
+  std::vector<int32_t> h_voff;  // host copy of voff[B+1] (per-sample staging offsets)
   DevBuf meta;  // int32: nv[B], ne[B], voff[B+1], zoff[B+1], eoff[B+1]
   const int32_t* nv = nullptr;
   const int32_t* ne = nullptr;

@@ -508,6 +508,7 @@ ATHENA_API int athena_cuda_batch_create(athena_handle_t* batch, int32_t num_grap
   eoffv[B] = (int32_t)E;
 
   std::unique_ptr<Batch> b(new Batch);
+  b->h_voff.assign(h_voff, h_voff + B + 1);
   b->B = B;
   b->V = V;
   b->Z = Z;

@@ -35,6 +35,8 @@ struct Layer : Object {
   DevBuf tile_part;          // CTA partials of the fused Duvenaud reverse sweep (tile_fma.cu)
   bool tile_fwd = false;     // the last forward ran on the fused tile kernel (saved: z_t only)
   const float* fwd_e = nullptr;  // device edge features of the last forward
+  std::vector<char> staged;  // per-sample marks of athena_cuda_layer_backward_stage
+  int64_t num_staged = 0;
   Batch* fwd_batch = nullptr;
   int64_t fwd_V = -1;
   const float* fwd_x = nullptr;  // device input of the last forward (valid until the next one)
@@ -914,6 +916,59 @@ ATHENA_API int athena_cuda_layer_backward(athena_handle_t layer, athena_handle_t
     ATH_CUDA(cudaStreamSynchronize(st));
   }
   return ATHENA_OK;
+}
+
+// per-sample staging of the upstream gradient (the autodiff seam)
+static int stage_run(Layer* L, Batch* b) {
+  ATH_TRY(layer_backward_dev(L, b, L->stage_g.as<float>(), nullptr));
+  L->staged.assign(L->staged.size(), 0);
+  L->num_staged = 0;
+  return record_mark();
+}
+
+ATHENA_API int athena_cuda_layer_backward_stage(athena_handle_t layer, athena_handle_t batch,
+                                                int32_t sample, const float* grad_output,
+                                                int64_t count) {
+  Layer* L = static_cast<Layer*>(lookup_object(layer, Kind::Layer));
+  Batch* b = static_cast<Batch*>(lookup_object(batch, Kind::Batch));
+  if (!L || !b) return ATHENA_ERR_HANDLE;
+  ATH_REQUIRE(L->fwd_batch == b && L->fwd_V == b->V, ATHENA_ERR_STATE,
+              "backward_stage: no forward pass on this batch");
+  ATH_REQUIRE(sample >= 0 && sample < b->B && grad_output, ATHENA_ERR_ARG,
+              "backward_stage: bad sample %d (batch of %d) or null gradient", sample, b->B);
+  const int W = L->out_width();
+  const int64_t row0 = L->kind == 0 ? b->h_voff[sample] : sample;
+  const int64_t rows = L->kind == 0 ? b->h_voff[sample + 1] - b->h_voff[sample] : 1;
+  ATH_REQUIRE(count == rows * W, ATHENA_ERR_ARG,
+              "backward_stage: sample %d has %lld gradient values, caller passed %lld", sample,
+              (long long)(rows * W), (long long)count);
+  const int64_t total = L->out_rows(b) * W;
+  cudaStream_t st = ctx().stream;
+  if ((int64_t)L->staged.size() != b->B || L->num_staged == 0) {
+    ATH_TRY(L->stage_g.reserve(sizeof(float) * (size_t)std::max<int64_t>(total, 1)));
+    ATH_CUDA(cudaMemsetAsync(L->stage_g.p, 0, sizeof(float) * (size_t)std::max<int64_t>(total, 1), st));
+    L->staged.assign((size_t)b->B, 0);
+    L->num_staged = 0;
+  }
+  ATH_REQUIRE(!L->staged[sample], ATHENA_ERR_STATE,
+              "backward_stage: sample %d was already staged for this sweep", sample);
+  if (count > 0)
+    ATH_CUDA(cudaMemcpyAsync(L->stage_g.as<float>() + row0 * W, grad_output,
+                             sizeof(float) * (size_t)count, cudaMemcpyHostToDevice, st));
+  L->staged[sample] = 1;
+  L->num_staged += 1;
+  if (L->num_staged == b->B) return stage_run(L, b);
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_layer_backward_flush(athena_handle_t layer, athena_handle_t batch) {
+  Layer* L = static_cast<Layer*>(lookup_object(layer, Kind::Layer));
+  Batch* b = static_cast<Batch*>(lookup_object(batch, Kind::Batch));
+  if (!L || !b) return ATHENA_ERR_HANDLE;
+  ATH_REQUIRE(L->fwd_batch == b && L->fwd_V == b->V, ATHENA_ERR_STATE,
+              "backward_flush: no forward pass on this batch");
+  if (L->num_staged == 0) return ATHENA_OK;
+  return stage_run(L, b);
 }
 
 // ---- network ABI -------------------------------------------------------------------

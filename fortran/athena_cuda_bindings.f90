@@ -83,6 +83,8 @@ module athena__cuda_bindings
   public :: athena_cuda_comm_unique_id, athena_cuda_comm_init, athena_cuda_comm_destroy
   public :: athena_cuda_comm_info, athena_cuda_shard_graphs
   public :: athena_cuda_comm_p2p_export, athena_cuda_comm_p2p_import
+  public :: athena_cuda_layer_backward_stage, athena_cuda_layer_backward_flush
+  public :: athena_cuda_layer_backward_stage_pure
   public :: athena_cuda_check
 
   interface
@@ -236,6 +238,36 @@ module athena__cuda_bindings
        integer(c_int64_t), value :: layer, batch
        type(c_ptr), value :: grad_output, grad_input
        integer(c_int32_t), value :: mem
+       integer(c_int) :: rc
+     end function
+
+     ! per-sample staging of the upstream gradient (the autodiff seam)
+     function athena_cuda_layer_backward_stage(layer, batch, sample, grad_output, count) &
+          bind(C, name="athena_cuda_layer_backward_stage") result(rc)
+       import :: c_int, c_int32_t, c_int64_t, c_float
+       integer(c_int64_t), value :: layer, batch
+       integer(c_int32_t), value :: sample
+       real(c_float), intent(in) :: grad_output(*)
+       integer(c_int64_t), value :: count
+       integer(c_int) :: rc
+     end function
+     !> The same C symbol under a PURE interface: diffstruc declares its get_partial_*_val
+     !> callbacks pure (athena_diffstruc_extd_sub_kipf.f90:85), and a pure procedure may only
+     !> reference pure procedures.  The C function has no Fortran-visible side effect: it
+     !> copies `grad_output` to the device and touches device state only.
+     pure function athena_cuda_layer_backward_stage_pure(layer, batch, sample, grad_output, &
+          count) bind(C, name="athena_cuda_layer_backward_stage") result(rc)
+       import :: c_int, c_int32_t, c_int64_t, c_float
+       integer(c_int64_t), value :: layer, batch
+       integer(c_int32_t), value :: sample
+       real(c_float), intent(in) :: grad_output(*)
+       integer(c_int64_t), value :: count
+       integer(c_int) :: rc
+     end function
+     function athena_cuda_layer_backward_flush(layer, batch) &
+          bind(C, name="athena_cuda_layer_backward_flush") result(rc)
+       import :: c_int, c_int64_t
+       integer(c_int64_t), value :: layer, batch
        integer(c_int) :: rc
      end function
 

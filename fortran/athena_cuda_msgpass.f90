@@ -11,8 +11,9 @@
 !>   train batch loop         athena_network_sub.f90:3611-3670
 !>
 !> Written against athena v2.1.1 / graphstruc v0.2.1 / diffstruc v1.2.0.  Not
-!> compiled in the development image (no Fortran compiler there); the C ABI it
-!> calls is what tests/ exercise through ctypes in the same call order.
+!> compiled in the development image (no Fortran compiler there); the same ABI calls in the
+!> same order are compiled and run from C by tests/c_driver/fake_athena.c (per-sample
+!> gradient staging included) and from Python by tests/.
 module athena__cuda_msgpass
   use, intrinsic :: iso_c_binding
   use coreutils, only: real32
@@ -24,6 +25,8 @@ module athena__cuda_msgpass
 
   public :: cuda_graph_batch_type
   public :: cuda_msgpass_forward, cuda_msgpass_backward
+  public :: cuda_register_output_nodes, get_partial_cuda_layer_val
+  public :: cuda_network_update, cuda_train_batch
   public :: cuda_optimiser_desc
 
   !> Device twin of graph(:) -- built once per mini-batch and shared by every
@@ -144,6 +147,134 @@ contains
     call athena_cuda_check(athena_cuda_layer_backward(layer_handle, batch%handle, &
          c_loc(upstream_grad), gi, ATHENA_MEM_HOST))
   end subroutine cuda_msgpass_backward
+
+  !> The autodiff seam.  After the device forward every output(1,s) (Kipf) or output(1,1)
+  !> (Duvenaud, one [num_outputs, batch] array) is turned into a leaf-like node of the
+  !> expression graph whose operand is the layer's first parameter array -- the operand
+  !> that requires a gradient, so loss%grad_reverse (athena_network_sub.f90:3645) visits the
+  !> node and calls its get_partial_left_val with the upstream gradient of THAT sample.
+  !> The two handles and the sample index travel in the node's integer `indices` array
+  !> (the field kipf_propagate uses for adj_ia, athena_diffstruc_extd_sub_kipf.f90:48).
+  !>   indices(1:2) = layer handle, indices(3:4) = batch handle (int64 as two int32),
+  !>   indices(5)   = 0-based sample index, or -1 for a graph-level [num_outputs, batch] array
+  subroutine cuda_register_output_nodes(output, params1, layer_handle, batch, graph_level)
+    class(array_type), dimension(:,:), intent(inout), target :: output
+    type(array_type), intent(in), target :: params1
+    integer(c_int64_t), intent(in) :: layer_handle
+    type(cuda_graph_batch_type), intent(in) :: batch
+    logical, intent(in) :: graph_level
+    integer :: s
+    integer(c_int32_t) :: h(2)
+
+    do s = 1, size(output, 2)
+       if (allocated(output(1,s)%indices)) deallocate(output(1,s)%indices)
+       allocate(output(1,s)%indices(5))
+       h = transfer(layer_handle, h)
+       output(1,s)%indices(1:2) = h
+       h = transfer(batch%handle, h)
+       output(1,s)%indices(3:4) = h
+       output(1,s)%indices(5) = merge(-1, s - 1, graph_level)
+       output(1,s)%get_partial_left_val => get_partial_cuda_layer_val
+       output(1,s)%left_operand => params1
+       output(1,s)%owns_left_operand = .false.
+       output(1,s)%requires_grad = .true.
+       output(1,s)%is_forward = params1%is_forward
+       output(1,s)%operation = 'cuda_msgpass'
+       output(1,s)%is_temporary = .false.
+    end do
+  end subroutine cuda_register_output_nodes
+
+  !> get_partial_left_val of those nodes (same signature as
+  !> get_partial_kipf_propagate_left_val, athena_diffstruc_extd_sub_kipf.f90:85-95).
+  !> The upstream gradient of the sample is staged on the device; when the last sample of
+  !> the batch arrives the library runs the reverse sweep of the whole batch and
+  !> accumulates the parameter gradients there.  `output` is the gradient diffstruc adds
+  !> to params(1)%grad on the host: zero -- the device holds the gradients, and the
+  !> replacement body of network%update (cuda_network_update) steps from them.
+  !> Errors cannot stop a pure procedure; a failed call leaves the error text for the next
+  !> checked call (athena_cuda_network_update reports ATHENA_ERR_STATE).
+  pure subroutine get_partial_cuda_layer_val(this, upstream_grad, output)
+    class(array_type), intent(in) :: this
+    real(real32), dimension(:,:), intent(in) :: upstream_grad
+    real(real32), dimension(:,:), intent(out) :: output
+    integer(c_int64_t) :: layer_handle, batch_handle
+    integer(c_int32_t) :: sample
+    integer(c_int) :: rc
+    integer :: s
+
+    layer_handle = transfer(this%indices(1:2), layer_handle)
+    batch_handle = transfer(this%indices(3:4), batch_handle)
+    output = 0._real32
+    if (this%indices(5) >= 0) then
+       sample = int(this%indices(5), c_int32_t)
+       rc = athena_cuda_layer_backward_stage_pure(layer_handle, batch_handle, sample, &
+            upstream_grad, int(size(upstream_grad), c_int64_t))
+    else
+       ! graph-level output [num_outputs, batch]: column s is sample s
+       do s = 1, size(upstream_grad, 2)
+          rc = athena_cuda_layer_backward_stage_pure(layer_handle, batch_handle, &
+               int(s - 1, c_int32_t), upstream_grad(:, s), &
+               int(size(upstream_grad, 1), c_int64_t))
+       end do
+    end if
+  end subroutine get_partial_cuda_layer_val
+
+  !> Body of network%update (athena_network_sub.f90:2816-2929) for a network whose learnable
+  !> layers live on the device: the iteration counter, the learning-rate schedule and the
+  !> clip / minimise / zero-gradients sequence keep their order; the flat parameter and
+  !> gradient vectors never visit the host.
+  subroutine cuda_network_update(net_handle, learning_rate)
+    integer(c_int64_t), intent(in) :: net_handle
+    real(real32), intent(in) :: learning_rate   !! lr_decay%get_lr(lr0, iter), host side
+    call athena_cuda_check(athena_cuda_network_set_learning_rate(net_handle, learning_rate))
+    call athena_cuda_check(athena_cuda_network_update(net_handle))
+  end subroutine cuda_network_update
+
+  !> One iteration of the batch loop of network%train (athena_network_sub.f90:3611-3670) for a
+  !> pure message-passing network: get_sample + set_graph (batch%create), forward, loss_eval
+  !> (MSE), grad_reverse, update -- one library call; returns batch_loss (:3650).
+  !>   graph    this%input_graph(start_index:end_index) of the batch
+  !>   target   expected output of the batch: Kipf-last [F_T, sum of vertices]; Duvenaud-last
+  !>            [num_outputs, batch]
+  function cuda_train_batch(net_handle, graph, target, global_batch, learning_rate) &
+       result(batch_loss)
+    integer(c_int64_t), intent(in) :: net_handle
+    type(graph_type), dimension(:), intent(in) :: graph
+    real(real32), dimension(:,:), intent(in), target :: target
+    integer, intent(in) :: global_batch
+    real(real32), intent(in) :: learning_rate
+    real(real32) :: batch_loss
+    type(cuda_graph_batch_type) :: batch
+    real(real32), allocatable, target :: x(:,:), e(:,:)
+    real(c_float), target :: loss
+    type(c_ptr) :: e_ptr
+    integer :: s, v0, e0, fv, fe
+
+    call batch%create(graph)
+    fv = graph(1)%num_vertex_features
+    fe = graph(1)%num_edge_features
+    allocate(x(fv, batch%num_vertices))
+    v0 = 0
+    do s = 1, size(graph)
+       x(:, v0 + 1 : v0 + graph(s)%num_vertices) = graph(s)%vertex_features
+       v0 = v0 + graph(s)%num_vertices
+    end do
+    e_ptr = c_null_ptr
+    if (fe > 0) then
+       allocate(e(fe, batch%num_edges))
+       e0 = 0
+       do s = 1, size(graph)
+          e(:, e0 + 1 : e0 + graph(s)%num_edges) = graph(s)%edge_features
+          e0 = e0 + graph(s)%num_edges
+       end do
+       e_ptr = c_loc(e)
+    end if
+    call athena_cuda_check(athena_cuda_network_set_learning_rate(net_handle, learning_rate))
+    call athena_cuda_check(athena_cuda_network_train_step(net_handle, batch%handle, c_loc(x), &
+         e_ptr, c_loc(target), ATHENA_MEM_HOST, int(global_batch, c_int32_t), c_loc(loss)))
+    batch_loss = loss
+    call batch%destroy()
+  end function cuda_train_batch
 
   !> network%compile: describe athena's optimiser object to athena_cuda_network_compile.
   !> The decayed learning rate is passed per update with

@@ -253,6 +253,23 @@ int athena_cuda_layer_forward(athena_handle_t layer, athena_handle_t batch,
 int athena_cuda_layer_backward(athena_handle_t layer, athena_handle_t batch,
                                const float* grad_output, float* grad_input, int32_t mem);
 
+/*
+ * The same reverse sweep, fed one SAMPLE at a time: the shape in which diffstruc's
+ * loss%grad_reverse reaches a layer whose output(1,s) are separate autodiff nodes (one
+ * get_partial_*_val callback per sample, athena_diffstruc_extd_sub_kipf.f90:85-95).
+ *   sample        0-based index into the batch
+ *   grad_output   that sample's upstream gradient: Kipf [nv_s][F_T]; Duvenaud / full
+ *                 [num_outputs]; host memory
+ *   count         number of floats in grad_output (checked)
+ * The gradient is parked in the layer's staging buffer; when the last sample of the batch
+ * has been staged the reverse sweep of the whole batch runs (parameter gradients
+ * accumulate on the device, no input gradient is produced).  _flush runs it with zero
+ * gradients for the samples that were not staged (a loss that ignores some samples).
+ */
+int athena_cuda_layer_backward_stage(athena_handle_t layer, athena_handle_t batch, int32_t sample,
+                                     const float* grad_output, int64_t count);
+int athena_cuda_layer_backward_flush(athena_handle_t layer, athena_handle_t batch);
+
 /* ------------------------------------------------------------------------ */
 /* network: the train-step skeleton around the layers                        */
 /* (network_type%add/compile/forward/train/update/predict,                   */
