@@ -18,7 +18,8 @@ LIB_PATH = os.environ.get("ATHENA_CUDA_LIB") or os.path.join(_HERE, "lib", "liba
 CSRC = os.path.join(_HERE, "csrc")
 
 MEM_HOST, MEM_DEVICE = 0, 1
-ACT = {"none": 0, "linear": 1, "relu": 2, "leaky_relu": 3, "sigmoid": 4, "tanh": 5, "softmax": 6}
+ACT = {"none": 0, "linear": 1, "relu": 2, "leaky_relu": 3, "sigmoid": 4, "tanh": 5, "softmax": 6,
+       "swish": 7}
 OPT_SGD, OPT_ADAM, OPT_RMSPROP, OPT_ADAGRAD = 0, 1, 2, 3
 REG_NONE, REG_L1, REG_L2, REG_L1L2 = 0, 1, 2, 3
 COMM_ID_BYTES = 128
@@ -108,6 +109,7 @@ def lib() -> C.CDLL:
         "athena_cuda_network_create": [PH],
         "athena_cuda_network_destroy": [H],
         "athena_cuda_network_add": [H, H],
+        "athena_cuda_network_add_inputs": [H, H, I32, P, I32],
         "athena_cuda_network_compile": [H, P],
         "athena_cuda_network_num_params": [H, PI64],
         "athena_cuda_network_set_params": [H, P, I64],

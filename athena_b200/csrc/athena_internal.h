@@ -308,6 +308,12 @@ int launch_segment_sum(const float* Y, int N, const int32_t* voff, int32_t B, fl
 int launch_readout_bwd(int act, const float* S, const float* gout, const int32_t* vgraph,
                        float* dY, int64_t V, int N);
 int launch_add_inplace(float* dst, const float* src, int64_t n);
+// swish (beta = 1): H = X / (1 + exp(-X)); backward on the saved pre-activation X
+int launch_swish_fwd(const float* X, float* H, int64_t n);
+int launch_swish_bwd(const float* X, const float* G, float* out, int64_t n);
+// dst[m, doff : doff + w] (=|+=) src[m, soff : soff + w]   (concatenation and its reverse)
+int launch_copy_cols(float* dst, int ldd, int doff, const float* src, int lds, int soff, int w,
+                     int64_t M, int accumulate);
 // Y[m, n] = act( Y[m, n] + bias[n] )   (bias may be null; act may be softmax over n)
 int launch_bias_act(float* Y, const float* bias, int64_t M, int N, int act);
 // dst[n] += sum_m G[m, n]   (ascending m, one thread per column: deterministic)

@@ -473,6 +473,59 @@ int launch_segment_sum(const float* Y, int N, const int32_t* voff, int32_t B, fl
   return ATHENA_OK;
 }
 
+// swish_array / get_partial_swish_val with beta = 1 (athena_diffstruc_extd_sub.f90:434, 480-484)
+__global__ void k_swish_fwd(const float* __restrict__ X, float* __restrict__ H, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float x = X[i];
+    H[i] = x * (1.f / (1.f + expf(-x)));
+  }
+}
+__global__ void k_swish_bwd(const float* __restrict__ X, const float* G, float* out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float x = X[i], e = expf(x), d = e + 1.f;
+    out[i] = G[i] * e * (x + e + 1.f) / (d * d);
+  }
+}
+int launch_swish_fwd(const float* X, float* H, int64_t n) {
+  if (n == 0) return ATHENA_OK;
+  int blocks = (int)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx().sm_count * 16);
+  k_swish_fwd<<<blocks, 256, 0, ctx().stream>>>(X, H, n);
+  ATH_LAUNCHED_T("swish_fwd");
+  return ATHENA_OK;
+}
+int launch_swish_bwd(const float* X, const float* G, float* out, int64_t n) {
+  if (n == 0) return ATHENA_OK;
+  int blocks = (int)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx().sm_count * 16);
+  k_swish_bwd<<<blocks, 256, 0, ctx().stream>>>(X, G, out, n);
+  ATH_LAUNCHED_T("swish_bwd");
+  return ATHENA_OK;
+}
+
+__global__ void k_copy_cols(float* __restrict__ dst, int ldd, int doff, const float* __restrict__ src,
+                            int lds, int soff, int w, long long M, int accumulate) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < M * w; i += stride) {
+    const long long m = i / w;
+    const int c = (int)(i - m * w);
+    const float v = src[m * lds + soff + c];
+    float* d = dst + m * ldd + doff + c;
+    *d = accumulate ? *d + v : v;
+  }
+}
+int launch_copy_cols(float* dst, int ldd, int doff, const float* src, int lds, int soff, int w,
+                     int64_t M, int accumulate) {
+  if (M == 0 || w == 0) return ATHENA_OK;
+  int blocks = (int)std::min<int64_t>(cdiv(M * w, 256), (int64_t)ctx().sm_count * 16);
+  k_copy_cols<<<blocks, 256, 0, ctx().stream>>>(dst, ldd, doff, src, lds, soff, w, M, accumulate);
+  ATH_LAUNCHED_T("copy_cols");
+  return ATHENA_OK;
+}
+
 __global__ void k_add_inplace(float* __restrict__ dst, const float* __restrict__ src, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;

@@ -30,6 +30,7 @@ struct Layer : Object {
   // saved by forward for the reverse sweep
   std::vector<std::unique_ptr<DevBuf>> P, H, S, GZ, TN;  // TN: per-step dW partials (fused path)
   std::vector<std::unique_ptr<DevBuf>> MK;               // sign bits of step t's pre-activation
+  std::vector<std::unique_ptr<DevBuf>> Y;                // pre-activation of step t (swish only)
   std::vector<char> mask_valid;                          // MK[t] written by the last forward
   DevBuf Ae, out_buf, g0, g1, g2, tn_scratch, stage_x, stage_e, stage_g, stage_gin;
   DevBuf tile_part;          // CTA partials of the fused Duvenaud reverse sweep (tile_fma.cu)
@@ -79,8 +80,10 @@ static void layer_layout(Layer* L) {
   L->GZ.clear();
   L->TN.clear();
   L->MK.clear();
+  L->Y.clear();
   L->mask_valid.assign(L->T, 0);
   for (int t = 0; t < L->T; ++t) {
+    L->Y.emplace_back(new DevBuf);
     L->TN.emplace_back(new DevBuf);
     L->MK.emplace_back(new DevBuf);
     L->P.emplace_back(new DevBuf);
@@ -120,14 +123,29 @@ static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out,
                         FwdOpts* fo = nullptr) {
   const int64_t V = b->V;
   const float* in = x;
+  // swish differentiates on the pre-activation (get_partial_swish_val,
+  // athena_diffstruc_extd_sub.f90:472-486): the step kernels run without activation into Y_t,
+  // which is kept, and H_t = swish(Y_t) is one elementwise pass
+  const bool swish = L->act == ATHENA_ACT_SWISH;
+  const int kact = swish ? ATHENA_ACT_NONE : L->act;
   for (int t = 1; t <= L->T; ++t) {
     const int Fi = L->nvf[t - 1], Fo = L->nvf[t];
     DevBuf& P = *L->P[t - 1];
     DevBuf& H = *L->H[t - 1];
     ATH_TRY(P.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fi, 1)));
     ATH_TRY(H.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fo, 1)));
+    float* Hk = H.as<float>();  // where the step kernel writes
+    if (swish) {
+      ATH_TRY(L->Y[t - 1]->reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fo, 1)));
+      Hk = L->Y[t - 1]->as<float>();
+    }
+    auto step_done = [&]() -> int {
+      if (swish) ATH_TRY(launch_swish_fwd(Hk, H.as<float>(), V * Fo));
+      in = H.as<float>();
+      return ATHENA_OK;
+    };
     L->mask_valid[t - 1] = 0;
-    if (fo && fo->mse_target && t == L->T && L->act != ATHENA_ACT_SOFTMAX &&
+    if (fo && fo->mse_target && t == L->T && L->act != ATHENA_ACT_SOFTMAX && !swish &&
         pipe_gather_supported(b, Fi, Fo)) {
       ATH_TRY(main_wait(fo->target_ready));
       fo->target_ready = nullptr;
@@ -147,40 +165,38 @@ static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out,
         mk = L->MK[t - 1]->as<uint32_t>();
         L->mask_valid[t - 1] = 1;
       }
-      ATH_TRY(launch_pipe_gather_fwd(b, in, L->params + L->poff[t - 1], P.as<float>(),
-                                     H.as<float>(), Fi, Fo, L->act, mk));
-      in = H.as<float>();
+      ATH_TRY(launch_pipe_gather_fwd(b, in, L->params + L->poff[t - 1], P.as<float>(), Hk, Fi, Fo,
+                                     kact, mk));
+      ATH_TRY(step_done());
       continue;
     }
     if (tile_kipf_supported(b, Fi, Fo)) {
       // small graphs, narrow features: propagate + transform + activation in one FP32 tile kernel
       ATH_TRY(launch_tile_kipf_fwd(b, in, L->params + L->poff[t - 1],
-                                   L->inference ? nullptr : P.as<float>(), H.as<float>(), Fi, Fo,
-                                   L->act));
-      in = H.as<float>();
+                                   L->inference ? nullptr : P.as<float>(), Hk, Fi, Fo, kact));
+      ATH_TRY(step_done());
       continue;
     }
-    if (L->act != ATHENA_ACT_SOFTMAX && agg_tc_supported(Fi, Fo, in, H.as<float>())) {
+    if (L->act != ATHENA_ACT_SOFTMAX && agg_tc_supported(Fi, Fo, in, Hk)) {
       // large graph, wide features: SpMM + tcgen05 transform in one pass; the aggregate
       // is only written when a reverse sweep may follow
       ATH_TRY(launch_agg_tc_fwd(b, in, L->params + L->poff[t - 1],
-                                L->inference ? nullptr : P.as<float>(), H.as<float>(), L->act));
-      in = H.as<float>();
+                                L->inference ? nullptr : P.as<float>(), Hk, kact));
+      ATH_TRY(step_done());
       continue;
     }
     // P = D^-1/2 A D^-1/2 . in      (kipf_propagate)
     ATH_TRY(launch_aggregate(b->row_ptr, b->col, b->coef, in, Fi, Fi, P.as<float>(), Fi, V, 0,
                              nullptr, 0, b->long_rows, b->long_counts));
     // H = act( P . W_t )            (matmul + activation%apply)
-    if (L->act != ATHENA_ACT_SOFTMAX &&
-        tc_rows_supported(Fi, Fo, Fi, Fo, P.as<float>(), H.as<float>())) {
-      ATH_TRY(launch_tc_rows(false, P.as<float>(), Fi, nullptr, 0, L->params + L->poff[t - 1],
-                             H.as<float>(), Fo, V, Fo, Fi, L->act));
+    if (L->act != ATHENA_ACT_SOFTMAX && tc_rows_supported(Fi, Fo, Fi, Fo, P.as<float>(), Hk)) {
+      ATH_TRY(launch_tc_rows(false, P.as<float>(), Fi, nullptr, 0, L->params + L->poff[t - 1], Hk,
+                             Fo, V, Fo, Fi, kact));
     } else {
-      ATH_TRY(launch_gemm_nn(P.as<float>(), Fi, L->params + L->poff[t - 1], H.as<float>(), Fo, V,
-                             Fo, Fi, L->act, GroupDesc{}));
+      ATH_TRY(launch_gemm_nn(P.as<float>(), Fi, L->params + L->poff[t - 1], Hk, Fo, V, Fo, Fi, kact,
+                             GroupDesc{}));
     }
-    in = H.as<float>();
+    ATH_TRY(step_done());
   }
   *out = in;
   return ATHENA_OK;
@@ -209,7 +225,9 @@ static int duvenaud_forward(Layer* L, Batch* b, const float* x, const float* e,
   const int64_t V = b->V;
   L->tile_fwd = false;
   L->fwd_e = e;
-  if (tile_duv_supported(b, L->T, L->nvf.data(), L->nef, L->max_deg - L->min_deg + 1, L->n_out)) {
+  const bool swish = L->act == ATHENA_ACT_SWISH;
+  if (!swish &&
+      tile_duv_supported(b, L->T, L->nvf.data(), L->nef, L->max_deg - L->min_deg + 1, L->n_out)) {
     // every time step and the readout of the whole layer in ONE launch (tile_fma.cu); only
     // z_t is kept for the reverse sweep
     ATH_REQUIRE(L->nef == 0 || e != nullptr, ATHENA_ERR_ARG,
@@ -267,8 +285,16 @@ static int duvenaud_forward(Layer* L, Batch* b, const float* x, const float* e,
     gd.D = D;
     gd.wstride = (int64_t)Fo * K;
     gd.scale_by_group = 1;
-    ATH_TRY(launch_gemm_nn(A.as<float>(), ld, L->params + L->poff[t - 1], Zt.as<float>(), Fo, V,
-                           Fo, K, L->act, gd));
+    if (swish) {
+      DevBuf& Yt = *L->Y[t - 1];
+      ATH_TRY(Yt.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * Fo, 1)));
+      ATH_TRY(launch_gemm_nn(A.as<float>(), ld, L->params + L->poff[t - 1], Yt.as<float>(), Fo, V,
+                             Fo, K, ATHENA_ACT_NONE, gd));
+      ATH_TRY(launch_swish_fwd(Yt.as<float>(), Zt.as<float>(), V * Fo));
+    } else {
+      ATH_TRY(launch_gemm_nn(A.as<float>(), ld, L->params + L->poff[t - 1], Zt.as<float>(), Fo, V,
+                             Fo, K, L->act, gd));
+    }
     in = Zt.as<float>();
   }
   // readout: out(:,s) = sum_t sum_v ract( R_t . z_t )(:,v)
@@ -296,8 +322,18 @@ static int full_forward(Layer* L, Batch* b, const float* x, const float** out) {
   ATH_TRY(H.reserve(sizeof(float) * (size_t)std::max<int64_t>(B * No, 1)));
   ATH_TRY(launch_gemm_nn(x, Ni, L->params + L->poff[0], H.as<float>(), No, B, No, Ni,
                          ATHENA_ACT_NONE, GroupDesc{}));
-  ATH_TRY(launch_bias_act(H.as<float>(), L->use_bias ? L->params + L->poff[1] : nullptr, B, No,
-                          L->act));
+  if (L->act == ATHENA_ACT_SWISH) {
+    DevBuf& Y = *L->Y[0];
+    ATH_TRY(Y.reserve(sizeof(float) * (size_t)std::max<int64_t>(B * No, 1)));
+    ATH_TRY(launch_bias_act(H.as<float>(), L->use_bias ? L->params + L->poff[1] : nullptr, B, No,
+                            ATHENA_ACT_NONE));
+    ATH_CUDA(cudaMemcpyAsync(Y.p, H.p, sizeof(float) * (size_t)(B * No), cudaMemcpyDeviceToDevice,
+                             ctx().stream));
+    ATH_TRY(launch_swish_fwd(Y.as<float>(), H.as<float>(), B * No));
+  } else {
+    ATH_TRY(launch_bias_act(H.as<float>(), L->use_bias ? L->params + L->poff[1] : nullptr, B, No,
+                            L->act));
+  }
   *out = H.as<float>();
   return ATHENA_OK;
 }
@@ -307,7 +343,10 @@ static int full_backward(Layer* L, Batch* b, const float* gout, float* gin) {
   const int64_t B = b->B;
   ATH_TRY(L->g0.reserve(sizeof(float) * (size_t)std::max<int64_t>(B * No, 1)));
   const float* gz = gout;
-  if (L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR) {
+  if (L->act == ATHENA_ACT_SWISH) {
+    ATH_TRY(launch_swish_bwd(L->Y[0]->as<float>(), gout, L->g0.as<float>(), B * No));
+    gz = L->g0.as<float>();
+  } else if (L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR) {
     ATH_TRY(launch_act_bwd(L->act, L->H[0]->as<float>(), gout, L->g0.as<float>(), B, No));
     gz = L->g0.as<float>();
   }
@@ -355,12 +394,21 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
   ATH_TRY(L->g0.reserve(bytes));
   ATH_TRY(L->g1.reserve(bytes));
   ATH_TRY(L->g2.reserve(bytes));
-  const bool nonlinear = L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR;
+  const bool swish = L->act == ATHENA_ACT_SWISH;
+  const bool nonlinear = L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR && !swish;
   const float* g = gout;                // gradient w.r.t. the step output H_t ...
   bool preact = opt.gout_is_preact;     // ... or already w.r.t. the pre-activation (gY_t)
   if (opt.folded) *opt.folded = false;
   for (int t = L->T; t >= 1; --t) {
     const int Fi = L->nvf[t - 1], Fo = L->nvf[t];
+    if (swish && !preact) {
+      // gY_t = gH_t * swish'(Y_t) on the saved pre-activation; the fused kernels below then
+      // see a layer without activation
+      float* dst = (g == L->g0.as<float>()) ? L->g2.as<float>() : L->g0.as<float>();
+      ATH_TRY(launch_swish_bwd(L->Y[t - 1]->as<float>(), g, dst, V * Fo));
+      g = dst;
+    }
+    if (swish) preact = false;  // nonlinear == false: g is used as gY_t as it stands
     const float* Pt = L->P[t - 1]->as<float>();
     const float* Ht = L->H[t - 1]->as<float>();
     const float* Wt = L->params + L->poff[t - 1];
@@ -431,7 +479,7 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
         if (opt.folded) *opt.folded = true;
       }
       ATH_TRY(launch_pipe_gather_bwd(b, gy, Wt, Hin, dst, Fo, Fi, act_e, mk));
-      preact = t > 1;  // dst already is gY_{t-1}
+      preact = t > 1 && !swish;  // dst already is gY_{t-1}
     } else {
       // dP = W_t^T gY, then dH(:,u) += dP(:,v) for every CSR entry (v,u): CSC gather, NO coefficient
       if (nt_tc) {
@@ -494,7 +542,10 @@ static int duvenaud_backward(Layer* L, Batch* b, const float* gout, float* gin,
     const int Fi = L->nvf[t - 1], Fo = L->nvf[t], K = Fi + L->nef, ld = L->ldA(t);
     const float* gz = L->GZ[t - 1]->as<float>();
     const float* gzp = gz;
-    if (L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR) {
+    if (L->act == ATHENA_ACT_SWISH) {
+      ATH_TRY(launch_swish_bwd(L->Y[t - 1]->as<float>(), gz, L->g0.as<float>(), V * Fo));
+      gzp = L->g0.as<float>();
+    } else if (L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR) {
       ATH_TRY(launch_act_bwd(L->act, L->H[t - 1]->as<float>(), gz, L->g0.as<float>(), V, Fo));
       gzp = L->g0.as<float>();
     }
@@ -549,6 +600,14 @@ struct Network : Object {
   OptimState opt;
   DevBuf stage_x, stage_e, stage_t, gbuf, loss_scratch;
   std::vector<std::unique_ptr<DevBuf>> gin;  // input gradient of layer l (l >= 1)
+  // network%add(layer, input_list, operator = 'concatenate') (athena_network_sub.f90:764-830):
+  // sources of layer l, in list order: -1 the network input, k >= 0 layer k; empty = the plain
+  // chain (layer l - 1, or the network input for l = 0)
+  std::vector<std::vector<int>> inputs;
+  std::vector<int> consumers;                 // how many layers read layer l's output
+  std::vector<std::unique_ptr<DevBuf>> cat;   // concatenated input of layer l
+  std::vector<std::unique_ptr<DevBuf>> gsum;  // summed output gradient of layer l (skip links)
+  bool has_skips = false;
   float* pinned_loss = nullptr;
   int edge_width() const {  // edge features are consumed by the Duvenaud layer (if any)
     for (const Layer* L : layers)
@@ -586,13 +645,34 @@ static int stage_in_side(DevBuf& buf, const float* src, int64_t count, int mem,
   return ATHENA_OK;
 }
 
+static int src_width(const Network* N, int src) {
+  const Layer* S = src < 0 ? N->layers.front() : N->layers[src];
+  return src < 0 ? S->nvf[0] : S->nvf[S->T];
+}
+
 static int net_forward_dev(Network* N, Batch* b, const float* x, const float* e,
                            const float** out, FwdOpts* fo = nullptr) {
   const float* in = x;
+  std::vector<const float*> outs(N->layers.size(), nullptr);
   for (size_t l = 0; l < N->layers.size(); ++l) {
+    Layer* L = N->layers[l];
+    if (N->has_skips && !N->inputs[l].empty()) {
+      // concat_layer_type%combine (athena_concat_layer.f90:413-456): the sources' vertex
+      // features side by side, in list order
+      const int Fin = L->nvf[0];
+      DevBuf& cat = *N->cat[l];
+      ATH_TRY(cat.reserve(sizeof(float) * (size_t)std::max<int64_t>(b->V * Fin, 1)));
+      int off = 0;
+      for (int src : N->inputs[l]) {
+        const int w = src_width(N, src);
+        ATH_TRY(launch_copy_cols(cat.as<float>(), Fin, off, src < 0 ? x : outs[src], w, 0, w, b->V, 0));
+        off += w;
+      }
+      in = cat.as<float>();
+    }
     const float* o = nullptr;
-    ATH_TRY(layer_forward_dev(N->layers[l], b, in, e, &o,
-                              l + 1 == N->layers.size() ? fo : nullptr));
+    ATH_TRY(layer_forward_dev(L, b, in, e, &o, l + 1 == N->layers.size() ? fo : nullptr));
+    outs[l] = o;
     in = o;
   }
   *out = in;
@@ -646,7 +726,7 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
   // the activation derivative of the last Kipf layer is folded into the loss gradient
   auto foldable = [](const Layer* L) {
     return L->kind == 0 && L->act != ATHENA_ACT_NONE && L->act != ATHENA_ACT_LINEAR &&
-           L->act != ATHENA_ACT_SOFTMAX;
+           L->act != ATHENA_ACT_SOFTMAX && L->act != ATHENA_ACT_SWISH;
   };
   bool g_preact = false;
   DeferList defer;
@@ -666,28 +746,65 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
                              N->gbuf.as<float>(), gflat + N->n, N->loss_scratch));
   }
   const float* g = N->gbuf.as<float>();
-  for (int l = (int)N->layers.size() - 1; l >= 0; --l) {
+  const int nl = (int)N->layers.size();
+  // with skip links the gradient of a layer output is the sum of what its consumers send back,
+  // added in the order of the reverse sweep (last consumer first)
+  std::vector<char> gset(N->has_skips ? nl : 0, 0);
+  for (int l = nl - 1; l >= 0; --l) {
+    Layer* L = N->layers[l];
+    const bool concat = N->has_skips && !N->inputs[l].empty();
+    // the plain hand-over (this layer's input gradient IS the previous layer's output
+    // gradient, activation derivatives folded across the boundary) needs a sole consumer
+    const bool chain = !concat && (!N->has_skips || l == 0 || N->consumers[l - 1] == 1);
+    if (N->has_skips && l < nl - 1) {
+      if (!gset[l]) continue;  // nobody consumed this layer's output
+      if (N->consumers[l] != 1 || !N->inputs[l + 1].empty()) g = N->gsum[l]->as<float>();
+    }
+    bool needs_gin = l > 0;
+    if (concat) {
+      needs_gin = false;
+      for (int src : N->inputs[l]) needs_gin = needs_gin || src >= 0;
+    }
     float* gi = nullptr;
-    if (l > 0) {
+    if (needs_gin) {
       DevBuf& buf = *N->gin[l];
-      ATH_TRY(buf.reserve(sizeof(float) * (size_t)std::max<int64_t>(
-                                                N->layers[l]->in_rows(b) * N->layers[l]->nvf[0], 1)));
+      ATH_TRY(buf.reserve(sizeof(float) * (size_t)std::max<int64_t>(L->in_rows(b) * L->nvf[0], 1)));
       gi = buf.as<float>();
     }
     BwdOpts opt;
     bool folded = false;
     opt.gout_is_preact = g_preact;
-    opt.fold_act = (l > 0 && foldable(N->layers[l - 1])) ? N->layers[l - 1]->act : ATHENA_ACT_NONE;
-    if (l > 0) {
+    opt.fold_act = (chain && l > 0 && foldable(N->layers[l - 1])) ? N->layers[l - 1]->act
+                                                                   : ATHENA_ACT_NONE;
+    if (chain && l > 0) {
       const Layer* prev = N->layers[l - 1];
       if (prev->kind == 0 && prev->mask_valid[prev->T - 1])
         opt.fold_mask = prev->MK[prev->T - 1]->as<uint32_t>();
     }
     opt.folded = &folded;
     opt.defer = &defer;
-    ATH_TRY(layer_backward_dev(N->layers[l], b, g, gi, opt));
+    ATH_TRY(layer_backward_dev(L, b, g, gi, opt));
     g_preact = folded;
-    g = gi;
+    if (chain) {
+      if (N->has_skips && l > 0) gset[l - 1] = 1;
+      g = gi;
+      continue;
+    }
+    // split the input gradient back over the sources (concat_layer: the reverse of combine)
+    const int Fin = L->nvf[0];
+    int off = 0;
+    std::vector<int> plain{l - 1};
+    for (int src : concat ? N->inputs[l] : plain) {
+      const int w = src_width(N, src);
+      if (src >= 0) {
+        DevBuf& acc = *N->gsum[src];
+        ATH_TRY(acc.reserve(sizeof(float) * (size_t)std::max<int64_t>(b->V * w, 1)));
+        ATH_TRY(launch_copy_cols(acc.as<float>(), w, 0, gi, Fin, off, w, b->V, gset[src] ? 1 : 0));
+        gset[src] = 1;
+      }
+      off += w;
+    }
+    g = nullptr;
   }
   ATH_TRY(launch_pipe_tn_pending(&defer));  // all queued dW products in one launch
   // gradient exchange over peer memory when it is set up (comm_p2p_*), else NCCL
@@ -726,7 +843,7 @@ using namespace athena;
 
 // ---- layer ABI ---------------------------------------------------------------------
 
-static int check_act(int a) { return a >= ATHENA_ACT_NONE && a <= ATHENA_ACT_SOFTMAX; }
+static int check_act(int a) { return a >= ATHENA_ACT_NONE && a <= ATHENA_ACT_SWISH; }
 
 ATHENA_API int athena_cuda_kipf_layer_create(athena_handle_t* layer, int32_t num_time_steps,
                                              const int32_t* num_vertex_features,
@@ -771,6 +888,8 @@ ATHENA_API int athena_cuda_duvenaud_layer_create(athena_handle_t* layer, int32_t
               "duvenaud_layer_create: need 1 <= min_vertex_degree <= max_vertex_degree");
   ATH_REQUIRE(check_act(message_activation) && check_act(readout_activation), ATHENA_ERR_ARG,
               "duvenaud_layer_create: unknown activation");
+  ATH_REQUIRE(readout_activation != ATHENA_ACT_SWISH, ATHENA_ERR_ARG,
+              "duvenaud_layer_create: swish is supported as message activation only");
   std::unique_ptr<Layer> L(new Layer);
   L->kind = 1;
   L->T = num_time_steps;
@@ -1018,6 +1137,60 @@ ATHENA_API int athena_cuda_network_add(athena_handle_t net, athena_handle_t laye
   L->adopted = true;
   N->layers.push_back(L);
   N->handles.push_back(layer);
+  N->inputs.resize(N->layers.size());
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_network_add_inputs(athena_handle_t net, athena_handle_t layer,
+                                              int32_t num_inputs, const int32_t* input_list,
+                                              int32_t merge_operator) {
+  Network* N = static_cast<Network*>(lookup_object(net, Kind::Network));
+  Layer* L = static_cast<Layer*>(lookup_object(layer, Kind::Layer));
+  if (!N || !L) return ATHENA_ERR_HANDLE;
+  ATH_REQUIRE(!N->compiled, ATHENA_ERR_STATE, "network_add: network already compiled");
+  ATH_REQUIRE(!L->adopted, ATHENA_ERR_STATE, "network_add: layer already belongs to a network");
+  ATH_REQUIRE(num_inputs >= 1 && num_inputs <= 8 && input_list, ATHENA_ERR_ARG,
+              "network_add: input_list must hold 1..8 entries");
+  // operator 1 = concatenate; 2 (add) is accepted by the reference's add() but has no
+  // message-passing user; anything else is "invalid operator" (athena_network_sub.f90:820-823)
+  ATH_REQUIRE(merge_operator == ATHENA_MERGE_CONCATENATE, ATHENA_ERR_ARG,
+              "network_add: invalid operator %d (only concatenate is supported)", merge_operator);
+  ATH_REQUIRE(L->kind == 0, ATHENA_ERR_ARG,
+              "network_add: only Kipf layers take an input_list (vertex-level concatenation)");
+  const int nl = (int)N->layers.size();  // layers added before this one
+  ATH_REQUIRE(nl >= 1 || (num_inputs == 1 && input_list[0] == 0), ATHENA_ERR_ARG,
+              "network_add: the first layer can only read the network input");
+  std::vector<int> srcs;
+  int width = 0;
+  for (int i = 0; i < num_inputs; ++i) {
+    const int id = input_list[i];
+    // ids as network%add resolves them (athena_network_sub.f90:832-853): 0 the input layer,
+    // k > 0 the k-th added layer, k < 0 counted back from this layer (-1 = the previous one)
+    ATH_REQUIRE(id > -(nl + 1) && id <= nl, ATHENA_ERR_ARG,
+                "network_add: input vertex index %d out of range (%d:%d)", id, -nl, nl);
+    const int src = id == 0 ? -1 : (id < 0 ? nl + id : id - 1);
+    if (src >= 0) {
+      ATH_REQUIRE(N->layers[src]->kind == 0, ATHENA_ERR_ARG,
+                  "network_add: source layer %d is not a Kipf layer", src + 1);
+      width += N->layers[src]->nvf[N->layers[src]->T];
+    } else {
+      ATH_REQUIRE(nl == 0 || N->layers.front()->kind == 0, ATHENA_ERR_ARG,
+                  "network_add: the network input is not a vertex-feature input");
+      width += nl == 0 ? L->nvf[0] : N->layers.front()->nvf[0];
+    }
+    srcs.push_back(src);
+  }
+  ATH_REQUIRE(width == L->nvf[0], ATHENA_ERR_ARG,
+              "network_add: layer expects %d vertex features, the listed sources supply %d",
+              L->nvf[0], width);
+  L->adopted = true;
+  N->layers.push_back(L);
+  N->handles.push_back(layer);
+  N->inputs.resize(N->layers.size());
+  if (!(nl == 0) && !(srcs.size() == 1 && srcs[0] == nl - 1)) {
+    N->inputs.back() = srcs;
+    N->has_skips = true;
+  }
   return ATHENA_OK;
 }
 
@@ -1056,7 +1229,21 @@ ATHENA_API int athena_cuda_network_compile(athena_handle_t net,
     L->own_grads.release();
   }
   N->gin.clear();
-  for (size_t l = 0; l < N->layers.size(); ++l) N->gin.emplace_back(new DevBuf);
+  N->cat.clear();
+  N->gsum.clear();
+  N->inputs.resize(N->layers.size());
+  N->consumers.assign(N->layers.size(), 0);
+  for (size_t l = 0; l < N->layers.size(); ++l) {
+    N->gin.emplace_back(new DevBuf);
+    N->cat.emplace_back(new DevBuf);
+    N->gsum.emplace_back(new DevBuf);
+    if (N->inputs[l].empty()) {
+      if (l > 0) N->consumers[l - 1] += 1;
+    } else {
+      for (int src : N->inputs[l])
+        if (src >= 0) N->consumers[src] += 1;
+    }
+  }
   N->opt.d = *optimiser;
   N->opt.lr = optimiser->learning_rate;
   N->opt.iter = 0;

@@ -157,13 +157,33 @@ class network_type:
         self.compiled = False
 
     # -- construction -------------------------------------------------------
-    def add(self, layer: msgpass_layer_type):
+    _OPERATORS = {"||": 1, "concat": 1, "concatenate": 1, "append": 1, "+": 2, "add": 2}
+
+    def add(self, layer: msgpass_layer_type, input_list: Optional[Sequence[int]] = None,
+            output_list=None, operator=None):
+        """network%add(layer, input_list, output_list, operator) (athena_network_sub.f90:764-830).
+        input_list ids: 0 = the input layer, k > 0 = the k-th added layer, k < 0 = counted back
+        from this layer (-1 = the previously added one); operator 'concatenate' (default) joins
+        the sources' vertex features in list order (example/msgpass_euler/src/main.f90:192-255)."""
         if not layer.handle and hasattr(layer, "_create"):
             if not self.model:
                 raise AthenaCudaError(-2, "network_add: the first layer must be a message-passing layer")
             layer._create(self.model[-1].num_outputs if self.model[-1].name != "kipf"
                           else self.model[-1].num_vertex_features[-1])
-        check(lib().athena_cuda_network_add(self.handle, layer.handle))
+        if output_list is not None:
+            raise AthenaCudaError(-2, "network_add: output_list is outside the CUDA path")
+        if input_list is None:
+            check(lib().athena_cuda_network_add(self.handle, layer.handle))
+        else:
+            op = 1
+            if operator is not None:
+                op = operator if isinstance(operator, int) else \
+                    self._OPERATORS.get(str(operator).strip().lower(), 0)
+            if op < 1 or op > 2:
+                raise AthenaCudaError(-2, "invalid operator")  # stop_program("invalid operator")
+            ids = np.ascontiguousarray(input_list, np.int32)
+            check(lib().athena_cuda_network_add_inputs(self.handle, layer.handle, ids.size,
+                                                       ptr(ids), op))
         layer._owned = False  # the network owns the device object now
         self.model.append(layer)
 

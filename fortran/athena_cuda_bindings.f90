@@ -34,7 +34,7 @@ module athena__cuda_bindings
   integer(c_int32_t), parameter, public :: ATHENA_ACT_LEAKY_RELU = 3
   integer(c_int32_t), parameter, public :: ATHENA_ACT_SIGMOID = 4
   integer(c_int32_t), parameter, public :: ATHENA_ACT_TANH = 5
-  integer(c_int32_t), parameter, public :: ATHENA_ACT_SOFTMAX = 6
+  integer(c_int32_t), parameter, public :: ATHENA_ACT_SOFTMAX = 6, ATHENA_ACT_SWISH = 7
 
   integer(c_int32_t), parameter, public :: ATHENA_OPT_SGD = 0
   integer(c_int32_t), parameter, public :: ATHENA_OPT_ADAM = 1
@@ -74,6 +74,7 @@ module athena__cuda_bindings
   public :: athena_cuda_layer_zero_gradients
   public :: athena_cuda_layer_forward, athena_cuda_layer_backward
   public :: athena_cuda_network_create, athena_cuda_network_destroy, athena_cuda_network_add
+  public :: athena_cuda_network_add_inputs
   public :: athena_cuda_network_compile, athena_cuda_network_num_params
   public :: athena_cuda_network_set_params, athena_cuda_network_get_params
   public :: athena_cuda_network_get_gradients, athena_cuda_network_set_learning_rate
@@ -286,6 +287,16 @@ module athena__cuda_bindings
      function athena_cuda_network_add(net, layer) bind(C, name="athena_cuda_network_add") result(rc)
        import :: c_int, c_int64_t
        integer(c_int64_t), value :: net, layer
+       integer(c_int) :: rc
+     end function
+     !! network%add(layer, input_list, operator) (athena_network_sub.f90:764-830): the ids are
+     !! passed as the caller wrote them (0 = input layer, k > 0, k < 0); operator 1 = concatenate
+     function athena_cuda_network_add_inputs(net, layer, num_inputs, input_list, merge_operator) &
+          bind(C, name="athena_cuda_network_add_inputs") result(rc)
+       import :: c_int, c_int32_t, c_int64_t
+       integer(c_int64_t), value :: net, layer
+       integer(c_int32_t), value :: num_inputs, merge_operator
+       integer(c_int32_t), intent(in) :: input_list(*)
        integer(c_int) :: rc
      end function
      function athena_cuda_network_compile(net, optimiser) &

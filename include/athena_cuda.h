@@ -50,7 +50,7 @@ typedef int64_t athena_handle_t;
 #define ATHENA_ERR_STATE (-5)     /* call order violated (e.g. backward before forward) */
 #define ATHENA_ERR_COMM (-6)      /* NCCL failure / NCCL not loadable */
 
-/* activation ids: athena_activation_{none,linear,relu,leaky_relu,sigmoid,tanh,softmax}.f90
+/* activation ids: athena_activation_{none,linear,relu,leaky_relu,sigmoid,tanh,softmax,swish}.f90
  * (scale = 1, threshold = 0, leaky alpha = 0.01: athena_activation_leaky_relu.f90:83-85;
  *  softmax is per vertex over features, dim=2: athena_activation_softmax.f90:183-203) */
 #define ATHENA_ACT_NONE 0
@@ -60,6 +60,9 @@ typedef int64_t athena_handle_t;
 #define ATHENA_ACT_SIGMOID 4
 #define ATHENA_ACT_TANH 5
 #define ATHENA_ACT_SOFTMAX 6
+/* swish, beta = 1 (athena_activation_swish.f90:29-34; x / (1 + exp(-x)),
+ * athena_diffstruc_extd_sub.f90:424-486); message / dense activations only */
+#define ATHENA_ACT_SWISH 7
 
 /* optimiser kinds: athena_optimiser.f90:634-673 (sgd), :1027-1091 (adam) */
 #define ATHENA_OPT_SGD 0
@@ -284,6 +287,24 @@ int athena_cuda_network_destroy(athena_handle_t net);
  * which only full layers may follow.  The network takes ownership of the layer's
  * parameters (re-homed into one flat buffer, layer order x params order). */
 int athena_cuda_network_add(athena_handle_t net, athena_handle_t layer);
+/* network%add(layer, input_list, operator = 'concatenate') (athena_network_sub.f90:764-830; the
+ * skip-connected Kipf stack of example/msgpass_euler/src/main.f90:192-255): the layer's vertex
+ * input is the concatenation, along the feature axis and in list order, of the vertex outputs
+ * of the listed sources (concat_layer_type%combine, athena_concat_layer.f90:413-456).
+ *   input_list[i] = 0    the network's input features (the input layer)
+ *                 = k>0  the k-th layer added to this network (1-based)
+ *                 = k<0  counted back from the layer being added: -1 = the layer added last
+ *                        (vertex_index = num_vertices + input_list(i), :848-849)
+ * ids outside (-n, n], n = layers added so far, are ATHENA_ERR_ARG ("input vertex index out of
+ * range", :835-847), as is any operator but concatenate ("invalid operator", :820-823; the
+ * reference also accepts 'add', which no message-passing network uses).
+ * Sources and the layer itself must be Kipf layers; the sum of the source widths must equal
+ * the layer's num_vertex_features(0).  In the reverse sweep the input gradient is split back
+ * over the sources; a layer read by several consumers receives the sum of their shares, added
+ * in the order of the reverse sweep (the network input receives none). */
+#define ATHENA_MERGE_CONCATENATE 1
+int athena_cuda_network_add_inputs(athena_handle_t net, athena_handle_t layer, int32_t num_inputs,
+                                   const int32_t* input_list, int32_t merge_operator);
 
 typedef struct athena_optimiser_desc {
   int32_t kind;          /* ATHENA_OPT_* */

@@ -62,7 +62,8 @@ enum {
   ACT_LEAKY_RELU = 3,
   ACT_SIGMOID = 4,
   ACT_TANH = 5,
-  ACT_SOFTMAX = 6
+  ACT_SOFTMAX = 6,
+  ACT_SWISH = 7
 };
 
 API int oracle_real_bytes(void) { return (int)sizeof(real); }
@@ -342,6 +343,12 @@ API void oracle_activation(int kind, int F, int V, const real *x, real *y) {
   case ACT_SOFTMAX:
     oracle_softmax_cols(F, V, x, y);
     break;
+  case ACT_SWISH:
+    /* swish_array, beta = 1 (athena_activation_swish.f90:31):
+     * output = input * (1 / (1 + exp(-beta * input))), athena_diffstruc_extd_sub.f90:434 */
+    for (size_t i = 0; i < n; ++i)
+      y[i] = x[i] * ((real)1 / ((real)1 + R_EXP(-(real)1 * x[i])));
+    break;
   }
 }
 
@@ -372,6 +379,22 @@ API void oracle_activation_bwd(int kind, int F, int V, const real *y,
   case ACT_SOFTMAX:
     oracle_softmax_cols_bwd(F, V, y, g, dx);
     break;
+  }
+}
+
+/* The same with the PRE-activation x at hand: swish is the one activation whose derivative
+ * is written on the input, get_partial_swish_val (athena_diffstruc_extd_sub.f90:472-486):
+ *   exp_term = exp(beta x) ; out = g * exp_term * (beta x + exp_term + 1) / (exp_term + 1)^2  */
+API void oracle_activation_bwd_x(int kind, int F, int V, const real *x, const real *y,
+                                 const real *g, real *dx) {
+  if (kind != ACT_SWISH) {
+    oracle_activation_bwd(kind, F, V, y, g, dx);
+    return;
+  }
+  size_t n = (size_t)F * V;
+  for (size_t i = 0; i < n; ++i) {
+    real e = R_EXP((real)1 * x[i]);
+    dx[i] = g[i] * e * ((real)1 * x[i] + e + (real)1) / R_POW(e + (real)1, (real)2);
   }
 }
 
@@ -578,6 +601,13 @@ typedef struct {
   int min_deg, max_deg, n_out;
   int act, ract; /* message activation, readout activation */
   int use_bias;  /* full_layer_type%use_bias */
+  /* network%add(layer, input_list, operator='concatenate') (athena_network_sub.f90:764-830,
+   * example/msgpass_euler/src/main.f90:192-255): n_in = 0: the previous layer (or the network
+   * input for the first); else the vertex features of the listed sources are concatenated
+   * along the feature axis in list order (concat_layers(..., dim = 1), athena_concat_layer.f90:
+   * 448): src = -1 the network input, src = k >= 0 layer k of the stack.  Kipf layers only. */
+  int n_in;
+  int in[4];
 } oracle_layer_t;
 
 /* width of a graph-level ([n, batch]) layer output */
@@ -606,15 +636,18 @@ API int oracle_layer_num_params(const oracle_layer_t *L) {
 typedef struct {
   real **P; /* per step: propagated / aggregated input  */
   real **H; /* per step: activated output               */
+  real **Y; /* per step: pre-activation (swish differentiates on it) */
 } saved_t;
 
 static void saved_free(saved_t *s, int T) {
   for (int t = 0; t < T; ++t) {
     free(s->P[t]);
     free(s->H[t]);
+    if (s->Y) free(s->Y[t]);
   }
   free(s->P);
   free(s->H);
+  free(s->Y);
 }
 
 /* update_message_kipf for ONE sample.  athena_kipf_msgpass_layer.f90:940-957 */
@@ -623,6 +656,7 @@ static const real *kipf_forward_sample(const oracle_layer_t *L, const real *para
                                        const real *x, saved_t *sv) {
   sv->P = (real **)calloc(L->T, sizeof(real *));
   sv->H = (real **)calloc(L->T, sizeof(real *));
+  sv->Y = (real **)calloc(L->T, sizeof(real *));
   const real *in = x;
   const real *w = params;
   for (int t = 1; t <= L->T; ++t) {
@@ -633,7 +667,7 @@ static const real *kipf_forward_sample(const oracle_layer_t *L, const real *para
     oracle_kipf_propagate(Fi, V, in, ia, ja, P);
     oracle_matmul(Fo, Fi, V, w, P, Y);
     oracle_activation(L->act, Fo, V, Y, H);
-    free(Y);
+    sv->Y[t - 1] = Y;
     sv->P[t - 1] = P;
     sv->H[t - 1] = H;
     in = H;
@@ -656,7 +690,7 @@ static void kipf_backward_sample(const oracle_layer_t *L, const real *params,
     int Fi = L->nvf[t - 1], Fo = L->nvf[t];
     woff -= (size_t)Fo * Fi;
     real *gy = (real *)malloc(sizeof(real) * (size_t)Fo * V + 8);
-    oracle_activation_bwd(L->act, Fo, V, sv->H[t - 1], g, gy);
+    oracle_activation_bwd_x(L->act, Fo, V, sv->Y[t - 1], sv->H[t - 1], g, gy);
     oracle_matmul_bwd_left(Fo, Fi, V, gy, sv->P[t - 1], dparams + woff);
     free(g);
     g = NULL;
@@ -680,6 +714,7 @@ static const real *full_forward_sample(const oracle_layer_t *L, const real *para
   int Ni = L->nvf[0], No = L->nvf[1];
   sv->P = (real **)calloc(1, sizeof(real *));
   sv->H = (real **)calloc(1, sizeof(real *));
+  sv->Y = (real **)calloc(1, sizeof(real *));
   real *xs = (real *)malloc(sizeof(real) * (size_t)Ni + 8);
   real *z = (real *)malloc(sizeof(real) * (size_t)No + 8);
   real *y = (real *)malloc(sizeof(real) * (size_t)No + 8);
@@ -690,7 +725,7 @@ static const real *full_forward_sample(const oracle_layer_t *L, const real *para
     for (int o = 0; o < No; ++o) z[o] = z[o] + b[o];
   }
   oracle_activation(L->act, No, 1, z, y);
-  free(z);
+  sv->Y[0] = z;
   sv->P[0] = xs;
   sv->H[0] = y;
   return y;
@@ -704,7 +739,7 @@ static void full_backward_sample(const oracle_layer_t *L, const real *params,
                                  real *dx) {
   int Ni = L->nvf[0], No = L->nvf[1];
   real *gz = (real *)malloc(sizeof(real) * (size_t)No + 8);
-  oracle_activation_bwd(L->act, No, 1, sv->H[0], g_out, gz);
+  oracle_activation_bwd_x(L->act, No, 1, sv->Y[0], sv->H[0], g_out, gz);
   oracle_matmul_bwd_left(No, Ni, 1, gz, sv->P[0], dparams);
   if (L->use_bias) {
     real *db = dparams + (size_t)No * Ni;
@@ -724,6 +759,7 @@ static void duvenaud_forward_sample(const oracle_layer_t *L, const real *params,
   int D = L->max_deg - L->min_deg + 1;
   sv->P = (real **)calloc(L->T, sizeof(real *));
   sv->H = (real **)calloc(L->T, sizeof(real *));
+  sv->Y = (real **)calloc(L->T, sizeof(real *));
   const real *in = x;
   const real *w = params;
   for (int t = 1; t <= L->T; ++t) {
@@ -734,7 +770,7 @@ static void duvenaud_forward_sample(const oracle_layer_t *L, const real *params,
     oracle_duvenaud_propagate(Fi, L->nef, V, in, e, ia, ja, A);
     oracle_duvenaud_update(K, Fo, V, A, w, ia, L->min_deg, L->max_deg, Zp);
     oracle_activation(L->act, Fo, V, Zp, Z);
-    free(Zp);
+    sv->Y[t - 1] = Zp;
     sv->P[t - 1] = A;
     sv->H[t - 1] = Z;
     in = Z;
@@ -800,7 +836,7 @@ static void duvenaud_backward_sample(const oracle_layer_t *L, const real *params
   for (int t = T; t >= 1; --t) {
     int Fi = L->nvf[t - 1], Fo = L->nvf[t], K = Fi + L->nef;
     real *gzp = (real *)malloc(sizeof(real) * (size_t)Fo * V + 8);
-    oracle_activation_bwd(L->act, Fo, V, sv->H[t - 1], gz[t - 1], gzp);
+    oracle_activation_bwd_x(L->act, Fo, V, sv->Y[t - 1], sv->H[t - 1], gz[t - 1], gzp);
     oracle_duvenaud_update_bwd_weight(K, Fo, V, gzp, sv->P[t - 1], ia, L->min_deg,
                                       L->max_deg, dparams + woff[t - 1]);
     if (t > 1 || dx) {
@@ -869,18 +905,42 @@ API real oracle_stack_fwd_bwd(int n_layers, const oracle_layer_t *layers,
   const int *ja = ja_cat;
   size_t voff = 0, eoff = 0;
   saved_t *sv = (saved_t *)calloc(n_layers, sizeof(saved_t));
+  /* output width / rows of every layer (node-level layers: rows = V of the sample) */
+  const real **outp = (const real **)calloc(n_layers, sizeof(real *));
+  real **catb = (real **)calloc(n_layers, sizeof(real *));
+  real **gacc = (real **)calloc(n_layers, sizeof(real *));
   for (int s = 0; s < B; ++s) {
     int V = nv[s];
     int nz = ia[V] - 1;
-    const real *in = x_cat + voff * F0;
+    const real *xs = x_cat + voff * F0;
+    const real *in = xs; /* most recent node-level output */
     const real *es = e_cat ? e_cat + eoff * Fe : NULL;
     real *dout = NULL;      /* graph-level output of this sample (final layer) */
     real *duv_tmp = NULL;   /* Duvenaud output when dense layers follow it */
     const real *vec = NULL; /* current graph-level vector */
     for (int l = 0; l < n_layers; ++l) {
       const oracle_layer_t *L = &layers[l];
+      catb[l] = NULL;
       if (L->kind == 0) {
-        in = kipf_forward_sample(L, params + poff[l], V, ia, ja, in, &sv[l]);
+        const real *lin = in;
+        if (L->n_in > 0) {
+          /* concatenate the sources along the feature axis, in list order */
+          int Fin = L->nvf[0];
+          real *cat = (real *)malloc(sizeof(real) * (size_t)Fin * V + 8);
+          int off = 0;
+          for (int j = 0; j < L->n_in; ++j) {
+            int src = L->in[j];
+            int w = src < 0 ? F0 : layers[src].nvf[layers[src].T];
+            const real *sp = src < 0 ? xs : outp[src];
+            for (int v = 0; v < V; ++v)
+              memcpy(cat + (size_t)v * Fin + off, sp + (size_t)v * w, sizeof(real) * (size_t)w);
+            off += w;
+          }
+          catb[l] = cat;
+          lin = cat;
+        }
+        in = kipf_forward_sample(L, params + poff[l], V, ia, ja, lin, &sv[l]);
+        outp[l] = in;
       } else if (L->kind == 1) {
         real *dst = out + (size_t)s * L->n_out;
         if (l != n_layers - 1) {
@@ -889,8 +949,10 @@ API real oracle_stack_fwd_bwd(int n_layers, const oracle_layer_t *layers,
         }
         duvenaud_forward_sample(L, params + poff[l], V, ia, ja, in, es, &sv[l], dst);
         vec = dst;
+        outp[l] = dst;
       } else {
         vec = full_forward_sample(L, params + poff[l], vec, &sv[l]);
+        outp[l] = vec;
       }
     }
     if (last->kind != 0) {
@@ -925,32 +987,69 @@ API real oracle_stack_fwd_bwd(int n_layers, const oracle_layer_t *layers,
         oracle_mse_cell_bwd(n, dout, ts, g, denom);
       }
       if (dparams) {
+        /* reverse sweep: the gradient of every layer output is the sum of what its consumers
+         * send back (one consumer in a plain stack) */
+        for (int l = 0; l < n_layers; ++l) gacc[l] = NULL;
+        gacc[n_layers - 1] = g;
+        g = NULL;
         for (int l = n_layers - 1; l >= 0; --l) {
           const oracle_layer_t *L = &layers[l];
+          real *gl = gacc[l];
+          if (!gl) continue; /* nobody consumed this layer's output */
+          int nsrc = (L->kind == 0 && L->n_in > 0) ? L->n_in : 1;
+          int srcs[4], need_dx = 0;
+          for (int j = 0; j < nsrc; ++j) {
+            srcs[j] = (L->kind == 0 && L->n_in > 0) ? L->in[j] : l - 1;
+            if (srcs[j] >= 0) need_dx = 1;
+          }
           int Fi = L->nvf[0];
           size_t dx_n = L->kind == 2 ? (size_t)Fi : (size_t)Fi * V;
-          real *dx = (l > 0) ? (real *)malloc(sizeof(real) * dx_n + 8) : NULL;
+          real *dx = need_dx ? (real *)malloc(sizeof(real) * dx_n + 8) : NULL;
           if (L->kind == 0)
-            kipf_backward_sample(L, params + poff[l], V, ia, ja, &sv[l], g,
-                                 dparams + poff[l], dx);
+            kipf_backward_sample(L, params + poff[l], V, ia, ja, &sv[l], gl, dparams + poff[l], dx);
           else if (L->kind == 1)
-            duvenaud_backward_sample(L, params + poff[l], V, ia, ja, &sv[l], g,
+            duvenaud_backward_sample(L, params + poff[l], V, ia, ja, &sv[l], gl,
                                      dparams + poff[l], dx);
           else
-            full_backward_sample(L, params + poff[l], &sv[l], g, dparams + poff[l], dx);
-          free(g);
-          g = dx;
+            full_backward_sample(L, params + poff[l], &sv[l], gl, dparams + poff[l], dx);
+          if (dx) {
+            int off = 0;
+            for (int j = 0; j < nsrc; ++j) {
+              int src = srcs[j];
+              int w = (L->kind == 0 && L->n_in > 0)
+                          ? (src < 0 ? F0 : layers[src].nvf[layers[src].T])
+                          : Fi;
+              if (src >= 0) {
+                size_t rows = L->kind == 2 ? 1 : (size_t)V;
+                if (!gacc[src]) gacc[src] = (real *)calloc(rows * (size_t)w + 2, sizeof(real));
+                for (size_t v = 0; v < rows; ++v)
+                  for (int f = 0; f < w; ++f)
+                    gacc[src][v * w + f] = gacc[src][v * w + f] + dx[v * (size_t)Fi + off + f];
+              }
+              off += w;
+            }
+            free(dx);
+          }
+          free(gl);
+          gacc[l] = NULL;
         }
       }
       free(g);
     }
-    for (int l = 0; l < n_layers; ++l) saved_free(&sv[l], layers[l].T);
+    for (int l = 0; l < n_layers; ++l) {
+      saved_free(&sv[l], layers[l].T);
+      free(catb[l]);
+      catb[l] = NULL;
+    }
     free(duv_tmp);
     ia += V + 1;
     ja += 2 * (size_t)nz;
     voff += (size_t)V;
     eoff += (size_t)ne[s];
   }
+  free(outp);
+  free(catb);
+  free(gacc);
   free(sv);
   free(poff);
   return loss;

@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _BUILD = os.path.join(_HERE, "_build")
 
 ACT = {"none": 0, "linear": 1, "relu": 2, "leaky_relu": 3, "sigmoid": 4,
-       "tanh": 5, "softmax": 6}
+       "tanh": 5, "softmax": 6, "swish": 7}
 
 
 def build(force: bool = False) -> None:
@@ -39,7 +39,8 @@ def build(force: bool = False) -> None:
 class _LayerT(C.Structure):
     _fields_ = [("kind", C.c_int), ("T", C.c_int), ("nvf", C.c_int * 17),
                 ("nef", C.c_int), ("min_deg", C.c_int), ("max_deg", C.c_int),
-                ("n_out", C.c_int), ("act", C.c_int), ("ract", C.c_int), ("use_bias", C.c_int)]
+                ("n_out", C.c_int), ("act", C.c_int), ("ract", C.c_int), ("use_bias", C.c_int),
+                ("n_in", C.c_int), ("inputs", C.c_int * 4)]
 
 
 @dataclass
@@ -57,6 +58,10 @@ class LayerSpec:
     activation: str = "none"
     readout_activation: str = "softmax"
     use_bias: bool = True
+    # network%add(layer, input_list, operator='concatenate'): sources whose vertex features are
+    # concatenated (in order) to form this layer's input; -1 = the network input, k >= 0 = layer
+    # k of the stack.  None: the previous layer.
+    inputs: Optional[Sequence[int]] = None
 
     def to_c(self) -> _LayerT:
         L = _LayerT()
@@ -75,6 +80,10 @@ class LayerSpec:
         L.n_out = self.num_outputs
         L.act = ACT[self.activation]
         L.ract = ACT[self.readout_activation]
+        L.n_in = 0 if self.inputs is None else len(self.inputs)
+        assert L.n_in <= 4
+        for i, src in enumerate(self.inputs or []):
+            L.inputs[i] = src
         return L
 
 
@@ -240,6 +249,15 @@ class Oracle:
         V, F = y.shape
         out = np.empty_like(y)
         self.lib.oracle_activation_bwd(ACT[kind], F, V, self.rp(y), self.rp(g), self.rp(out))
+        return out
+
+    def activation_bwd_x(self, kind, x, y, g):
+        """Derivative with the pre-activation at hand (swish differentiates on it)."""
+        x = self.r(x); y = self.r(y); g = self.r(g)
+        V, F = y.shape
+        out = np.empty_like(y)
+        self.lib.oracle_activation_bwd_x(ACT[kind], F, V, self.rp(x), self.rp(y), self.rp(g),
+                                         self.rp(out))
         return out
 
     def mse_cell(self, p, e):

@@ -26,7 +26,7 @@
 
 /* ---- the oracle's C interface (oracle/athena_oracle.c, float build) ---- */
 typedef struct {
-  int kind, T, nvf[17], nef, min_deg, max_deg, n_out, act, ract, use_bias;
+  int kind, T, nvf[17], nef, min_deg, max_deg, n_out, act, ract, use_bias, n_in, in[4];
 } oracle_layer_t;
 typedef struct {
   int kind;

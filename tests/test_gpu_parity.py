@@ -299,10 +299,14 @@ def test_duvenaud_self_loop_without_edge_feature(cuda, oracle32):
 # ---------------------------------------------------------------------------
 # network: loss, gradients, optimiser steps
 # ---------------------------------------------------------------------------
-def _train_compare(cuda, oracle32, specs, layers, p, target, optim: OptimSpec, ab_opt, steps=5):
+def _train_compare(cuda, oracle32, specs, layers, p, target, optim: OptimSpec, ab_opt, steps=5,
+                   input_lists=None, oracle64=None):
     net = ab.network_type()
-    for L in layers:
-        net.add(L)
+    for k, L in enumerate(layers):
+        if input_lists is not None and input_lists[k] is not None:
+            net.add(L, input_list=input_lists[k], operator="concatenate")
+        else:
+            net.add(L)
     net.compile(ab_opt, loss_method="mse", batch_size=p.B)
     n = oracle32.num_params(specs)
     assert net.num_params == n
@@ -315,7 +319,11 @@ def _train_compare(cuda, oracle32, specs, layers, p, target, optim: OptimSpec, a
     loss_ref, out_ref, g_ref = oracle32.stack_fwd_bwd(specs, params, ob, target)
     loss = net.loss_and_gradients(batch, target)
     assert abs(loss - loss_ref) <= 1e-5 * max(1.0, abs(loss_ref))
-    assert rel_err(net.get_gradients(), g_ref) <= RTOL_ACT
+    if oracle64 is None:
+        assert rel_err(net.get_gradients(), g_ref) <= RTOL_ACT
+    else:   # long reductions: the float64 shadow arbitrates (helpers.assert_parity)
+        _, _, g64 = oracle64.stack_fwd_bwd(specs, params, ob, target)
+        assert_parity(net.get_gradients(), g_ref, g64, RTOL_ACT, "network gradients")
     assert rel_err(net.forward(batch), out_ref) <= RTOL_ACT
     net.update()                                   # consumes those gradients (step 1)
     ref = params.copy()
@@ -644,3 +652,132 @@ def test_kipf_fused_training_ragged_graphs(cuda, oracle32, act2, optim):
         o = OptimSpec("adam", lr=2e-3, clip_norm=0.5)
         a = ab.adam_optimiser_type(2e-3, clip_dict=ab.clip_type(clip_norm=0.5))
     _train_compare(cuda, oracle32, specs, layers, p, target, o, a, steps=4)
+
+
+# ---------------------------------------------------------------------------
+# f2: skip connections (network%add(..., input_list, operator='concatenate')) and swish
+# ---------------------------------------------------------------------------
+def _euler_graphs():
+    """The bump-channel mesh of example/msgpass_euler as mod_read_euler.f90:14-53 builds it:
+    generate_adjacency(index_list) and NO self loops (tests/golden/make_euler_fixture.py)."""
+    d = np.load(os.path.join(GOLD, "euler_bump.npz"))
+    graphs, targets = [], []
+    for s in (1, 2):
+        g = ab.graph_type()
+        g.set_num_vertices(d[f"in_{s}"].shape[0], d[f"in_{s}"].shape[1])
+        g.vertex_features[:] = d[f"in_{s}"]
+        g.set_num_edges(d["index_list"].shape[0])
+        g.generate_adjacency(d["index_list"])
+        graphs.append(g)
+        targets.append(d[f"out_{s}"])
+    return graphs, np.concatenate(targets)
+
+
+EULER_WIDTHS = [(3, 6), (9, 14), (17, 32), (35, 64), (67, 32), (35, 14), (17, 7)]
+EULER_ACTS = ["softmax"] * 6 + ["swish"]
+
+
+def test_euler_skip_network_training_parity(cuda, oracle32, oracle64):
+    """example/msgpass_euler/src/main.f90:182-276 on its real 12 800-vertex mesh: seven Kipf
+    layers, each after the first reading [input | previous] (input_list = [0, -1]), softmax
+    message activations and a swish head, Adam lr 2e-2 with clip(-1, 1), batch of 2 graphs."""
+    from oracle.oracle import LayerSpec
+    graphs, target = _euler_graphs()
+    p = ab.pack_graphs(graphs)
+    assert p.V == 25600 and p.Z == 2 * 2 * 37681
+    specs, layers, lists = [], [], []
+    for k, ((fi, fo), act) in enumerate(zip(EULER_WIDTHS, EULER_ACTS)):
+        specs.append(LayerSpec("kipf", [fi, fo], 1, activation=act,
+                               inputs=None if k == 0 else [-1, k - 1]))
+        layers.append(ab.kipf_msgpass_layer_type([fi, fo], 1, act))
+        lists.append(None if k == 0 else [0, -1])
+    _train_compare(cuda, oracle32, specs, layers, p, target,
+                   OptimSpec("adam", lr=2e-2, clip_min=-1.0, clip_max=1.0),
+                   ab.adam_optimiser_type(2e-2, clip_dict=ab.clip_type(-1.0, 1.0)), steps=4,
+                   input_lists=lists, oracle64=oracle64)
+
+
+@pytest.mark.parametrize("shape", ["tiles64", "ragged"])
+def test_skip_network_two_consumers_parity(cuda, oracle32, oracle64, shape):
+    """A layer read by two later layers (gradient = sum of both consumers' slices), ids given
+    absolutely (k), relatively (-k) and as 0 = the network input; on a tileable batch the
+    fused tile kernels run underneath."""
+    from oracle.oracle import LayerSpec
+    rng = np.random.default_rng(77)
+    if shape == "tiles64":
+        p = synth.regular_batch(10, 64, 4, 64, rng)
+        F0, w = 64, [64, 64, 32, 16]
+    else:
+        p = synth.molecular_batch(23, 5, 0, rng, nv_range=(2, 40), self_loop_features=False)
+        F0, w = 5, [7, 6, 9, 4]
+    # L1: x -> w0 (relu) ; L2: L1 -> w1 (tanh) ; L3: [L1 | L2] -> w2 (sigmoid) ;
+    # L4: [x | L3 | L1] -> w3 (swish)
+    specs = [LayerSpec("kipf", [F0, w[0]], 1, activation="relu"),
+             LayerSpec("kipf", [w[0], w[1]], 1, activation="tanh"),
+             LayerSpec("kipf", [w[0] + w[1], w[2]], 1, activation="sigmoid", inputs=[0, 1]),
+             LayerSpec("kipf", [F0 + w[2] + w[0], w[3]], 1, activation="swish", inputs=[-1, 2, 0])]
+    layers = [ab.kipf_msgpass_layer_type([F0, w[0]], 1, "relu"),
+              ab.kipf_msgpass_layer_type([w[0], w[1]], 1, "tanh"),
+              ab.kipf_msgpass_layer_type([w[0] + w[1], w[2]], 1, "sigmoid"),
+              ab.kipf_msgpass_layer_type([F0 + w[2] + w[0], w[3]], 1, "swish")]
+    lists = [None, None, [1, -1], [0, 3, -3]]
+    target = rng.standard_normal((p.V, w[3])).astype(np.float32)
+    _train_compare(cuda, oracle32, specs, layers, p, target, OptimSpec("sgd", lr=0.05),
+                   ab.sgd_optimiser_type(0.05), input_lists=lists, oracle64=oracle64)
+
+
+def test_network_add_input_list_rules(cuda):
+    """Errors of network%add(layer, input_list, operator): ids out of range
+    (athena_network_sub.f90:835-847), invalid operator (:820-823), widths that do not add up."""
+    net = ab.network_type()
+    net.add(ab.kipf_msgpass_layer_type([3, 6], 1, "softmax"))
+    with pytest.raises(ab.AthenaCudaError):
+        net.add(ab.kipf_msgpass_layer_type([9, 4], 1), input_list=[0, 2])       # layer 2 is itself
+    with pytest.raises(ab.AthenaCudaError):
+        net.add(ab.kipf_msgpass_layer_type([9, 4], 1), input_list=[0, -2])      # before the input
+    with pytest.raises(ab.AthenaCudaError):
+        net.add(ab.kipf_msgpass_layer_type([8, 4], 1), input_list=[0, -1])      # 3 + 6 != 8
+    with pytest.raises(ab.AthenaCudaError):
+        net.add(ab.kipf_msgpass_layer_type([9, 4], 1), input_list=[0, -1], operator="*")
+    with pytest.raises(ab.AthenaCudaError):
+        net.add(ab.duvenaud_msgpass_layer_type([9], [0], 1, 3, 5), input_list=[0, -1])
+    net.add(ab.kipf_msgpass_layer_type([9, 4], 1), input_list=[0, -1], operator="concatenate")
+    net.add(ab.kipf_msgpass_layer_type([13, 2], 1), input_list=[1, 0, 2], operator="||")
+    net.destroy()
+
+
+@pytest.mark.parametrize("kind", ["kipf_tiles", "kipf_T2_ragged", "duvenaud", "full"])
+def test_swish_layer_parity(cuda, oracle32, kind):
+    """swish (athena_activation_swish.f90:29-34) as message / dense activation: forward and the
+    derivative on the saved pre-activation (get_partial_swish_val)."""
+    rng = np.random.default_rng(zlib.crc32(kind.encode()))
+    x = None
+    if kind == "kipf_tiles":
+        p = synth.regular_batch(9, 64, 5, 64, rng)
+        spec, L = kipf_spec([64, 64], 1, "swish"), ab.kipf_msgpass_layer_type([64, 64], 1, "swish")
+    elif kind == "kipf_T2_ragged":
+        p = synth.molecular_batch(15, 6, 0, rng, nv_range=(1, 30), self_loop_features=False)
+        spec, L = kipf_spec([6, 9, 5], 2, "swish"), ab.kipf_msgpass_layer_type([6, 9, 5], 2, "swish")
+    elif kind == "duvenaud":
+        p = synth.chemical_batch(6, rng)
+        spec = duvenaud_spec([6] * 3, 1, 2, 1, 10, 5, "swish", "softmax")
+        L = ab.duvenaud_msgpass_layer_type([6], [1], 2, 10, 5, message_activation="swish")
+    else:
+        p = synth.chemical_batch(11, rng)
+        spec, L = full_spec(7, 5, "swish"), ab.full_layer_type(5, 7, activation="swish")
+        x = rng.standard_normal((11, 7)).astype(np.float32)
+    n = oracle32.num_params([spec])
+    params = random_params(n, rng, 0.4)
+    L.set_params(params)
+    L.set_graph(p)
+    ob = to_oracle_batch(p)
+    out_shape = oracle32.out_shape([spec], ob)
+    g = rng.standard_normal(out_shape).astype(np.float32)
+    out_ref, grad_ref, dx_ref = oracle32.layer_fwd_bwd(spec, params, ob, g_out=g, want_dx=True, x=x)
+    out = L.forward(x) if x is not None else L.forward()
+    assert rel_err(out, out_ref) <= RTOL_ACT
+    L.zero_gradients()
+    dx = L.backward(g, want_input_grad=True)
+    assert rel_err(L.get_gradients(), grad_ref) <= RTOL_ACT
+    assert rel_err(dx, dx_ref) <= RTOL_ACT
+    L.destroy()

@@ -284,3 +284,185 @@ def test_integer_structures_small_example(oracle32):
     assert bkt.tolist() == [0, 1, 0, 0] and perm.tolist() == [0, 2, 3, 1] and ptr.tolist() == [0, 3, 4]
     with pytest.raises(ValueError):
         oracle32.batch_build([2], [0], [1, 2, 3], np.array([[1, 0], [3, 0]], np.int32))
+
+
+# -- independent float64 dense derivation of Kipf on the reference's own fixture graphs ------
+def _fixture_graph(num_vertices, index_list, self_loops):
+    from athena_b200.graph import graph_type
+    g = graph_type()
+    g.set_num_vertices(num_vertices, 1)
+    g.set_num_edges(len(index_list))
+    g.generate_adjacency(index_list)
+    if self_loops:
+        g.add_self_loops()
+    return g
+
+
+def _dense_kipf(g, x, w, Fo):
+    """H = D^-1/2 A D^-1/2 X W^T with a dense adjacency in float64 (A[v, u] = multiplicity of u
+    in row v, D = CSR row lengths): the textbook form of _sub_kipf.f90:29-46 +
+    athena_kipf_msgpass_layer.f90:951, derived without the CSR walk."""
+    V = g.num_vertices
+    A = np.zeros((V, V))
+    for v in range(V):
+        for nb, _ in g.adj_ja[g.adj_ia[v] - 1:g.adj_ia[v + 1] - 1]:
+            A[v, nb - 1] += 1.0
+    d = np.diff(g.adj_ia).astype(np.float64)
+    Dm = np.diag(d ** -0.5)
+    Wm = np.asarray(w, np.float64).reshape(x.shape[1], Fo).T     # column-major [Fo, Fi]
+    P = Dm @ A @ Dm @ np.asarray(x, np.float64)
+    return P, P @ Wm.T
+
+
+@pytest.mark.parametrize("self_loops", [False, True])
+@pytest.mark.parametrize("fixture", ["kipf_layer_6v8e", "msgpass_network_5v6e"])
+def test_kipf_matches_dense_float64_on_reference_fixture_graphs(oracle32, oracle64, fixture,
+                                                                self_loops):
+    if fixture == "kipf_layer_6v8e":       # test/test_kipf_msgpass_layer.f90:78-90
+        V, il = 6, [(1, 2), (1, 3), (2, 3), (2, 4), (3, 5), (4, 5), (4, 6), (5, 6)]
+    else:                                  # test/test_msgpass_network.f90:264-271
+        V, il = 5, [(1, 2), (1, 3), (2, 3), (2, 4), (3, 5), (4, 5)]
+    g = _fixture_graph(V, il, self_loops)
+    rng = np.random.default_rng(5)
+    Fi, Fo = 8, 5
+    x = rng.standard_normal((V, Fi))
+    w = rng.standard_normal(Fi * Fo) * 0.4
+    P_d, Y_d = _dense_kipf(g, x, w, Fo)
+    b = Batch(np.array([V], np.int32), np.array([g.num_edges], np.int32), g.adj_ia, g.adj_ja, x)
+    for o, tol in ((oracle64, 1e-13), (oracle32, 2e-6)):
+        P = o.kipf_propagate(x, g.adj_ia, g.adj_ja)
+        assert rel_err(P, P_d) <= tol
+        out, dp, dx = o.layer_fwd_bwd(kipf_spec([Fi, Fo], 1), w, b, np.ones((V, Fo)), want_dx=True)
+        assert rel_err(out, Y_d) <= tol
+        # dW = gY^T P (column-major [Fo, Fi]) -- untouched by the backward quirk
+        dW_d = (np.ones((V, Fo)).T @ P_d).T.ravel()
+        assert rel_err(dp, dW_d) <= tol
+        # dX = A^T (gY W): the live reverse pass scatters WITHOUT the D^-1/2 factors
+        Wm = np.asarray(w, np.float64).reshape(Fi, Fo).T
+        A = np.zeros((V, V))
+        for v in range(V):
+            for nb, _ in g.adj_ja[g.adj_ia[v] - 1:g.adj_ia[v + 1] - 1]:
+                A[v, nb - 1] += 1.0
+        assert rel_err(dx, A.T @ (np.ones((V, Fo)) @ Wm)) <= tol
+
+
+# -- swish: athena_activation_swish.f90:29-34, athena_diffstruc_extd_sub.f90:424-486 --------
+def test_swish_forward_and_derivative(oracle32, oracle64):
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((7, 5)) * 3.0
+    y64 = oracle64.activation("swish", x)
+    assert rel_err(y64, x / (1.0 + np.exp(-x))) <= 1e-15
+    assert rel_err(oracle32.activation("swish", x), y64) <= 1e-6
+    g = rng.standard_normal(x.shape)
+    d64 = oracle64.activation_bwd_x("swish", x, y64, g)
+    s = 1.0 / (1.0 + np.exp(-x))
+    assert rel_err(d64, g * (s + x * s * (1.0 - s))) <= 1e-13        # closed form
+    h = 1e-6
+    num = (oracle64.activation("swish", x + h) - oracle64.activation("swish", x - h)) / (2 * h)
+    assert rel_err(d64, g * num) <= 1e-8                             # central difference
+    assert rel_err(oracle32.activation_bwd_x("swish", x, y64, g), d64) <= 2e-6
+    # every other activation: the _x form is the plain one
+    for kind in ("relu", "sigmoid", "tanh", "softmax", "leaky_relu", "none"):
+        y = oracle64.activation(kind, x)
+        assert np.array_equal(oracle64.activation_bwd_x(kind, x, y, g),
+                              oracle64.activation_bwd(kind, y, g))
+
+
+# -- network%add(layer, input_list, operator='concatenate') ------------------------------------
+def _skip_stack(F0, widths, acts, T=1):
+    """The msgpass_euler topology (example/msgpass_euler/src/main.f90:182-255): every layer
+    after the first reads [network input | previous layer]."""
+    specs, prev = [], None
+    for k, (w, a) in enumerate(zip(widths, acts)):
+        if k == 0:
+            specs.append(LayerSpec("kipf", [F0] + [w] * T, T, activation=a))
+        else:
+            specs.append(LayerSpec("kipf", [F0 + prev] + [w] * T, T, activation=a,
+                                   inputs=[-1, k - 1]))
+        prev = w
+    return specs
+
+
+def test_concat_stack_equals_manual_composition(oracle64):
+    """The stack with skip links against the same network composed by hand from single-layer
+    calls: concatenation in list order on the way forward, column split + sum on the way back
+    (concat_layer_type%combine, athena_concat_layer.f90:413-456)."""
+    from athena_b200 import synth
+    rng = np.random.default_rng(21)
+    p = synth.regular_batch(3, 9, 3, 3, rng)
+    b = Batch(p.nv, p.ne, p.ia, p.ja, p.x.astype(np.float64), None)
+    specs = _skip_stack(3, [4, 6, 2], ["softmax", "tanh", "swish"])
+    n = [oracle64.num_params([s]) for s in specs]
+    params = rng.standard_normal(sum(n)) * 0.5
+    off = np.concatenate([[0], np.cumsum(n)])
+    target = rng.standard_normal((p.V, 2))
+    loss, out, dp = oracle64.stack_fwd_bwd(specs, params, b, target)
+    # by hand
+    x0 = b.x
+    ins, outs = [], []
+    for k, s in enumerate(specs):
+        xin = x0 if k == 0 else np.concatenate([x0, outs[-1]], axis=1)
+        ins.append(xin)
+        o, _, _ = oracle64.layer_fwd_bwd(s, params[off[k]:off[k + 1]], b, x=xin)
+        outs.append(o)
+    assert rel_err(out, outs[-1]) <= 1e-14
+    # MSE per graph cell: g = (p - e) / (F * V_s)
+    voff = np.concatenate([[0], np.cumsum(p.nv)])
+    g = np.zeros_like(out)
+    loss_h = 0.0
+    for s in range(p.B):
+        sl = slice(voff[s], voff[s + 1])
+        cnt = out.shape[1] * p.nv[s]
+        g[sl] = (out[sl] - target[sl]) / cnt
+        loss_h += ((out[sl] - target[sl]) ** 2).sum() / (2 * cnt)
+    assert abs(loss - loss_h) <= 1e-13 * abs(loss_h)
+    dp_h = np.zeros_like(params)
+    for k in range(len(specs) - 1, -1, -1):
+        _, dpk, dx = oracle64.layer_fwd_bwd(specs[k], params[off[k]:off[k + 1]], b, g,
+                                            want_dx=True, x=ins[k])
+        dp_h[off[k]:off[k + 1]] = dpk
+        if k > 0:
+            g = np.ascontiguousarray(dx[:, 3:])      # the previous layer's share
+    assert rel_err(dp, dp_h) <= 1e-13
+
+
+def test_concat_two_consumers_sum_gradients(oracle64):
+    """A layer read by two later layers receives the SUM of their input-gradient slices."""
+    from athena_b200 import synth
+    rng = np.random.default_rng(22)
+    p = synth.regular_batch(2, 7, 2, 3, rng)
+    b = Batch(p.nv, p.ne, p.ia, p.ja, p.x.astype(np.float64), None)
+    specs = [LayerSpec("kipf", [3, 4], 1, activation="tanh"),
+             LayerSpec("kipf", [4, 5], 1, activation="sigmoid"),
+             LayerSpec("kipf", [9, 2], 1, activation="none", inputs=[0, 1])]
+    n = [oracle64.num_params([s]) for s in specs]
+    off = np.concatenate([[0], np.cumsum(n)])
+    params = rng.standard_normal(sum(n)) * 0.5
+    target = rng.standard_normal((p.V, 2))
+    loss, out, dp = oracle64.stack_fwd_bwd(specs, params, b, target)
+    # finite differences of the loss in float64
+    h = 1e-6
+    num = np.zeros_like(params)
+    for i in range(params.size):
+        pp = params.copy(); pp[i] += h
+        pm = params.copy(); pm[i] -= h
+        num[i] = (oracle64.stack_fwd_bwd(specs, pp, b, target, want_grads=False)[0] -
+                  oracle64.stack_fwd_bwd(specs, pm, b, target, want_grads=False)[0]) / (2 * h)
+    # the last layer's weights see no reverse propagate: exact derivative there; the earlier
+    # layers go through the un-normalised reverse pass (the reference's quirk) and are
+    # checked against the manual composition instead
+    assert rel_err(dp[off[2]:], num[off[2]:]) <= 1e-7
+    o0, _, _ = oracle64.layer_fwd_bwd(specs[0], params[off[0]:off[1]], b)
+    o1, _, _ = oracle64.layer_fwd_bwd(specs[1], params[off[1]:off[2]], b, x=o0)
+    cat = np.concatenate([o0, o1], axis=1)
+    voff = np.concatenate([[0], np.cumsum(p.nv)])
+    g = np.zeros_like(out)
+    for s in range(p.B):
+        sl = slice(voff[s], voff[s + 1])
+        g[sl] = (out[sl] - target[sl]) / (out.shape[1] * p.nv[s])
+    _, dp2, dx2 = oracle64.layer_fwd_bwd(specs[2], params[off[2]:], b, g, want_dx=True, x=cat)
+    _, dp1, dx1 = oracle64.layer_fwd_bwd(specs[1], params[off[1]:off[2]], b,
+                                         np.ascontiguousarray(dx2[:, 4:]), want_dx=True, x=o0)
+    _, dp0, _ = oracle64.layer_fwd_bwd(specs[0], params[off[0]:off[1]], b,
+                                       np.ascontiguousarray(dx2[:, :4]) + dx1)
+    assert rel_err(dp, np.concatenate([dp0, dp1, dp2])) <= 1e-13
