@@ -687,6 +687,371 @@ ATHENA_API int athena_cuda_batch_create(athena_handle_t* batch, int32_t num_grap
   return ATHENA_OK;
 }
 
+// ---- graphstruc-side construction on the device -------------------------------------------
+// graph%generate_adjacency(index_list) (+ graph%add_self_loops()), the calls every reader of the
+// reference makes before set_graph (example_library/src/mod_read_chemical_graphs.f90:275-276,
+// example/msgpass_euler/src/mod_read_euler.f90:48, example/msgpass_chemical/src/main.f90:108).
+// graphstruc v0.2.1 is an un-vendored dependency (fpm.toml:21) and no athena test pins the
+// order of its neighbour lists; the order built here is the one of the host restatement
+// (athena_b200/graph.py): undirected edge k = (i, j) is listed in row i and -- if i /= j -- in
+// row j with edge id k, rows in ascending edge id; add_self_loops appends (v, 0) to every row
+// that lists no v.  Bit-exact against that restatement (tests/test_gpu_parity.py).
+namespace athena {
+
+constexpr int LOOP_KEY = INT_MAX - 1;  // sorts behind every edge id
+
+__global__ void k_edges_count(int B, int E, const int32_t* __restrict__ voff,
+                              const int32_t* __restrict__ eoff, const int2* __restrict__ il,
+                              int32_t* __restrict__ cnt, int32_t* __restrict__ hasself,
+                              int32_t* __restrict__ status) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= E) return;
+  int s = find_segment(eoff, B, k);
+  int2 e = il[k];
+  int nvs = voff[s + 1] - voff[s];
+  if (e.x < 1 || e.x > nvs || e.y < 1 || e.y > nvs) {
+    atomicMin(status, s);
+    return;
+  }
+  int gi = voff[s] + e.x - 1, gj = voff[s] + e.y - 1;
+  atomicAdd(cnt + gi, 1);
+  if (gi != gj) atomicAdd(cnt + gj, 1);
+  else hasself[gi] = 1;
+}
+
+__global__ void k_edges_loops(int V, const int32_t* __restrict__ hasself, int32_t* __restrict__ cnt) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < V && !hasself[v]) cnt[v] += 1;
+}
+
+__global__ void k_edges_fill(int B, int E, int V, int loops, const int32_t* __restrict__ voff,
+                             const int32_t* __restrict__ eoff, const int2* __restrict__ il,
+                             const int32_t* __restrict__ hasself, int32_t* __restrict__ cursor,
+                             int32_t* __restrict__ key, int32_t* __restrict__ nb) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < E) {
+    int s = find_segment(eoff, B, k);
+    int2 e = il[k];
+    int nvs = voff[s + 1] - voff[s];
+    if (!(e.x < 1 || e.x > nvs || e.y < 1 || e.y > nvs)) {
+      int gi = voff[s] + e.x - 1, gj = voff[s] + e.y - 1;
+      int kl = k - eoff[s] + 1;  // edge id inside its graph, 1-based
+      int pos = atomicAdd(cursor + gi, 1);
+      key[pos] = kl;
+      nb[pos] = gj;
+      if (gi != gj) {
+        pos = atomicAdd(cursor + gj, 1);
+        key[pos] = kl;
+        nb[pos] = gi;
+      }
+    }
+  }
+  if (loops && k < V && !hasself[k]) {
+    int pos = atomicAdd(cursor + k, 1);
+    key[pos] = LOOP_KEY;
+    nb[pos] = k;
+  }
+}
+
+// adj_ia / adj_ja of every graph in the layout athena_cuda_batch_create takes; 8 lanes per row
+__global__ void k_edges_emit(int B, int V, const int32_t* __restrict__ voff,
+                             const int32_t* __restrict__ off, const int32_t* __restrict__ key,
+                             const int32_t* __restrict__ nb, int32_t* __restrict__ ia_cat,
+                             int2* __restrict__ ja_cat, int32_t* __restrict__ nz) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int lane = (int)(t & 7);
+  if ((t >> 3) >= V) return;
+  int gv = (int)(t >> 3);
+  int s = find_segment(voff, B, gv);
+  int v0 = voff[s], z0 = off[v0];
+  int beg = off[gv], end = off[gv + 1];
+  if (lane == 0) {
+    ia_cat[gv + s] = beg - z0 + 1;
+    if (gv + 1 == voff[s + 1]) {
+      ia_cat[gv + s + 1] = end - z0 + 1;
+      nz[s] = end - z0;
+    }
+  }
+  for (int w = beg + lane; w < end; w += 8) {
+    int kk = key[w];
+    ja_cat[w] = make_int2(nb[w] - v0 + 1, kk == LOOP_KEY ? 0 : kk);
+  }
+}
+
+__global__ void k_merge_status(int32_t* __restrict__ dst, const int32_t* __restrict__ src) {
+  atomicMin(dst, *src);
+}
+
+// ONNX graph inputs of a message-passing layer (athena_onnx_msgpass_utils.f90:53-92,
+// example/msgpass_chemical/validate_onnx.py:38-57): edge_index [3, ncsr] int64, 0-based --
+// row 0 the neighbour (source), row 1 the edge-feature index (-1: none), row 2 the vertex whose
+// row the entry belongs to (target), entries in CSR order -- and degree [num_nodes] int64.
+__global__ void k_onnx_rows(int B, int V, const int32_t* __restrict__ voff,
+                            const int32_t* __restrict__ zoff, const long long* __restrict__ degree,
+                            int32_t* __restrict__ cnt) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  int s = find_segment(voff, B, v);
+  long long d = degree[v];
+  long long cap = (long long)zoff[s + 1] - zoff[s];
+  cnt[v] = (int)(d < 0 ? 0 : (d > cap ? cap + 1 : d));
+}
+
+__global__ void k_onnx_emit(int B, int V, int Z, const int32_t* __restrict__ voff,
+                            const int32_t* __restrict__ zoff, const int32_t* __restrict__ off,
+                            const long long* __restrict__ ei, int32_t* __restrict__ ia_cat,
+                            int2* __restrict__ ja_cat, int32_t* __restrict__ status) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < V) {
+    int s = find_segment(voff, B, t);
+    // the degrees of graph s must add up to exactly its ncsr entries
+    if (off[voff[s]] != zoff[s] || off[voff[s + 1]] != zoff[s + 1]) atomicMin(status, s);
+    ia_cat[t + s] = off[t] - zoff[s] + 1;
+    if (t + 1 == voff[s + 1]) ia_cat[t + s + 1] = off[t + 1] - zoff[s] + 1;
+  }
+  if (t < Z) {
+    int s = find_segment(zoff, B, t);
+    int n = zoff[s + 1] - zoff[s], wl = t - zoff[s];
+    int nvs = voff[s + 1] - voff[s];
+    const long long* blk = ei + 3ll * zoff[s];
+    long long src = blk[wl], ef = blk[n + wl], tgt = blk[2ll * n + wl];
+    bool ok = tgt >= 0 && tgt < nvs;
+    if (ok) {
+      int gv = voff[s] + (int)tgt;
+      ok = off[gv] <= t && t < off[gv + 1];  // the entry lies inside its target's row
+    }
+    if (!ok) atomicMin(status, s);
+    int nbv = (src >= 0 && src < nvs) ? (int)src + 1 : 0;  // 0: flagged by the CSR build
+    int eidv = (ef >= 0 && ef < INT_MAX - 1) ? (int)ef + 1 : 0;
+    ja_cat[t] = make_int2(nbv, eidv);
+  }
+}
+
+// hands the scratch that holds adj_ia / adj_ja to the batch (the build is asynchronous)
+static void adopt(DevBuf& dst, DevBuf& src) {
+  dst.release();
+  dst.p = src.p;
+  dst.cap = src.cap;
+  src.p = nullptr;
+  src.cap = 0;
+}
+
+}  // namespace athena
+
+static int graph_offsets(int B, const int32_t* num_vertices, const int32_t* counts,
+                         std::vector<int32_t>& voff, std::vector<int32_t>& coff, const char* who) {
+  int64_t V = 0, C = 0;
+  voff.resize((size_t)B + 1);
+  coff.resize((size_t)B + 1);
+  for (int s = 0; s < B; ++s) {
+    ATH_REQUIRE(num_vertices[s] >= 0 && counts[s] >= 0, ATHENA_ERR_ARG,
+                "%s: negative size in graph %d", who, s);
+    voff[s] = (int32_t)V;
+    coff[s] = (int32_t)C;
+    V += num_vertices[s];
+    C += counts[s];
+    ATH_REQUIRE(V < INT32_MAX / 2 && C < INT32_MAX / 4, ATHENA_ERR_ARG,
+                "%s: batch exceeds int32 indexing", who);
+  }
+  voff[B] = (int32_t)V;
+  coff[B] = (int32_t)C;
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_batch_create_from_edges(athena_handle_t* batch, int32_t num_graphs,
+                                                   const int32_t* num_vertices,
+                                                   const int32_t* num_edges,
+                                                   const int32_t* index_list,
+                                                   int32_t add_self_loops, int32_t mem,
+                                                   int32_t validate) {
+  ATH_TRY(ensure_init());
+  ATH_REQUIRE(batch && num_vertices && num_edges, ATHENA_ERR_ARG,
+              "batch_create_from_edges: null argument");
+  ATH_REQUIRE(num_graphs >= 1, ATHENA_ERR_ARG, "batch_create_from_edges: num_graphs = %d",
+              num_graphs);
+  ATH_REQUIRE(mem == ATHENA_MEM_HOST || mem == ATHENA_MEM_DEVICE, ATHENA_ERR_ARG,
+              "batch_create_from_edges: bad mem %d", mem);
+  const int B = num_graphs;
+  std::vector<int32_t> voff, eoff;
+  ATH_TRY(graph_offsets(B, num_vertices, num_edges, voff, eoff, "batch_create_from_edges"));
+  const int64_t V = voff[B], E = eoff[B];
+  ATH_REQUIRE(E == 0 || index_list, ATHENA_ERR_ARG, "batch_create_from_edges: null index_list");
+  const int64_t Zmax = 2 * E + (add_self_loops ? V : 0);
+  cudaStream_t st = ctx().stream;
+  // scratch: voff | eoff | nz | status | cnt(V+1) | hasself | cursor | key | nb | ia | (pad) ja
+  const size_t Vp = (size_t)round_up(V + 2, 4), Zp = (size_t)round_up(Zmax + 2, 4);
+  const size_t Bp = (size_t)round_up(B + 2, 4), Ep = (size_t)round_up(2 * E + 2, 4);
+  const size_t ia_ints = (size_t)round_up(V + B + 2, 4);
+  const int ntiles = (int)cdiv(V + 1, SCAN_TILE) + 1;
+  size_t total = 3 * Bp + 4 + 3 * Vp + 2 * Zp + ia_ints + 2 * Zp + (size_t)round_up(ntiles, 4) +
+                 (mem == ATHENA_MEM_HOST ? Ep : 0);
+  DevBuf work;
+  ATH_TRY(work.reserve(sizeof(int32_t) * total));
+  int32_t* p = work.as<int32_t>();
+  int32_t* d_voff = p; p += Bp;
+  int32_t* d_eoff = p; p += Bp;
+  int32_t* d_nz = p; p += Bp;
+  int32_t* status = p; p += 4;
+  int32_t* cnt = p; p += Vp;
+  int32_t* hasself = p; p += Vp;
+  int32_t* cursor = p; p += Vp;
+  int32_t* key = p; p += Zp;
+  int32_t* nb = p; p += Zp;
+  int32_t* d_ia = p; p += ia_ints;
+  int32_t* d_ja = p; p += 2 * Zp;
+  int32_t* tile_sums = p; p += round_up(ntiles, 4);
+  const int32_t* d_il = index_list;
+  ATH_CUDA(cudaMemcpyAsync(d_voff, voff.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, st));
+  ATH_CUDA(cudaMemcpyAsync(d_eoff, eoff.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, st));
+  if (mem == ATHENA_MEM_HOST && E > 0) {
+    ATH_CUDA(cudaMemcpyAsync(p, index_list, sizeof(int32_t) * 2 * (size_t)E, cudaMemcpyHostToDevice, st));
+    d_il = p;
+  } else if (E > 0) {
+    ATH_REQUIRE((reinterpret_cast<uintptr_t>(index_list) & 7) == 0, ATHENA_ERR_ARG,
+                "batch_create_from_edges: device index_list must be 8-byte aligned");
+  }
+  const int32_t status_init[4] = {INT_MAX, 0, 0, 0};
+  ATH_CUDA(cudaMemcpyAsync(status, status_init, sizeof(status_init), cudaMemcpyHostToDevice, st));
+  ATH_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * 2 * Vp, st));  // cnt and hasself
+  ATH_CUDA(cudaMemsetAsync(d_nz, 0, sizeof(int32_t) * Bp, st));
+  const int2* il2 = reinterpret_cast<const int2*>(d_il);
+  if (E > 0) {
+    k_edges_count<<<(int)cdiv(E, 256), 256, 0, st>>>(B, (int)E, d_voff, d_eoff, il2, cnt, hasself,
+                                                    status);
+    ATH_LAUNCHED();
+  }
+  if (add_self_loops && V > 0) {
+    k_edges_loops<<<(int)cdiv(V, 256), 256, 0, st>>>((int)V, hasself, cnt);
+    ATH_LAUNCHED();
+  }
+  ATH_TRY(exclusive_scan(cnt, cnt, (int)V, tile_sums));  // cnt -> row offsets, cnt[V] = Z
+  if (V > 0) {
+    ATH_CUDA(cudaMemcpyAsync(cursor, cnt, sizeof(int32_t) * (size_t)V, cudaMemcpyDeviceToDevice, st));
+    const int64_t n = std::max<int64_t>(E, add_self_loops ? V : 0);
+    if (n > 0) {
+      k_edges_fill<<<(int)cdiv(n, 256), 256, 0, st>>>(B, (int)E, (int)V, add_self_loops ? 1 : 0,
+                                                     d_voff, d_eoff, il2, hasself, cursor, key, nb);
+      ATH_LAUNCHED();
+    }
+    // rows in ascending edge id (the fill claimed slots in arbitrary order); `cursor` is
+    // free again and holds the list of rows longer than a warp
+    k_csc_sort_short<<<(int)cdiv(V * 32, 256), 256, 0, st>>>((int)V, cnt, key, nb, cursor, status + 1);
+    ATH_LAUNCHED();
+    size_t smem = sizeof(unsigned long long) * LONG_SMEM_KEYS;
+    ATH_CUDA(cudaFuncSetAttribute(k_csc_sort_long, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    k_csc_sort_long<<<ctx().sm_count, 1024, smem, st>>>(cnt, key, nb, cursor, status + 1);
+    ATH_LAUNCHED();
+    k_edges_emit<<<(int)cdiv(V * 8, 256), 256, 0, st>>>(B, (int)V, d_voff, cnt, key, nb, d_ia,
+                                                       reinterpret_cast<int2*>(d_ja), d_nz);
+    ATH_LAUNCHED();
+  }
+  // the entry counts per graph are data (self edges, missing loops): B integers come back
+  std::vector<int32_t> h_nz((size_t)B, 0);
+  ATH_CUDA(cudaMemcpyAsync(h_nz.data(), d_nz, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+  ATH_CUDA(cudaStreamSynchronize(st));
+  athena_handle_t h = 0;
+  ATH_TRY(athena_cuda_batch_create(&h, B, num_vertices, num_edges, h_nz.data(), d_ia, d_ja,
+                                   ATHENA_MEM_DEVICE, 0));
+  Batch* b = static_cast<Batch*>(lookup_object(h, Kind::Batch));
+  k_merge_status<<<1, 1, 0, st>>>(b->status.as<int32_t>(), status);
+  ATH_LAUNCHED();
+  adopt(b->raw, work);
+  *batch = h;
+  if (validate) {
+    int rc = athena_cuda_batch_status(h);
+    if (rc != ATHENA_OK) {
+      destroy_object(h, Kind::Batch);
+      *batch = 0;
+      return rc;
+    }
+  }
+  return ATHENA_OK;
+}
+
+ATHENA_API int athena_cuda_batch_create_from_edge_index(athena_handle_t* batch, int32_t num_graphs,
+                                                        const int32_t* num_vertices,
+                                                        const int32_t* num_edges,
+                                                        const int32_t* num_entries,
+                                                        const int64_t* edge_index,
+                                                        const int64_t* degree, int32_t mem,
+                                                        int32_t validate) {
+  ATH_TRY(ensure_init());
+  ATH_REQUIRE(batch && num_vertices && num_edges && num_entries, ATHENA_ERR_ARG,
+              "batch_create_from_edge_index: null argument");
+  ATH_REQUIRE(num_graphs >= 1, ATHENA_ERR_ARG, "batch_create_from_edge_index: num_graphs = %d",
+              num_graphs);
+  ATH_REQUIRE(mem == ATHENA_MEM_HOST || mem == ATHENA_MEM_DEVICE, ATHENA_ERR_ARG,
+              "batch_create_from_edge_index: bad mem %d", mem);
+  const int B = num_graphs;
+  std::vector<int32_t> voff, zoff;
+  ATH_TRY(graph_offsets(B, num_vertices, num_entries, voff, zoff, "batch_create_from_edge_index"));
+  const int64_t V = voff[B], Z = zoff[B];
+  ATH_REQUIRE((V == 0 || degree) && (Z == 0 || edge_index), ATHENA_ERR_ARG,
+              "batch_create_from_edge_index: null edge_index / degree");
+  cudaStream_t st = ctx().stream;
+  const size_t Vp = (size_t)round_up(V + 2, 4), Zp = (size_t)round_up(Z + 2, 4);
+  const size_t Bp = (size_t)round_up(B + 2, 4);
+  const size_t ia_ints = (size_t)round_up(V + B + 2, 4);
+  const int ntiles = (int)cdiv(V + 1, SCAN_TILE) + 1;
+  size_t total = 2 * Bp + 4 + Vp + ia_ints + 2 * Zp + (size_t)round_up(ntiles, 4) +
+                 (mem == ATHENA_MEM_HOST ? 2 * (3 * Zp + Vp) : 0);
+  DevBuf work;
+  ATH_TRY(work.reserve(sizeof(int32_t) * total));
+  int32_t* p = work.as<int32_t>();
+  int32_t* d_voff = p; p += Bp;
+  int32_t* d_zoff = p; p += Bp;
+  int32_t* status = p; p += 4;
+  int32_t* cnt = p; p += Vp;
+  int32_t* d_ia = p; p += ia_ints;
+  int32_t* d_ja = p; p += 2 * Zp;
+  int32_t* tile_sums = p; p += round_up(ntiles, 4);
+  const long long* d_ei = reinterpret_cast<const long long*>(edge_index);
+  const long long* d_deg = reinterpret_cast<const long long*>(degree);
+  if (mem == ATHENA_MEM_HOST) {
+    long long* q = reinterpret_cast<long long*>(p);
+    if (Z > 0)
+      ATH_CUDA(cudaMemcpyAsync(q, edge_index, sizeof(int64_t) * 3 * (size_t)Z, cudaMemcpyHostToDevice, st));
+    d_ei = q;
+    q += 3 * Zp;
+    if (V > 0)
+      ATH_CUDA(cudaMemcpyAsync(q, degree, sizeof(int64_t) * (size_t)V, cudaMemcpyHostToDevice, st));
+    d_deg = q;
+  }
+  ATH_CUDA(cudaMemcpyAsync(d_voff, voff.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, st));
+  ATH_CUDA(cudaMemcpyAsync(d_zoff, zoff.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, st));
+  const int32_t status_init[4] = {INT_MAX, 0, 0, 0};
+  ATH_CUDA(cudaMemcpyAsync(status, status_init, sizeof(status_init), cudaMemcpyHostToDevice, st));
+  if (V > 0) {
+    k_onnx_rows<<<(int)cdiv(V, 256), 256, 0, st>>>(B, (int)V, d_voff, d_zoff, d_deg, cnt);
+    ATH_LAUNCHED();
+  }
+  ATH_TRY(exclusive_scan(cnt, cnt, (int)V, tile_sums));
+  const int64_t n = std::max(V, Z);
+  if (n > 0) {
+    k_onnx_emit<<<(int)cdiv(n, 256), 256, 0, st>>>(B, (int)V, (int)Z, d_voff, d_zoff, cnt, d_ei,
+                                                  d_ia, reinterpret_cast<int2*>(d_ja), status);
+    ATH_LAUNCHED();
+  }
+  athena_handle_t h = 0;
+  ATH_TRY(athena_cuda_batch_create(&h, B, num_vertices, num_edges, num_entries, d_ia, d_ja,
+                                   ATHENA_MEM_DEVICE, 0));
+  Batch* b = static_cast<Batch*>(lookup_object(h, Kind::Batch));
+  k_merge_status<<<1, 1, 0, st>>>(b->status.as<int32_t>(), status);
+  ATH_LAUNCHED();
+  adopt(b->raw, work);
+  *batch = h;
+  if (validate) {
+    int rc = athena_cuda_batch_status(h);
+    if (rc != ATHENA_OK) {
+      destroy_object(h, Kind::Batch);
+      *batch = 0;
+      return rc;
+    }
+  }
+  return ATHENA_OK;
+}
+
 ATHENA_API int athena_cuda_batch_destroy(athena_handle_t batch) {
   return destroy_object(batch, Kind::Batch);
 }

@@ -38,6 +38,50 @@ class GraphBatch:
         self.handle = h.value
         self.B, self.V, self.Z, self.E = p.B, p.V, p.Z, p.E
 
+    @classmethod
+    def _adopt(cls, handle: int, packed: Optional[PackedGraphs] = None) -> "GraphBatch":
+        self = cls.__new__(cls)
+        self.handle = handle
+        self.packed = packed
+        b, v, z, e = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib().athena_cuda_batch_info(handle, C.byref(b), C.byref(v), C.byref(z), C.byref(e)))
+        self.B, self.V, self.Z, self.E = b.value, v.value, z.value, e.value
+        return self
+
+    @classmethod
+    def from_edges(cls, num_vertices, index_lists: Sequence, add_self_loops: bool = False,
+                   validate: bool = True) -> "GraphBatch":
+        """generate_adjacency(index_list) (+ add_self_loops) on the device
+        (athena_cuda_batch_create_from_edges): index_lists[s] = [E_s, 2] 1-based pairs."""
+        nv = np.ascontiguousarray(num_vertices, np.int32)
+        ils = [np.ascontiguousarray(il, np.int32).reshape(-1, 2) for il in index_lists]
+        ne = np.asarray([il.shape[0] for il in ils], np.int32)
+        il = np.ascontiguousarray(np.concatenate(ils) if ils else np.zeros((0, 2)), np.int32)
+        h = C.c_int64()
+        check(lib().athena_cuda_batch_create_from_edges(C.byref(h), nv.size, ptr(nv), ptr(ne),
+                                                        ptr(il), int(add_self_loops),
+                                                        _lib.MEM_HOST, int(validate)))
+        return cls._adopt(h.value)
+
+    @classmethod
+    def from_edge_index(cls, num_vertices, num_edges, edge_indices: Sequence, degree,
+                        validate: bool = True) -> "GraphBatch":
+        """The ONNX graph inputs of athena's message-passing export: edge_indices[s] = int64
+        [3, ncsr_s] (source, edge-feature index, target; 0-based), degree int64 [V]
+        (athena_onnx_msgpass_utils.f90:53-92)."""
+        nv = np.ascontiguousarray(num_vertices, np.int32)
+        ne = np.ascontiguousarray(num_edges, np.int32)
+        eis = [np.ascontiguousarray(ei, np.int64).reshape(3, -1) for ei in edge_indices]
+        nz = np.asarray([ei.shape[1] for ei in eis], np.int32)
+        ei = np.ascontiguousarray(np.concatenate([e.ravel() for e in eis]) if eis
+                                  else np.zeros(0), np.int64)
+        deg = np.ascontiguousarray(degree, np.int64)
+        h = C.c_int64()
+        check(lib().athena_cuda_batch_create_from_edge_index(
+            C.byref(h), nv.size, ptr(nv), ptr(ne), ptr(nz), ptr(ei), ptr(deg), _lib.MEM_HOST,
+            int(validate)))
+        return cls._adopt(h.value)
+
     def export(self, what: str) -> np.ndarray:
         n = {"row_ptr": self.V + 1, "col": self.Z, "eid": self.Z, "deg": self.V, "vgraph": self.V,
              "csc_ptr": self.V + 1, "csc_src": self.Z, "csc_ent": self.Z, "bucket": self.V,

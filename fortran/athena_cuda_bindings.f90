@@ -75,6 +75,7 @@ module athena__cuda_bindings
   public :: athena_cuda_layer_forward, athena_cuda_layer_backward
   public :: athena_cuda_network_create, athena_cuda_network_destroy, athena_cuda_network_add
   public :: athena_cuda_network_add_inputs
+  public :: athena_cuda_batch_create_from_edges, athena_cuda_batch_create_from_edge_index
   public :: athena_cuda_network_compile, athena_cuda_network_num_params
   public :: athena_cuda_network_set_params, athena_cuda_network_get_params
   public :: athena_cuda_network_get_gradients, athena_cuda_network_set_learning_rate
@@ -127,6 +128,27 @@ module athena__cuda_bindings
        integer(c_int32_t), intent(in) :: adj_ia(*)   ! concatenated adj_ia of every sample
        integer(c_int32_t), intent(in) :: adj_ja(2,*) ! concatenated adj_ja(2,:) of every sample
        integer(c_int32_t), value :: mem, validate
+       integer(c_int) :: rc
+     end function
+     !! graph%generate_adjacency(index_list) (+ graph%add_self_loops()) on the device
+     function athena_cuda_batch_create_from_edges(batch, num_graphs, num_vertices, num_edges, &
+          index_list, add_self_loops, mem, validate) &
+          bind(C, name="athena_cuda_batch_create_from_edges") result(rc)
+       import :: c_int, c_int32_t, c_int64_t
+       integer(c_int64_t), intent(out) :: batch
+       integer(c_int32_t), value :: num_graphs, add_self_loops, mem, validate
+       integer(c_int32_t), intent(in) :: num_vertices(*), num_edges(*), index_list(*)
+       integer(c_int) :: rc
+     end function
+     !! ONNX graph inputs: edge_index [3, ncsr] + degree (athena_onnx_msgpass_utils.f90:53-92)
+     function athena_cuda_batch_create_from_edge_index(batch, num_graphs, num_vertices, &
+          num_edges, num_entries, edge_index, degree, mem, validate) &
+          bind(C, name="athena_cuda_batch_create_from_edge_index") result(rc)
+       import :: c_int, c_int32_t, c_int64_t
+       integer(c_int64_t), intent(out) :: batch
+       integer(c_int32_t), value :: num_graphs, mem, validate
+       integer(c_int32_t), intent(in) :: num_vertices(*), num_edges(*), num_entries(*)
+       integer(c_int64_t), intent(in) :: edge_index(*), degree(*)
        integer(c_int) :: rc
      end function
      function athena_cuda_batch_destroy(batch) bind(C, name="athena_cuda_batch_destroy") result(rc)

@@ -157,6 +157,46 @@ int athena_cuda_batch_create(athena_handle_t* batch, int32_t num_graphs,
                              const int32_t* num_vertices, const int32_t* num_edges,
                              const int32_t* num_entries, const int32_t* adj_ia,
                              const int32_t* adj_ja, int32_t mem, int32_t validate);
+
+/*
+ * The same batch built from the EDGE LISTS, i.e. with graph%generate_adjacency(index_list) and
+ * (optionally) graph%add_self_loops() done on the device -- the two graphstruc calls every
+ * reader of the reference makes before set_graph (example/example_library/src/
+ * mod_read_chemical_graphs.f90:275-276, example/msgpass_euler/src/mod_read_euler.f90:48,
+ * example/msgpass_chemical/src/main.f90:108, test/test_kipf_msgpass_layer.f90:93).
+ *   index_list      concatenation of the graphs' index_list(2, num_edges(s)): 1-based vertex
+ *                   pairs (i, j) of the undirected edges, edge k of a graph = its k-th pair
+ * Each edge k = (i, j) is listed in row i and, if i /= j, in row j, with edge id k; a row is in
+ * ascending edge id.  add_self_loops != 0 appends (v, edge id 0) to every row that lists no v.
+ * (graphstruc v0.2.1 is not vendored with the reference, fpm.toml:21, and no athena test pins
+ * its neighbour order: this is the order of the host restatement athena_b200/graph.py, against
+ * which the device build is bit-exact.)  An index outside 1..num_vertices(s) is
+ * ATHENA_ERR_GRAPH as above.  The per-graph entry counts are data dependent, so this call
+ * synchronises once (num_graphs integers come back).
+ */
+int athena_cuda_batch_create_from_edges(athena_handle_t* batch, int32_t num_graphs,
+                                        const int32_t* num_vertices, const int32_t* num_edges,
+                                        const int32_t* index_list, int32_t add_self_loops,
+                                        int32_t mem, int32_t validate);
+
+/*
+ * The same batch from the graph inputs of athena's ONNX message-passing export
+ * (emit_msgpass_graph_inputs, athena_onnx_msgpass_utils.f90:53-92; built from the CSR by
+ * example/msgpass_chemical/validate_onnx.py:38-57):
+ *   edge_index      per graph an int64 [3, num_entries(s)] block, row-major, 0-based:
+ *                   row 0 = neighbour (source), row 1 = edge-feature index (adj_ja(2,w) - 1;
+ *                   negative: none), row 2 = the vertex whose row holds the entry (target);
+ *                   entries in CSR order (grouped by target, ascending); blocks concatenated
+ *   degree          int64 [sum num_vertices]: CSR row lengths
+ * ATHENA_ERR_GRAPH if the degrees of a graph do not add up to its num_entries, an entry does
+ * not lie in its target's row, or an index is out of range.
+ */
+int athena_cuda_batch_create_from_edge_index(athena_handle_t* batch, int32_t num_graphs,
+                                             const int32_t* num_vertices,
+                                             const int32_t* num_edges,
+                                             const int32_t* num_entries,
+                                             const int64_t* edge_index, const int64_t* degree,
+                                             int32_t mem, int32_t validate);
 int athena_cuda_batch_destroy(athena_handle_t batch);
 int athena_cuda_batch_status(athena_handle_t batch); /* synchronises; 0 or ATHENA_ERR_GRAPH */
 int athena_cuda_batch_info(athena_handle_t batch, int32_t* num_graphs, int64_t* num_vertices,

@@ -169,3 +169,42 @@ def test_synthetic_configs_have_the_documented_shapes():
                           zip(np.cumsum(np.r_[0, p.nv[:-1] + 1]), p.nv)])
     assert deg.max() <= 5 and deg.min() >= 3             # degree <= 4 + self loop
     assert p.ja[:, 1].min() >= 1                           # self loops carry edge features
+
+
+def test_extxyz_reader_follows_the_reference_reader():
+    """athena_b200/read_chemical_graphs.py on the real data set (fixture of database.xyz):
+    the sizes SURVEY.md section 8d re-derived from mod_read_chemical_graphs.f90:196-278
+    (46 undirected edges per cell on average, 32..61; degree 6..17 before the self loop),
+    the vertex-feature layout of :268-272 and edge features in (0.5, 3.0) / 3.0."""
+    import os
+    from athena_b200.read_chemical_graphs import get_graph_from_basis, parse_extxyz
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                             "chemical_database.npz"))
+    assert d["energy"].size == 198
+    ne, degs = [], []
+    for s in range(0, 198, 9):
+        g = get_graph_from_basis(d["lattice"][s], ["C"] * 8, d["positions"][s], d["forces"][s])
+        assert g.num_vertices == 8 and g.num_vertex_features == 6 and g.num_edge_features == 1
+        ne.append(g.num_edges)
+        degs.extend(np.diff(g.adj_ia))
+        assert g.adj_ja.shape[0] == 2 * g.num_edges          # no self images below 3 A here
+        assert np.allclose(g.vertex_features[:, 3], 0.06) and \
+            np.allclose(g.vertex_features[:, 4], 12.011 / 52.0)
+        assert np.all(g.edge_features > 0.5 / 3.0) and np.all(g.edge_features < 1.0)
+        # feature 6 = (edges found from this atom to itself or LATER atoms) / 6
+        cnt = np.zeros(8)
+        for v in range(8):
+            for nb, k in g.adj_ja[g.adj_ia[v] - 1:g.adj_ia[v + 1] - 1]:
+                if nb >= v + 1:
+                    cnt[v] += 1
+        assert np.allclose(g.vertex_features[:, 5], cnt / 6.0)
+        assert np.allclose(g.vertex_features[:, :3], d["forces"][s], rtol=1e-6)
+    assert 32 <= min(ne) and max(ne) <= 61 and 6 <= min(degs) and max(degs) <= 17
+    txt = ('2\nLattice="4.0 0.0 0.0 0.0 4.0 0.0 0.0 0.0 4.0" Properties=species:S:1:pos:R:3:'
+           'forces:R:3 energy=-1.5 free_energy=-9.0 pbc="T T T"\n'
+           'C 0.0 0.0 0.0 0.1 0.2 0.3\nC 1.0 0.0 0.0 -0.1 -0.2 -0.3\n\n')
+    fr = parse_extxyz(txt)
+    assert len(fr) == 1 and fr[0]["energy"] == -1.5 and fr[0]["positions"].shape == (2, 3)
+    g = get_graph_from_basis(fr[0]["lattice"], fr[0]["species"], fr[0]["positions"], fr[0]["forces"])
+    # distances: 1.0 (the pair) and 3.0 (pair through the far face) -- 3.0 is NOT < cutoff_max
+    assert g.num_edges == 1 and abs(float(g.edge_features[0, 0]) - 1.0 / 3.0) < 1e-6

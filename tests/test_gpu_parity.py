@@ -781,3 +781,189 @@ def test_swish_layer_parity(cuda, oracle32, kind):
     assert rel_err(L.get_gradients(), grad_ref) <= RTOL_ACT
     assert rel_err(dx, dx_ref) <= RTOL_ACT
     L.destroy()
+
+
+# ---------------------------------------------------------------------------
+# f3 / f4: graph construction on the device, real chemical data, ONNX graph inputs
+# ---------------------------------------------------------------------------
+BATCH_INTS = ("row_ptr", "col", "eid", "deg", "vgraph", "csc_ptr", "csc_src", "csc_ent")
+
+
+def _host_graphs(nvs, index_lists, loops):
+    graphs = []
+    for nv, il in zip(nvs, index_lists):
+        g = ab.graph_type()
+        g.set_num_vertices(int(nv), 1)
+        g.set_num_edges(len(il), 0)
+        g.generate_adjacency([tuple(int(t) for t in e) for e in il])
+        if loops:
+            g.add_self_loops()
+        graphs.append(g)
+    return graphs
+
+
+def _random_edge_lists(rng, B, nv_max, e_max, self_edges=True):
+    nvs, ils = [], []
+    for _ in range(B):
+        nv = int(rng.integers(0, nv_max + 1))
+        ne = int(rng.integers(0, e_max + 1)) if nv > 0 else 0
+        il = rng.integers(1, max(nv, 1) + 1, (ne, 2)).astype(np.int32)
+        if not self_edges and ne:
+            il = il[il[:, 0] != il[:, 1]]
+        nvs.append(nv)
+        ils.append(il)
+    return nvs, ils
+
+
+@pytest.mark.parametrize("loops", [False, True])
+@pytest.mark.parametrize("case", ["fixtures", "random", "star", "dup_hub"])
+def test_generate_adjacency_on_device_is_bit_exact(cuda, case, loops):
+    """athena_cuda_batch_create_from_edges against the host restatement of
+    generate_adjacency / add_self_loops fed through the CSR route: every integer structure of
+    the batch identical (empty graphs, isolated vertices, self edges, repeated edges, hubs)."""
+    rng = np.random.default_rng(zlib.crc32(f"{case}{loops}".encode()))
+    if case == "fixtures":     # test_kipf_msgpass_layer.f90:83-90, test_msgpass_network.f90:264-271
+        nvs = [6, 5, 6]
+        ils = [np.array([[1, 2], [1, 3], [2, 3], [2, 4], [3, 5], [4, 5], [4, 6], [5, 6]]),
+               np.array([[1, 2], [1, 3], [2, 3], [2, 4], [3, 5], [4, 5]])]
+        ils.append(ils[0])
+    elif case == "random":
+        nvs, ils = _random_edge_lists(rng, 57, 40, 150)
+        nvs[3], ils[3] = 0, np.zeros((0, 2), np.int32)        # an empty graph
+        nvs[9], ils[9] = 7, np.zeros((0, 2), np.int32)        # seven isolated vertices
+    elif case == "star":        # one 40 000-leaf hub: the long-row sort
+        n = 40001
+        il = np.stack([np.ones(n - 1, np.int32), rng.permutation(np.arange(2, n + 1))], 1)
+        nvs, ils = [5, n, 3], [np.array([[1, 2], [5, 4]]), il.astype(np.int32), np.array([[3, 3]])]
+    else:                       # repeated edges onto a few hubs (rows of 33..2000 entries)
+        nvs, ils = [300], [np.stack([rng.integers(1, 4, 5000), rng.integers(1, 301, 5000)], 1)]
+    graphs = _host_graphs(nvs, ils, loops)
+    p = ab.pack_graphs(graphs, with_features=False)
+    ref = ab.GraphBatch(p)
+    dev = ab.GraphBatch.from_edges(nvs, ils, add_self_loops=loops)
+    assert (dev.B, dev.V, dev.Z, dev.E) == (ref.B, ref.V, ref.Z, ref.E)
+    for k in BATCH_INTS:
+        assert np.array_equal(dev.export(k), ref.export(k)), k
+    assert np.array_equal(dev.export("coef"), ref.export("coef"))
+    ref.destroy()
+    dev.destroy()
+
+
+def test_generate_adjacency_on_device_rejects_bad_index(cuda):
+    with pytest.raises(ab.AthenaCudaError) as ei:
+        ab.GraphBatch.from_edges([4, 3], [np.array([[1, 2]]), np.array([[1, 2], [2, 4]])])
+    assert ei.value.code == -4 and "sample 2" in str(ei.value)
+    with pytest.raises(ab.AthenaCudaError):
+        ab.GraphBatch.from_edges([4], [np.array([[0, 2]])], add_self_loops=True)
+
+
+def _edge_index_of(g):
+    """build_edge_index of example/msgpass_chemical/validate_onnx.py:38-57."""
+    ncsr = g.adj_ja.shape[0]
+    ei = np.zeros((3, ncsr), np.int64)
+    k = 0
+    for v in range(g.num_vertices):
+        for j in range(g.adj_ia[v] - 1, g.adj_ia[v + 1] - 1):
+            ei[0, k] = g.adj_ja[j, 0] - 1
+            ei[1, k] = g.adj_ja[j, 1] - 1
+            ei[2, k] = v
+            k += 1
+    return ei, np.diff(g.adj_ia).astype(np.int64)
+
+
+def test_onnx_edge_index_ingestion_is_bit_exact(cuda):
+    """[3, ncsr] edge_index + degree (athena_onnx_msgpass_utils.f90:53-92) -> the same batch as
+    the CSR route, self loops (edge-feature index -1) included."""
+    rng = np.random.default_rng(8)
+    nvs, ils = _random_edge_lists(rng, 23, 30, 90)
+    graphs = _host_graphs(nvs, ils, True)
+    for g, il in zip(graphs, ils):
+        g.num_edges = len(il)
+    p = ab.pack_graphs(graphs, with_features=False)
+    ref = ab.GraphBatch(p)
+    pairs = [_edge_index_of(g) for g in graphs]
+    deg = np.concatenate([d for _, d in pairs])
+    dev = ab.GraphBatch.from_edge_index(p.nv, p.ne, [e for e, _ in pairs], deg)
+    for k in BATCH_INTS:
+        assert np.array_equal(dev.export(k), ref.export(k)), k
+    dev.destroy()
+    # degrees that do not add up / an entry outside its target's row / a bad source
+    bad = deg.copy(); bad[np.nonzero(deg)[0][0]] += 1
+    with pytest.raises(ab.AthenaCudaError):
+        ab.GraphBatch.from_edge_index(p.nv, p.ne, [e for e, _ in pairs], bad)
+    k = next(i for i, (e, _) in enumerate(pairs) if e.shape[1] > 3)
+    e_bad = [e.copy() for e, _ in pairs]
+    e_bad[k][2, 0], e_bad[k][2, -1] = e_bad[k][2, -1], e_bad[k][2, 0]
+    with pytest.raises(ab.AthenaCudaError):
+        ab.GraphBatch.from_edge_index(p.nv, p.ne, e_bad, deg)
+    e_bad = [e.copy() for e, _ in pairs]
+    e_bad[k][0, 1] = nvs[k]
+    with pytest.raises(ab.AthenaCudaError):
+        ab.GraphBatch.from_edge_index(p.nv, p.ne, e_bad, deg)
+    ref.destroy()
+
+
+def _chemical_dataset():
+    from athena_b200.read_chemical_graphs import get_graph_from_basis
+    d = np.load(os.path.join(GOLD, "chemical_database.npz"))
+    graphs = []
+    for s in range(d["energy"].size):
+        g = get_graph_from_basis(d["lattice"][s], ["C"] * 8, d["positions"][s], d["forces"][s])
+        graphs.append(g)
+    e = d["energy"].astype(np.float32)
+    labels = (e - e.min()) / (e.max() - e.min())      # main.f90:246-251
+    return graphs, labels
+
+
+def test_chemical_database_epoch_training_parity(cuda, oracle32):
+    """BASELINE configs[0] on its REAL data: the 198 cells of example/msgpass_chemical/
+    database.xyz read as mod_read_chemical_graphs.f90:196-278 reads them, add_self_loops,
+    Duvenaud(T=4, D=10, 10 outputs) -> full 128 -> 64 -> 1, Adam lr 1e-2 + clip_norm 0.1, batches
+    of 8 (the last one of 6), one whole epoch of network%train against the oracle; the graphs of
+    every batch are built on the device from the edge lists."""
+    graphs, labels = _chemical_dataset()
+    assert len(graphs) == 198
+    index_lists = []
+    for g in graphs:     # recover the undirected edge list: entry (nb, k) with nb >= row lists edge k
+        il = np.zeros((g.num_edges, 2), np.int32)
+        for v in range(g.num_vertices):
+            for nb, k in g.adj_ja[g.adj_ia[v] - 1:g.adj_ia[v + 1] - 1]:
+                if nb >= v + 1:
+                    il[k - 1] = (v + 1, nb)
+        index_lists.append(il)
+        g.add_self_loops()                            # main.f90:107-110
+    specs = [duvenaud_spec([6] * 5, 1, 4, 1, 10, 10), full_spec(10, 128, "leaky_relu"),
+             full_spec(128, 64, "leaky_relu"), full_spec(64, 1, "leaky_relu")]
+    net = ab.network_type()
+    net.add(ab.duvenaud_msgpass_layer_type([6], [1], 4, 10, 10))
+    for w in (128, 64, 1):
+        net.add(ab.full_layer_type(w, activation="leaky_relu"))
+    net.compile(ab.adam_optimiser_type(1e-2, clip_dict=ab.clip_type(clip_norm=0.1)), batch_size=8)
+    n = oracle32.num_params(specs)
+    assert net.num_params == n
+    rng = np.random.default_rng(2)
+    params = random_params(n, rng, 0.3)
+    net.set_params(params)
+    ref = params.copy()
+    s1 = np.zeros(n, np.float32); s2 = np.zeros(n, np.float32)
+    optim = OptimSpec("adam", lr=1e-2, clip_norm=0.1)
+    it = 0
+    for s0 in range(0, 198, 8):
+        gs = graphs[s0:s0 + 8]
+        p = ab.pack_graphs(gs)
+        tgt = labels[s0:s0 + 8].reshape(-1, 1)
+        dev = ab.GraphBatch.from_edges(p.nv, index_lists[s0:s0 + 8], add_self_loops=True)
+        dev.packed = p                                # features travel with the call
+        if s0 == 0:
+            host = ab.GraphBatch(p)
+            for k in BATCH_INTS:
+                assert np.array_equal(dev.export(k), host.export(k)), k
+            host.destroy()
+        it += 1
+        loss_ref, _ = oracle32.train_step(specs, ref, to_oracle_batch(p), tgt, optim, s1, s2, it)
+        loss = net.train_step(dev, tgt)
+        assert abs(loss - loss_ref) <= 1e-4 * max(1.0, abs(loss_ref)), (it, loss, loss_ref)
+        dev.destroy()
+    assert it == 25
+    assert rel_err(net.get_params(), ref) <= RTOL_PARAM
+    net.destroy()
