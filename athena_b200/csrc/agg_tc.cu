@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(AggCfg::THREADS, 1) k_agg_tc128(AggArgs a) {
           for (int k = 0; k < Cfg::RPW; ++k) {
             const int trow = warp * Cfg::RPW + k;
             float4 hi, lo;
-            split_tf32(acc[k], hi, lo);
+            split_tf32_safe(acc[k], hi, lo);
             const uint32_t off = (ch >> 3) * 16384 + sw128_off(trow, ch & 7);
             *reinterpret_cast<float4*>(sAhi + off) = hi;
             *reinterpret_cast<float4*>(sAlo + off) = lo;

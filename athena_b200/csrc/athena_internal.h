@@ -166,7 +166,8 @@ struct Batch : Object {
   DevBuf coef_buf;
   float* coef = nullptr;
   DevBuf scratch;
-  DevBuf status;  // int32[4]: [0] first bad graph + 1, [1] long-column count
+  DevBuf status;  // int32[4]: [0] first bad graph + 1, [1] long-column count, [2] multi-edge /
+                  // degree-0 flags, [3] non-finite feature seen by a tensor-core forward
   // Graph-aligned row tiles for the fused gather kernels (pipe_tc.cu): a tile is
   // a run of whole graphs with <= TILE_ROWS vertices and <= TILE_ENTRIES CSR
   // entries, so every neighbour of a tile row lies inside the tile (the batch is
@@ -189,6 +190,14 @@ struct Batch : Object {
   uint4* abits = nullptr;
   uint4* atbits = nullptr;
   int multi_edges = -1;
+  // The dense adjacency product also spreads a NaN / Inf FEATURE over its whole 128-row tile
+  // (0 * Inf), where the reference confines it to the vertex's neighbours.  The forward
+  // kernel reports such values in status[3]; the forward entry points then repeat the pass
+  // on the generic FP32 kernels (force_list: no fused tile kernel is chosen), which gather
+  // entry by entry and multiply in fp32 like the reference.  tcg_forwards counts tensor-core
+  // forward launches.
+  bool force_list = false;
+  int64_t tcg_forwards = 0;
   float* rsdeg = nullptr;    // [V]
   int32_t* vcount = nullptr; // [V] number of vertices of the vertex's graph (MSE cell size)
   // rows (CSR) / columns (CSC) with more than LONG_ROW entries: aggregated by a whole CTA

@@ -135,7 +135,7 @@ k_tc_rows(const float* __restrict__ A, int lda, const float* __restrict__ Hact, 
       int idx = tid + Cfg::THREADS * j;
       int row = idx / CH, ch = idx - row * CH;
       float4 hi, lo;
-      split_tf32(x[j], hi, lo);
+      split_tf32_safe(x[j], hi, lo);
       uint32_t off = (ch >> 3) * 16384 + sw128_off(row, ch & 7);
       *reinterpret_cast<float4*>(sAhi + off) = hi;
       *reinterpret_cast<float4*>(sAlo + off) = lo;

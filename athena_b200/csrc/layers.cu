@@ -841,6 +841,29 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
 
 using namespace athena;
 
+// Non-finite features on the tensor-core gather: see Batch::force_list.  begin() arms the
+// detector, retry() says whether the forward has to be repeated with the list gather.
+static int nonfinite_begin(Batch* b, int64_t* mark) {
+  b->force_list = false;
+  *mark = b->tcg_forwards;
+  if (b->abits != nullptr)
+    ATH_CUDA(cudaMemsetAsync(b->status.as<int32_t>() + 3, 0, sizeof(int32_t), ctx().stream));
+  return ATHENA_OK;
+}
+static int nonfinite_retry(Batch* b, int64_t mark, bool* again) {
+  *again = false;
+  if (b->tcg_forwards == mark) return ATHENA_OK;  // no tensor-core forward ran
+  int32_t flag = 0;
+  ATH_CUDA(cudaMemcpyAsync(&flag, b->status.as<int32_t>() + 3, sizeof(int32_t),
+                           cudaMemcpyDeviceToHost, ctx().stream));
+  ATH_CUDA(cudaStreamSynchronize(ctx().stream));
+  if (flag != 0) {
+    b->force_list = true;
+    *again = true;
+  }
+  return ATHENA_OK;
+}
+
 // ---- layer ABI ---------------------------------------------------------------------
 
 static int check_act(int a) { return a >= ATHENA_ACT_NONE && a <= ATHENA_ACT_SWISH; }
@@ -997,7 +1020,16 @@ ATHENA_API int athena_cuda_layer_forward(athena_handle_t layer, athena_handle_t 
   const float *dx = nullptr, *de = nullptr, *out = nullptr;
   ATH_TRY(stage_in(L->stage_x, vertex_features, L->in_rows(b) * L->nvf[0], mem, &dx));
   ATH_TRY(stage_in(L->stage_e, edge_features, b->E * L->nef, mem, &de));
+  int64_t nf_mark = 0;
+  bool again = false;
+  ATH_TRY(nonfinite_begin(b, &nf_mark));
   ATH_TRY(layer_forward_dev(L, b, dx, de, &out));
+  ATH_TRY(nonfinite_retry(b, nf_mark, &again));
+  if (again) {
+    int rc = layer_forward_dev(L, b, dx, de, &out);
+    b->force_list = false;
+    ATH_TRY(rc);
+  }
   ATH_TRY(record_mark());
   if (output) {
     size_t bytes = sizeof(float) * (size_t)(L->out_rows(b) * L->out_width());
@@ -1314,7 +1346,15 @@ ATHENA_API int athena_cuda_network_forward(athena_handle_t net, athena_handle_t 
   // network%predict runs in inference mode (athena_network_sub.f90:4226-4303): layers keep
   // nothing for a reverse sweep
   for (Layer* Lr : N->layers) Lr->inference = true;
-  int frc = net_forward_dev(N, b, dx, de, &out);
+  int64_t nf_mark = 0;
+  bool again = false;
+  int frc = nonfinite_begin(b, &nf_mark);
+  if (frc == ATHENA_OK) frc = net_forward_dev(N, b, dx, de, &out);
+  if (frc == ATHENA_OK) frc = nonfinite_retry(b, nf_mark, &again);
+  if (frc == ATHENA_OK && again) {
+    frc = net_forward_dev(N, b, dx, de, &out);
+    b->force_list = false;
+  }
   for (Layer* Lr : N->layers) {
     Lr->inference = false;
     Lr->fwd_batch = nullptr;  // a backward call must be preceded by a training forward

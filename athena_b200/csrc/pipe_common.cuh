@@ -51,6 +51,9 @@ struct GatherArgs {
   const uint32_t* mask_in;
   const uint4* abits;     // pipe_tcg: adjacency rows as bit masks (Batch::abits / atbits)
   long long num_rows;     // pipe_tcg: V (extent of the TMA tensor map of `aux`)
+  int32_t* nonfinite;     // pipe_tcg forward: set to 1 when a feature value is NaN / Inf (such a
+                          // value reaches every row of its tile through 0 * Inf in the dense
+                          // adjacency product; the caller re-runs with the list gather)
   int aux_tma;            // pipe_tcg fwd+MSE: the target tile arrives by TMA tensor copies
   // EPI_MSE (mse_loss_type%compute for graph outputs, athena_loss.f90:416-427)
   const int32_t* vcount;  // [V] vertices of the vertex's graph (Batch::vcount)

@@ -455,16 +455,16 @@ k_pipe_gather(GatherArgs a) {
       {
         const uint32_t o0 = sw128_off(row, ch0), o1 = sw128_off(row, ch1);
         float4 hi, lo;
-        split_tf32(acc[0], hi, lo);
+        split_tf32_safe(acc[0], hi, lo);
         *reinterpret_cast<float4*>(sAhi + o0) = hi;
         *reinterpret_cast<float4*>(sAlo + o0) = lo;
-        split_tf32(acc[1], hi, lo);
+        split_tf32_safe(acc[1], hi, lo);
         *reinterpret_cast<float4*>(sAhi + o1) = hi;
         *reinterpret_cast<float4*>(sAlo + o1) = lo;
-        split_tf32(acc[2], hi, lo);
+        split_tf32_safe(acc[2], hi, lo);
         *reinterpret_cast<float4*>(sAhi + 16384 + o0) = hi;
         *reinterpret_cast<float4*>(sAlo + 16384 + o0) = lo;
-        split_tf32(acc[3], hi, lo);
+        split_tf32_safe(acc[3], hi, lo);
         *reinterpret_cast<float4*>(sAhi + 16384 + o1) = hi;
         *reinterpret_cast<float4*>(sAlo + 16384 + o1) = lo;
       }
@@ -871,7 +871,7 @@ int launch_gather_t(const GatherArgs& a) {
 }  // namespace
 
 bool pipe_gather_supported(const Batch* b, int F, int N) {
-  return pipe_enabled() && b->num_tiles > 0 && F == 64 && N == 64;
+  return pipe_enabled() && !b->force_list && b->num_tiles > 0 && F == 64 && N == 64;
 }
 
 bool pipe_tn_supported(int K, int N) { return pipe_enabled() && K == 64 && (N == 64 || N == 32); }
@@ -895,6 +895,8 @@ int launch_pipe_gather_fwd(const Batch* b, const float* X, const float* W, float
   ATH_REQUIRE(F == 64 && N == 64, ATHENA_ERR_ARG, "pipe_gather_fwd: unsupported shape");
   if (pipe_tcg_supported(const_cast<Batch*>(b), F, N)) {
     a.abits = b->abits;
+    a.nonfinite = b->status.as<int32_t>() + 3;
+    const_cast<Batch*>(b)->tcg_forwards += 1;
     return launch_pipe_tcg(a, false, EPI_ACT);
   }
   return launch_gather_t<64, 64, false, EPI_ACT>(a);

@@ -599,6 +599,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
   } else {
     // ===================== split warps: ring -> scaled hi / lo B operand ================
     constexpr int LOADS = TILE_ROWS * (F / 4) / Cfg::SPLIT_THREADS;  // 16-byte chunks per thread
+    float nf = 0.f;  // x * 0 summed over everything this thread reads: NaN iff a value is not finite
     for (int j = -1; j < my_tiles; ++j) {
       const bool dry = j < 0;
       const int t = blockIdx.x + j * step;
@@ -643,6 +644,8 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
         const int row = idx >> 4, ch = idx & 15;
         float4 hi, lo;
         split_tf32(x[i], hi, lo);
+        if (EPI == EPI_ACT)
+          nf = fmaf(x[i].x, 0.f, fmaf(x[i].y, 0.f, fmaf(x[i].z, 0.f, fmaf(x[i].w, 0.f, nf))));
         const uint32_t off = (ch >> 3) * Cfg::OP_BLK + sw128b32_off(row, ch & 7);
         *reinterpret_cast<float4*>(sBhi + off) = hi;
         *reinterpret_cast<float4*>(sBlo + off) = lo;
@@ -653,6 +656,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
         if (tid == 0) TCG_TRACE(2, 4);
       }
     }
+    if (EPI == EPI_ACT && a.nonfinite != nullptr && nf != nf) atomicOr(a.nonfinite, 1);
   }
   tc_fence_before();
   __syncthreads();

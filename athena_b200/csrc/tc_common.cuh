@@ -361,5 +361,22 @@ __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& 
   lo.w = x.w - hi.w;
 }
 
+// The same for ACTIVATIONS on a forward path: hi of +-Inf is +-Inf and Inf - Inf would make the
+// low part NaN, turning an infinite feature into NaN where the reference's fp32 product keeps
+// +-Inf (which tanh / sigmoid then saturate to a finite value).
+__device__ __forceinline__ float lo_part(float x, float hi) {
+  return fabsf(x) == __int_as_float(0x7f800000) ? 0.f : x - hi;
+}
+__device__ __forceinline__ void split_tf32_safe(const float4& x, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+  hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+  hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+  hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+  lo.x = lo_part(x.x, hi.x);
+  lo.y = lo_part(x.y, hi.y);
+  lo.z = lo_part(x.z, hi.z);
+  lo.w = lo_part(x.w, hi.w);
+}
+
 }  // namespace tc
 }  // namespace athena

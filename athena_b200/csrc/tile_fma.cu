@@ -1267,7 +1267,7 @@ static void kipf_fill(KipfArgs* a, const KipfLayout& k) {
 // ---- host side ---------------------------------------------------------------------
 
 bool tile_kipf_supported(const Batch* b, int Fi, int Fo) {
-  if (!tile_fma_enabled() || b->num_tiles == 0 || b->col8 == nullptr) return false;
+  if (!tile_fma_enabled() || b->force_list || b->num_tiles == 0 || b->col8 == nullptr) return false;
   if (Fi < 1 || Fo < 1 || Fi > 128 || Fo > 128) return false;
   return tf_groups(kipf_layout(Fi, Fo, false).total_bytes, 1) > 0 &&
          tf_groups(kipf_layout(Fi, Fo, true).total_bytes, 1) > 0;

@@ -275,6 +275,13 @@ int athena_cuda_layer_zero_gradients(athena_handle_t layer);
  *                    may be NULL (result stays on the device for backward)
  *   mem              memory space of the three data pointers
  * Activations needed by the backward pass are kept on the device.
+  * Non-finite inputs: a NaN / Inf feature value reaches exactly the rows that list its vertex,
+ * as in the reference's entry-by-entry gather (athena_diffstruc_extd_sub_kipf.f90:36-45).  The
+ * tensor-core gather of small-graph batches would spread it over the vertex's 128-row tile, so
+ * the forward kernels flag such values and layer_forward / network_forward repeat the pass
+ * with the list gather (one extra synchronisation per call on tileable batches).  A TRAINING
+ * step is not repeated: its loss sums over all samples and its weight gradients over all
+ * vertices, so loss and parameters are NaN in the reference and here alike.
  */
 int athena_cuda_layer_forward(athena_handle_t layer, athena_handle_t batch,
                               const float* vertex_features, const float* edge_features,

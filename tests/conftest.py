@@ -31,3 +31,21 @@ def cuda():
     import athena_b200 as ab
     ab.check(ab.lib().athena_cuda_init(-1))
     return ab
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Dump the norm-wise / element-wise error pairs the parity comparisons saw."""
+    try:
+        import json
+        import helpers
+        if not helpers.ELEM_LOG:
+            return
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        log = sorted(helpers.ELEM_LOG, key=lambda t: -t[1])
+        with open(os.path.join(out, "elem_err.json"), "w") as f:
+            json.dump({"comparisons": len(log), "floor": helpers.ELEM_FLOOR,
+                       "worst_elementwise": log[:20],
+                       "max_normwise": max(t[0] for t in log)}, f, indent=1)
+    except Exception:
+        pass

@@ -9,15 +9,50 @@ RTOL_ACT = 1e-5     # forward activations and gradients, fp32, relative
 RTOL_PARAM = 1e-4   # parameters after N training steps, relative
 
 
+# Element-wise companion of the norm-wise metric: every element is compared relative to ITS OWN
+# reference magnitude, with an absolute floor of ELEM_FLOOR x the largest reference magnitude
+# (an element that is the cancelled sum of much larger terms carries the rounding noise of those
+# terms in the reference's fp32 arithmetic too, so below the floor a relative error is
+# meaningless).  Asserted at ELEM_TOL wherever rel_err is asserted at <= 1e-5.
+ELEM_FLOOR = 1e-3
+ELEM_TOL = 1e-4
+ELEM_LOG = []      # (norm-wise, element-wise) of every comparison, dumped by conftest.py
+
+
+def elem_rel_err(a, b, floor: float = ELEM_FLOOR) -> float:
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.size == 0:
+        return 0.0
+    fin = np.isfinite(b)
+    if not fin.all():
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[np.isinf(b)], b[np.isinf(b)])
+        a, b = a[fin], b[fin]
+        if a.size == 0:
+            return 0.0
+    scale = max(float(np.abs(b).max()), 1e-30)
+    return float((np.abs(a - b) / np.maximum(np.abs(b), floor * scale)).max())
+
+
 def rel_err(a, b) -> float:
-    """max |a-b| relative to the largest reference magnitude (norm-wise relative error)."""
+    """max |a-b| relative to the largest reference magnitude (norm-wise relative error).
+    Every call also records the element-wise metric (elem_rel_err) and fails when a comparison
+    that is within 1e-5 norm-wise is worse than ELEM_TOL element-wise."""
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     assert a.shape == b.shape, (a.shape, b.shape)
     if a.size == 0:
         return 0.0
     scale = max(float(np.abs(b).max()), 1e-30)
-    return float(np.abs(a - b).max() / scale)
+    err = float(np.abs(a - b).max() / scale)
+    if np.isfinite(err):
+        ew = elem_rel_err(a, b)
+        ELEM_LOG.append((err, ew))
+        if err <= RTOL_ACT:
+            assert ew <= ELEM_TOL, (f"element-wise relative error {ew:.3e} > {ELEM_TOL:g} "
+                                    f"(norm-wise {err:.3e})")
+    return err
 
 
 def to_oracle_batch(p: PackedGraphs) -> Batch:

@@ -967,3 +967,43 @@ def test_chemical_database_epoch_training_parity(cuda, oracle32):
     assert it == 25
     assert rel_err(net.get_params(), ref) <= RTOL_PARAM
     net.destroy()
+
+
+@pytest.mark.parametrize("entry", ["layer", "network"])
+def test_nonfinite_features_stay_confined_to_neighbours(cuda, oracle32, entry):
+    """A NaN / Inf feature reaches exactly the rows that list its vertex, as in the reference's
+    entry-by-entry gather (_sub_kipf.f90:36-45).  The tensor-core gather would spread it over
+    the vertex's whole 128-row tile (0 * Inf in the dense adjacency product): the forward
+    kernel detects it and the pass is repeated with the list gather."""
+    rng = np.random.default_rng(99)
+    p = synth.regular_batch(8, 64, 3, 64, rng)       # tileable, F = 64: the tcgen05 path
+    x = p.x.copy()
+    x[5, 7] = np.nan          # graph 0
+    x[64 + 9, 0] = np.inf     # graph 1 (same 128-row tile as graph 0)
+    x[300, 63] = -np.inf      # graph 4
+    spec = kipf_spec([64, 64], 1, "tanh")
+    params = random_params(64 * 64, rng, 0.2)
+    ob = Batch(p.nv, p.ne, p.ia, p.ja, x, None)
+    ref, _, _ = oracle32.layer_fwd_bwd(spec, params, ob)
+    if entry == "layer":
+        L = ab.kipf_msgpass_layer_type([64, 64], 1, "tanh")
+        L.set_params(params)
+        L.set_graph(p)
+        out = L.forward(x)
+        clean = L.forward(p.x)                        # the next call is back on the tensor core
+        L.destroy()
+    else:
+        net = ab.network_type()
+        net.add(ab.kipf_msgpass_layer_type([64, 64], 1, "tanh"))
+        net.compile(ab.sgd_optimiser_type(0.1), batch_size=p.B)
+        net.set_params(params)
+        gb = ab.GraphBatch(p)
+        out = net.forward(gb, vertex_features=x)
+        clean = net.forward(gb, vertex_features=p.x)
+        net.destroy()
+    bad = ~np.isfinite(ref)
+    assert bad.any() and bad.sum() < 40 * 64          # only neighbours of the three vertices
+    assert np.array_equal(~np.isfinite(out), bad)
+    assert np.abs(out[~bad] - ref[~bad]).max() <= RTOL_ACT * np.abs(ref[~bad]).max()
+    ref_clean, _, _ = oracle32.layer_fwd_bwd(spec, params, to_oracle_batch(p))
+    assert rel_err(clean, ref_clean) <= RTOL_ACT
