@@ -95,6 +95,33 @@ void prof_mark(const char* tag);  // no-op unless profiling is on
     }                                                                          \
   } while (0)
 
+// Programmatic dependent launch: the kernel may start (block scheduling, TMEM allocation,
+// barrier set-up, instruction-cache warm-up) while the previous kernel of the stream drains;
+// it calls pdl_wait() before it touches anything the previous kernel wrote.  Kernels launched
+// this way MUST call pdl_wait().  ATHENA_CUDA_DISABLE_PDL=1 launches them plainly.
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+
 // Grow-only device buffer: layers keep their activations in these so that a
 // training loop performs no cudaMalloc after the first (largest) batch.
 struct DevBuf {

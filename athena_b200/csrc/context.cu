@@ -16,6 +16,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("ATHENA_CUDA_DISABLE_PDL");
+    on = (e && atoi(e) != 0) ? 0 : 1;
+  }
+  return on == 1;
+}
+
 Context& ctx() {
   static Context c;
   return c;

@@ -300,6 +300,8 @@ __global__ void __launch_bounds__(FIN_THREADS)
 k_finalize(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
            float* __restrict__ s2, long long n, FinArgs f, StepArgs a) {
   __shared__ float red[FIN_GROUPS][FIN_ELEMS];
+  pdl_launch_dependents();
+  pdl_wait();
   const int e = threadIdx.x % FIN_ELEMS, grp = threadIdx.x / FIN_ELEMS;
   const long long i = (long long)blockIdx.x * FIN_ELEMS + e;
   float sum = 0.f;
@@ -530,9 +532,9 @@ int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts
     f.loss_acc = loss_acc;
     f.do_step = (last && st) ? 1 : 0;
     f.xout = last ? xout : nullptr;
-    k_finalize<<<(unsigned)cdiv(n, FIN_ELEMS), FIN_THREADS, 0, s>>>(
-        params, grads, st ? st->s1.as<float>() : nullptr, st ? st->s2.as<float>() : nullptr, n, f,
-        a);
+    ATH_CUDA(launch_pdl(k_finalize, dim3((unsigned)cdiv(n, FIN_ELEMS)), dim3(FIN_THREADS), 0, s,
+                        params, grads, st ? st->s1.as<float>() : nullptr,
+                        st ? st->s2.as<float>() : nullptr, (long long)n, f, a));
     ATH_LAUNCHED_T(f.do_step ? "finalize_step" : "finalize");
   } while (done < dl.jobs.size());
   return ATHENA_OK;

@@ -586,6 +586,8 @@ k_pipe_tn(TnJobs jobs) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();  // the set-up above overlapped the previous kernel's tail
   // stages of job q owned by this CTA; every role walks the jobs in order with running
   // counters: j over stages (ring / operand-buffer phases), gcount over accumulator groups
   auto tiles_of = [&](int q) { return (jobs.M[q] + Cfg::RS - 1) / Cfg::RS; };
@@ -895,6 +897,7 @@ int launch_pipe_gather_fwd(const Batch* b, const float* X, const float* W, float
   ATH_REQUIRE(F == 64 && N == 64, ATHENA_ERR_ARG, "pipe_gather_fwd: unsupported shape");
   if (pipe_tcg_supported(const_cast<Batch*>(b), F, N)) {
     a.abits = b->abits;
+    a.num_rows = b->V;
     a.nonfinite = b->status.as<int32_t>() + 3;
     const_cast<Batch*>(b)->tcg_forwards += 1;
     return launch_pipe_tcg(a, false, EPI_ACT);
@@ -951,6 +954,7 @@ int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const
   ATH_REQUIRE(F == 64 && N == 64, ATHENA_ERR_ARG, "pipe_gather_bwd: unsupported shape");
   if (pipe_tcg_supported(const_cast<Batch*>(b), F, N)) {
     a.abits = b->atbits;
+    a.num_rows = b->V;
     return launch_pipe_tcg(a, true, EPI_ACTGRAD);
   }
   return launch_gather_t<64, 64, true, EPI_ACTGRAD>(a);
@@ -977,7 +981,7 @@ static int launch_pipe_tn_t(const TnPending* jobs, int njobs, DeferList* defer) 
     tj.part[q] = jobs[q].scratch->template as<float>();
     tj.M[q] = jobs[q].M;
   }
-  k_pipe_tn<N><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(tj);
+  ATH_CUDA(launch_pdl(k_pipe_tn<N>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, ctx().stream, tj));
   ATH_LAUNCHED_T("pipe_tn");
   for (int q = 0; q < njobs; ++q) {
     float* part = jobs[q].scratch->template as<float>();

@@ -133,18 +133,123 @@ struct TcgCfg {
   // The cp.async path (padded tile in the same region) remains for unaligned targets.
   static constexpr bool AUX_TMA = EPI == EPI_MSE;
   static constexpr int AUX_TMA_TILE = TILE_ROWS * N * 4;
-  static constexpr int OFF_AUX = (OFF_RING + NS * STAGE_BYTES + 1023) / 1024 * 1024;
+  static constexpr int OFF_BAR = OFF_RING + NS * STAGE_BYTES;    // barriers (256 B) + loss_red (512 B)
+  static constexpr int OFF_AUX = (OFF_BAR + 256 + 512 + 1023) / 1024 * 1024;
   static constexpr int AUX_BYTES = AUX_TMA ? 2 * AUX_TMA_TILE : EPI != EPI_ACT ? AUX_TILE : 0;
-  static constexpr int OFF_BAR = OFF_AUX + AUX_BYTES;
-  static constexpr int OFF_EPI = OFF_BAR + 256 + 512;
-  static constexpr int FIX_PATCH = 32 * 16;                      // floats per fix-warp patch (16-column groups)
-  static constexpr int EPI_PATCH_FLOATS = EPI_PATCH;             // pipe::epilogue_tile: 32-column groups
-  static constexpr int OFF_FIX = OFF_EPI + 4 * EPI_PATCH_FLOATS * 4;
-  static constexpr int FIX_BYTES = EPI != EPI_ACTGRAD ? 4 * FIX_PATCH * 4 : 0;  // P is stored forward only
+  // Output staging for the TMA tensor stores: every fix / epilogue warp owns the 32 rows of its
+  // TMEM lane quarter as two [32 rows x 32 floats] boxes in the 128-byte-swizzled layout
+  // (16-byte chunk c of row r at chunk c ^ (r % 8): row-per-thread STS.128 is conflict-free),
+  // which one lane hands to cp.async.bulk.tensor -- no read-back through the LSU, no STG.
+  // fwd + MSE writes the gradient IN PLACE over the target tile it has just read.
+  static constexpr int WARP_STAGE = 2 * 32 * 128;                // 8 KB
+  static constexpr int OFF_EPI = (OFF_AUX + AUX_BYTES + 1023) / 1024 * 1024;
+  static constexpr int EPI_STAGE_BYTES = EPI != EPI_MSE ? 4 * WARP_STAGE : 0;
+  static constexpr int OFF_FIX = OFF_EPI + EPI_STAGE_BYTES;
+  static constexpr int FIX_BYTES = EPI != EPI_ACTGRAD ? 4 * WARP_STAGE : 0;  // P is stored forward only
   static constexpr int SMEM = 1024 + OFF_FIX + FIX_BYTES;
   static_assert(SMEM <= 232448, "shared memory budget");
   static constexpr uint32_t T_ADJ = 0, T_P = 128, T_O = 384;     // TMEM columns
 };
+
+// byte offset of 16-byte chunk c (0..15) of row r (0..31) inside a warp's staging area: two
+// [32 rows x 128 B] boxes (columns 0..31 | 32..63) in the TMA 128-byte swizzle
+__device__ __forceinline__ uint32_t stage_off(int r, int c) {
+  return static_cast<uint32_t>((c >> 3) * 4096 + r * 128 + (((c & 7) ^ (r & 7)) << 4));
+}
+
+// rows [0, rows) of a warp's staging area -> global rows (the fallback of the tensor store for
+// a warp whose 32 rows are not all inside the tile, or without a tensor map): 16 lanes per row,
+// conflict-free LDS.128, full-line STG.128.  box_pitch: bytes between the two column boxes.
+__device__ __forceinline__ void stage_copy_out(const uint8_t* stage, uint32_t box_pitch, int rows,
+                                               float* __restrict__ grow0, int lane) {
+#pragma unroll
+  for (int it = 0; it < 16; ++it) {
+    const int idx = it * 32 + lane;
+    const int r = idx >> 4, c = idx & 15;
+    if (r < rows)
+      *reinterpret_cast<float4*>(grow0 + r * 64 + c * 4) = *reinterpret_cast<const float4*>(
+          stage + (c >> 3) * box_pitch + r * 128 + (((c & 7) ^ (r & 7)) << 4));
+  }
+}
+
+// Epilogue of one tile for the warp that owns TMEM lanes 32q .. 32q+31 (thread = row), as
+// pipe::epilogue_tile, but the results leave through a swizzled staging area and TMA tensor
+// stores (see TcgCfg::WARP_STAGE).
+//   EPI_ACT      out = act(v)                              -> this warp's staging area
+//   EPI_ACTGRAD  out = v .* act'(aux | sign bits)          -> this warp's staging area
+//   EPI_MSE      out = act'(p) .* (p - target) * scale     -> IN PLACE over the target values
+//                (AUX_SWZ: the TMA-loaded tile, `dst` = its base; else this thread's padded row)
+// Returns this row's loss share (EPI_MSE).  `dst_rows`: base the thread's chunks are written
+// relative to (staging area of the warp, or the 128-row target tile with row_in_dst = 32 q + lane).
+template <int ACT, int EPI, bool AUX_SWZ>
+__device__ __forceinline__ float tcg_epilogue(uint32_t tacc, int q, int lane, bool dry,
+                                              uint8_t* dst, uint32_t box_pitch, int row_in_dst,
+                                              const float* aux_row, float row_scale,
+                                              uint64_t* acc_empty, uint32_t* mask_out_row,
+                                              bool use_mask, const uint32_t (&mask_in)[2]) {
+  constexpr int N = 64;
+  float lsum = 0.f;
+  const bool padded_inplace = EPI == EPI_MSE && !AUX_SWZ;
+  auto chunk_ptr = [&](int col) -> float4* {
+    if (padded_inplace) return reinterpret_cast<float4*>(const_cast<float*>(aux_row) + col);
+    const int c = col >> 2;
+    return reinterpret_cast<float4*>(dst + (c >> 3) * box_pitch + row_in_dst * 128 +
+                                     (((c & 7) ^ (row_in_dst & 7)) << 4));
+  };
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t mbits = 0;
+#pragma unroll
+    for (int cg = 0; cg < 2; ++cg) {
+      float vh[16];
+      const int col0 = half * 32 + cg * 16;
+      tmem_ld16(tacc + (static_cast<uint32_t>(q * 32) << 16) + col0, vh);
+      if (half == 1 && cg == 1) {
+        tc_fence_before();
+        mbar_arrive(acc_empty);  // the accumulator buffer may be overwritten now
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        float o[4] = {vh[i], vh[i + 1], vh[i + 2], vh[i + 3]};
+        float4* ptr = chunk_ptr(col0 + i);
+        if (EPI == EPI_ACT) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (ACT == ATHENA_ACT_RELU || ACT == ATHENA_ACT_LEAKY_RELU)
+              mbits |= (o[k] > 0.f ? 1u : 0u) << (cg * 16 + i + k);
+            o[k] = act_fwd<ACT>(o[k]);
+          }
+        } else if (EPI == EPI_ACTGRAD && use_mask) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool pos = (mask_in[half] >> (cg * 16 + i + k)) & 1u;
+            o[k] = pos ? o[k] : (ACT == ATHENA_ACT_LEAKY_RELU ? o[k] * 0.01f : 0.f);
+          }
+        } else if (EPI == EPI_MSE) {
+          const float4 t4 = *ptr;  // the target sits where the gradient goes
+          const float t[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float pk = act_fwd<ACT>(o[k]);
+            const float d = pk - t[k];
+            if (row_scale != 0.f) lsum += d * d * row_scale;
+            o[k] = act_bwd<ACT>(pk, d * row_scale);
+          }
+        } else if (ACT != ATHENA_ACT_NONE) {
+          const float4 h4 = *reinterpret_cast<const float4*>(aux_row + col0 + i);
+          const float h[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[k] = act_bwd<ACT>(h[k], o[k]);
+        }
+        if (!dry) *ptr = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    if (EPI == EPI_ACT && mask_out_row != nullptr &&
+        (ACT == ATHENA_ACT_RELU || ACT == ATHENA_ACT_LEAKY_RELU))
+      mask_out_row[half] = mbits;
+  }
+  return lsum;
+}
 
 // Every role runs its loop body once "dry" (iteration -1: an empty tile, no barrier traffic,
 // scratch TMEM buffers) before the first real tile.  A CTA only owns ~14 tiles, and the
@@ -154,7 +259,8 @@ struct TcgCfg {
 // is in flight; it must execute the same instructions, hence one loop, not a copy.
 template <bool TRANSB, int EPI>
 __global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1)
-k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
+k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
+           const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap p_map) {
   using Cfg = TcgCfg<EPI>;
   constexpr int F = Cfg::F, N = Cfg::N;
   extern __shared__ uint8_t smem_raw[];
@@ -219,6 +325,10 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the tail of the previous
+  // kernel; from here on its results (features, gradients, updated weights) are read
+  pdl_launch_dependents();
+  pdl_wait();
   const bool has_coef = a.rs != nullptr;
   constexpr int ns = Cfg::NS;
   int my_tiles = 0;
@@ -362,9 +472,10 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
   } else if (warp >= Cfg::EPI_WARP0) {
     // ===================== epilogue: TMEM -> registers -> global rows ==================
     const int q = warp - Cfg::EPI_WARP0;
-    float* patch = reinterpret_cast<float*>(smem + Cfg::OFF_EPI) + q * Cfg::EPI_PATCH_FLOATS;
+    uint8_t* stage = smem + Cfg::OFF_EPI + q * Cfg::WARP_STAGE;  // EPI != EPI_MSE
     const bool use_mask = (EPI == EPI_ACTGRAD) && a.mask_in != nullptr;
     const bool use_aux = (EPI != EPI_ACT) && a.aux != nullptr && !use_mask;
+    const bool out_tma = (a.store_tma & 1) != 0;
     const int my_row = q * 32 + lane;
     auto tile_at = [&](int t) { return t < a.num_tiles ? __ldg(a.tiles + t) : make_int4(0, 0, 0, 0); };
     auto count_at = [&](int t) {
@@ -405,8 +516,8 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
       const int4 ti = dry ? make_int4(0, 0, 0, 0) : __ldg(a.tiles + t);
       const int count = count_next;
       if (!dry) count_next = count_at(t + step);
-      float* out_tile = a.out + static_cast<size_t>(ti.x) * N;
       const bool row_valid = my_row < ti.y;
+      const int rows_valid = min(32, ti.y - q * 32);  // rows of this warp inside the tile (<= 0: none)
       uint32_t m0 = 0, m1 = 0;
       uint32_t* mout = nullptr;
       if (row_valid) {
@@ -416,6 +527,11 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
           m1 = __ldg(a.mask_in + grow * 2 + 1);
         }
         if (EPI == EPI_ACT && a.mask_out != nullptr) mout = a.mask_out + grow * 2;
+      }
+      // the staging area is free again once the previous tile's tensor stores have read it
+      if (EPI != EPI_MSE) {
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
       }
       if (!dry) {
         if (q == 0 && lane == 0) TCG_TRACE(5, 0);
@@ -429,23 +545,25 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
       }
-      const float* aux_row =
-          aux_tma ? reinterpret_cast<const float*>(smem + Cfg::OFF_AUX +
-                                                   (j & 1) * Cfg::AUX_TMA_TILE)
-                  : sAux + my_row * AUX_PITCH;
+      uint8_t* aux_tile = smem + Cfg::OFF_AUX + (j & 1) * Cfg::AUX_TMA_TILE;  // aux_tma only
+      const float* aux_row = sAux + my_row * AUX_PITCH;                       // padded tile
       const uint32_t tacc = tmem + Cfg::T_O + b * N;
       uint64_t* release = dry ? dummy : &o_empty[b];
       const float scale =
           (EPI == EPI_MSE && row_valid) ? 1.f / static_cast<float>(N * count) : 0.f;
       const int act = use_aux || use_mask || EPI == EPI_ACT ? a.act : ATHENA_ACT_NONE;
       const uint32_t min_w[2] = {m0, m1};
-#define TCG_EPI(ACT)                                                                          \
-  lsum += (Cfg::AUX_TMA && aux_tma)                                                            \
-              ? epilogue_tile<ACT, EPI, N, false, 0, N / 32, Cfg::AUX_TMA>(                     \
-                    tacc, q, lane, ti.y, out_tile, aux_row, scale, patch, release, false, mout, \
-                    use_mask, min_w)                                                            \
-              : epilogue_tile<ACT, EPI, N, false>(tacc, q, lane, ti.y, out_tile, aux_row, scale, \
-                                                  patch, release, false, mout, use_mask, min_w)
+      const bool inplace_swz = EPI == EPI_MSE && aux_tma;
+      uint8_t* dst = inplace_swz ? aux_tile : stage;
+      const uint32_t box_pitch = inplace_swz ? TILE_ROWS * 128 : 4096;
+      const int row_in_dst = inplace_swz ? my_row : lane;
+#define TCG_EPI(ACT)                                                                            \
+  lsum += inplace_swz ? tcg_epilogue<ACT, EPI, true>(tacc, q, lane, dry, dst, box_pitch,         \
+                                                     row_in_dst, aux_row, scale, release, mout,  \
+                                                     use_mask, min_w)                            \
+                      : tcg_epilogue<ACT, EPI, false>(tacc, q, lane, dry, dst, box_pitch,        \
+                                                      row_in_dst, aux_row, scale, release, mout, \
+                                                      use_mask, min_w)
       switch (act) {
         case ATHENA_ACT_RELU: TCG_EPI(ATHENA_ACT_RELU); break;
         case ATHENA_ACT_LEAKY_RELU: TCG_EPI(ATHENA_ACT_LEAKY_RELU); break;
@@ -454,6 +572,38 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
         default: TCG_EPI(ATHENA_ACT_NONE); break;
       }
 #undef TCG_EPI
+      // hand the rows to the TMA (a full warp of rows) or copy them out (ragged tile end)
+      fence_async_smem();
+      __syncwarp();
+      float* grow0 = a.out + (static_cast<size_t>(ti.x) + q * 32) * N;
+      if (EPI == EPI_MSE && !aux_tma) {
+        // padded target tile, gradient written in place: rows of 272 B
+        if (!dry) {
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const int idx = it * 32 + lane;
+            const int r = idx >> 4, c = idx & 15;
+            if (r < rows_valid)
+              *reinterpret_cast<float4*>(grow0 + r * N + c * 4) =
+                  *reinterpret_cast<const float4*>(sAux + (q * 32 + r) * AUX_PITCH + c * 4);
+          }
+          __syncwarp();
+        }
+      } else {
+        const uint8_t* src = inplace_swz ? aux_tile + q * 4096 : stage;
+        if (out_tma && rows_valid == 32) {
+          if (lane == 0) {
+            tma_store_2d(&out_map, 0, ti.x + q * 32, src);
+            tma_store_2d(&out_map, 32, ti.x + q * 32, src + box_pitch);
+            bulk_commit();
+            if (inplace_swz) bulk_wait_read0();  // the target buffer is handed back below
+          }
+          __syncwarp();
+        } else if (rows_valid > 0) {
+          stage_copy_out(src, box_pitch, rows_valid, grow0, lane);
+          __syncwarp();
+        }
+      }
       if (dry) {
         lsum = 0.f;  // whatever the scratch accumulator held
         mbar_arrive(warm);
@@ -466,12 +616,14 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
         issue_aux(t + step);  // the first tile right after the dry pass
       }
     }
+    if (lane == 0) bulk_wait_read0();  // shared memory stays valid until the last store has read it
     if (EPI == EPI_MSE) loss_red[my_row] = lsum;
   } else if (warp >= Cfg::FIX_WARP0) {
     // ===================== fix warps: P * deg_v^-1/2 -> hi / lo back into TMEM, P -> global ====
     const int q = warp - Cfg::FIX_WARP0;
     const int my_row = q * 32 + lane;
-    float* patch = reinterpret_cast<float*>(smem + Cfg::OFF_FIX) + q * Cfg::FIX_PATCH;
+    uint8_t* stage = smem + Cfg::OFF_FIX + q * Cfg::WARP_STAGE;  // P staging (forward only)
+    const bool p_tma = (a.store_tma & 2) != 0;
     auto rs_at = [&](int t) {
       float w = 1.f;
       if (has_coef && t < a.num_tiles) {
@@ -496,7 +648,10 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
       tc_fence_after();
       const uint32_t tp = tmem + Cfg::T_P + b * 128 + (static_cast<uint32_t>(q * 32) << 16);
       const bool store_p = EPI != EPI_ACTGRAD && a.P != nullptr;
-      float* p_tile = a.P + static_cast<size_t>(ti.x) * F;
+      if (store_p) {  // the previous tile's tensor stores have read the staging area
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+      }
 #pragma unroll 1
       for (int g = 0; g < F / 16; ++g) {
         // P = (A . Xhi + A . Xlo) * deg_v^-1/2 ; hi -> columns 0..63, lo -> columns 64..127
@@ -516,26 +671,13 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
         for (int i = 0; i < 16; ++i) hi[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
         tmem_st16(tp + 64 + g * 16, hi);
         if (!dry && g == 0 && q == 0 && lane == 0) TCG_TRACE(4, 4);
-        if (store_p) {
-          // coalesced store of the propagated tile (the operand of dW = P^T gY) through a
-          // [32 rows][16 floats] patch whose 16-byte chunks are XOR-permuted with (row / 2) % 4:
-          // row-per-thread STS.128 and the two-rows-per-quarter-warp LDS.128 are conflict-free
-          const int sw = (lane >> 1) & 3;
+        if (store_p && !dry) {
+          // the propagated tile (the operand of dW = P^T gY) goes to the swizzled staging area;
+          // one TMA tensor store per column box follows below
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            *reinterpret_cast<float4*>(patch + lane * 16 + ((k ^ sw) << 2)) =
+            *reinterpret_cast<float4*>(stage + stage_off(lane, g * 4 + k)) =
                 make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int idx = it * 32 + lane;
-            const int r = idx >> 2, c = idx & 3;
-            const int trow = q * 32 + r;
-            if (trow < ti.y)
-              *reinterpret_cast<float4*>(p_tile + static_cast<size_t>(trow) * F + g * 16 + c * 4) =
-                  *reinterpret_cast<const float4*>(patch + r * 16 + ((c ^ ((r >> 1) & 3)) << 2));
-          }
-          __syncwarp();
         }
         if (!dry && g == 0 && q == 0 && lane == 0) TCG_TRACE(4, 5);
       }
@@ -547,7 +689,24 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
         mbar_arrive(&p_fixed[b]);
         if (q == 0 && lane == 0) TCG_TRACE(4, 2);
       }
+      if (store_p && !dry) {
+        const int rows_valid = min(32, ti.y - q * 32);
+        fence_async_smem();
+        __syncwarp();
+        if (p_tma && rows_valid == 32) {
+          if (lane == 0) {
+            tma_store_2d(&p_map, 0, ti.x + q * 32, stage);
+            tma_store_2d(&p_map, 32, ti.x + q * 32, stage + 4096);
+            bulk_commit();
+          }
+        } else if (rows_valid > 0) {
+          stage_copy_out(stage, 4096, rows_valid,
+                         a.P + (static_cast<size_t>(ti.x) + q * 32) * F, lane);
+        }
+        __syncwarp();
+      }
     }
+    if (lane == 0) bulk_wait_read0();
   } else if (warp >= Cfg::BUILD_WARP0) {
     // ===================== build warps: adjacency bits -> TMEM A operand ================
     const int q = warp - Cfg::BUILD_WARP0;
@@ -681,9 +840,11 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map) {
   if (warp == Cfg::MMA_WARP) tmem_dealloc<512>(tmem);
 }
 
-// 2-D tensor map of a dense [rows][64] fp32 array, box = [128 rows][32 floats], 128-byte
-// swizzle.  The driver entry point is resolved at run time (no link-time libcuda dependency).
-static bool make_row_tile_map(const float* base, long long rows, CUtensorMap* out) {
+// 2-D tensor map of a dense [rows][64] fp32 array, box = [box_rows][32 floats], 128-byte
+// swizzle (box_rows = 128: the target tile of fwd + MSE; 32: one warp's rows for the stores).
+// The driver entry point is resolved at run time (no link-time libcuda dependency).
+static bool make_row_tile_map(const float* base, long long rows, CUtensorMap* out,
+                              int box_rows = TILE_ROWS) {
   using Fn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                           const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                           CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -701,7 +862,7 @@ static bool make_row_tile_map(const float* base, long long rows, CUtensorMap* ou
   if (!fn || rows <= 0 || (reinterpret_cast<uintptr_t>(base) & 15u) != 0) return false;
   const cuuint64_t gdim[2] = {64, static_cast<cuuint64_t>(rows)};
   const cuuint64_t gstr[1] = {64 * sizeof(float)};
-  const cuuint32_t box[2] = {32, TILE_ROWS};
+  const cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box,
             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -731,6 +892,21 @@ int launch_tcg_t(const GatherArgs& a) {
                make_row_tile_map(a.aux, a.num_rows, &aux_map))
                   ? 1
                   : 0;
+  // TMA tensor stores of the output (and of the propagated tile): [32 rows x 32 floats] boxes
+  alignas(64) CUtensorMap out_map, p_map;
+  memset(&out_map, 0, sizeof(out_map));
+  memset(&p_map, 0, sizeof(p_map));
+  static int no_store_tma = -1;
+  if (no_store_tma < 0) {
+    const char* e = getenv("ATHENA_DEBUG_NO_STORE_TMA");  // A/B switch: LDS / STG copy-out
+    no_store_tma = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  b.store_tma = 0;
+  if (!no_store_tma) {
+    if (a.out != nullptr && make_row_tile_map(a.out, a.num_rows, &out_map, 32)) b.store_tma |= 1;
+    if (EPI != EPI_ACTGRAD && a.P != nullptr && make_row_tile_map(a.P, a.num_rows, &p_map, 32))
+      b.store_tma |= 2;
+  }
   static int trace_left = -1;
   static long long* trace_buf = nullptr;
   if (trace_left < 0) {
@@ -745,7 +921,8 @@ int launch_tcg_t(const GatherArgs& a) {
     const char* e = getenv("ATHENA_DEBUG_TRACE_BLOCK");
     b.dbg = e ? atoi(e) : 0;
   }
-  k_pipe_tcg<TRANSB, EPI><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(b, aux_map);
+  ATH_CUDA(launch_pdl(k_pipe_tcg<TRANSB, EPI>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM,
+                      ctx().stream, b, aux_map, out_map, p_map));
   if (trace_left > 0) {
     --trace_left;
     std::vector<long long> h(trace_n);

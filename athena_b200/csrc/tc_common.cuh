@@ -82,6 +82,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
       : "memory");
 }
 
+// TMA tensor copy, shared -> global (2-D tiled tensor map), tracked by the issuing thread's
+// bulk async-group: commit after the copies of a tile, wait_read before the staging buffer is
+// written again (or the CTA exits).
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int x, int y, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::
+                   "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(smem_src))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // generic-proxy shared-memory writes -> visible to the async proxy (UMMA reads)
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
