@@ -242,6 +242,7 @@ int batch_bucketize(Batch* b, int min_deg, int max_deg, BucketSet** out);
 // kernels (spmm.cu / dense.cu / misc.cu): host launchers, all on ctx().stream
 // ---------------------------------------------------------------------------
 struct DeferList;
+struct P2PSignal;
 
 // out[v, 0:F] (+)= sum_{w in row v} c_w * X[col[w], 0:F]   (entries with col < 0 skipped)
 // coef == nullptr -> c_w = 1.  accumulate != 0 -> adds to the existing out.
@@ -403,7 +404,7 @@ bool finalize_can_step(const OptimState& st);
 // written to xout[0..n] -- the staging buffer of the peer-memory exchange.
 int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts, float* loss_acc,
                     float* params, float* grads, int64_t n, OptimState* st,
-                    float* xout = nullptr);
+                    float* xout = nullptr, const P2PSignal* sig = nullptr);
 
 // comm (comm.cu)
 int comm_allreduce_sum(float* buf, int64_t n);  // no-op when no communicator
@@ -418,11 +419,29 @@ struct P2PState {
   size_t cap = 0;                      // floats per slot
   uint32_t epoch = 0;                  // exchanges done so far
   float* xbuf[P2P_MAX_WORLD] = {};     // [2][cap] staging buffer of every rank (own = local)
-  uint32_t* flags[P2P_MAX_WORLD] = {}; // [2][P2P_MAX_WORLD] arrival flags of every rank
+  uint32_t* flags[P2P_MAX_WORLD] = {}; // [2][P2P_MAX_WORLD] arrival flags of every rank, then
+                                       // (own array only) [P2P_DONE] block counter of the
+                                       // signalling kernel, [P2P_ERR] sticky time-out flag
+  bool failed = false;                 // a wait timed out: every later exchange is ATHENA_ERR_COMM
 };
+constexpr int P2P_DONE = 2 * P2P_MAX_WORLD, P2P_ERR = P2P_DONE + 1, P2P_FLAG_WORDS = P2P_DONE + 8;
+// what the kernel that finishes the local gradients needs to tell the peers "slot complete"
+struct P2PSignal {
+  uint32_t* flags[P2P_MAX_WORLD];
+  unsigned int* done;  // blocks of the signalling kernel that have finished (last one signals)
+  int world = 0, rank = 0, slot = 0;
+  uint32_t epoch = 0;
+};
+// fills `sig` for the NEXT exchange (the one launch_p2p_sum_step will wait for)
+void p2p_next_signal(P2PSignal* sig);
+// reads the sticky time-out flag (synchronises the stream); ATHENA_ERR_COMM if set
+int p2p_check();
 P2PState& p2p();
 // sums the staged gradients of all ranks in rank order (bitwise identical everywhere) into
 // `grads` [0, n] -- or, with st != nullptr, applies the optimiser step and zeroes them
-int launch_p2p_sum_step(float* params, float* grads, int64_t n, OptimState* st);
+// signalled: the kernel that staged the gradients (launch_finalize with a P2PSignal) already
+// published the slot; otherwise this kernel does it itself
+int launch_p2p_sum_step(float* params, float* grads, int64_t n, OptimState* st,
+                        bool signalled = false);
 
 }  // namespace athena

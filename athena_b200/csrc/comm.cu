@@ -125,9 +125,9 @@ ATHENA_API int athena_cuda_comm_p2p_export(char handle[ATHENA_P2P_HANDLE_BYTES])
   if (!g_p2p_local_x) {
     // plain cudaMalloc (not the pool): IPC handles cover whole allocations
     ATH_CUDA(cudaMalloc(&g_p2p_local_x, 2 * P2P_CAP_FLOATS * sizeof(float)));
-    ATH_CUDA(cudaMalloc(&g_p2p_local_f, 2 * P2P_MAX_WORLD * sizeof(uint32_t)));
+    ATH_CUDA(cudaMalloc(&g_p2p_local_f, P2P_FLAG_WORDS * sizeof(uint32_t)));
     ATH_CUDA(cudaMemset(g_p2p_local_x, 0, 2 * P2P_CAP_FLOATS * sizeof(float)));
-    ATH_CUDA(cudaMemset(g_p2p_local_f, 0, 2 * P2P_MAX_WORLD * sizeof(uint32_t)));
+    ATH_CUDA(cudaMemset(g_p2p_local_f, 0, P2P_FLAG_WORDS * sizeof(uint32_t)));
   }
   cudaIpcMemHandle_t hx, hf;
   ATH_CUDA(cudaIpcGetMemHandle(&hx, g_p2p_local_x));

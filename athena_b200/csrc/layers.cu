@@ -811,18 +811,20 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
   P2PState& P = p2p();
   const bool use_p2p = P.ready && P.world > 1 && (size_t)(N->n + 1) <= P.cap;
   float* xout = use_p2p ? P.xbuf[P.rank] + (size_t)((P.epoch + 1) & 1u) * P.cap : nullptr;
+  P2PSignal sig;
+  if (use_p2p) p2p_next_signal(&sig);
   if (!defer.jobs.empty() || fo.fused || use_p2p) {
     const bool fuse_step = step_too && finalize_can_step(N->opt);
     ATH_TRY(launch_finalize(defer, fo.fused ? fo.loss_part : nullptr, fo.num_parts, gflat + N->n,
                             N->flat_params.as<float>(), gflat, N->n,
-                            fuse_step ? &N->opt : nullptr, xout));
+                            fuse_step ? &N->opt : nullptr, xout, use_p2p ? &sig : nullptr));
     if (stepped) *stepped = fuse_step;
   }
   if (use_p2p) {
     // signal + wait + sum over NVLink + (when no clipping intervenes) the step, in one kernel
     const bool p2p_step = step_too && !N->opt.d.clip_min_max && !N->opt.d.clip_norm_on;
     ATH_TRY(launch_p2p_sum_step(N->flat_params.as<float>(), gflat, N->n,
-                                p2p_step ? &N->opt : nullptr));
+                                p2p_step ? &N->opt : nullptr, /*signalled=*/true));
     if (stepped) *stepped = p2p_step;
   } else {
     ATH_TRY(comm_allreduce_sum(gflat, N->n + 1));
@@ -833,6 +835,7 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
                              st));
     ATH_CUDA(cudaStreamSynchronize(st));
     *loss = *N->pinned_loss;
+    if (use_p2p) ATH_TRY(p2p_check());
   }
   return ATHENA_OK;
 }
@@ -1421,5 +1424,6 @@ ATHENA_API int athena_cuda_network_last_loss(athena_handle_t net, float* loss) {
                            cudaMemcpyDeviceToHost, st));
   ATH_CUDA(cudaStreamSynchronize(st));
   *loss = *N->pinned_loss;
+  ATH_TRY(p2p_check());  // a gradient exchange that timed out surfaces here
   return ATHENA_OK;
 }

@@ -294,7 +294,12 @@ struct FinArgs {
   float* loss_acc;
   int do_step;
   float* xout;  // optional copy of the finished gradients + loss slot (peer-memory exchange)
+  P2PSignal sig;  // sig.world > 0: the last block to finish tells every peer "slot complete"
 };
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __global__ void __launch_bounds__(FIN_THREADS)
 k_finalize(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
@@ -355,6 +360,22 @@ k_finalize(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
       if (f.xout) f.xout[n] = loss;
     }
   }
+  if (f.sig.world > 0) {
+    // The staged vector is complete when every block has written its slice: the last block
+    // to arrive publishes it to all peers with system-scope release stores over NVLink, so the
+    // exchange kernel only waits (its progress never depends on one of its own blocks).
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int prev = atomicAdd(f.sig.done, 1u);
+      if (prev + 1 == gridDim.x) {
+        *f.sig.done = 0;
+        __threadfence_system();
+        for (int r = 0; r < f.sig.world; ++r)
+          st_release_sys(f.sig.flags[r] + f.sig.slot * P2P_MAX_WORLD + f.sig.rank, f.sig.epoch);
+      }
+    }
+  }
 }
 
 // ---- peer-memory gradient exchange fused with the step -----------------------------
@@ -372,11 +393,11 @@ struct P2PArgs {
   uint32_t epoch;
   int slot;
   int do_step;
+  int signal;            // 1: this kernel also publishes the local slot (no k_finalize before it)
+  long long timeout_ns;  // bounded wait: a missing peer sets the sticky error word instead of
+  uint32_t* err;         // hanging the GPU; the host then reports ATHENA_ERR_COMM
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -393,14 +414,25 @@ k_p2p_sum_step(float* __restrict__ p, float* __restrict__ g, float* __restrict__
                float* __restrict__ s2, long long n, P2PArgs x, StepArgs a) {
   if (threadIdx.x < x.world) {
     const int r = threadIdx.x;
-    if (blockIdx.x == 0) {
+    if (x.signal && blockIdx.x == 0) {
       __threadfence_system();  // the staged vector (written by the previous kernel) first
       st_release_sys(x.flags[r] + x.slot * P2P_MAX_WORLD + x.rank, x.epoch);
     }
     const uint32_t* mine = x.flags[x.rank] + x.slot * P2P_MAX_WORLD + r;
-    while (ld_acquire_sys(mine) != x.epoch) __nanosleep(64);
+    long long t0 = 0;
+    while (ld_acquire_sys(mine) != x.epoch) {
+      __nanosleep(64);
+      long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > x.timeout_ns || *reinterpret_cast<volatile uint32_t*>(x.err) != 0u) {
+        atomicExch(x.err, 1u);  // rank r never arrived: give up, the step is not applied
+        break;
+      }
+    }
   }
   __syncthreads();
+  if (*reinterpret_cast<volatile uint32_t*>(x.err) != 0u) return;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
   // issue all peer loads first (independent NVLink round trips overlap), then add in rank order
@@ -484,12 +516,39 @@ bool finalize_can_step(const OptimState& st) {
 // buffer; with `st` != nullptr also performs the optimiser step (caller checked
 // finalize_can_step).  More than FIN_MAX_JOBS reductions are flushed in several launches,
 // the step riding on the last one.
-int launch_p2p_sum_step(float* params, float* grads, int64_t n, OptimState* st) {
+void p2p_next_signal(P2PSignal* sig) {
+  P2PState& P = p2p();
+  *sig = P2PSignal{};
+  sig->world = P.world;
+  sig->rank = P.rank;
+  sig->epoch = P.epoch + 1;
+  sig->slot = (int)((P.epoch + 1) & 1u);
+  sig->done = reinterpret_cast<unsigned int*>(P.flags[P.rank] + P2P_DONE);
+  for (int r = 0; r < P.world; ++r) sig->flags[r] = P.flags[r];
+}
+
+int p2p_check() {
+  P2PState& P = p2p();
+  if (!P.ready) return ATHENA_OK;
+  uint32_t err = 0;
+  ATH_CUDA(cudaMemcpyAsync(&err, P.flags[P.rank] + P2P_ERR, sizeof(err), cudaMemcpyDeviceToHost,
+                           ctx().stream));
+  ATH_CUDA(cudaStreamSynchronize(ctx().stream));
+  if (err != 0) P.failed = true;
+  ATH_REQUIRE(!P.failed, ATHENA_ERR_COMM,
+              "p2p exchange: timed out waiting for a peer's gradients (a rank is missing or "
+              "out of step); parameters were not updated");
+  return ATHENA_OK;
+}
+
+int launch_p2p_sum_step(float* params, float* grads, int64_t n, OptimState* st, bool signalled) {
   P2PState& P = p2p();
   ATH_REQUIRE(P.ready && (size_t)(n + 1) <= P.cap, ATHENA_ERR_STATE,
               "p2p exchange: not initialised or gradient vector too long");
   StepArgs a{};
   if (st) ATH_TRY(step_prepare(n, *st, &a));
+  ATH_REQUIRE(!P.failed, ATHENA_ERR_COMM,
+              "p2p exchange: an earlier exchange timed out waiting for a peer");
   P2PArgs x{};
   P.epoch += 1;
   x.world = P.world;
@@ -497,6 +556,14 @@ int launch_p2p_sum_step(float* params, float* grads, int64_t n, OptimState* st) 
   x.epoch = P.epoch;
   x.slot = (int)(P.epoch & 1u);
   x.do_step = st ? 1 : 0;
+  x.signal = signalled ? 0 : 1;
+  static long long timeout_ns = -1;
+  if (timeout_ns < 0) {
+    const char* e = getenv("ATHENA_CUDA_P2P_TIMEOUT_MS");
+    timeout_ns = (e && atoll(e) > 0 ? atoll(e) : 20000ll) * 1000000ll;
+  }
+  x.timeout_ns = timeout_ns;
+  x.err = P.flags[P.rank] + P2P_ERR;
   for (int r = 0; r < P.world; ++r) {
     x.x[r] = P.xbuf[r] + (size_t)x.slot * P.cap;
     x.flags[r] = P.flags[r];
@@ -509,7 +576,8 @@ int launch_p2p_sum_step(float* params, float* grads, int64_t n, OptimState* st) 
 }
 
 int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts, float* loss_acc,
-                    float* params, float* grads, int64_t n, OptimState* st, float* xout) {
+                    float* params, float* grads, int64_t n, OptimState* st, float* xout,
+                    const P2PSignal* sig) {
   if (n == 0) return ATHENA_OK;
   cudaStream_t s = ctx().stream;
   StepArgs a{};
@@ -532,6 +600,7 @@ int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts
     f.loss_acc = loss_acc;
     f.do_step = (last && st) ? 1 : 0;
     f.xout = last ? xout : nullptr;
+    if (last && xout && sig) f.sig = *sig;
     ATH_CUDA(launch_pdl(k_finalize, dim3((unsigned)cdiv(n, FIN_ELEMS)), dim3(FIN_THREADS), 0, s,
                         params, grads, st ? st->s1.as<float>() : nullptr,
                         st ? st->s2.as<float>() : nullptr, (long long)n, f, a));

@@ -213,3 +213,28 @@ def chemical_batch(B: int, rng: np.random.Generator, n: int = 8, Fv: int = 6, Fe
     packed.x = rng.random((B * n, Fv), dtype=np.float32)
     packed.e = (0.17 + 0.83 * rng.random((packed.E, Fe))).astype(np.float32)
     return packed
+
+
+def edge_lists(p: PackedGraphs) -> Tuple[np.ndarray, np.ndarray]:
+    """The undirected edge lists a packed batch was generated from, as graphstruc holds them
+    before generate_adjacency: (num_edges [B], index_list [sum num_edges, 2]) with 1-based
+    vertex pairs per graph, edge k of a graph = its k-th pair (edge id k of adj_ja(2, :)).
+    Self loops with edge id 0 (add_self_loops) are not edges."""
+    nv = p.nv.astype(np.int64)
+    voff = np.concatenate([[0], np.cumsum(nv)])
+    zoff = np.concatenate([[0], np.cumsum(p.nz.astype(np.int64))])
+    deg = np.concatenate([np.diff(p.ia[voff[s] + s:voff[s + 1] + s + 1]) for s in range(p.B)]) \
+        if p.B < 64 else None
+    if deg is None:   # vectorised: row lengths from the concatenated per-graph row pointers
+        ia = p.ia.astype(np.int64)
+        idx = np.arange(voff[-1]) + np.repeat(np.arange(p.B), nv)
+        deg = ia[idx + 1] - ia[idx]
+    row_local = np.repeat(np.arange(voff[-1]) - np.repeat(voff[:-1], nv), deg) + 1
+    graph = np.repeat(np.repeat(np.arange(p.B), nv), deg)
+    nb, eid = p.ja[:, 0].astype(np.int64), p.ja[:, 1].astype(np.int64)
+    keep = (eid > 0) & (nb >= row_local)      # each undirected edge once (self edges: nb == row)
+    g, e, a, b = graph[keep], eid[keep], row_local[keep], nb[keep]
+    order = np.lexsort((e, g))
+    ne = np.bincount(g, minlength=p.B).astype(np.int32)
+    il = np.stack([a[order], b[order]], axis=1).astype(np.int32)
+    return ne, np.ascontiguousarray(il)

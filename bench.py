@@ -642,20 +642,35 @@ def main():
     # ---- leg 2: end to end through the public API with HOST buffers ------------------
     e2e = None
     if not args.no_e2e:
+        from athena_b200 import synth
         nbuf = 2
         host = []
         for i in range(nbuf):
             q, tg = (p, target_h) if i == 0 else make_workload(rank + 100 * i)
-            h = {"nv": q.nv, "ne": q.ne, "nz": q.nz}
-            for key, arr in (("ia", q.ia), ("ja", q.ja), ("x", q.x), ("t", tg)):
+            ne_e, il = synth.edge_lists(q)
+            h = {"nv": q.nv, "ne": q.ne, "nz": q.nz, "ne_e": ne_e}
+            for key, arr in (("ia", q.ia), ("ja", q.ja), ("x", q.x), ("t", tg), ("il", il)):
                 buf = ab.pinned_empty(arr.shape, arr.dtype)
                 buf[...] = arr
                 h[key] = buf
             host.append(h)
-        h2d = sum(host[0][k].nbytes for k in ("ia", "ja", "x", "t")) + 5 * 4 * (B + 1)
         lossf = C.c_float()
 
-        def e2e_step(i):
+        # (a) the reference's own flow: the reader hands over EDGE LISTS, generate_adjacency +
+        #     add_self_loops build the CSR -- here on the device (athena_cuda_batch_create_from_edges)
+        def e2e_step_edges(i):
+            h = host[i % nbuf]
+            bh = C.c_int64()
+            ab.check(L.athena_cuda_batch_create_from_edges(
+                C.byref(bh), B, ab.ptr(h["nv"]), ab.ptr(h["ne_e"]), ab.ptr(h["il"]), 1,
+                ab.MEM_HOST, 0))
+            ab.check(L.athena_cuda_network_train_step(net.handle, bh.value, ab.ptr(h["x"]), None,
+                                                      ab.ptr(h["t"]), ab.MEM_HOST, global_B,
+                                                      C.byref(lossf)))
+            ab.check(L.athena_cuda_batch_destroy(bh.value))
+
+        # (b) graphs that arrive with their CSR already built on the host (adj_ia / adj_ja)
+        def e2e_step_csr(i):
             h = host[i % nbuf]
             bh = C.c_int64()
             ab.check(L.athena_cuda_batch_create(C.byref(bh), B, ab.ptr(h["nv"]), ab.ptr(h["ne"]),
@@ -666,18 +681,43 @@ def main():
                                                       C.byref(lossf)))
             ab.check(L.athena_cuda_batch_destroy(bh.value))
 
-        for i in range(max(3, args.warmup // 2)):
-            e2e_step(i)
-        barrier()
+        def time_e2e(step_fn, keys):
+            for i in range(max(3, args.warmup // 2)):
+                step_fn(i)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                step_fn(i)
+            ab.check(L.athena_cuda_synchronize())
+            dt = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            h2d = sum(host[0][k].nbytes for k in keys) + 4 * 4 * (B + 1)
+            return {"value": world * Z * args.steps / dt, "unit": "edges/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                    "ms_per_step": dt / args.steps * 1e3,
+                    "host_to_device_GBps_all_ranks": world * h2d / (dt / args.steps) / 1e9}
+
+        e_edges = time_e2e(e2e_step_edges, ("il", "x", "t"))
+        e_edges["d2h_bytes_per_step"] = 4 + 4 * B   # + the per-graph entry counts of the CSR build
+        e_csr = time_e2e(e2e_step_csr, ("ia", "ja", "x", "t"))
+        e2e = dict(e_edges)
+        e2e["input"] = ("edge lists (index_list) + features + targets from pinned host memory; "
+                        "CSR built on the device (generate_adjacency + add_self_loops)")
+        e2e["csr_upload"] = e_csr   # the same step fed with host-built adj_ia / adj_ja
+
+        # (c) dataset-resident epochs (network%train is handed the whole data set once,
+        #     athena_network_sub.f90:3564-3565): batches and features stay on the device, a
+        #     step moves nothing but the loss.  Reported beside, never instead of, the above.
         t0 = time.perf_counter()
         for i in range(args.steps):
-            e2e_step(i)
-        ab.check(L.athena_cuda_synchronize())
+            ab.check(L.athena_cuda_network_train_step(net.handle, batch.handle, ab.ptr(x_d), None,
+                                                      ab.ptr(t_d), ab.MEM_DEVICE, global_B,
+                                                      C.byref(lossf)))
         dt = max_over_ranks(time.perf_counter() - t0)
         barrier()
-        e2e = {"value": world * Z * args.steps / dt, "unit": "edges/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-               "ms_per_step": dt / args.steps * 1e3}
+        e2e["dataset_resident"] = {"value": world * Z * args.steps / dt, "unit": "edges/s",
+                                   "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
+                                   "ms_per_step": dt / args.steps * 1e3}
 
     # ---- the other BASELINE.json configs ----------------------------------------------
     def sum_over_ranks(x):

@@ -1007,3 +1007,37 @@ def test_nonfinite_features_stay_confined_to_neighbours(cuda, oracle32, entry):
     assert np.abs(out[~bad] - ref[~bad]).max() <= RTOL_ACT * np.abs(ref[~bad]).max()
     ref_clean, _, _ = oracle32.layer_fwd_bwd(spec, params, to_oracle_batch(p))
     assert rel_err(clean, ref_clean) <= RTOL_ACT
+
+
+@pytest.mark.parametrize("kind", ["kipf", "duvenaud"])
+def test_dataset_resident_training_equals_streaming(cuda, kind):
+    """network%train with the data set kept on the device (the reference keeps it in memory for
+    the whole call, athena_network_sub.f90:3564-3565) is the same computation as re-sending
+    every mini-batch: identical losses and bitwise identical parameters."""
+    rng = np.random.default_rng(41)
+
+    def make():
+        net = ab.network_type()
+        if kind == "kipf":
+            net.add(ab.kipf_msgpass_layer_type([8, 16], 1, "tanh"))
+            net.add(ab.kipf_msgpass_layer_type([16, 4], 1, "none"))
+        else:
+            net.add(ab.duvenaud_msgpass_layer_type([6], [1], 2, 10, 4))
+        net.compile(ab.adam_optimiser_type(5e-3), batch_size=8)
+        return net
+    if kind == "kipf":
+        p = synth.molecular_batch(37, 8, 0, rng, nv_range=(3, 20), self_loop_features=False)
+        target = rng.standard_normal((p.V, 4)).astype(np.float32)
+    else:
+        p = synth.chemical_batch(37, rng)
+        target = rng.random((37, 4)).astype(np.float32)
+    a, b = make(), make()
+    params = random_params(a.num_params, rng, 0.3)
+    a.set_params(params)
+    b.set_params(params)
+    ha = a.train(p, target, num_epochs=3, shuffle_batches=True, seed=5)
+    hb = b.train(p, target, num_epochs=3, shuffle_batches=True, seed=5, resident=True)
+    assert ha == hb
+    assert np.array_equal(a.get_params(), b.get_params())
+    a.destroy()
+    b.destroy()
