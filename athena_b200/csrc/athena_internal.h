@@ -404,7 +404,9 @@ bool finalize_can_step(const OptimState& st);
 // written to xout[0..n] -- the staging buffer of the peer-memory exchange.
 int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts, float* loss_acc,
                     float* params, float* grads, int64_t n, OptimState* st,
-                    float* xout = nullptr, const P2PSignal* sig = nullptr);
+                    float* xout = nullptr, const P2PSignal* sig = nullptr, int exchange = 0);
+// exchange != 0: the peer-memory sum (+ the step when st != nullptr) rides on the same launch
+bool finalize_can_exchange(int64_t n);
 
 // comm (comm.cu)
 int comm_allreduce_sum(float* buf, int64_t n);  // no-op when no communicator

@@ -947,9 +947,17 @@ ATHENA_API int athena_cuda_batch_create_from_edges(athena_handle_t* batch, int32
     ATH_LAUNCHED();
   }
   // the entry counts per graph are data (self edges, missing loops): B integers come back
-  std::vector<int32_t> h_nz((size_t)B, 0);
-  ATH_CUDA(cudaMemcpyAsync(h_nz.data(), d_nz, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+  // (through a pinned buffer: a pageable destination would stage the copy)
+  static int32_t* pinned_nz = nullptr;
+  static size_t pinned_cap = 0;
+  if ((size_t)B > pinned_cap) {
+    if (pinned_nz) cudaFreeHost(pinned_nz);
+    pinned_cap = (size_t)round_up(B, 1024);
+    ATH_CUDA(cudaHostAlloc((void**)&pinned_nz, sizeof(int32_t) * pinned_cap, cudaHostAllocDefault));
+  }
+  ATH_CUDA(cudaMemcpyAsync(pinned_nz, d_nz, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   ATH_CUDA(cudaStreamSynchronize(st));
+  std::vector<int32_t> h_nz(pinned_nz, pinned_nz + B);
   athena_handle_t h = 0;
   ATH_TRY(athena_cuda_batch_create(&h, B, num_vertices, num_edges, h_nz.data(), d_ia, d_ja,
                                    ATHENA_MEM_DEVICE, 0));

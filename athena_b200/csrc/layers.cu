@@ -813,20 +813,24 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
   float* xout = use_p2p ? P.xbuf[P.rank] + (size_t)((P.epoch + 1) & 1u) * P.cap : nullptr;
   P2PSignal sig;
   if (use_p2p) p2p_next_signal(&sig);
+  const bool p2p_step = step_too && !N->opt.d.clip_min_max && !N->opt.d.clip_norm_on;
+  // one launch folds the partials, publishes the slot, waits for the peers, sums and steps
+  const bool fuse_exchange = use_p2p && defer.jobs.size() <= 8 && finalize_can_exchange(N->n);
   if (!defer.jobs.empty() || fo.fused || use_p2p) {
     const bool fuse_step = step_too && finalize_can_step(N->opt);
+    OptimState* fst = fuse_exchange ? (p2p_step ? &N->opt : nullptr) : (fuse_step ? &N->opt : nullptr);
     ATH_TRY(launch_finalize(defer, fo.fused ? fo.loss_part : nullptr, fo.num_parts, gflat + N->n,
-                            N->flat_params.as<float>(), gflat, N->n,
-                            fuse_step ? &N->opt : nullptr, xout, use_p2p ? &sig : nullptr));
-    if (stepped) *stepped = fuse_step;
+                            N->flat_params.as<float>(), gflat, N->n, fst, xout,
+                            use_p2p ? &sig : nullptr, fuse_exchange ? 1 : 0));
+    if (stepped) *stepped = fuse_exchange ? p2p_step : fuse_step;
   }
-  if (use_p2p) {
-    // signal + wait + sum over NVLink + (when no clipping intervenes) the step, in one kernel
-    const bool p2p_step = step_too && !N->opt.d.clip_min_max && !N->opt.d.clip_norm_on;
+  if (use_p2p && !fuse_exchange) {
+    // signal (done by the finalize launch) + wait + sum over NVLink + (when no clipping
+    // intervenes) the step, in one kernel
     ATH_TRY(launch_p2p_sum_step(N->flat_params.as<float>(), gflat, N->n,
                                 p2p_step ? &N->opt : nullptr, /*signalled=*/true));
     if (stepped) *stepped = p2p_step;
-  } else {
+  } else if (!use_p2p) {
     ATH_TRY(comm_allreduce_sum(gflat, N->n + 1));
   }
   ATH_TRY(record_mark());

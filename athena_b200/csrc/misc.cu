@@ -295,10 +295,27 @@ struct FinArgs {
   int do_step;
   float* xout;  // optional copy of the finished gradients + loss slot (peer-memory exchange)
   P2PSignal sig;  // sig.world > 0: the last block to finish tells every peer "slot complete"
+  // exchange fused into this launch (the whole grid is co-resident): after the signal every
+  // block waits for the peers' flags, adds the staged vectors of all ranks in rank order and
+  // (xstep) applies the optimiser step -- what k_p2p_sum_step does in a launch of its own
+  int xfused, xstep;
+  const float* xin[P2P_MAX_WORLD];
+  long long timeout_ns;
+  uint32_t* err;
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
 }
 
 __global__ void __launch_bounds__(FIN_THREADS)
@@ -376,6 +393,43 @@ k_finalize(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
       }
     }
   }
+  if (f.xfused) {
+    if (threadIdx.x < f.sig.world) {
+      const uint32_t* mine =
+          f.sig.flags[f.sig.rank] + f.sig.slot * P2P_MAX_WORLD + threadIdx.x;
+      long long t0 = 0;
+      while (ld_acquire_sys(mine) != f.sig.epoch) {
+        __nanosleep(64);
+        long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        if (now - t0 > f.timeout_ns || *reinterpret_cast<volatile uint32_t*>(f.err) != 0u) {
+          atomicExch(f.err, 1u);
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    if (*reinterpret_cast<volatile uint32_t*>(f.err) != 0u) return;
+    const bool loss_slot = blockIdx.x == 0 && threadIdx.x == FIN_ELEMS;  // one spare thread
+    if ((grp == 0 && i < n) || loss_slot) {
+      const long long k = loss_slot ? n : i;
+      float v[P2P_MAX_WORLD];
+#pragma unroll
+      for (int r = 0; r < P2P_MAX_WORLD; ++r)
+        v[r] = r < f.sig.world ? ld_relaxed_sys(f.xin[r] + k) : 0.f;
+      float tot = 0.f;
+#pragma unroll
+      for (int r = 0; r < P2P_MAX_WORLD; ++r)
+        if (r < f.sig.world) tot += v[r];
+      if (loss_slot || !f.xstep) {
+        g[k] = tot;
+      } else {
+        step_one(p, s1, s2, k, tot, a);
+        g[k] = 0.f;
+      }
+    }
+  }
 }
 
 // ---- peer-memory gradient exchange fused with the step -----------------------------
@@ -398,16 +452,6 @@ struct P2PArgs {
   uint32_t* err;         // hanging the GPU; the host then reports ATHENA_ERR_COMM
 };
 
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
-}
 
 __global__ void __launch_bounds__(RED_THREADS)
 k_p2p_sum_step(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
@@ -516,6 +560,15 @@ bool finalize_can_step(const OptimState& st) {
 // buffer; with `st` != nullptr also performs the optimiser step (caller checked
 // finalize_can_step).  More than FIN_MAX_JOBS reductions are flushed in several launches,
 // the step riding on the last one.
+static long long p2p_timeout_ns() {
+  static long long t = -1;
+  if (t < 0) {
+    const char* e = getenv("ATHENA_CUDA_P2P_TIMEOUT_MS");
+    t = (e && atoll(e) > 0 ? atoll(e) : 20000ll) * 1000000ll;
+  }
+  return t;
+}
+
 void p2p_next_signal(P2PSignal* sig) {
   P2PState& P = p2p();
   *sig = P2PSignal{};
@@ -557,12 +610,7 @@ int launch_p2p_sum_step(float* params, float* grads, int64_t n, OptimState* st, 
   x.slot = (int)(P.epoch & 1u);
   x.do_step = st ? 1 : 0;
   x.signal = signalled ? 0 : 1;
-  static long long timeout_ns = -1;
-  if (timeout_ns < 0) {
-    const char* e = getenv("ATHENA_CUDA_P2P_TIMEOUT_MS");
-    timeout_ns = (e && atoll(e) > 0 ? atoll(e) : 20000ll) * 1000000ll;
-  }
-  x.timeout_ns = timeout_ns;
+  x.timeout_ns = p2p_timeout_ns();
   x.err = P.flags[P.rank] + P2P_ERR;
   for (int r = 0; r < P.world; ++r) {
     x.x[r] = P.xbuf[r] + (size_t)x.slot * P.cap;
@@ -575,13 +623,39 @@ int launch_p2p_sum_step(float* params, float* grads, int64_t n, OptimState* st, 
   return ATHENA_OK;
 }
 
+// The exchange can ride on the finalize launch when all its blocks are resident at once (every
+// block waits for the peers after the LAST local block has published the slot).
+bool finalize_can_exchange(int64_t n) {
+  static int cap = -1;
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("ATHENA_CUDA_NO_FUSED_EXCHANGE");
+    off = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  if (cap < 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finalize, FIN_THREADS, 0) !=
+        cudaSuccess)
+      per_sm = 0;
+    cap = per_sm * ctx().sm_count;
+  }
+  return !off && cdiv(n, FIN_ELEMS) <= cap;
+}
+
 int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts, float* loss_acc,
                     float* params, float* grads, int64_t n, OptimState* st, float* xout,
-                    const P2PSignal* sig) {
+                    const P2PSignal* sig, int exchange) {
   if (n == 0) return ATHENA_OK;
   cudaStream_t s = ctx().stream;
   StepArgs a{};
   if (st) ATH_TRY(step_prepare(n, *st, &a));
+  P2PState& PS = p2p();
+  if (exchange) {
+    ATH_REQUIRE(sig && xout && PS.ready && dl.jobs.size() <= (size_t)FIN_MAX_JOBS, ATHENA_ERR_STATE,
+                "finalize: fused exchange without a prepared slot");
+    ATH_REQUIRE(!PS.failed, ATHENA_ERR_COMM,
+                "p2p exchange: an earlier exchange timed out waiting for a peer");
+  }
   size_t done = 0;
   do {
     FinArgs f{};
@@ -598,13 +672,22 @@ int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts
     f.loss_part = last ? loss_part : nullptr;
     f.loss_nparts = loss_nparts;
     f.loss_acc = loss_acc;
-    f.do_step = (last && st) ? 1 : 0;
+    f.do_step = (last && st && !exchange) ? 1 : 0;
     f.xout = last ? xout : nullptr;
     if (last && xout && sig) f.sig = *sig;
+    if (last && exchange) {
+      f.xfused = 1;
+      f.xstep = st ? 1 : 0;
+      for (int r = 0; r < PS.world; ++r) f.xin[r] = PS.xbuf[r] + (size_t)sig->slot * PS.cap;
+      f.timeout_ns = p2p_timeout_ns();
+      f.err = PS.flags[PS.rank] + P2P_ERR;
+      PS.epoch += 1;  // this launch IS the exchange
+    }
     ATH_CUDA(launch_pdl(k_finalize, dim3((unsigned)cdiv(n, FIN_ELEMS)), dim3(FIN_THREADS), 0, s,
                         params, grads, st ? st->s1.as<float>() : nullptr,
                         st ? st->s2.as<float>() : nullptr, (long long)n, f, a));
-    ATH_LAUNCHED_T(f.do_step ? "finalize_step" : "finalize");
+    ATH_LAUNCHED_T(f.xfused ? (f.xstep ? "finalize_exchange_step" : "finalize_exchange")
+                            : f.do_step ? "finalize_step" : "finalize");
   } while (done < dl.jobs.size());
   return ATHENA_OK;
 }
