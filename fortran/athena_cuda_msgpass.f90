@@ -27,6 +27,7 @@ module athena__cuda_msgpass
   public :: cuda_msgpass_forward, cuda_msgpass_backward
   public :: cuda_register_output_nodes, get_partial_cuda_layer_val
   public :: cuda_network_update, cuda_train_batch
+  public :: cuda_network_add, cuda_batch_from_edges
   public :: cuda_optimiser_desc
 
   !> Device twin of graph(:) -- built once per mini-batch and shared by every
@@ -84,6 +85,54 @@ contains
        this%handle = 0_c_int64_t
     end if
   end subroutine batch_destroy
+
+  !> graph%generate_adjacency(index_list) [+ graph%add_self_loops()] for a whole mini-batch on
+  !> the device: what the readers do per sample before set_graph
+  !> (example_library/src/mod_read_chemical_graphs.f90:275-276, example/msgpass_euler/src/
+  !> mod_read_euler.f90:48, example/msgpass_chemical/src/main.f90:108).  index_list is the
+  !> concatenation of the samples' index_list(2, num_edges(s)).
+  subroutine cuda_batch_from_edges(this, num_vertices, num_edges, index_list, self_loops)
+    class(cuda_graph_batch_type), intent(inout) :: this
+    integer(c_int32_t), intent(in) :: num_vertices(:), num_edges(:)
+    integer(c_int32_t), intent(in) :: index_list(:,:)
+    logical, intent(in) :: self_loops
+    call this%destroy()
+    call athena_cuda_check(athena_cuda_batch_create_from_edges(this%handle, &
+         int(size(num_vertices), c_int32_t), num_vertices, num_edges, index_list, &
+         merge(1_c_int32_t, 0_c_int32_t, self_loops), ATHENA_MEM_HOST, 1_c_int32_t))
+    this%num_graphs = size(num_vertices)
+    this%num_vertices = sum(num_vertices)
+    this%num_edges = sum(num_edges)
+  end subroutine cuda_batch_from_edges
+
+  !> network%add(layer, input_list, operator) (athena_network_sub.f90:764-830) for a device
+  !> layer: the ids go through as the caller wrote them (0 = input layer, k > 0 the k-th added
+  !> layer, k < 0 counted back from this one); "||" / "concat" / "concatenate" / "append" = 1
+  !> as in :808-811, anything the device path does not implement stops like the reference's
+  !> "invalid operator".
+  subroutine cuda_network_add(net_handle, layer_handle, input_list, operator)
+    integer(c_int64_t), intent(in) :: net_handle, layer_handle
+    integer, dimension(:), optional, intent(in) :: input_list
+    character(*), optional, intent(in) :: operator
+    integer(c_int32_t) :: op
+    if (.not. present(input_list)) then
+       call athena_cuda_check(athena_cuda_network_add(net_handle, layer_handle))
+       return
+    end if
+    op = 1_c_int32_t
+    if (present(operator)) then
+       select case (trim(operator))
+       case ("||", "concat", "concatenate", "append")
+          op = 1_c_int32_t
+       case ("+", "add")
+          op = 2_c_int32_t
+       case default
+          op = 0_c_int32_t
+       end select
+    end if
+    call athena_cuda_check(athena_cuda_network_add_inputs(net_handle, layer_handle, &
+         int(size(input_list), c_int32_t), int(input_list, c_int32_t), op))
+  end subroutine cuda_network_add
 
   !> Body of update_message_* + update_readout_*: input(1,s)%val(F,V_s) and
   !> input(2,s)%val(Fe,E_s) are concatenated over s (already contiguous per
