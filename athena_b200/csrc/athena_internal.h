@@ -67,6 +67,10 @@ struct Context {
   bool mark_valid = false;
   cudaEvent_t ev_pool[32] = {};
   int ev_next = 0;
+  // direction in which the next fused tile kernel walks its tiles; flips with every launch so
+  // that a kernel starts with what its predecessor wrote last (L2-resident), and is reset at
+  // the start of every forward / train call (results stay bitwise reproducible per call)
+  bool tile_reverse = false;
 };
 Context& ctx();
 int ensure_init();

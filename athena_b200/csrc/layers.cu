@@ -117,6 +117,7 @@ struct FwdOpts {
   int num_parts = 0;
   bool fused = false;
   float mse_denom = 0.f;  // Duvenaud-last: num_outputs * global batch (one [no, batch] cell)
+  bool in_network = false;  // the network walk owns Context::tile_reverse
 };
 
 static int kipf_forward(Layer* L, Batch* b, const float* x, const float** out,
@@ -361,6 +362,7 @@ static int full_backward(Layer* L, Batch* b, const float* gout, float* gin) {
 
 int layer_forward_dev(Layer* L, Batch* b, const float* x, const float* e, const float** out,
                       FwdOpts* fo = nullptr) {
+  if (fo == nullptr || !fo->in_network) ctx().tile_reverse = false;  // per-call determinism
   ATH_REQUIRE(x != nullptr || b->V == 0, ATHENA_ERR_ARG, "forward: vertex_features is null");
   L->fwd_batch = b;
   L->fwd_V = b->V;
@@ -654,6 +656,10 @@ static int net_forward_dev(Network* N, Batch* b, const float* x, const float* e,
                            const float** out, FwdOpts* fo = nullptr) {
   const float* in = x;
   std::vector<const float*> outs(N->layers.size(), nullptr);
+  ctx().tile_reverse = false;  // the walk alternates from here: results reproducible per call
+  FwdOpts inner;
+  inner.in_network = true;
+  if (fo) fo->in_network = true;
   for (size_t l = 0; l < N->layers.size(); ++l) {
     Layer* L = N->layers[l];
     if (N->has_skips && !N->inputs[l].empty()) {
@@ -671,7 +677,7 @@ static int net_forward_dev(Network* N, Batch* b, const float* x, const float* e,
       in = cat.as<float>();
     }
     const float* o = nullptr;
-    ATH_TRY(layer_forward_dev(L, b, in, e, &o, l + 1 == N->layers.size() ? fo : nullptr));
+    ATH_TRY(layer_forward_dev(L, b, in, e, &o, (l + 1 == N->layers.size() && fo) ? fo : &inner));
     outs[l] = o;
     in = o;
   }

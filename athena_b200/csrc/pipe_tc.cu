@@ -501,6 +501,7 @@ struct TnJobs {
   const float* G[TN_MAX_JOBS];
   float* part[TN_MAX_JOBS];   // [gridDim.x][K * N] per job
   long long M[TN_MAX_JOBS];
+  int reverse;                // walk the stages of every job from the last to the first
 };
 
 template <int N>
@@ -607,7 +608,7 @@ k_pipe_tn(TnJobs jobs) {
         const int s = j % Cfg::NS;
         const uint32_t ph = (j / Cfg::NS) & 1;
         mbar_wait(&empty[s], ph ^ 1u);
-        const long long r0 = t * Cfg::RS;
+        const long long r0 = (jobs.reverse ? ntiles - 1 - t : t) * Cfg::RS;
         const int rows = static_cast<int>(min(static_cast<long long>(Cfg::RS), M - r0));
         uint8_t* st = ring + s * Cfg::STAGE_BYTES;
         mbar_arrive_expect_tx(&full[s], rows * (K + N) * 4);
@@ -718,7 +719,7 @@ k_pipe_tn(TnJobs jobs) {
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
         const int s = j % Cfg::NS;
         const uint32_t ph = (j / Cfg::NS) & 1;
-        const long long r0 = t * Cfg::RS;
+        const long long r0 = (jobs.reverse ? ntiles - 1 - t : t) * Cfg::RS;
         const int rows = static_cast<int>(min(static_cast<long long>(Cfg::RS), M - r0));
         const float* raw = reinterpret_cast<const float*>(ring + s * Cfg::STAGE_BYTES);
         mbar_wait(&full[s], ph);
@@ -760,7 +761,7 @@ k_pipe_tn(TnJobs jobs) {
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
         const int s = j % Cfg::NS;
         const uint32_t ph = (j / Cfg::NS) & 1;
-        const long long r0 = t * Cfg::RS;
+        const long long r0 = (jobs.reverse ? ntiles - 1 - t : t) * Cfg::RS;
         const int rows = static_cast<int>(min(static_cast<long long>(Cfg::RS), M - r0));
         const uint8_t* st = ring + s * Cfg::STAGE_BYTES + Cfg::P_RAW;
         mbar_wait(&full[s], ph);
@@ -974,12 +975,16 @@ static int launch_pipe_tn_t(const TnPending* jobs, int njobs, DeferList* defer) 
   const int grid = (int)std::min<int64_t>(max_tiles, (int64_t)ctx().sm_count);
   TnJobs tj{};
   tj.n = njobs;
+  // the product queued LAST reads the gradient the reverse sweep has just written: it runs
+  // first, and the stages are walked against the direction of the kernel that wrote them
+  tj.reverse = ctx().tile_reverse ? 1 : 0;
   for (int q = 0; q < njobs; ++q) {
-    ATH_TRY(jobs[q].scratch->reserve(sizeof(float) * (size_t)grid * Cfg::K * N));
-    tj.P[q] = jobs[q].P;
-    tj.G[q] = jobs[q].G;
-    tj.part[q] = jobs[q].scratch->template as<float>();
-    tj.M[q] = jobs[q].M;
+    const int src = njobs - 1 - q;
+    ATH_TRY(jobs[src].scratch->reserve(sizeof(float) * (size_t)grid * Cfg::K * N));
+    tj.P[q] = jobs[src].P;
+    tj.G[q] = jobs[src].G;
+    tj.part[q] = jobs[src].scratch->template as<float>();
+    tj.M[q] = jobs[src].M;
   }
   ATH_CUDA(launch_pdl(k_pipe_tn<N>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, ctx().stream, tj));
   ATH_LAUNCHED_T("pipe_tn");

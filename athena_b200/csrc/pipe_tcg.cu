@@ -88,6 +88,11 @@ __device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity, int 
 #endif
 }
 
+// Consecutive kernels of a step walk the tiles in opposite directions (GatherArgs::reverse):
+// what the previous kernel wrote LAST (still in the 126 MB L2, much of it not even written
+// back yet) is what this kernel reads FIRST.  `t` stays the logical index everywhere.
+#define TCG_TILE(t) (a.reverse ? a.num_tiles - 1 - (t) : (t))
+
 constexpr int TCG_TRACE_TILES = 16;
 #define TCG_TRACE(role, slot)                                                            \
   do {                                                                                   \
@@ -366,7 +371,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
         TCG_TRACE(0, 0);
         mbar_wait_g(&empty[s], ph ^ 1u, 0);
         TCG_TRACE(0, 1);
-        const int4 ti = __ldg(a.tiles + t);
+        const int4 ti = __ldg(a.tiles + TCG_TILE(t));
         const int r0 = ti.x, nrows = ti.y;
         const int ra = r0 & ~3, rcnt = (r0 + nrows - ra + 3) & ~3;
         uint8_t* st = ring + s * Cfg::STAGE_BYTES;
@@ -385,7 +390,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
       for (int t = blockIdx.x; t < a.num_tiles; t += step, ++j) {
         const int b = j & 1;
         mbar_wait_g(&aux_empty[b], ((j >> 1) & 1) ^ 1u, 13);
-        const int4 ti = __ldg(a.tiles + t);
+        const int4 ti = __ldg(a.tiles + TCG_TILE(t));
         mbar_arrive_expect_tx(&aux_full[b], Cfg::AUX_TMA_TILE);
         tma_load_2d(sAuxT + b * Cfg::AUX_TMA_TILE, &aux_map, 0, ti.x, &aux_full[b]);
         tma_load_2d(sAuxT + b * Cfg::AUX_TMA_TILE + TILE_ROWS * 128, &aux_map, 32, ti.x,
@@ -477,11 +482,11 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
     const bool use_aux = (EPI != EPI_ACT) && a.aux != nullptr && !use_mask;
     const bool out_tma = (a.store_tma & 1) != 0;
     const int my_row = q * 32 + lane;
-    auto tile_at = [&](int t) { return t < a.num_tiles ? __ldg(a.tiles + t) : make_int4(0, 0, 0, 0); };
+    auto tile_at = [&](int t) { return t < a.num_tiles ? __ldg(a.tiles + TCG_TILE(t)) : make_int4(0, 0, 0, 0); };
     auto count_at = [&](int t) {
       int c = 1;
       if (EPI == EPI_MSE && t < a.num_tiles) {
-        const int4 ti = __ldg(a.tiles + t);
+        const int4 ti = __ldg(a.tiles + TCG_TILE(t));
         if (my_row < ti.y) c = __ldg(a.vcount + ti.x + my_row);
       }
       return c;
@@ -513,7 +518,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
       const bool dry = j < 0;
       const int t = blockIdx.x + j * step;
       const int b = dry ? 1 : (j & 1);
-      const int4 ti = dry ? make_int4(0, 0, 0, 0) : __ldg(a.tiles + t);
+      const int4 ti = dry ? make_int4(0, 0, 0, 0) : __ldg(a.tiles + TCG_TILE(t));
       const int count = count_next;
       if (!dry) count_next = count_at(t + step);
       const bool row_valid = my_row < ti.y;
@@ -627,7 +632,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
     auto rs_at = [&](int t) {
       float w = 1.f;
       if (has_coef && t < a.num_tiles) {
-        const int4 ti = __ldg(a.tiles + t);
+        const int4 ti = __ldg(a.tiles + TCG_TILE(t));
         if (my_row < ti.y) w = __ldg(a.rs + ti.x + my_row);
       }
       return w;
@@ -637,7 +642,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
       const bool dry = j < 0;
       const int t = blockIdx.x + j * step;
       const int b = dry ? 1 : (j & 1);
-      const int4 ti = dry ? make_int4(0, 0, 0, 0) : __ldg(a.tiles + t);
+      const int4 ti = dry ? make_int4(0, 0, 0, 0) : __ldg(a.tiles + TCG_TILE(t));
       const float wv = w_next;
       if (!dry) {
         w_next = rs_at(t + step);
@@ -714,7 +719,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
     auto bits_at = [&](int t) {
       uint4 w = make_uint4(0u, 0u, 0u, 0u);
       if (t < a.num_tiles) {
-        const int4 ti = __ldg(a.tiles + t);
+        const int4 ti = __ldg(a.tiles + TCG_TILE(t));
         if (my_row < ti.y) w = __ldg(a.abits + ti.x + my_row);
       }
       return w;
@@ -765,7 +770,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
       const int jr = dry ? 0 : j;
       const int s = jr % ns;
       const uint32_t ph = (jr / ns) & 1;
-      const int4 ti = dry ? make_int4(0, 0, 0, 0) : __ldg(a.tiles + t);
+      const int4 ti = dry ? make_int4(0, 0, 0, 0) : __ldg(a.tiles + TCG_TILE(t));
       const int r0 = ti.x, nrows = ti.y;
       const uint8_t* st = ring + s * Cfg::STAGE_BYTES;
       const float* rss = reinterpret_cast<const float*>(st + Cfg::X_BYTES) + (r0 - (r0 & ~3));
@@ -881,6 +886,13 @@ int launch_tcg_t(const GatherArgs& a) {
   const int grid = std::min(a.num_tiles, ctx().sm_count);
   GatherArgs b = a;
   b.trace = nullptr;
+  b.reverse = ctx().tile_reverse ? 1 : 0;
+  static int no_reverse = -1;
+  if (no_reverse < 0) {
+    const char* e = getenv("ATHENA_DEBUG_NO_REVERSE");  // A/B switch: always first to last
+    no_reverse = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  if (!no_reverse) ctx().tile_reverse = !ctx().tile_reverse;
   alignas(64) CUtensorMap aux_map;
   memset(&aux_map, 0, sizeof(aux_map));
   static int no_tma = -1;
