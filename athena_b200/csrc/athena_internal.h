@@ -104,6 +104,8 @@ void prof_mark(const char* tag);  // no-op unless profiling is on
 // it calls pdl_wait() before it touches anything the previous kernel wrote.  Kernels launched
 // this way MUST call pdl_wait().  ATHENA_CUDA_DISABLE_PDL=1 launches them plainly.
 bool pdl_enabled();
+constexpr int L2_HINTS_DEFAULT = 23;  // measured best: read-once loads and P stores evict_first, nothing evict_last
+int l2_hint_mask();  // ATHENA_DEBUG_L2_HINTS (see pipe_tcg.cu)
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                               cudaStream_t stream, Args&&... args) {

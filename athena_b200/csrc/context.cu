@@ -16,6 +16,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int l2_hint_mask() {
+  static int m = -1;
+  if (m < 0) {
+    const char* e = getenv("ATHENA_DEBUG_L2_HINTS");
+    m = e ? atoi(e) : L2_HINTS_DEFAULT;
+  }
+  return m;
+}
+
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {

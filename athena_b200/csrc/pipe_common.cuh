@@ -57,6 +57,8 @@ struct GatherArgs {
   int aux_tma;            // pipe_tcg fwd+MSE: the target tile arrives by TMA tensor copies
   int store_tma;          // pipe_tcg: bit 0 / 1: `out` / `P` leave through TMA tensor stores
   int reverse;            // pipe_tcg: walk the tiles from the last to the first
+  // L2 policies of the bulk copies (0 default, 1 evict_first, 2 evict_last):
+  int hint_x, hint_aux, hint_out, hint_p;
   // EPI_MSE (mse_loss_type%compute for graph outputs, athena_loss.f90:416-427)
   const int32_t* vcount;  // [V] vertices of the vertex's graph (Batch::vcount)
   float* loss_part;       // [gridDim.x] sum over this CTA's rows of (p-e)^2 / (N * nv_s)

@@ -502,6 +502,7 @@ struct TnJobs {
   float* part[TN_MAX_JOBS];   // [gridDim.x][K * N] per job
   long long M[TN_MAX_JOBS];
   int reverse;                // walk the stages of every job from the last to the first
+  int evict_first;            // both operands are read for the last time: L2 evict_first
 };
 
 template <int N>
@@ -612,8 +613,14 @@ k_pipe_tn(TnJobs jobs) {
         const int rows = static_cast<int>(min(static_cast<long long>(Cfg::RS), M - r0));
         uint8_t* st = ring + s * Cfg::STAGE_BYTES;
         mbar_arrive_expect_tx(&full[s], rows * (K + N) * 4);
-        bulk_g2s(st, P + r0 * K, rows * K * 4, &full[s]);
-        bulk_g2s(st + Cfg::P_RAW, G + r0 * N, rows * N * 4, &full[s]);
+        if (jobs.evict_first) {
+          const uint64_t pol = l2_policy_evict_first();
+          bulk_g2s_hint(st, P + r0 * K, rows * K * 4, &full[s], pol);
+          bulk_g2s_hint(st + Cfg::P_RAW, G + r0 * N, rows * N * 4, &full[s], pol);
+        } else {
+          bulk_g2s(st, P + r0 * K, rows * K * 4, &full[s]);
+          bulk_g2s(st + Cfg::P_RAW, G + r0 * N, rows * N * 4, &full[s]);
+        }
       }
       __syncwarp();
       job_sync<Cfg::THREADS>();
@@ -978,6 +985,7 @@ static int launch_pipe_tn_t(const TnPending* jobs, int njobs, DeferList* defer) 
   // the product queued LAST reads the gradient the reverse sweep has just written: it runs
   // first, and the stages are walked against the direction of the kernel that wrote them
   tj.reverse = ctx().tile_reverse ? 1 : 0;
+  tj.evict_first = (l2_hint_mask() & 16) ? 1 : 0;
   for (int q = 0; q < njobs; ++q) {
     const int src = njobs - 1 - q;
     ATH_TRY(jobs[src].scratch->reserve(sizeof(float) * (size_t)grid * Cfg::K * N));

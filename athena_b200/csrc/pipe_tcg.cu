@@ -364,6 +364,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
   if (warp == Cfg::PRODUCER_WARP) {
     // ===================== producer: TMA bulk copies into the ring =====================
     if (lane == 0) {
+      const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
       int j = 0;
       for (int t = blockIdx.x; t < a.num_tiles; t += step, ++j) {
         const int s = j % ns;
@@ -377,7 +378,9 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
         uint8_t* st = ring + s * Cfg::STAGE_BYTES;
         const uint32_t xb = nrows * F * 4, rb = rcnt * 4;
         mbar_arrive_expect_tx(&full[s], xb + (has_coef ? rb : 0u));
-        bulk_g2s(st, a.X + static_cast<size_t>(r0) * F, xb, &full[s]);
+        if (a.hint_x == 1) bulk_g2s_hint(st, a.X + static_cast<size_t>(r0) * F, xb, &full[s], pol_first);
+        else if (a.hint_x == 2) bulk_g2s_hint(st, a.X + static_cast<size_t>(r0) * F, xb, &full[s], pol_last);
+        else bulk_g2s(st, a.X + static_cast<size_t>(r0) * F, xb, &full[s]);
         if (has_coef) bulk_g2s(st + Cfg::X_BYTES, a.rs + ra, rb, &full[s]);
       }
     }
@@ -392,9 +395,16 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
         mbar_wait_g(&aux_empty[b], ((j >> 1) & 1) ^ 1u, 13);
         const int4 ti = __ldg(a.tiles + TCG_TILE(t));
         mbar_arrive_expect_tx(&aux_full[b], Cfg::AUX_TMA_TILE);
-        tma_load_2d(sAuxT + b * Cfg::AUX_TMA_TILE, &aux_map, 0, ti.x, &aux_full[b]);
-        tma_load_2d(sAuxT + b * Cfg::AUX_TMA_TILE + TILE_ROWS * 128, &aux_map, 32, ti.x,
-                    &aux_full[b]);
+        if (a.hint_aux == 1) {
+          const uint64_t pol = l2_policy_evict_first();
+          tma_load_2d_hint(sAuxT + b * Cfg::AUX_TMA_TILE, &aux_map, 0, ti.x, &aux_full[b], pol);
+          tma_load_2d_hint(sAuxT + b * Cfg::AUX_TMA_TILE + TILE_ROWS * 128, &aux_map, 32, ti.x,
+                           &aux_full[b], pol);
+        } else {
+          tma_load_2d(sAuxT + b * Cfg::AUX_TMA_TILE, &aux_map, 0, ti.x, &aux_full[b]);
+          tma_load_2d(sAuxT + b * Cfg::AUX_TMA_TILE + TILE_ROWS * 128, &aux_map, 32, ti.x,
+                      &aux_full[b]);
+        }
       }
     }
   } else if (warp == Cfg::MMA_WARP) {
@@ -598,8 +608,14 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
         const uint8_t* src = inplace_swz ? aux_tile + q * 4096 : stage;
         if (out_tma && rows_valid == 32) {
           if (lane == 0) {
-            tma_store_2d(&out_map, 0, ti.x + q * 32, src);
-            tma_store_2d(&out_map, 32, ti.x + q * 32, src + box_pitch);
+            if (a.hint_out == 2) {
+              const uint64_t pol = l2_policy_evict_last();
+              tma_store_2d_hint(&out_map, 0, ti.x + q * 32, src, pol);
+              tma_store_2d_hint(&out_map, 32, ti.x + q * 32, src + box_pitch, pol);
+            } else {
+              tma_store_2d(&out_map, 0, ti.x + q * 32, src);
+              tma_store_2d(&out_map, 32, ti.x + q * 32, src + box_pitch);
+            }
             bulk_commit();
             if (inplace_swz) bulk_wait_read0();  // the target buffer is handed back below
           }
@@ -700,8 +716,14 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
         __syncwarp();
         if (p_tma && rows_valid == 32) {
           if (lane == 0) {
-            tma_store_2d(&p_map, 0, ti.x + q * 32, stage);
-            tma_store_2d(&p_map, 32, ti.x + q * 32, stage + 4096);
+            if (a.hint_p == 1) {
+              const uint64_t pol = l2_policy_evict_first();
+              tma_store_2d_hint(&p_map, 0, ti.x + q * 32, stage, pol);
+              tma_store_2d_hint(&p_map, 32, ti.x + q * 32, stage + 4096, pol);
+            } else {
+              tma_store_2d(&p_map, 0, ti.x + q * 32, stage);
+              tma_store_2d(&p_map, 32, ti.x + q * 32, stage + 4096);
+            }
             bulk_commit();
           }
         } else if (rows_valid > 0) {
@@ -886,6 +908,19 @@ int launch_tcg_t(const GatherArgs& a) {
   const int grid = std::min(a.num_tiles, ctx().sm_count);
   GatherArgs b = a;
   b.trace = nullptr;
+  // L2 policies of the bulk copies: what this kernel reads for the last time must not evict
+  // what the next kernel reads first.  ATHENA_DEBUG_L2_HINTS = bit mask (A/B runs): 1 input
+  // tile evict_first (forward), 2 target evict_first, 4 P store evict_first (only the dW
+  // product at the end of the reverse sweep reads it), 8 output store evict_last (the next
+  // kernel's input), 16 dW product: operands evict_first.
+  const int hints = l2_hint_mask();
+  // 32 / 64: gradient written by fwd + MSE / by the reverse step evict_last; 128: the reverse
+  // step's input gradient (read again by the dW product) evict_last
+  b.hint_x = EPI == EPI_ACTGRAD ? ((hints & 128) ? 2 : 0) : ((hints & 1) ? 1 : 0);
+  b.hint_aux = (hints & 2) && EPI == EPI_MSE ? 1 : 0;
+  b.hint_p = (hints & 4) ? 1 : 0;
+  b.hint_out = EPI == EPI_ACT ? ((hints & 8) ? 2 : 0)
+               : EPI == EPI_MSE ? ((hints & 32) ? 2 : 0) : ((hints & 64) ? 2 : 0);
   b.reverse = ctx().tile_reverse ? 1 : 0;
   static int no_reverse = -1;
   if (no_reverse < 0) {
