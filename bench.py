@@ -700,15 +700,19 @@ def main():
         e_edges = time_e2e(e2e_step_edges, ("il", "x", "t"))
         e_edges["d2h_bytes_per_step"] = 4 + 4 * B   # + the per-graph entry counts of the CSR build
         e_csr = time_e2e(e2e_step_csr, ("ia", "ja", "x", "t"))
-        # headline: graph_type samples as athena's set_graph receives them (adj_ia / adj_ja built
-        # by the caller), as in round 1; the edge-list route ships 10 % fewer bytes but pays one
-        # small read-back (the entry counts) in the middle of the step
-        e2e = dict(e_csr)
-        e2e["input"] = ("adj_ia / adj_ja + features + targets from pinned host memory "
-                        "(athena_cuda_batch_create + athena_cuda_network_train_step)")
+        # headline = the faster of the two public routes (both ship every byte of the step from
+        # pinned host memory): graph_type samples with the CSR built by the caller (adj_ia /
+        # adj_ja, as set_graph receives them) or EDGE LISTS with generate_adjacency +
+        # add_self_loops done on the device (10 % fewer bytes, one small read-back in the middle
+        # of the step: slower on an idle host, faster once several ranks share the host's memory)
+        e_csr["input"] = ("adj_ia / adj_ja + features + targets from pinned host memory "
+                          "(athena_cuda_batch_create + athena_cuda_network_train_step)")
         e_edges["input"] = ("edge lists (index_list) + features + targets from pinned host memory; "
-                            "CSR built on the device (generate_adjacency + add_self_loops)")
-        e2e["from_edge_lists"] = e_edges
+                            "CSR built on the device (athena_cuda_batch_create_from_edges + "
+                            "athena_cuda_network_train_step)")
+        best, other = (e_csr, e_edges) if e_csr["value"] >= e_edges["value"] else (e_edges, e_csr)
+        e2e = dict(best)
+        e2e["other_route"] = other
 
         # (c) dataset-resident epochs (network%train is handed the whole data set once,
         #     athena_network_sub.f90:3564-3565): batches and features stay on the device, a
