@@ -73,6 +73,37 @@ k_aggregate(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col
         if (HAS_COEF) myc = __ldg(coef + myw);
       }
       const int cnt = min(G, end - w0);
+      if (MAXC == 1 && G >= 4) {
+        // four neighbour rows in flight per lane group: the gathers of a batch are issued
+        // before the first of them is consumed (a row of a few hundred entries is otherwise a
+        // chain of dependent L2 / HBM round trips); the sums still run in entry order
+        const int ch = cbase + lg;
+        for (int j = 0; j < cnt; j += 4) {
+          int u[4];
+          float c[4];
+          Vec<VEC> x[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            u[jj] = __shfl_sync(gmask, mycol, (j + jj) & (G - 1), G);
+            c[jj] = HAS_COEF ? __shfl_sync(gmask, myc, (j + jj) & (G - 1), G) : 1.f;
+            if (j + jj >= cnt) u[jj] = -1;
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) x[jj].v[i] = 0.f;
+            if (u[jj] >= 0 && ch < nch) x[jj].load(X + (size_t)u[jj] * ldx + ch * VEC);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            if (u[jj] < 0) continue;  // "no edge feature" marker / past the row's end
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)
+              acc[0][i] = HAS_COEF ? fmaf(c[jj], x[jj].v[i], acc[0][i]) : acc[0][i] + x[jj].v[i];
+          }
+        }
+        continue;
+      }
 #pragma unroll 4
       for (int j = 0; j < cnt; ++j) {
         const int u = __shfl_sync(gmask, mycol, j, G);
