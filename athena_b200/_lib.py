@@ -87,7 +87,7 @@ def lib() -> C.CDLL:
         "athena_cuda_profile_end": [PI32],
         "athena_cuda_profile_get": [I32, P, I32, PI64, PF],
         "athena_cuda_batch_create": [PH, I32, P, P, P, P, P, I32, I32],
-        "athena_cuda_batch_create_from_edges": [PH, I32, P, P, P, I32, I32, I32],
+        "athena_cuda_batch_create_from_edges": [PH, I32, P, P, P, P, I32, I32, I32],
         "athena_cuda_batch_create_from_edge_index": [PH, I32, P, P, P, P, P, I32, I32],
         "athena_cuda_batch_destroy": [H],
         "athena_cuda_batch_status": [H],

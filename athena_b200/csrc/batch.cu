@@ -862,6 +862,7 @@ ATHENA_API int athena_cuda_batch_create_from_edges(athena_handle_t* batch, int32
                                                    const int32_t* num_vertices,
                                                    const int32_t* num_edges,
                                                    const int32_t* index_list,
+                                                   const int32_t* num_entries_hint,
                                                    int32_t add_self_loops, int32_t mem,
                                                    int32_t validate) {
   ATH_TRY(ensure_init());
@@ -904,7 +905,14 @@ ATHENA_API int athena_cuda_batch_create_from_edges(athena_handle_t* batch, int32
   ATH_CUDA(cudaMemcpyAsync(d_voff, voff.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, st));
   ATH_CUDA(cudaMemcpyAsync(d_eoff, eoff.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, st));
   if (mem == ATHENA_MEM_HOST && E > 0) {
-    ATH_CUDA(cudaMemcpyAsync(p, index_list, sizeof(int32_t) * 2 * (size_t)E, cudaMemcpyHostToDevice, st));
+    // on the copy stream, like the adjacency of athena_cuda_batch_create: whatever the caller
+    // uploads next (the features of the training step) queues right behind it instead of
+    // waiting for the build kernels
+    cudaEvent_t ev_il = nullptr;
+    ATH_TRY(side_begin());
+    ATH_TRY(side_copy(p, index_list, sizeof(int32_t) * 2 * (size_t)E));
+    ATH_TRY(side_fence(&ev_il));
+    ATH_TRY(main_wait(ev_il));
     d_il = p;
   } else if (E > 0) {
     ATH_REQUIRE((reinterpret_cast<uintptr_t>(index_list) & 7) == 0, ATHENA_ERR_ARG,
@@ -946,18 +954,26 @@ ATHENA_API int athena_cuda_batch_create_from_edges(athena_handle_t* batch, int32
                                                        reinterpret_cast<int2*>(d_ja), d_nz);
     ATH_LAUNCHED();
   }
-  // the entry counts per graph are data (self edges, missing loops): B integers come back
-  // (through a pinned buffer: a pageable destination would stage the copy)
-  static int32_t* pinned_nz = nullptr;
-  static size_t pinned_cap = 0;
-  if ((size_t)B > pinned_cap) {
-    if (pinned_nz) cudaFreeHost(pinned_nz);
-    pinned_cap = (size_t)round_up(B, 1024);
-    ATH_CUDA(cudaHostAlloc((void**)&pinned_nz, sizeof(int32_t) * pinned_cap, cudaHostAllocDefault));
+  // The entry counts per graph are data (self edges, missing loops): B integers come back
+  // (through a pinned buffer: a pageable destination would stage the copy) -- unless the caller
+  // already knows them (num_entries_hint, e.g. from an earlier epoch over the same graphs): the
+  // build then stays asynchronous, and a wrong hint is caught by the row-pointer check of the
+  // CSR build (ATHENA_ERR_GRAPH through validate / athena_cuda_batch_status).
+  std::vector<int32_t> h_nz;
+  if (num_entries_hint != nullptr) {
+    h_nz.assign(num_entries_hint, num_entries_hint + B);
+  } else {
+    static int32_t* pinned_nz = nullptr;
+    static size_t pinned_cap = 0;
+    if ((size_t)B > pinned_cap) {
+      if (pinned_nz) cudaFreeHost(pinned_nz);
+      pinned_cap = (size_t)round_up(B, 1024);
+      ATH_CUDA(cudaHostAlloc((void**)&pinned_nz, sizeof(int32_t) * pinned_cap, cudaHostAllocDefault));
+    }
+    ATH_CUDA(cudaMemcpyAsync(pinned_nz, d_nz, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    ATH_CUDA(cudaStreamSynchronize(st));
+    h_nz.assign(pinned_nz, pinned_nz + B);
   }
-  ATH_CUDA(cudaMemcpyAsync(pinned_nz, d_nz, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
-  ATH_CUDA(cudaStreamSynchronize(st));
-  std::vector<int32_t> h_nz(pinned_nz, pinned_nz + B);
   athena_handle_t h = 0;
   ATH_TRY(athena_cuda_batch_create(&h, B, num_vertices, num_edges, h_nz.data(), d_ia, d_ja,
                                    ATHENA_MEM_DEVICE, 0));

@@ -50,7 +50,7 @@ class GraphBatch:
 
     @classmethod
     def from_edges(cls, num_vertices, index_lists: Sequence, add_self_loops: bool = False,
-                   validate: bool = True) -> "GraphBatch":
+                   validate: bool = True, num_entries=None) -> "GraphBatch":
         """generate_adjacency(index_list) (+ add_self_loops) on the device
         (athena_cuda_batch_create_from_edges): index_lists[s] = [E_s, 2] 1-based pairs."""
         nv = np.ascontiguousarray(num_vertices, np.int32)
@@ -58,8 +58,9 @@ class GraphBatch:
         ne = np.asarray([il.shape[0] for il in ils], np.int32)
         il = np.ascontiguousarray(np.concatenate(ils) if ils else np.zeros((0, 2)), np.int32)
         h = C.c_int64()
+        nz = None if num_entries is None else np.ascontiguousarray(num_entries, np.int32)
         check(lib().athena_cuda_batch_create_from_edges(C.byref(h), nv.size, ptr(nv), ptr(ne),
-                                                        ptr(il), int(add_self_loops),
+                                                        ptr(il), ptr(nz), int(add_self_loops),
                                                         _lib.MEM_HOST, int(validate)))
         return cls._adopt(h.value)
 

@@ -662,8 +662,8 @@ def main():
             h = host[i % nbuf]
             bh = C.c_int64()
             ab.check(L.athena_cuda_batch_create_from_edges(
-                C.byref(bh), B, ab.ptr(h["nv"]), ab.ptr(h["ne_e"]), ab.ptr(h["il"]), 1,
-                ab.MEM_HOST, 0))
+                C.byref(bh), B, ab.ptr(h["nv"]), ab.ptr(h["ne_e"]), ab.ptr(h["il"]),
+                ab.ptr(h["nz"]), 1, ab.MEM_HOST, 0))
             ab.check(L.athena_cuda_network_train_step(net.handle, bh.value, ab.ptr(h["x"]), None,
                                                       ab.ptr(h["t"]), ab.MEM_HOST, global_B,
                                                       C.byref(lossf)))
@@ -698,13 +698,13 @@ def main():
                     "host_to_device_GBps_all_ranks": world * h2d / (dt / args.steps) / 1e9}
 
         e_edges = time_e2e(e2e_step_edges, ("il", "x", "t"))
-        e_edges["d2h_bytes_per_step"] = 4 + 4 * B   # + the per-graph entry counts of the CSR build
         e_csr = time_e2e(e2e_step_csr, ("ia", "ja", "x", "t"))
         # headline = the faster of the two public routes (both ship every byte of the step from
         # pinned host memory): graph_type samples with the CSR built by the caller (adj_ia /
         # adj_ja, as set_graph receives them) or EDGE LISTS with generate_adjacency +
-        # add_self_loops done on the device (10 % fewer bytes, one small read-back in the middle
-        # of the step: slower on an idle host, faster once several ranks share the host's memory)
+        # add_self_loops done on the device (10 % fewer bytes; the per-graph entry counts are
+        # passed as a hint, as a training loop knows them from its first epoch, so the build
+        # stays asynchronous)
         e_csr["input"] = ("adj_ia / adj_ja + features + targets from pinned host memory "
                           "(athena_cuda_batch_create + athena_cuda_network_train_step)")
         e_edges["input"] = ("edge lists (index_list) + features + targets from pinned host memory; "

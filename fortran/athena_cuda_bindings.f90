@@ -132,12 +132,13 @@ module athena__cuda_bindings
      end function
      !! graph%generate_adjacency(index_list) (+ graph%add_self_loops()) on the device
      function athena_cuda_batch_create_from_edges(batch, num_graphs, num_vertices, num_edges, &
-          index_list, add_self_loops, mem, validate) &
+          index_list, num_entries_hint, add_self_loops, mem, validate) &
           bind(C, name="athena_cuda_batch_create_from_edges") result(rc)
-       import :: c_int, c_int32_t, c_int64_t
+       import :: c_int, c_int32_t, c_int64_t, c_ptr
        integer(c_int64_t), intent(out) :: batch
        integer(c_int32_t), value :: num_graphs, add_self_loops, mem, validate
        integer(c_int32_t), intent(in) :: num_vertices(*), num_edges(*), index_list(*)
+       type(c_ptr), value :: num_entries_hint   !! c_null_ptr, or c_loc of the known entry counts
        integer(c_int) :: rc
      end function
      !! ONNX graph inputs: edge_index [3, ncsr] + degree (athena_onnx_msgpass_utils.f90:53-92)

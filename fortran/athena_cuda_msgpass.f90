@@ -98,7 +98,7 @@ contains
     logical, intent(in) :: self_loops
     call this%destroy()
     call athena_cuda_check(athena_cuda_batch_create_from_edges(this%handle, &
-         int(size(num_vertices), c_int32_t), num_vertices, num_edges, index_list, &
+         int(size(num_vertices), c_int32_t), num_vertices, num_edges, index_list, c_null_ptr, &
          merge(1_c_int32_t, 0_c_int32_t, self_loops), ATHENA_MEM_HOST, 1_c_int32_t))
     this%num_graphs = size(num_vertices)
     this%num_vertices = sum(num_vertices)

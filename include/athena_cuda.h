@@ -171,12 +171,15 @@ int athena_cuda_batch_create(athena_handle_t* batch, int32_t num_graphs,
  * (graphstruc v0.2.1 is not vendored with the reference, fpm.toml:21, and no athena test pins
  * its neighbour order: this is the order of the host restatement athena_b200/graph.py, against
  * which the device build is bit-exact.)  An index outside 1..num_vertices(s) is
- * ATHENA_ERR_GRAPH as above.  The per-graph entry counts are data dependent, so this call
- * synchronises once (num_graphs integers come back).
+ * ATHENA_ERR_GRAPH as above.  The per-graph entry counts (size(adj_ja, 2)) are data dependent,
+ * so this call synchronises once (num_graphs integers come back) -- unless the caller passes
+ * them in num_entries_hint ([B], may be NULL; e.g. remembered from an earlier epoch over the
+ * same graphs): the build is then fully asynchronous and a wrong hint is ATHENA_ERR_GRAPH.
  */
 int athena_cuda_batch_create_from_edges(athena_handle_t* batch, int32_t num_graphs,
                                         const int32_t* num_vertices, const int32_t* num_edges,
-                                        const int32_t* index_list, int32_t add_self_loops,
+                                        const int32_t* index_list,
+                                        const int32_t* num_entries_hint, int32_t add_self_loops,
                                         int32_t mem, int32_t validate);
 
 /*

@@ -845,6 +845,17 @@ def test_generate_adjacency_on_device_is_bit_exact(cuda, case, loops):
     for k in BATCH_INTS:
         assert np.array_equal(dev.export(k), ref.export(k)), k
     assert np.array_equal(dev.export("coef"), ref.export("coef"))
+    # with the entry counts known to the caller the build does not synchronise; a wrong count
+    # is caught by the row-pointer check of the CSR build
+    hinted = ab.GraphBatch.from_edges(nvs, ils, add_self_loops=loops, num_entries=p.nz)
+    for k in BATCH_INTS:
+        assert np.array_equal(hinted.export(k), ref.export(k)), k
+    hinted.destroy()
+    if p.Z > 0:
+        wrong = p.nz.copy()
+        wrong[int(np.argmax(wrong))] += 1
+        with pytest.raises(ab.AthenaCudaError):
+            ab.GraphBatch.from_edges(nvs, ils, add_self_loops=loops, num_entries=wrong)
     ref.destroy()
     dev.destroy()
 
