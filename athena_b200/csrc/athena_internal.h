@@ -380,6 +380,9 @@ struct OptimState {
   int64_t iter = 0;
   DevBuf s1, s2;   // velocity | m, v
   DevBuf scratch;  // norm partials
+  // > 0: launch_finalize already clamped the gradients and left this many partial sums of
+  // squares in `scratch`; launch_update then goes straight to the step
+  int presum_nb = 0;
 };
 // clip + optimiser step + zero the gradients (athena_network_sub.f90:2904-2927)
 int launch_update(float* params, float* grads, int64_t n, OptimState& st);
@@ -410,7 +413,8 @@ bool finalize_can_step(const OptimState& st);
 // written to xout[0..n] -- the staging buffer of the peer-memory exchange.
 int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts, float* loss_acc,
                     float* params, float* grads, int64_t n, OptimState* st,
-                    float* xout = nullptr, const P2PSignal* sig = nullptr, int exchange = 0);
+                    float* xout = nullptr, const P2PSignal* sig = nullptr, int exchange = 0,
+                    OptimState* presum = nullptr);
 // exchange != 0: the peer-memory sum (+ the step when st != nullptr) rides on the same launch
 bool finalize_can_exchange(int64_t n);
 

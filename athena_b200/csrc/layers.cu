@@ -819,15 +819,18 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
   float* xout = use_p2p ? P.xbuf[P.rank] + (size_t)((P.epoch + 1) & 1u) * P.cap : nullptr;
   P2PSignal sig;
   if (use_p2p) p2p_next_signal(&sig);
-  const bool p2p_step = step_too && !N->opt.d.clip_min_max && !N->opt.d.clip_norm_on;
+  const bool p2p_step = step_too && !N->opt.d.clip_norm_on;  // min / max rides along (step_one)
   // one launch folds the partials, publishes the slot, waits for the peers, sums and steps
   const bool fuse_exchange = use_p2p && defer.jobs.size() <= 8 && finalize_can_exchange(N->n);
   if (!defer.jobs.empty() || fo.fused || use_p2p) {
     const bool fuse_step = step_too && finalize_can_step(N->opt);
     OptimState* fst = fuse_exchange ? (p2p_step ? &N->opt : nullptr) : (fuse_step ? &N->opt : nullptr);
+    // norm clipping on one GPU: the finalize launch clamps and pre-sums for the step that follows
+    OptimState* presum = (step_too && fst == nullptr && !use_p2p && comm_world_size() == 1 &&
+                          N->opt.d.clip_norm_on) ? &N->opt : nullptr;
     ATH_TRY(launch_finalize(defer, fo.fused ? fo.loss_part : nullptr, fo.num_parts, gflat + N->n,
                             N->flat_params.as<float>(), gflat, N->n, fst, xout,
-                            use_p2p ? &sig : nullptr, fuse_exchange ? 1 : 0));
+                            use_p2p ? &sig : nullptr, fuse_exchange ? 1 : 0, presum));
     if (stepped) *stepped = fuse_exchange ? p2p_step : fuse_step;
   }
   if (use_p2p && !fuse_exchange) {

@@ -183,6 +183,8 @@ struct StepArgs {
   int nesterov;
   int norm_on;
   float clip_norm;
+  int clamp;        // clip_type min / max (athena_clipper.f90:165-207): elementwise, before the norm
+  float cmin, cmax;
   float bc1, bc2;
   int reg;          // ATHENA_REG_*
   float l1, l2;
@@ -194,6 +196,9 @@ struct StepArgs {
 __device__ __forceinline__ void step_one(float* __restrict__ p, float* __restrict__ s1,
                                          float* __restrict__ s2, long long i, float gr,
                                          const StepArgs& a) {
+  // clip_type%apply, min / max part: elementwise (idempotent: callers that clipped already, or
+  // scaled a clipped value by a norm factor <= 1, are unaffected)
+  if (a.clamp) gr = fmaxf(a.cmin, fminf(a.cmax, gr));
   if (a.reg != ATHENA_REG_NONE) {
     // regulariser%regularise inside minimise_* (athena_regulariser.f90:99, 117, 135-136),
     // in the reference's order of operations
@@ -298,6 +303,11 @@ struct FinArgs {
   // exchange fused into this launch (the whole grid is co-resident): after the signal every
   // block waits for the peers' flags, adds the staged vectors of all ranks in rank order and
   // (xstep) applies the optimiser step -- what k_p2p_sum_step does in a launch of its own
+  // norm clipping without a pass of its own: the gradients are clamped here and every block
+  // leaves the sum of squares of its slice for k_step (sumsq_part[gridDim.x])
+  float* sumsq_part;
+  int clamp;
+  float cmin, cmax;
   int xfused, xstep;
   const float* xin[P2P_MAX_WORLD];
   long long timeout_ns;
@@ -353,6 +363,7 @@ k_finalize(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
   }
   red[grp][e] = sum;
   __syncthreads();
+  float sq = 0.f;
   if (grp == 0 && i < n) {
     float gr = g[i];
 #pragma unroll
@@ -361,9 +372,18 @@ k_finalize(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
       step_one(p, s1, s2, i, gr, a);
       g[i] = 0.f;
     } else {
+      if (f.sumsq_part != nullptr && f.clamp) gr = fmaxf(f.cmin, fminf(f.cmax, gr));
       g[i] = gr;
       if (f.xout) f.xout[i] = gr;
     }
+    sq = gr * gr;
+  }
+  if (f.sumsq_part != nullptr && grp == 0) {
+    // grp == 0 is exactly warp 0 (FIN_ELEMS = 32): fixed-order butterfly over the slice (lanes
+    // past the end of the vector contribute zeros)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (e == 0) f.sumsq_part[blockIdx.x] = sq;
   }
   if (blockIdx.x == 0 && (f.loss_part != nullptr || f.xout != nullptr)) {
     __syncthreads();
@@ -525,6 +545,9 @@ static int step_prepare(int64_t n, OptimState& st, StepArgs* a) {
   a->nesterov = d.nesterov;
   a->norm_on = d.clip_norm_on;
   a->clip_norm = d.clip_norm;
+  a->clamp = d.clip_min_max;
+  a->cmin = d.clip_min;
+  a->cmax = d.clip_max;
   a->reg = d.regulariser;
   a->l1 = d.l1;
   a->l2 = d.l2;
@@ -541,19 +564,26 @@ int launch_update(float* params, float* grads, int64_t n, OptimState& st) {
   ATH_TRY(step_prepare(n, st, &a));
   int nb = red_blocks(n);
   const athena_optimiser_desc& d = st.d;
-  if (d.clip_min_max || d.clip_norm_on) {
+  int npart = nb;
+  if (st.presum_nb > 0) {
+    npart = st.presum_nb;  // clamped and summed by launch_finalize
+    st.presum_nb = 0;
+  } else if (d.clip_norm_on) {
+    // (min / max alone is applied inside the step)
     k_clip_sumsq<<<nb, RED_THREADS, 0, s>>>(grads, n, d.clip_min_max, d.clip_min, d.clip_max,
                                             st.scratch.as<float>());
     ATH_LAUNCHED_T("clip_sumsq");
   }
   k_step<<<nb, RED_THREADS, 0, s>>>(params, grads, st.s1.as<float>(), st.s2.as<float>(), n,
-                                    st.scratch.as<float>(), nb, a);
+                                    st.scratch.as<float>(), npart, a);
   ATH_LAUNCHED_T("optimiser_step");
   return ATHENA_OK;
 }
 
 bool finalize_can_step(const OptimState& st) {
-  return !st.d.clip_min_max && !st.d.clip_norm_on && comm_world_size() == 1;
+  // min / max clipping is elementwise and rides along (step_one); norm clipping needs the
+  // global sum of squares first
+  return !st.d.clip_norm_on && comm_world_size() == 1;
 }
 
 // Folds the deferred partial reductions (and the loss partials) into the flat gradient
@@ -644,8 +674,14 @@ bool finalize_can_exchange(int64_t n) {
 
 int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts, float* loss_acc,
                     float* params, float* grads, int64_t n, OptimState* st, float* xout,
-                    const P2PSignal* sig, int exchange) {
+                    const P2PSignal* sig, int exchange, OptimState* presum) {
   if (n == 0) return ATHENA_OK;
+  // norm clipping: this launch clamps and leaves the partial sums of squares for the step
+  const int fin_grid = (int)cdiv(n, FIN_ELEMS);
+  if (presum != nullptr && (st != nullptr || xout != nullptr || !presum->d.clip_norm_on ||
+                            fin_grid > 2048 || dl.jobs.size() > (size_t)FIN_MAX_JOBS))
+    presum = nullptr;
+  if (presum) ATH_TRY(presum->scratch.reserve(sizeof(float) * (size_t)std::max(fin_grid, 1024)));
   cudaStream_t s = ctx().stream;
   StepArgs a{};
   if (st) ATH_TRY(step_prepare(n, *st, &a));
@@ -673,6 +709,13 @@ int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts
     f.loss_nparts = loss_nparts;
     f.loss_acc = loss_acc;
     f.do_step = (last && st && !exchange) ? 1 : 0;
+    if (last && presum) {
+      f.sumsq_part = presum->scratch.as<float>();
+      f.clamp = presum->d.clip_min_max;
+      f.cmin = presum->d.clip_min;
+      f.cmax = presum->d.clip_max;
+      presum->presum_nb = fin_grid;
+    }
     f.xout = last ? xout : nullptr;
     if (last && xout && sig) f.sig = *sig;
     if (last && exchange) {
