@@ -288,8 +288,11 @@ bool tc_rows_supported(int K, int N, int lda, int ldc, const void* A, const void
 bool tc_tn_supported(int K, int N, int lda1, int lda2, const void* A1, const void* A2);
 int launch_tc_rows(bool transb, const float* A, int lda, const float* Hact, int act_in,
                    const float* W, float* C, int ldc, int64_t M, int N, int K, int act_out);
+// defer != nullptr: the fold of the per-CTA partials is queued for launch_finalize (the
+// scratch buffer must then stay untouched until the end of the reverse sweep)
 int launch_tc_tn(const float* A1, int lda1, const float* A2, int lda2, const float* Hact,
-                 int act_in, float* dW, int64_t M, int N, int K, DevBuf& scratch);
+                 int act_in, float* dW, int64_t M, int N, int K, DevBuf& scratch,
+                 DeferList* defer = nullptr);
 
 // fused warp-specialised tcgen05 kernels for batches of small graphs (pipe_tc.cu)
 bool pipe_gather_supported(const Batch* b, int F, int N);

@@ -199,26 +199,27 @@ k_tc_rows(const float* __restrict__ A, int lda, const float* __restrict__ Hact, 
 }
 
 // ---------------------------------------------------------------------------
-// dW = A1^T . A2 over all rows (K = 64 features of A1 stacked hi|lo -> M' = 128)
+// dW = A1^T . A2 over all rows (K = 64 features of A1 stacked hi|lo -> M' = 128; K = 32:
+// hi | lo | 64 zero rows, the same M' = 128 instruction shape)
 // ---------------------------------------------------------------------------
-template <int N>
+template <int KW, int N>
 struct TnCfg {
-  static constexpr int K = 64;
+  static constexpr int K = KW;
   static constexpr int THREADS = 512;
   static constexpr int RS = 64;                      // rows per stage
   static constexpr int BLK = RS * 128;               // [64 rows x 32 feats] = 8192 B
-  static constexpr int A1_BYTES = 2 * (K / 32) * BLK;        // hi blocks then lo blocks
+  static constexpr int A1_BYTES = 4 * BLK;                   // hi blocks, lo blocks (, zero blocks)
   static constexpr int A2_HALF = (N / 32) * BLK;             // hi (or lo) of A2
   static constexpr int STAGE = A1_BYTES + 2 * A2_HALF;
   static constexpr int SMEM = 1024 + 2 * STAGE + 64;
   static constexpr int TMEM_COLS = (N <= 32 ? 32 : 64);
 };
 
-template <int N>
+template <int KW, int N>
 __global__ void __launch_bounds__(512, 1)
 k_tc_tn(const float* __restrict__ A1, int lda1, const float* __restrict__ A2, int lda2,
         const float* __restrict__ Hact, int act_in, float* __restrict__ part, long long M) {
-  using Cfg = TnCfg<N>;
+  using Cfg = TnCfg<KW, N>;
   constexpr int K = Cfg::K;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -241,6 +242,13 @@ k_tc_tn(const float* __restrict__ A1, int lda1, const float* __restrict__ A2, in
   constexpr int LOADS = Cfg::RS * CHT / Cfg::THREADS;
   static_assert(Cfg::RS * CHT % Cfg::THREADS == 0, "loader mapping");
   const long long ntiles = (M + Cfg::RS - 1) / Cfg::RS;
+  if (K < 64) {
+    // the unused half of the M' = 128 operand: zero rows, written once
+    for (int st = 0; st < 2; ++st)
+      for (int e = tid; e < (4 - 2 * (K / 32)) * Cfg::BLK / 16; e += Cfg::THREADS)
+        reinterpret_cast<float4*>(smem + st * Cfg::STAGE + 2 * (K / 32) * Cfg::BLK)[e] =
+            make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   uint32_t phase[2] = {0u, 0u};
   int it = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -313,13 +321,13 @@ k_tc_tn(const float* __restrict__ A1, int lda1, const float* __restrict__ A2, in
   }
   tc_fence_after();
   float* sOut = reinterpret_cast<float*>(smem);  // [64][N] (stage buffers are free now)
-  if (it >= 1 && warp < 4) {
-    // lanes 0..63: hi(A1)^T.A2, lanes 64..127: lo(A1)^T.A2
+  constexpr int NQ = 2 * (K / 32);  // warps that hold results: hi lanes [0, K), lo lanes [K, 2K)
+  if (it >= 1 && warp < NQ) {
     const int q = warp;
     float v[32];
     for (int pass = 0; pass < 2; ++pass) {
-      if ((q >> 1) == pass) {
-        const int feat = (q & 1) * 32 + lane;
+      if (q / (K / 32) == pass) {
+        const int feat = (q % (K / 32)) * 32 + lane;
         for (int cg = 0; cg < N / 32; ++cg) {
           tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + cg * 32, v);
 #pragma unroll
@@ -329,7 +337,7 @@ k_tc_tn(const float* __restrict__ A1, int lda1, const float* __restrict__ A2, in
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NQ * 32) : "memory");
     }
   }
   tc_fence_before();
@@ -369,7 +377,7 @@ bool tc_rows_supported(int K, int N, int lda, int ldc, const void* A, const void
 }
 
 bool tc_tn_supported(int K, int N, int lda1, int lda2, const void* A1, const void* A2) {
-  return tc_enabled() && K == 64 && (N == 32 || N == 64) && lda1 == K && lda2 == N &&
+  return tc_enabled() && (K == 64 || K == 32) && (N == 32 || N == 64) && lda1 == K && lda2 == N &&
          aligned16(A1) && aligned16(A2);
 }
 
@@ -407,22 +415,26 @@ int launch_tc_rows(bool transb, const float* A, int lda, const float* Hact, int 
   ATH_REQUIRE(false, ATHENA_ERR_ARG, "tc_rows: unsupported shape K=%d N=%d", K, N);
 }
 
-template <int N>
+template <int K, int N>
 static int launch_tn_t(const float* A1, int lda1, const float* A2, int lda2, const float* Hact,
-                       int act_in, float* dW, int64_t M, DevBuf& scratch) {
-  using Cfg = TnCfg<N>;
+                       int act_in, float* dW, int64_t M, DevBuf& scratch, DeferList* defer) {
+  using Cfg = TnCfg<K, N>;
   static bool attr = false;
   if (!attr) {
-    ATH_CUDA(cudaFuncSetAttribute(k_tc_tn<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ATH_CUDA(cudaFuncSetAttribute(k_tc_tn<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM));
     attr = true;
   }
   int64_t ntiles = cdiv(M, Cfg::RS);
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx().sm_count);
   ATH_TRY(scratch.reserve(sizeof(float) * (size_t)grid * Cfg::K * N));
-  k_tc_tn<N><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(A1, lda1, A2, lda2, Hact, act_in,
-                                                             scratch.as<float>(), M);
+  k_tc_tn<K, N><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(A1, lda1, A2, lda2, Hact, act_in,
+                                                                scratch.as<float>(), M);
   ATH_LAUNCHED_T("tc_tn");
+  if (defer) {  // the fold of the per-CTA partials rides on the finalize launch
+    defer->jobs.push_back(DeferJob{scratch.as<float>(), grid, Cfg::K * N, dW});
+    return ATHENA_OK;
+  }
   k_tc_tn_reduce<<<(unsigned)cdiv((int64_t)Cfg::K * N, 128), 128, 0, ctx().stream>>>(
       scratch.as<float>(), grid, Cfg::K * N, dW);
   ATH_LAUNCHED_T("tc_tn_reduce");
@@ -431,11 +443,17 @@ static int launch_tn_t(const float* A1, int lda1, const float* A2, int lda2, con
 
 // dW[K x N] += A1^T . (A2 .* act_in'(Hact))
 int launch_tc_tn(const float* A1, int lda1, const float* A2, int lda2, const float* Hact,
-                 int act_in, float* dW, int64_t M, int N, int K, DevBuf& scratch) {
+                 int act_in, float* dW, int64_t M, int N, int K, DevBuf& scratch,
+                 DeferList* defer) {
   if (M == 0) return ATHENA_OK;
-  ATH_REQUIRE(K == 64, ATHENA_ERR_ARG, "tc_tn: K must be 64");
-  if (N == 64) return launch_tn_t<64>(A1, lda1, A2, lda2, Hact, act_in, dW, M, scratch);
-  if (N == 32) return launch_tn_t<32>(A1, lda1, A2, lda2, Hact, act_in, dW, M, scratch);
+  ATH_REQUIRE(K == 64 || K == 32, ATHENA_ERR_ARG, "tc_tn: K must be 32 or 64");
+#define ATH_TN(KK, NN) \
+  return launch_tn_t<KK, NN>(A1, lda1, A2, lda2, Hact, act_in, dW, M, scratch, defer)
+  if (K == 64 && N == 64) ATH_TN(64, 64);
+  if (K == 64 && N == 32) ATH_TN(64, 32);
+  if (K == 32 && N == 64) ATH_TN(32, 64);
+  if (K == 32 && N == 32) ATH_TN(32, 32);
+#undef ATH_TN
   ATH_REQUIRE(false, ATHENA_ERR_ARG, "tc_tn: unsupported N=%d", N);
 }
 

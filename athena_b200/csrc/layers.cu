@@ -417,7 +417,11 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
     float* dWt = L->grads + L->poff[t - 1];
     const bool need_dp = (t > 1 || gin);
     const bool need_act = nonlinear && !preact;
-    if (tile_kipf_supported(b, Fi, Fo) && !pipe_gather_supported(b, Fo, Fi)) {
+    // the fused tcgen05 reverse step at width 32 takes act' from sign bits only
+    const bool pipe_bwd_ok =
+        pipe_gather_supported(b, Fo, Fi) &&
+        (Fi == 64 || t == 1 || !nonlinear || L->mask_valid[t - 2] != 0);
+    if (tile_kipf_supported(b, Fi, Fo) && !pipe_bwd_ok) {
       // act', dW partials, dP = gY W^T and the un-normalised CSC scatter in one FP32 tile kernel
       float* dst = gin;
       if (t > 1) dst = (g == L->g2.as<float>()) ? L->g0.as<float>() : L->g2.as<float>();
@@ -438,7 +442,7 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
     }
     // fused path: one tcgen05 kernel gathers gY_t over the CSC, multiplies by W_t^T and applies
     // act'(H_{t-1}); the un-normalised scatter commutes with the linear map
-    const bool fused_dp = need_dp && L->act != ATHENA_ACT_SOFTMAX && pipe_gather_supported(b, Fo, Fi);
+    const bool fused_dp = need_dp && L->act != ATHENA_ACT_SOFTMAX && pipe_bwd_ok;
     const bool fused_tn = Fi == 64 && pipe_tn_supported(Fi, Fo);
     const bool tn_tc = !fused_tn && tc_tn_supported(Fi, Fo, Fi, Fo, Pt, g);
     const bool nt_tc = need_dp && !fused_dp && tc_rows_supported(Fo, Fi, Fo, Fi, g, L->g1.as<float>());
@@ -458,7 +462,8 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
       // join the batched launch at the end of the sweep
       ATH_TRY(launch_pipe_tn(Pt, gy, dWt, V, Fo, *L->TN[t - 1], opt.defer, L->T == 1));
     } else if (tn_tc) {
-      ATH_TRY(launch_tc_tn(Pt, Fi, gy, Fo, Hact, L->act, dWt, V, Fo, Fi, L->tn_scratch));
+      // per-step partial buffer: with a DeferList the fold waits for the finalize launch
+      ATH_TRY(launch_tc_tn(Pt, Fi, gy, Fo, Hact, L->act, dWt, V, Fo, Fi, *L->TN[t - 1], opt.defer));
     } else {
       ATH_TRY(launch_gemm_tn(Pt, Fi, gy, Fo, dWt, V, Fo, Fi, GroupDesc{}, L->tn_scratch));
     }
@@ -474,7 +479,8 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
         if (L->mask_valid[t - 2]) mk = L->MK[t - 2]->as<uint32_t>();
         act_e = L->act;
       } else if (t == 1 && opt.fold_act != ATHENA_ACT_NONE && opt.fold_act != ATHENA_ACT_LINEAR &&
-                 opt.fold_act != ATHENA_ACT_SOFTMAX && L->fwd_x != nullptr) {
+                 opt.fold_act != ATHENA_ACT_SOFTMAX && L->fwd_x != nullptr &&
+                 (Fi == 64 || opt.fold_mask != nullptr)) {
         Hin = L->fwd_x;  // the producing layer's output
         mk = opt.fold_mask;
         act_e = opt.fold_act;

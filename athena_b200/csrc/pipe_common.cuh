@@ -183,6 +183,6 @@ __device__ __forceinline__ float epilogue_tile(uint32_t tacc, int q, int lane, i
 
 // pipe_tcg.cu: the same three fused steps with the gather on the tensor core
 bool pipe_tcg_supported(Batch* b, int F, int N);
-int launch_pipe_tcg(const pipe::GatherArgs& a, bool transb, int epi);
+int launch_pipe_tcg(const pipe::GatherArgs& a, bool transb, int epi, int width = 64);
 
 }  // namespace athena

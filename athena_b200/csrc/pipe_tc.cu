@@ -881,7 +881,15 @@ int launch_gather_t(const GatherArgs& a) {
 }  // namespace
 
 bool pipe_gather_supported(const Batch* b, int F, int N) {
-  return pipe_enabled() && !b->force_list && b->num_tiles > 0 && F == 64 && N == 64;
+  if (!pipe_enabled() || b->force_list || b->num_tiles == 0 || F != N) return false;
+  if (F == 64) return true;  // tensor-core gather, or the list gather for multi-edge batches
+  // width 32: the tensor-core gather only, and only for batches that fill the machine: below
+  // two tiles per SM the FP32 tile kernels (tile_fma.cu) are as fast (latency-bound) and an
+  // order of magnitude closer to the exact result (1e-7 instead of the 1e-6 of truncating
+  // tensor-core accumulation), which ill-conditioned optimiser steps (classical-L2 Adam)
+  // amplify
+  return F == 32 && b->num_tiles >= 2 * ctx().sm_count &&
+         pipe_tcg_supported(const_cast<Batch*>(b), F, N);
 }
 
 bool pipe_tn_supported(int K, int N) { return pipe_enabled() && K == 64 && (N == 64 || N == 32); }
@@ -902,14 +910,15 @@ int launch_pipe_gather_fwd(const Batch* b, const float* X, const float* W, float
   a.aux = nullptr;
   a.act = act;
   a.mask_out = mask_out;
-  ATH_REQUIRE(F == 64 && N == 64, ATHENA_ERR_ARG, "pipe_gather_fwd: unsupported shape");
+  ATH_REQUIRE(F == N && (F == 64 || F == 32), ATHENA_ERR_ARG, "pipe_gather_fwd: unsupported shape");
   if (pipe_tcg_supported(const_cast<Batch*>(b), F, N)) {
     a.abits = b->abits;
     a.num_rows = b->V;
     a.nonfinite = b->status.as<int32_t>() + 3;
     const_cast<Batch*>(b)->tcg_forwards += 1;
-    return launch_pipe_tcg(a, false, EPI_ACT);
+    return launch_pipe_tcg(a, false, EPI_ACT, F);
   }
+  ATH_REQUIRE(F == 64, ATHENA_ERR_ARG, "pipe_gather_fwd: width %d needs the tensor-core gather", F);
   return launch_gather_t<64, 64, false, EPI_ACT>(a);
 }
 
@@ -933,13 +942,15 @@ int launch_pipe_gather_fwd_mse(const Batch* b, const float* X, const float* W, f
   a.act = act;
   a.vcount = b->vcount;
   a.loss_part = loss_part;
-  ATH_REQUIRE(F == 64 && N == 64, ATHENA_ERR_ARG, "pipe_gather_fwd_mse: unsupported shape");
+  ATH_REQUIRE(F == N && (F == 64 || F == 32), ATHENA_ERR_ARG,
+              "pipe_gather_fwd_mse: unsupported shape");
   *num_parts = std::min(b->num_tiles, ctx().sm_count);
   if (pipe_tcg_supported(const_cast<Batch*>(b), F, N)) {
     a.abits = b->abits;
     a.num_rows = b->V;
-    return launch_pipe_tcg(a, false, EPI_MSE);
+    return launch_pipe_tcg(a, false, EPI_MSE, F);
   }
+  ATH_REQUIRE(F == 64, ATHENA_ERR_ARG, "pipe_gather_fwd_mse: width %d needs the tensor-core gather", F);
   return launch_gather_t<64, 64, false, EPI_MSE>(a);
 }
 
@@ -959,12 +970,13 @@ int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const
   a.aux = (act != ATHENA_ACT_NONE && act != ATHENA_ACT_LINEAR) ? Hin : nullptr;
   a.mask_in = (act == ATHENA_ACT_RELU || act == ATHENA_ACT_LEAKY_RELU) ? mask_in : nullptr;
   a.act = act;
-  ATH_REQUIRE(F == 64 && N == 64, ATHENA_ERR_ARG, "pipe_gather_bwd: unsupported shape");
+  ATH_REQUIRE(F == N && (F == 64 || F == 32), ATHENA_ERR_ARG, "pipe_gather_bwd: unsupported shape");
   if (pipe_tcg_supported(const_cast<Batch*>(b), F, N)) {
     a.abits = b->atbits;
     a.num_rows = b->V;
-    return launch_pipe_tcg(a, true, EPI_ACTGRAD);
+    return launch_pipe_tcg(a, true, EPI_ACTGRAD, F);
   }
+  ATH_REQUIRE(F == 64, ATHENA_ERR_ARG, "pipe_gather_bwd: width %d needs the tensor-core gather", F);
   return launch_gather_t<64, 64, true, EPI_ACTGRAD>(a);
 }
 

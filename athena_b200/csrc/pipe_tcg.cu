@@ -100,9 +100,12 @@ constexpr int TCG_TRACE_TILES = 16;
       a.trace[((role) * TCG_TRACE_TILES + j) * 8 + (slot)] = clock64();                  \
   } while (0)
 
-template <int EPI>
+template <int EPI, int FW>
 struct TcgCfg {
-  static constexpr int F = 64, N = 64;
+  // square steps of width 64 or 32 (F = N = FW); the 32-wide variant supports the forward,
+  // fwd + MSE with a TMA-fed target and the reverse step with sign bits / without activation
+  static_assert(FW == 64 || FW == 32, "feature width");
+  static constexpr int F = FW, N = FW;
   // Ring stages.  The split warps pull a stage into registers as soon as it lands, so the
   // next copy is issued almost immediately; deeper rings measured the same or slower (fwd
   // 60.1 / 61.6 / 62.0 us for 1 / 2 / 3 stages), so the shared memory is left to the L1.
@@ -146,7 +149,7 @@ struct TcgCfg {
   // (16-byte chunk c of row r at chunk c ^ (r % 8): row-per-thread STS.128 is conflict-free),
   // which one lane hands to cp.async.bulk.tensor -- no read-back through the LSU, no STG.
   // fwd + MSE writes the gradient IN PLACE over the target tile it has just read.
-  static constexpr int WARP_STAGE = 2 * 32 * 128;                // 8 KB
+  static constexpr int WARP_STAGE = (N / 32) * 32 * 128;         // 8 KB at N = 64
   static constexpr int OFF_EPI = (OFF_AUX + AUX_BYTES + 1023) / 1024 * 1024;
   static constexpr int EPI_STAGE_BYTES = EPI != EPI_MSE ? 4 * WARP_STAGE : 0;
   static constexpr int OFF_FIX = OFF_EPI + EPI_STAGE_BYTES;
@@ -165,14 +168,16 @@ __device__ __forceinline__ uint32_t stage_off(int r, int c) {
 // rows [0, rows) of a warp's staging area -> global rows (the fallback of the tensor store for
 // a warp whose 32 rows are not all inside the tile, or without a tensor map): 16 lanes per row,
 // conflict-free LDS.128, full-line STG.128.  box_pitch: bytes between the two column boxes.
+template <int N>
 __device__ __forceinline__ void stage_copy_out(const uint8_t* stage, uint32_t box_pitch, int rows,
                                                float* __restrict__ grow0, int lane) {
+  constexpr int NC = N / 4;  // 16-byte chunks per row
 #pragma unroll
-  for (int it = 0; it < 16; ++it) {
+  for (int it = 0; it < NC; ++it) {
     const int idx = it * 32 + lane;
-    const int r = idx >> 4, c = idx & 15;
+    const int r = idx / NC, c = idx % NC;
     if (r < rows)
-      *reinterpret_cast<float4*>(grow0 + r * 64 + c * 4) = *reinterpret_cast<const float4*>(
+      *reinterpret_cast<float4*>(grow0 + r * N + c * 4) = *reinterpret_cast<const float4*>(
           stage + (c >> 3) * box_pitch + r * 128 + (((c & 7) ^ (r & 7)) << 4));
   }
 }
@@ -186,13 +191,12 @@ __device__ __forceinline__ void stage_copy_out(const uint8_t* stage, uint32_t bo
 //                (AUX_SWZ: the TMA-loaded tile, `dst` = its base; else this thread's padded row)
 // Returns this row's loss share (EPI_MSE).  `dst_rows`: base the thread's chunks are written
 // relative to (staging area of the warp, or the 128-row target tile with row_in_dst = 32 q + lane).
-template <int ACT, int EPI, bool AUX_SWZ>
+template <int ACT, int EPI, bool AUX_SWZ, int N>
 __device__ __forceinline__ float tcg_epilogue(uint32_t tacc, int q, int lane, bool dry,
                                               uint8_t* dst, uint32_t box_pitch, int row_in_dst,
                                               const float* aux_row, float row_scale,
                                               uint64_t* acc_empty, uint32_t* mask_out_row,
-                                              bool use_mask, const uint32_t (&mask_in)[2]) {
-  constexpr int N = 64;
+                                              bool use_mask, const uint32_t (&mask_in)[N / 32]) {
   float lsum = 0.f;
   const bool padded_inplace = EPI == EPI_MSE && !AUX_SWZ;
   auto chunk_ptr = [&](int col) -> float4* {
@@ -202,14 +206,14 @@ __device__ __forceinline__ float tcg_epilogue(uint32_t tacc, int q, int lane, bo
                                      (((c & 7) ^ (row_in_dst & 7)) << 4));
   };
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
+  for (int half = 0; half < N / 32; ++half) {
     uint32_t mbits = 0;
 #pragma unroll
     for (int cg = 0; cg < 2; ++cg) {
       float vh[16];
       const int col0 = half * 32 + cg * 16;
       tmem_ld16(tacc + (static_cast<uint32_t>(q * 32) << 16) + col0, vh);
-      if (half == 1 && cg == 1) {
+      if (half == N / 32 - 1 && cg == 1) {
         tc_fence_before();
         mbar_arrive(acc_empty);  // the accumulator buffer may be overwritten now
       }
@@ -262,11 +266,11 @@ __device__ __forceinline__ float tcg_epilogue(uint32_t tacc, int q, int lane, bo
 // thousand clocks per role, serialised along the tile-0 dependency chain = a third of the
 // kernel).  The dry pass takes those misses in all roles AT ONCE while the first TMA copy
 // is in flight; it must execute the same instructions, hence one loop, not a copy.
-template <bool TRANSB, int EPI>
-__global__ void __launch_bounds__(TcgCfg<EPI>::THREADS, 1)
+template <bool TRANSB, int EPI, int FW>
+__global__ void __launch_bounds__(TcgCfg<EPI, FW>::THREADS, 1)
 k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
            const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap p_map) {
-  using Cfg = TcgCfg<EPI>;
+  using Cfg = TcgCfg<EPI, FW>;
   constexpr int F = Cfg::F, N = Cfg::N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -397,13 +401,15 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
         mbar_arrive_expect_tx(&aux_full[b], Cfg::AUX_TMA_TILE);
         if (a.hint_aux == 1) {
           const uint64_t pol = l2_policy_evict_first();
-          tma_load_2d_hint(sAuxT + b * Cfg::AUX_TMA_TILE, &aux_map, 0, ti.x, &aux_full[b], pol);
-          tma_load_2d_hint(sAuxT + b * Cfg::AUX_TMA_TILE + TILE_ROWS * 128, &aux_map, 32, ti.x,
-                           &aux_full[b], pol);
+#pragma unroll
+          for (int h = 0; h < N / 32; ++h)
+            tma_load_2d_hint(sAuxT + b * Cfg::AUX_TMA_TILE + h * TILE_ROWS * 128, &aux_map, 32 * h,
+                             ti.x, &aux_full[b], pol);
         } else {
-          tma_load_2d(sAuxT + b * Cfg::AUX_TMA_TILE, &aux_map, 0, ti.x, &aux_full[b]);
-          tma_load_2d(sAuxT + b * Cfg::AUX_TMA_TILE + TILE_ROWS * 128, &aux_map, 32, ti.x,
-                      &aux_full[b]);
+#pragma unroll
+          for (int h = 0; h < N / 32; ++h)
+            tma_load_2d(sAuxT + b * Cfg::AUX_TMA_TILE + h * TILE_ROWS * 128, &aux_map, 32 * h,
+                        ti.x, &aux_full[b]);
         }
       }
     }
@@ -465,7 +471,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
 #pragma unroll
         for (int k8 = 0; k8 < F / 8; ++k8) {
           const uint32_t wk = wAddr + (k8 >> 2) * Cfg::W_BLK + (k8 & 3) * 32;
-          umma_tf32_ts_w(leader, to, tp + 64 + k8 * 8, make_desc(wk, 16, 1024), IDESC_T,
+          umma_tf32_ts_w(leader, to, tp + F + k8 * 8, make_desc(wk, 16, 1024), IDESC_T,
                          k8 ? 1u : 0u);
           umma_tf32_ts_w(leader, to, tp + k8 * 8, make_desc(wk + N * 128, 16, 1024), IDESC_T, 1u);
         }
@@ -533,15 +539,17 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
       if (!dry) count_next = count_at(t + step);
       const bool row_valid = my_row < ti.y;
       const int rows_valid = min(32, ti.y - q * 32);  // rows of this warp inside the tile (<= 0: none)
-      uint32_t m0 = 0, m1 = 0;
+      uint32_t min_w[N / 32];
+#pragma unroll
+      for (int h = 0; h < N / 32; ++h) min_w[h] = 0u;
       uint32_t* mout = nullptr;
       if (row_valid) {
         const size_t grow = static_cast<size_t>(ti.x) + my_row;
         if (use_mask) {
-          m0 = __ldg(a.mask_in + grow * 2);
-          m1 = __ldg(a.mask_in + grow * 2 + 1);
+#pragma unroll
+          for (int h = 0; h < N / 32; ++h) min_w[h] = __ldg(a.mask_in + grow * (N / 32) + h);
         }
-        if (EPI == EPI_ACT && a.mask_out != nullptr) mout = a.mask_out + grow * 2;
+        if (EPI == EPI_ACT && a.mask_out != nullptr) mout = a.mask_out + grow * (N / 32);
       }
       // the staging area is free again once the previous tile's tensor stores have read it
       if (EPI != EPI_MSE) {
@@ -567,18 +575,17 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
       const float scale =
           (EPI == EPI_MSE && row_valid) ? 1.f / static_cast<float>(N * count) : 0.f;
       const int act = use_aux || use_mask || EPI == EPI_ACT ? a.act : ATHENA_ACT_NONE;
-      const uint32_t min_w[2] = {m0, m1};
       const bool inplace_swz = EPI == EPI_MSE && aux_tma;
       uint8_t* dst = inplace_swz ? aux_tile : stage;
       const uint32_t box_pitch = inplace_swz ? TILE_ROWS * 128 : 4096;
       const int row_in_dst = inplace_swz ? my_row : lane;
 #define TCG_EPI(ACT)                                                                            \
-  lsum += inplace_swz ? tcg_epilogue<ACT, EPI, true>(tacc, q, lane, dry, dst, box_pitch,         \
-                                                     row_in_dst, aux_row, scale, release, mout,  \
-                                                     use_mask, min_w)                            \
-                      : tcg_epilogue<ACT, EPI, false>(tacc, q, lane, dry, dst, box_pitch,        \
-                                                      row_in_dst, aux_row, scale, release, mout, \
-                                                      use_mask, min_w)
+  lsum += inplace_swz ? tcg_epilogue<ACT, EPI, true, N>(tacc, q, lane, dry, dst, box_pitch,      \
+                                                        row_in_dst, aux_row, scale, release,     \
+                                                        mout, use_mask, min_w)                   \
+                      : tcg_epilogue<ACT, EPI, false, N>(tacc, q, lane, dry, dst, box_pitch,     \
+                                                         row_in_dst, aux_row, scale, release,    \
+                                                         mout, use_mask, min_w)
       switch (act) {
         case ATHENA_ACT_RELU: TCG_EPI(ATHENA_ACT_RELU); break;
         case ATHENA_ACT_LEAKY_RELU: TCG_EPI(ATHENA_ACT_LEAKY_RELU); break;
@@ -595,9 +602,9 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
         // padded target tile, gradient written in place: rows of 272 B
         if (!dry) {
 #pragma unroll
-          for (int it = 0; it < 16; ++it) {
+          for (int it = 0; it < N / 4; ++it) {
             const int idx = it * 32 + lane;
-            const int r = idx >> 4, c = idx & 15;
+            const int r = idx / (N / 4), c = idx % (N / 4);
             if (r < rows_valid)
               *reinterpret_cast<float4*>(grow0 + r * N + c * 4) =
                   *reinterpret_cast<const float4*>(sAux + (q * 32 + r) * AUX_PITCH + c * 4);
@@ -610,18 +617,20 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
           if (lane == 0) {
             if (a.hint_out == 2) {
               const uint64_t pol = l2_policy_evict_last();
-              tma_store_2d_hint(&out_map, 0, ti.x + q * 32, src, pol);
-              tma_store_2d_hint(&out_map, 32, ti.x + q * 32, src + box_pitch, pol);
+#pragma unroll
+              for (int h = 0; h < N / 32; ++h)
+                tma_store_2d_hint(&out_map, 32 * h, ti.x + q * 32, src + h * box_pitch, pol);
             } else {
-              tma_store_2d(&out_map, 0, ti.x + q * 32, src);
-              tma_store_2d(&out_map, 32, ti.x + q * 32, src + box_pitch);
+#pragma unroll
+              for (int h = 0; h < N / 32; ++h)
+                tma_store_2d(&out_map, 32 * h, ti.x + q * 32, src + h * box_pitch);
             }
             bulk_commit();
             if (inplace_swz) bulk_wait_read0();  // the target buffer is handed back below
           }
           __syncwarp();
         } else if (rows_valid > 0) {
-          stage_copy_out(src, box_pitch, rows_valid, grow0, lane);
+          stage_copy_out<N>(src, box_pitch, rows_valid, grow0, lane);
           __syncwarp();
         }
       }
@@ -678,7 +687,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
         // P = (A . Xhi + A . Xlo) * deg_v^-1/2 ; hi -> columns 0..63, lo -> columns 64..127
         float v[16], vl[16];
         tmem_ld16_nowait(tp + g * 16, v);
-        tmem_ld16_nowait(tp + 64 + g * 16, vl);
+        tmem_ld16_nowait(tp + F + g * 16, vl);
         tmem_ld_wait();
         if (!dry && g == 0 && q == 0 && lane == 0) TCG_TRACE(4, 3);
         uint32_t hi[16];
@@ -690,7 +699,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
         tmem_st16(tp + g * 16, hi);
 #pragma unroll
         for (int i = 0; i < 16; ++i) hi[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
-        tmem_st16(tp + 64 + g * 16, hi);
+        tmem_st16(tp + F + g * 16, hi);
         if (!dry && g == 0 && q == 0 && lane == 0) TCG_TRACE(4, 4);
         if (store_p && !dry) {
           // the propagated tile (the operand of dW = P^T gY) goes to the swizzled staging area;
@@ -718,17 +727,19 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
           if (lane == 0) {
             if (a.hint_p == 1) {
               const uint64_t pol = l2_policy_evict_first();
-              tma_store_2d_hint(&p_map, 0, ti.x + q * 32, stage, pol);
-              tma_store_2d_hint(&p_map, 32, ti.x + q * 32, stage + 4096, pol);
+#pragma unroll
+              for (int h = 0; h < F / 32; ++h)
+                tma_store_2d_hint(&p_map, 32 * h, ti.x + q * 32, stage + h * 4096, pol);
             } else {
-              tma_store_2d(&p_map, 0, ti.x + q * 32, stage);
-              tma_store_2d(&p_map, 32, ti.x + q * 32, stage + 4096);
+#pragma unroll
+              for (int h = 0; h < F / 32; ++h)
+                tma_store_2d(&p_map, 32 * h, ti.x + q * 32, stage + h * 4096);
             }
             bulk_commit();
           }
         } else if (rows_valid > 0) {
-          stage_copy_out(stage, 4096, rows_valid,
-                         a.P + (static_cast<size_t>(ti.x) + q * 32) * F, lane);
+          stage_copy_out<F>(stage, 4096, rows_valid,
+                            a.P + (static_cast<size_t>(ti.x) + q * 32) * F, lane);
         }
         __syncwarp();
       }
@@ -805,7 +816,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
 #pragma unroll
       for (int i = 0; i < LOADS; ++i) {
         const int idx = tid + Cfg::SPLIT_THREADS * i;
-        const int row = idx >> 4;
+        const int row = idx / (F / 4);
         x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < nrows) {
           x[i] = *reinterpret_cast<const float4*>(st + idx * 16);
@@ -827,7 +838,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
 #pragma unroll
       for (int i = 0; i < LOADS; ++i) {
         const int idx = tid + Cfg::SPLIT_THREADS * i;
-        const int row = idx >> 4, ch = idx & 15;
+        const int row = idx / (F / 4), ch = idx % (F / 4);
         float4 hi, lo;
         split_tf32(x[i], hi, lo);
         if (EPI == EPI_ACT)
@@ -871,7 +882,7 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
 // swizzle (box_rows = 128: the target tile of fwd + MSE; 32: one warp's rows for the stores).
 // The driver entry point is resolved at run time (no link-time libcuda dependency).
 static bool make_row_tile_map(const float* base, long long rows, CUtensorMap* out,
-                              int box_rows = TILE_ROWS) {
+                              int box_rows = TILE_ROWS, int width = 64) {
   using Fn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                           const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                           CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -887,8 +898,8 @@ static bool make_row_tile_map(const float* base, long long rows, CUtensorMap* ou
       fn = reinterpret_cast<Fn>(p);
   }
   if (!fn || rows <= 0 || (reinterpret_cast<uintptr_t>(base) & 15u) != 0) return false;
-  const cuuint64_t gdim[2] = {64, static_cast<cuuint64_t>(rows)};
-  const cuuint64_t gstr[1] = {64 * sizeof(float)};
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstr[1] = {width * sizeof(float)};
   const cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box,
@@ -896,12 +907,12 @@ static bool make_row_tile_map(const float* base, long long rows, CUtensorMap* ou
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <bool TRANSB, int EPI>
+template <bool TRANSB, int EPI, int FW>
 int launch_tcg_t(const GatherArgs& a) {
-  using Cfg = TcgCfg<EPI>;
+  using Cfg = TcgCfg<EPI, FW>;
   static bool attr = false;
   if (!attr) {
-    ATH_CUDA(cudaFuncSetAttribute(k_pipe_tcg<TRANSB, EPI>,
+    ATH_CUDA(cudaFuncSetAttribute(k_pipe_tcg<TRANSB, EPI, FW>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
@@ -936,7 +947,7 @@ int launch_tcg_t(const GatherArgs& a) {
     no_tma = (e && atoi(e) != 0) ? 1 : 0;
   }
   b.aux_tma = (Cfg::AUX_TMA && !no_tma && a.aux != nullptr &&
-               make_row_tile_map(a.aux, a.num_rows, &aux_map))
+               make_row_tile_map(a.aux, a.num_rows, &aux_map, TILE_ROWS, FW))
                   ? 1
                   : 0;
   // TMA tensor stores of the output (and of the propagated tile): [32 rows x 32 floats] boxes
@@ -950,8 +961,9 @@ int launch_tcg_t(const GatherArgs& a) {
   }
   b.store_tma = 0;
   if (!no_store_tma) {
-    if (a.out != nullptr && make_row_tile_map(a.out, a.num_rows, &out_map, 32)) b.store_tma |= 1;
-    if (EPI != EPI_ACTGRAD && a.P != nullptr && make_row_tile_map(a.P, a.num_rows, &p_map, 32))
+    if (a.out != nullptr && make_row_tile_map(a.out, a.num_rows, &out_map, 32, FW))
+      b.store_tma |= 1;
+    if (EPI != EPI_ACTGRAD && a.P != nullptr && make_row_tile_map(a.P, a.num_rows, &p_map, 32, FW))
       b.store_tma |= 2;
   }
   static int trace_left = -1;
@@ -968,7 +980,7 @@ int launch_tcg_t(const GatherArgs& a) {
     const char* e = getenv("ATHENA_DEBUG_TRACE_BLOCK");
     b.dbg = e ? atoi(e) : 0;
   }
-  ATH_CUDA(launch_pdl(k_pipe_tcg<TRANSB, EPI>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM,
+  ATH_CUDA(launch_pdl(k_pipe_tcg<TRANSB, EPI, FW>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM,
                       ctx().stream, b, aux_map, out_map, p_map));
   if (trace_left > 0) {
     --trace_left;
@@ -1012,7 +1024,8 @@ bool pipe_tcg_supported(Batch* b, int F, int N) {
     const char* e = getenv("ATHENA_CUDA_DISABLE_TCG");
     off = (e && atoi(e) != 0) ? 1 : 0;
   }
-  if (off || b->num_tiles == 0 || F != 64 || N != 64 || b->abits == nullptr) return false;
+  if (off || b->num_tiles == 0 || F != N || (F != 64 && F != 32) || b->abits == nullptr)
+    return false;
   if (b->multi_edges < 0) {
     int32_t st[4] = {0, 0, 0, 0};
     if (cudaMemcpyAsync(st, b->status.p, sizeof(st), cudaMemcpyDeviceToHost, ctx().stream) !=
@@ -1024,11 +1037,24 @@ bool pipe_tcg_supported(Batch* b, int F, int N) {
   return b->multi_edges == 0;
 }
 
-int launch_pipe_tcg(const GatherArgs& a, bool transb, int epi) {
-  if (epi == EPI_ACT) return launch_tcg_t<false, EPI_ACT>(a);
-  if (epi == EPI_MSE) return launch_tcg_t<false, EPI_MSE>(a);
+int launch_pipe_tcg(const GatherArgs& a, bool transb, int epi, int width) {
+  ATH_REQUIRE(width == 64 || width == 32, ATHENA_ERR_ARG, "pipe_tcg: unsupported width %d", width);
+  if (width == 32) {
+    // no padded (non-TMA) operand tile at this width: the target must be TMA-addressable, the
+    // reverse step must take act' from sign bits (or have none)
+    ATH_REQUIRE(epi != EPI_ACTGRAD || a.aux == nullptr || a.mask_in != nullptr, ATHENA_ERR_ARG,
+                "pipe_tcg: width 32 needs sign bits for the activation derivative");
+    ATH_REQUIRE(epi != EPI_MSE || (reinterpret_cast<uintptr_t>(a.aux) & 15u) == 0, ATHENA_ERR_ARG,
+                "pipe_tcg: width 32 needs a 16-byte aligned target");
+    if (epi == EPI_ACT) return launch_tcg_t<false, EPI_ACT, 32>(a);
+    if (epi == EPI_MSE) return launch_tcg_t<false, EPI_MSE, 32>(a);
+    ATH_REQUIRE(transb && epi == EPI_ACTGRAD, ATHENA_ERR_ARG, "pipe_tcg: unsupported variant");
+    return launch_tcg_t<true, EPI_ACTGRAD, 32>(a);
+  }
+  if (epi == EPI_ACT) return launch_tcg_t<false, EPI_ACT, 64>(a);
+  if (epi == EPI_MSE) return launch_tcg_t<false, EPI_MSE, 64>(a);
   ATH_REQUIRE(transb && epi == EPI_ACTGRAD, ATHENA_ERR_ARG, "pipe_tcg: unsupported variant");
-  return launch_tcg_t<true, EPI_ACTGRAD>(a);
+  return launch_tcg_t<true, EPI_ACTGRAD, 64>(a);
 }
 
 }  // namespace athena

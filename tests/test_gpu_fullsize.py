@@ -188,3 +188,46 @@ def test_two_gpu_peer_memory_exchange_matches_nccl_and_single_gpu(cuda):
     r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("-> OK") == 2 and "FAIL" not in r.stdout, r.stdout
+
+
+def test_width32_tensor_core_steps_match_oracle(cuda, oracle32, oracle64):
+    """cfg4's Kipf layers (32 -> 32, relu) at a batch that fills the machine (> 2 tiles per SM):
+    the forward, fwd + MSE and reverse steps run on the 32-wide instantiation of the tcgen05
+    tile kernels (ragged tiles: V ~ U[10, 50] molecules), the weight gradients on k_tc_tn.
+    Loss, gradients (float64 arbitration for the long sums) and three SGD steps against the
+    oracle (the loss is a SUM over 1 500 graphs: small learning rate)."""
+    rng = np.random.default_rng(77)
+    p = synth.molecular_batch(1500, 32, 0, rng, self_loop_features=False)
+    assert p.V > 2 * 148 * 128 * 0.9
+    specs = [kipf_spec([32, 32], 1, "relu"), kipf_spec([32, 32], 1, "relu"),
+             kipf_spec([32, 32], 1, "none")]
+    net = ab.network_type()
+    for act in ("relu", "relu", "none"):
+        net.add(ab.kipf_msgpass_layer_type([32, 32], 1, act))
+    net.compile(ab.sgd_optimiser_type(2e-4), batch_size=p.B)
+    n = oracle32.num_params(specs)
+    params = random_params(n, rng, 0.3)
+    net.set_params(params)
+    target = rng.standard_normal((p.V, 32)).astype(np.float32)
+    batch = ab.GraphBatch(p)
+    ob = to_oracle_batch(p)
+    loss_ref, out_ref, g_ref = oracle32.stack_fwd_bwd(specs, params, ob, target)
+    _, _, g64 = oracle64.stack_fwd_bwd(specs, params, ob, target)
+    n0 = np.zeros(1, np.int64)
+    ab.lib().athena_cuda_launch_count(ab.ptr(n0))
+    loss = net.loss_and_gradients(batch, target)
+    n1 = np.zeros(1, np.int64)
+    ab.lib().athena_cuda_launch_count(ab.ptr(n1))
+    assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref)
+    assert_parity(net.get_gradients(), g_ref, g64, RTOL_ACT, "width-32 gradients")
+    assert rel_err(net.forward(batch), out_ref) <= RTOL_ACT
+    ref = params.copy()
+    s1 = np.zeros(n, np.float32); s2 = np.zeros(n, np.float32)
+    net.update()
+    oracle32.train_step(specs, ref, ob, target, OptimSpec("sgd", lr=2e-4), s1, s2, 1)
+    for it in (2, 3):
+        lr_, _ = oracle32.train_step(specs, ref, ob, target, OptimSpec("sgd", lr=2e-4), s1, s2, it)
+        l = net.train_step(batch, target)
+        assert abs(l - lr_) <= 1e-4 * abs(lr_)
+    assert rel_err(net.get_params(), ref) <= RTOL_PARAM
+    net.destroy()
