@@ -300,7 +300,10 @@ k_tc_tn(const float* __restrict__ A1, int lda1, const float* __restrict__ A2, in
     }
     fence_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
+      // converged-warp issue (the instruction is predicated on one elected lane): half the
+      // issue slots of a single-thread branch, see tc_common.cuh
+      const uint32_t leader = elect_one();
       tc_fence_after();
       const uint32_t a1 = smem_u32(sA1), b_hi = smem_u32(sA2hi), b_lo = smem_u32(sA2lo);
 #pragma unroll
@@ -308,10 +311,11 @@ k_tc_tn(const float* __restrict__ A1, int lda1, const float* __restrict__ A2, in
         uint64_t da = make_desc_mn32(a1 + ks * 1024, Cfg::BLK, 512);
         uint64_t dbh = make_desc_mn32(b_hi + ks * 1024, Cfg::BLK, 512);
         uint64_t dbl = make_desc_mn32(b_lo + ks * 1024, Cfg::BLK, 512);
-        umma_tf32(tmem, da, dbh, IDESC, (it | ks) ? 1u : 0u);
-        umma_tf32(tmem, da, dbl, IDESC, 1u);
+        umma_tf32_w(leader, tmem, da, dbh, IDESC, (it | ks) ? 1u : 0u);
+        umma_tf32_w(leader, tmem, da, dbl, IDESC, 1u);
       }
-      umma_commit(&bars[s]);
+      umma_commit_w(leader, &bars[s]);
+      __syncwarp();
     }
   }
   // drain: commits complete in issue order, so the last one covers everything
