@@ -118,6 +118,7 @@ def lib() -> C.CDLL:
         "athena_cuda_network_get_params": [H, P, I64],
         "athena_cuda_network_get_gradients": [H, P, I64],
         "athena_cuda_network_set_learning_rate": [H, F32],
+        "athena_cuda_network_set_iteration": [H, I64],
         "athena_cuda_network_forward": [H, H, P, P, P, I32],
         "athena_cuda_network_train_step": [H, H, P, P, P, I32, I32, PF],
         "athena_cuda_network_loss_and_gradients": [H, H, P, P, P, I32, I32, PF],

@@ -381,6 +381,7 @@ struct OptimState {
   athena_optimiser_desc d{};
   float lr = 0.f;
   int64_t iter = 0;
+  bool iter_external = false;  // the host owns the iteration counter (set_iteration)
   DevBuf s1, s2;   // velocity | m, v
   DevBuf scratch;  // norm partials
   // > 0: launch_finalize already clamped the gradients and left this many partial sums of

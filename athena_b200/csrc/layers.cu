@@ -1352,6 +1352,16 @@ ATHENA_API int athena_cuda_network_set_learning_rate(athena_handle_t net, float 
   return ATHENA_OK;
 }
 
+ATHENA_API int athena_cuda_network_set_iteration(athena_handle_t net, int64_t iteration) {
+  Network* N = static_cast<Network*>(lookup_object(net, Kind::Network));
+  if (!N) return ATHENA_ERR_HANDLE;
+  ATH_REQUIRE(iteration >= 1, ATHENA_ERR_ARG, "set_iteration: iteration = %lld (must be >= 1)",
+              (long long)iteration);
+  N->opt.iter = iteration;
+  N->opt.iter_external = true;
+  return ATHENA_OK;
+}
+
 ATHENA_API int athena_cuda_network_forward(athena_handle_t net, athena_handle_t batch,
                                            const float* vertex_features,
                                            const float* edge_features, float* output,

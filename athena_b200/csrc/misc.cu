@@ -534,7 +534,10 @@ static int step_prepare(int64_t n, OptimState& st, StepArgs* a) {
     ATH_CUDA(cudaMemsetAsync(st.s2.p, 0, sizeof(float) * (size_t)n, s));
   }
   ATH_TRY(st.scratch.reserve(sizeof(float) * 1024));
-  st.iter += 1;  // incremented BEFORE the step, athena_network_sub.f90:2834-2841
+  // incremented BEFORE the step (athena_network_sub.f90:2834-2841) -- unless the host keeps
+  // the counter (lr_decay%iterate_per_epoch advances it once per epoch, and Adam's bias
+  // correction reads the same counter)
+  if (!st.iter_external) st.iter += 1;
   const athena_optimiser_desc& d = st.d;
   a->kind = d.kind;
   a->lr = st.lr;

@@ -56,15 +56,63 @@ class l1l2_regulariser_type:
         self.l1, self.l2, self.decoupled = float(l1), float(l2), True
 
 
+class base_lr_decay_type:
+    """base_lr_decay_type: no decay (athena_lr_decay.f90:200-214)."""
+    iterate_per_epoch = False
+
+    def get_lr(self, learning_rate: float, iteration: int) -> float:
+        return float(np.float32(learning_rate))
+
+
+class exp_lr_decay_type(base_lr_decay_type):
+    """exp_lr_decay_type(decay_rate = 0.9): lr * exp(-iteration * decay_rate)
+    (athena_lr_decay.f90:127-143, 218-233)."""
+
+    def __init__(self, decay_rate: float = 0.9):
+        self.decay_rate = float(decay_rate)
+
+    def get_lr(self, learning_rate, iteration):
+        return float(np.float32(learning_rate) *
+                     np.exp(-np.float32(iteration) * np.float32(self.decay_rate), dtype=np.float32))
+
+
+class step_lr_decay_type(base_lr_decay_type):
+    """step_lr_decay_type(decay_rate = 0.1, decay_steps = 100): lr * decay_rate ** (iteration /
+    decay_steps), integer division, the counter advancing once per EPOCH
+    (athena_lr_decay.f90:146-170, 236-251)."""
+    iterate_per_epoch = True
+
+    def __init__(self, decay_rate: float = 0.1, decay_steps: int = 100):
+        self.decay_rate, self.decay_steps = float(decay_rate), int(decay_steps)
+
+    def get_lr(self, learning_rate, iteration):
+        return float(np.float32(learning_rate) *
+                     np.float32(self.decay_rate) ** (int(iteration) // self.decay_steps))
+
+
+class inv_lr_decay_type(base_lr_decay_type):
+    """inv_lr_decay_type(decay_rate = 0.001, decay_power = 1): lr * (1 + decay_rate * iteration)
+    ** (-decay_power) (athena_lr_decay.f90:173-195, 254-270)."""
+
+    def __init__(self, decay_rate: float = 0.001, decay_power: float = 1.0):
+        self.decay_rate, self.decay_power = float(decay_rate), float(decay_power)
+
+    def get_lr(self, learning_rate, iteration):
+        base = np.float32(1.0) + np.float32(self.decay_rate) * np.float32(iteration)
+        return float(np.float32(learning_rate) * base ** np.float32(-self.decay_power))
+
+
 class base_optimiser_type:
     kind = _lib.OPT_SGD
 
     def __init__(self, learning_rate: float = 0.01, clip_dict: Optional[clip_type] = None,
-                 regulariser=None):
+                 regulariser=None, lr_decay: Optional[base_lr_decay_type] = None):
         self.learning_rate = float(learning_rate)
         self.clip_dict = clip_dict or clip_type()
         self.regulariser = regulariser
+        self.lr_decay = lr_decay or base_lr_decay_type()
         self.iter = 0
+        self.epoch = 0
 
     def desc(self) -> OptimiserDesc:
         d = OptimiserDesc()
@@ -87,8 +135,9 @@ class sgd_optimiser_type(base_optimiser_type):
     kind = _lib.OPT_SGD
 
     def __init__(self, learning_rate: float = 0.01, momentum: float = 0.0, nesterov: bool = False,
-                 clip_dict: Optional[clip_type] = None, regulariser=None):
-        super().__init__(learning_rate, clip_dict, regulariser)
+                 clip_dict: Optional[clip_type] = None, regulariser=None,
+                 lr_decay: Optional[base_lr_decay_type] = None):
+        super().__init__(learning_rate, clip_dict, regulariser, lr_decay)
         self.momentum, self.nesterov = float(momentum), bool(nesterov)
 
     def desc(self):
@@ -102,8 +151,9 @@ class adam_optimiser_type(base_optimiser_type):
     kind = _lib.OPT_ADAM
 
     def __init__(self, learning_rate: float = 0.01, beta1: float = 0.9, beta2: float = 0.999,
-                 epsilon: float = 1e-8, clip_dict: Optional[clip_type] = None, regulariser=None):
-        super().__init__(learning_rate, clip_dict, regulariser)
+                 epsilon: float = 1e-8, clip_dict: Optional[clip_type] = None, regulariser=None,
+                 lr_decay: Optional[base_lr_decay_type] = None):
+        super().__init__(learning_rate, clip_dict, regulariser, lr_decay)
         self.beta1, self.beta2, self.epsilon = float(beta1), float(beta2), float(epsilon)
 
     def desc(self):
@@ -118,8 +168,9 @@ class rmsprop_optimiser_type(base_optimiser_type):
     kind = _lib.OPT_RMSPROP
 
     def __init__(self, learning_rate: float = 0.01, beta: float = 0.0, epsilon: float = 1e-8,
-                 clip_dict: Optional[clip_type] = None, regulariser=None):
-        super().__init__(learning_rate, clip_dict, regulariser)
+                 clip_dict: Optional[clip_type] = None, regulariser=None,
+                 lr_decay: Optional[base_lr_decay_type] = None):
+        super().__init__(learning_rate, clip_dict, regulariser, lr_decay)
         self.beta, self.epsilon = float(beta), float(epsilon)
 
     def desc(self):
@@ -134,8 +185,9 @@ class adagrad_optimiser_type(base_optimiser_type):
     kind = _lib.OPT_ADAGRAD
 
     def __init__(self, learning_rate: float = 0.01, epsilon: float = 1e-8,
-                 clip_dict: Optional[clip_type] = None, regulariser=None):
-        super().__init__(learning_rate, clip_dict, regulariser)
+                 clip_dict: Optional[clip_type] = None, regulariser=None,
+                 lr_decay: Optional[base_lr_decay_type] = None):
+        super().__init__(learning_rate, clip_dict, regulariser, lr_decay)
         self.epsilon = float(epsilon)
 
     def desc(self):
@@ -275,6 +327,23 @@ class network_type:
     def update(self):
         check(lib().athena_cuda_network_update(self.handle))
 
+    def _advance_optimiser(self):
+        """The head of network%update (athena_network_sub.f90:2834-2841, athena_optimiser.f90:414):
+        advance the optimiser's iteration counter -- once per epoch when the decay iterates per
+        epoch -- and hand the decayed learning rate (and, for per-epoch counters, the iteration
+        Adam's bias correction must use) to the device."""
+        o = self.optimiser
+        if o is None or type(o.lr_decay) is base_lr_decay_type:
+            return
+        if o.lr_decay.iterate_per_epoch:
+            if self.epoch > o.epoch:
+                o.epoch = self.epoch
+                o.iter += 1
+            check(lib().athena_cuda_network_set_iteration(self.handle, max(o.iter, 1)))
+        else:
+            o.iter += 1
+        self.set_learning_rate(o.lr_decay.get_lr(o.learning_rate, o.iter))
+
     # -- network%train -------------------------------------------------------
     def train(self, input: Union[Sequence[graph_type], PackedGraphs], output, num_epochs: int = 1,
               batch_size: Optional[int] = None, shuffle_batches: bool = True, verbose: int = 0,
@@ -316,6 +385,7 @@ class network_type:
                 rng.shuffle(order)
             avg = 0.0
             for b in order:
+                self._advance_optimiser()
                 s0, s1 = int(b) * bs, min((int(b) + 1) * bs, num_samples)
                 if resident:
                     if int(b) not in batches:

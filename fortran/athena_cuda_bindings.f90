@@ -74,7 +74,7 @@ module athena__cuda_bindings
   public :: athena_cuda_layer_zero_gradients
   public :: athena_cuda_layer_forward, athena_cuda_layer_backward
   public :: athena_cuda_network_create, athena_cuda_network_destroy, athena_cuda_network_add
-  public :: athena_cuda_network_add_inputs
+  public :: athena_cuda_network_add_inputs, athena_cuda_network_set_iteration
   public :: athena_cuda_batch_create_from_edges, athena_cuda_batch_create_from_edge_index
   public :: athena_cuda_network_compile, athena_cuda_network_num_params
   public :: athena_cuda_network_set_params, athena_cuda_network_get_params
@@ -362,6 +362,12 @@ module athena__cuda_bindings
        import :: c_int, c_int64_t, c_float
        integer(c_int64_t), value :: net
        real(c_float), value :: lr
+       integer(c_int) :: rc
+     end function
+     function athena_cuda_network_set_iteration(net, iteration) &
+          bind(C, name="athena_cuda_network_set_iteration") result(rc)
+       import :: c_int, c_int64_t
+       integer(c_int64_t), value :: net, iteration
        integer(c_int) :: rc
      end function
      function athena_cuda_network_forward(net, batch, vertex_features, edge_features, output, &

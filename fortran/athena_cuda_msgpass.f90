@@ -272,9 +272,13 @@ contains
   !> layers live on the device: the iteration counter, the learning-rate schedule and the
   !> clip / minimise / zero-gradients sequence keep their order; the flat parameter and
   !> gradient vectors never visit the host.
-  subroutine cuda_network_update(net_handle, learning_rate)
+  subroutine cuda_network_update(net_handle, learning_rate, iteration)
     integer(c_int64_t), intent(in) :: net_handle
     real(real32), intent(in) :: learning_rate   !! lr_decay%get_lr(lr0, iter), host side
+    integer, optional, intent(in) :: iteration  !! this%optimiser%iter when lr_decay iterates
+                                                !! per epoch (athena_network_sub.f90:2834-2838)
+    if (present(iteration)) call athena_cuda_check( &
+         athena_cuda_network_set_iteration(net_handle, int(iteration, c_int64_t)))
     call athena_cuda_check(athena_cuda_network_set_learning_rate(net_handle, learning_rate))
     call athena_cuda_check(athena_cuda_network_update(net_handle))
   end subroutine cuda_network_update

@@ -384,6 +384,13 @@ int athena_cuda_network_get_gradients(athena_handle_t net, float* host, int64_t 
 /* learning rate for the next update (host-side lr_decay%get_lr result,
  * athena_lr_decay.f90:200-216, stays a Fortran scalar). */
 int athena_cuda_network_set_learning_rate(athena_handle_t net, float lr);
+/* The optimiser's iteration counter as the host keeps it (this%optimiser%iter): by default the
+ * library increments its own counter before every step (athena_network_sub.f90:2834-2841); a
+ * network whose lr_decay iterates per epoch (step_lr_decay_type, athena_lr_decay.f90:169)
+ * advances it once per epoch only (:2834-2838) -- and Adam's bias corrections read the same
+ * counter (athena_optimiser.f90:1058-1059).  After this call the library uses the value given
+ * (>= 1) for the next steps and no longer increments it: call it before every step. */
+int athena_cuda_network_set_iteration(athena_handle_t net, int64_t iteration);
 
 /* network%forward / predict (athena_network_sub.f90:2639-2768, 4226-4303). */
 int athena_cuda_network_forward(athena_handle_t net, athena_handle_t batch,

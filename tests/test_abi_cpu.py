@@ -208,3 +208,21 @@ def test_extxyz_reader_follows_the_reference_reader():
     g = get_graph_from_basis(fr[0]["lattice"], fr[0]["species"], fr[0]["positions"], fr[0]["forces"])
     # distances: 1.0 (the pair) and 3.0 (pair through the far face) -- 3.0 is NOT < cutoff_max
     assert g.num_edges == 1 and abs(float(g.edge_features[0, 0]) - 1.0 / 3.0) < 1e-6
+
+
+def test_lr_decay_mirrors_follow_the_reference_formulas():
+    """athena_lr_decay.f90:218-270 in real32: exp lr*exp(-it*rate), step lr*rate**(it/steps)
+    with integer division and a per-epoch counter, inv lr*(1+rate*it)**(-power)."""
+    from athena_b200.network import (base_lr_decay_type, exp_lr_decay_type, inv_lr_decay_type,
+                                     step_lr_decay_type)
+    f = np.float32
+    assert base_lr_decay_type().get_lr(0.02, 7) == float(f(0.02))
+    e = exp_lr_decay_type(1e-3)
+    assert not e.iterate_per_epoch
+    assert abs(e.get_lr(2e-2, 150) - float(f(2e-2) * np.exp(f(-150) * f(1e-3)))) <= 1e-9
+    s = step_lr_decay_type(0.5, 5)
+    assert s.iterate_per_epoch
+    assert [s.get_lr(1.0, it) for it in (1, 4, 5, 9, 10)] == [1.0, 1.0, 0.5, 0.5, 0.25]
+    assert exp_lr_decay_type().decay_rate == 0.9 and step_lr_decay_type().decay_steps == 100
+    i = inv_lr_decay_type(0.01, 2.0)
+    assert abs(i.get_lr(0.1, 10) - 0.1 / 1.1 ** 2) <= 1e-8

@@ -1052,3 +1052,45 @@ def test_dataset_resident_training_equals_streaming(cuda, kind):
     assert np.array_equal(a.get_params(), b.get_params())
     a.destroy()
     b.destroy()
+
+
+@pytest.mark.parametrize("decay", ["exp", "step"])
+def test_lr_decay_training_parity(cuda, oracle32, decay):
+    """network%train with a decaying learning rate (athena_optimiser.f90:414 get_lr(lr, iter)):
+    exp decay per iteration (example/msgpass_euler: exp_lr_decay_type(1e-3)); step decay advances
+    the optimiser's counter once per EPOCH, and Adam's bias correction reads that same counter
+    (athena_network_sub.f90:2834-2841, athena_optimiser.f90:1058-1059)."""
+    rng = np.random.default_rng(13)
+    p = synth.molecular_batch(24, 6, 0, rng, nv_range=(3, 12), self_loop_features=False)
+    specs = [kipf_spec([6, 10], 1, "tanh"), kipf_spec([10, 3], 1, "none")]
+    lr0 = 0.02
+    dec = ab.exp_lr_decay_type(0.05) if decay == "exp" else ab.step_lr_decay_type(0.5, 2)
+    net = ab.network_type()
+    net.add(ab.kipf_msgpass_layer_type([6, 10], 1, "tanh"))
+    net.add(ab.kipf_msgpass_layer_type([10, 3], 1, "none"))
+    net.compile(ab.adam_optimiser_type(lr0, lr_decay=dec), batch_size=8)
+    n = oracle32.num_params(specs)
+    params = random_params(n, rng, 0.4)
+    net.set_params(params)
+    target = rng.standard_normal((p.V, 3)).astype(np.float32)
+    hist = net.train(p, target, num_epochs=4, shuffle_batches=False)
+    ref = params.copy()
+    s1 = np.zeros(n, np.float32); s2 = np.zeros(n, np.float32)
+    voff = np.concatenate([[0], np.cumsum(p.nv)])
+    it, hist_ref = 0, []
+    for epoch in range(1, 5):
+        if decay == "step":
+            it = epoch                                  # the counter advances once per epoch
+        tot = 0.0
+        for s0 in range(0, 24, 8):
+            if decay == "exp":
+                it += 1
+            q = p.slice(s0, s0 + 8)
+            o = OptimSpec("adam", lr=dec.get_lr(lr0, it))
+            l, _ = oracle32.train_step(specs, ref, to_oracle_batch(q),
+                                       target[voff[s0]:voff[s0 + 8]], o, s1, s2, it)
+            tot += l
+        hist_ref.append(tot / 3)
+    assert np.allclose(hist, hist_ref, rtol=1e-4)
+    assert rel_err(net.get_params(), ref) <= RTOL_PARAM
+    net.destroy()
