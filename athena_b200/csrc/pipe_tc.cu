@@ -588,8 +588,10 @@ k_pipe_tn(TnJobs jobs) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  pdl_launch_dependents();
   pdl_wait();  // the set-up above overlapped the previous kernel's tail
+  // only now may the NEXT kernel start: everything before this kernel has completed, so a
+  // dependent that skips ahead never overlaps a grid older than this one
+  pdl_launch_dependents();
   // stages of job q owned by this CTA; every role walks the jobs in order with running
   // counters: j over stages (ring / operand-buffer phases), gcount over accumulator groups
   auto tiles_of = [&](int q) { return (jobs.M[q] + Cfg::RS - 1) / Cfg::RS; };

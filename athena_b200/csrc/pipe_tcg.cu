@@ -336,8 +336,10 @@ k_pipe_tcg(GatherArgs a, const __grid_constant__ CUtensorMap aux_map,
   const uint32_t tmem = *tmem_slot;
   // programmatic dependent launch: everything above overlapped the tail of the previous
   // kernel; from here on its results (features, gradients, updated weights) are read
-  pdl_launch_dependents();
   pdl_wait();
+  // only now may the NEXT kernel start: everything before this kernel has completed, so a
+  // dependent that skips ahead never overlaps a grid older than this one
+  pdl_launch_dependents();
   const bool has_coef = a.rs != nullptr;
   constexpr int ns = Cfg::NS;
   int my_tiles = 0;
