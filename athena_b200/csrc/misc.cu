@@ -333,9 +333,8 @@ k_finalize(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
            float* __restrict__ s2, long long n, FinArgs f, StepArgs a) {
   __shared__ float red[FIN_GROUPS][FIN_ELEMS];
   pdl_wait();
-  // only now may the NEXT kernel start: everything before this kernel has completed, so a
-  // dependent that skips ahead never overlaps a grid older than this one
-  pdl_launch_dependents();
+  // (no early release of the next kernel: this one may write the parameters, which a forward
+  // kernel stages before its own wait)
   const int e = threadIdx.x % FIN_ELEMS, grp = threadIdx.x / FIN_ELEMS;
   const long long i = (long long)blockIdx.x * FIN_ELEMS + e;
   float sum = 0.f;
