@@ -714,6 +714,29 @@ def main():
         e2e = dict(best)
         e2e["other_route"] = other
 
+        # the platform's own ceiling for this step: every rank copies the same pinned buffers to
+        # its device with nothing else going on (all ranks at once) -- what the host's memory
+        # system and PCIe topology deliver to N GPUs, however the step is organised
+        def h2d_only():
+            for key, dst in (("x", x_d), ("t", t_d)):
+                ab.check(L.athena_cuda_memcpy_h2d(C.c_void_p(dst.addr), ab.ptr(host[0][key]),
+                                                  host[0][key].nbytes))
+        for _ in range(3):
+            h2d_only()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            h2d_only()
+        ab.check(L.athena_cuda_synchronize())
+        dt_copy = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        copy_bytes = host[0]["x"].nbytes + host[0]["t"].nbytes
+        e2e["host_ceiling"] = {
+            "h2d_GBps_all_ranks": world * copy_bytes * 10 / dt_copy / 1e9,
+            "ms_per_step_at_ceiling": e2e["h2d_bytes_per_step"] / (copy_bytes * 10 / dt_copy) * 1e3,
+            "how": "every rank copies its pinned feature + target buffers (134 MB) to its device "
+                   "10 times, all ranks at once, nothing else running"}
+
         # (c) dataset-resident epochs (network%train is handed the whole data set once,
         #     athena_network_sub.f90:3564-3565): batches and features stay on the device, a
         #     step moves nothing but the loss.  Reported beside, never instead of, the above.
