@@ -1094,3 +1094,64 @@ def test_lr_decay_training_parity(cuda, oracle32, decay):
     assert np.allclose(hist, hist_ref, rtol=1e-4)
     assert rel_err(net.get_params(), ref) <= RTOL_PARAM
     net.destroy()
+
+
+def test_generate_adjacency_from_device_edge_list(cuda):
+    """athena_cuda_batch_create_from_edges with the index list already in device memory
+    (ATHENA_MEM_DEVICE), e.g. produced by an earlier kernel: same batch as from host memory."""
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    nvs, ils = _random_edge_lists(rng, 31, 25, 70)
+    nv = np.asarray(nvs, np.int32)
+    ne = np.asarray([len(il) for il in ils], np.int32)
+    il = np.ascontiguousarray(np.concatenate(ils), np.int32)
+    ref = ab.GraphBatch.from_edges(nvs, ils, add_self_loops=True)
+    d_il = ab.DeviceArray.from_host(il)
+    h = C.c_int64()
+    ab.check(ab.lib().athena_cuda_batch_create_from_edges(
+        C.byref(h), nv.size, ab.ptr(nv), ab.ptr(ne), C.c_void_p(d_il.addr), None, 1,
+        ab.MEM_DEVICE, 1))
+    dev = ab.GraphBatch._adopt(h.value)
+    assert (dev.V, dev.Z) == (ref.V, ref.Z)
+    for k in BATCH_INTS:
+        assert np.array_equal(dev.export(k), ref.export(k)), k
+    dev.destroy()
+    ref.destroy()
+    d_il.free()
+
+
+def test_onnx_edge_index_single_large_graph_and_empty_graphs(cuda):
+    """One graph that is not tileable (5 000 vertices) and a batch with empty graphs through the
+    edge_index route."""
+    rng = np.random.default_rng(4)
+    nvs, ils = [5000, 0, 3, 0], [rng.integers(1, 5001, (20000, 2)).astype(np.int32),
+                                 np.zeros((0, 2), np.int32), np.array([[1, 2], [2, 3]], np.int32),
+                                 np.zeros((0, 2), np.int32)]
+    graphs = _host_graphs(nvs, ils, True)
+    p = ab.pack_graphs(graphs, with_features=False)
+    ref = ab.GraphBatch(p)
+    pairs = [_edge_index_of(g) for g in graphs]
+    dev = ab.GraphBatch.from_edge_index(p.nv, p.ne, [e for e, _ in pairs],
+                                        np.concatenate([d for _, d in pairs]))
+    for k in BATCH_INTS:
+        assert np.array_equal(dev.export(k), ref.export(k)), k
+    dev.destroy()
+    ref.destroy()
+
+
+def test_skip_network_multi_step_sources(cuda, oracle32, oracle64):
+    """Sources with several time steps: the concatenation takes the LAST step's width
+    (num_vertex_features(T)), the gradient re-enters the source layer at its last step."""
+    from oracle.oracle import LayerSpec
+    rng = np.random.default_rng(78)
+    p = synth.molecular_batch(17, 4, 0, rng, nv_range=(2, 25), self_loop_features=False)
+    specs = [LayerSpec("kipf", [4, 6, 5], 2, activation="tanh"),
+             LayerSpec("kipf", [9, 7, 3], 2, activation="sigmoid", inputs=[0, -1]),
+             LayerSpec("kipf", [12, 2], 1, activation="none", inputs=[-1, 0, 1])]
+    layers = [ab.kipf_msgpass_layer_type([4, 6, 5], 2, "tanh"),
+              ab.kipf_msgpass_layer_type([9, 7, 3], 2, "sigmoid"),
+              ab.kipf_msgpass_layer_type([12, 2], 1, "none")]
+    lists = [None, [1, 0], [0, 1, 2]]
+    target = rng.standard_normal((p.V, 2)).astype(np.float32)
+    _train_compare(cuda, oracle32, specs, layers, p, target, OptimSpec("adam", lr=0.01),
+                   ab.adam_optimiser_type(0.01), input_lists=lists, oracle64=oracle64)
