@@ -279,6 +279,89 @@ static void network_scenario(int n_layers, const oracle_layer_t* specs, const at
   free(params); free(target); free(s1); free(s2); free(grads); free(out_ref); free(p_dev);
 }
 
+/* ---- scenario C: example/msgpass_euler's shape of program: the reader hands over EDGE LISTS,
+ * generate_adjacency + add_self_loops run on the device, the layers are added with
+ * input_list = [0, -1] / operator "concatenate", the batch loop runs on the device ---------- */
+static void skip_scenario(const batch_t* b, const char* name) {
+  printf("%s\n", name);
+  /* the edge lists make_batch built its CSR from: edge k of a graph is listed in both rows with
+   * id k, so row v's entries (nb > v, id k) give back (v, nb) */
+  int* il = malloc(sizeof(int) * 2 * (b->E > 0 ? b->E : 1));
+  {
+    const int* ia = b->ia;
+    const int* ja = b->ja;
+    int e0 = 0;
+    for (int s = 0; s < b->B; ++s) {
+      for (int v = 0; v < b->nv[s]; ++v)
+        for (int w = ia[v] - 1; w < ia[v + 1] - 1; ++w) {
+          const int nb = ja[2 * w], k = ja[2 * w + 1];
+          if (k > 0 && nb > v + 1) il[2 * (e0 + k - 1)] = v + 1, il[2 * (e0 + k - 1) + 1] = nb;
+        }
+      ja += 2 * b->nz[s];
+      ia += b->nv[s] + 1;
+      e0 += b->ne[s];
+    }
+  }
+  /* kipf [4 -> 6, softmax] ; kipf [4 + 6 -> 5, softmax] <- [input | previous] ;
+   * kipf [4 + 5 -> 3, swish] <- [input | previous] */
+  oracle_layer_t sp[3];
+  memset(sp, 0, sizeof(sp));
+  const int widths[3][2] = {{4, 6}, {10, 5}, {9, 3}};
+  const int acts[3] = {ATHENA_ACT_SOFTMAX, ATHENA_ACT_SOFTMAX, ATHENA_ACT_SWISH};
+  athena_handle_t net = 0, L[3] = {0, 0, 0};
+  CHECK(athena_cuda_network_create(&net));
+  int np = 0;
+  for (int l = 0; l < 3; ++l) {
+    sp[l].kind = 0; sp[l].T = 1; sp[l].nvf[0] = widths[l][0]; sp[l].nvf[1] = widths[l][1];
+    sp[l].act = acts[l];
+    if (l > 0) { sp[l].n_in = 2; sp[l].in[0] = -1; sp[l].in[1] = l - 1; }
+    const int32_t nvf[2] = {widths[l][0], widths[l][1]};
+    CHECK(athena_cuda_kipf_layer_create(&L[l], 1, nvf, acts[l]));
+    const int32_t input_list[2] = {0, -1}; /* as example/msgpass_euler/src/main.f90:202 writes it */
+    if (l == 0) CHECK(athena_cuda_network_add(net, L[l]));
+    else CHECK(athena_cuda_network_add_inputs(net, L[l], 2, input_list, ATHENA_MERGE_CONCATENATE));
+    np += oracle_layer_num_params(&sp[l]);
+  }
+  oracle_optim_t oo;
+  memset(&oo, 0, sizeof(oo));
+  oo.kind = 1; oo.lr = 0.02f; oo.beta1 = 0.9f; oo.beta2 = 0.999f; oo.eps = 1e-8f;
+  oo.clip_flags = 1; oo.clip_min = -1.f; oo.clip_max = 1.f;
+  athena_optimiser_desc od;
+  memset(&od, 0, sizeof(od));
+  od.kind = ATHENA_OPT_ADAM; od.learning_rate = 0.02f; od.beta1 = 0.9f; od.beta2 = 0.999f;
+  od.epsilon = 1e-8f; od.clip_min_max = 1; od.clip_min = -1.f; od.clip_max = 1.f; od.l2_decoupled = 1;
+  CHECK(athena_cuda_network_compile(net, &od));
+  float* params = malloc(sizeof(float) * np);
+  for (int i = 0; i < np; ++i) params[i] = frand() * 0.8f;
+  CHECK(athena_cuda_network_set_params(net, params, np));
+  const long out_n = (long)b->V * 3;
+  float* target = malloc(sizeof(float) * out_n);
+  for (long i = 0; i < out_n; ++i) target[i] = frand();
+  float* s1 = calloc(np, sizeof(float));
+  float* s2 = calloc(np, sizeof(float));
+  float* grads = malloc(sizeof(float) * np);
+  float* out_ref = malloc(sizeof(float) * out_n);
+  double worst_loss = 0;
+  for (int it = 1; it <= 3; ++it) {
+    athena_handle_t batch = 0;
+    CHECK(athena_cuda_batch_create_from_edges(&batch, b->B, b->nv, b->ne, il, NULL, 1,
+                                              ATHENA_MEM_HOST, 1));
+    float loss = 0.f;
+    CHECK(athena_cuda_network_train_step(net, batch, b->x, NULL, target, ATHENA_MEM_HOST, b->B, &loss));
+    CHECK(athena_cuda_batch_destroy(batch));
+    float loss_ref = oracle_train_step(3, sp, params, b->B, b->nv, b->ne, b->ia, b->ja, b->x, NULL,
+                                       target, out_ref, grads, &oo, s1, s2, it);
+    double e = fabs((double)loss - loss_ref) / fmax(fabs((double)loss_ref), 1e-30);
+    if (e > worst_loss) worst_loss = e;
+  }
+  float* p_dev = malloc(sizeof(float) * np);
+  CHECK(athena_cuda_network_get_params(net, p_dev, np));
+  expect("batch loss over 3 iterations", worst_loss, 1e-5);
+  expect("parameters after 3 iterations", rel_err(p_dev, params, np), 1e-4);
+  CHECK(athena_cuda_network_destroy(net));
+  free(il); free(params); free(target); free(s1); free(s2); free(grads); free(out_ref); free(p_dev);
+}
+
 int main(void) {
   if (athena_cuda_init(-1) != 0) {
     fprintf(stderr, "fake_athena: %s\n", athena_cuda_last_error());
@@ -331,6 +414,10 @@ int main(void) {
     od.kind = ATHENA_OPT_ADAM; od.learning_rate = 0.01f; od.beta1 = 0.9f; od.beta2 = 0.999f;
     od.epsilon = 1e-8f; od.clip_norm_on = 1; od.clip_norm = 0.5f; od.l2_decoupled = 1;
     network_scenario(2, s, L, &b, &oo, &od, "B   Kipf -> Duvenaud network, batch loop of network%train on the device");
+  }
+  { /* C: skip-connected Kipf network from edge lists (example/msgpass_euler's call sequence) */
+    batch_t b = make_batch(6, nv, 4, 0);
+    skip_scenario(&b, "C   edge lists -> device CSR, network%add(input_list = [0, -1], 'concatenate'), swish head");
   }
   CHECK(athena_cuda_shutdown());
   printf(g_fail ? "fake_athena: MISMATCH\n" : "fake_athena: parity ok\n");
