@@ -329,6 +329,8 @@ int launch_gemm_tn(const float* A, int lda, const float* G, int ldg, float* dW, 
 // out may alias G (in-place use): no __restrict__ on those two
 __global__ void k_act_bwd(int act, const float* __restrict__ Y, const float* G, float* out,
                           long long n) {
+  pdl_wait();  // launched programmatically dependent
+  pdl_launch_dependents();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) out[i] = act_grad(act, Y[i], G[i]);
@@ -406,7 +408,7 @@ int launch_act_bwd(int act, const float* Y, const float* G, float* out, int64_t 
   } else {
     int64_t n = M * N;
     int blocks = (int)std::min<int64_t>(cdiv(n, 256), (int64_t)ctx().sm_count * 16);
-    k_act_bwd<<<blocks, 256, 0, st>>>(act, Y, G, out, n);
+    ATH_CUDA(launch_pdl(k_act_bwd, dim3(blocks), dim3(256), 0, st, act, Y, G, out, (long long)n));
   }
   ATH_LAUNCHED_T("act_bwd");
   return ATHENA_OK;

@@ -237,6 +237,8 @@ k_tc_tn(const float* __restrict__ A1, int lda1, const float* __restrict__ A2, in
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();  // TMEM allocation and barrier set-up overlapped the previous kernel's tail
+  pdl_launch_dependents();
   constexpr uint32_t IDESC = make_idesc(128, N, true, true);
   constexpr int CH1 = K / 4, CH2 = N / 4, CHT = CH1 + CH2;
   constexpr int LOADS = Cfg::RS * CHT / Cfg::THREADS;
@@ -432,8 +434,8 @@ static int launch_tn_t(const float* A1, int lda1, const float* A2, int lda2, con
   int64_t ntiles = cdiv(M, Cfg::RS);
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx().sm_count);
   ATH_TRY(scratch.reserve(sizeof(float) * (size_t)grid * Cfg::K * N));
-  k_tc_tn<K, N><<<grid, Cfg::THREADS, Cfg::SMEM, ctx().stream>>>(A1, lda1, A2, lda2, Hact, act_in,
-                                                                scratch.as<float>(), M);
+  ATH_CUDA(launch_pdl(k_tc_tn<K, N>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, ctx().stream, A1,
+                      lda1, A2, lda2, Hact, act_in, scratch.as<float>(), (long long)M));
   ATH_LAUNCHED_T("tc_tn");
   if (defer) {  // the fold of the per-CTA partials rides on the finalize launch
     defer->jobs.push_back(DeferJob{scratch.as<float>(), grid, Cfg::K * N, dW});

@@ -853,6 +853,8 @@ __device__ __forceinline__ void duv_update(int tid, int act, float* Z, const flo
 }
 
 __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs a) {
+  pdl_wait();  // launched programmatically dependent: nothing of the previous kernel is read
+  pdl_launch_dependents();  // (or overwritten) before it has completed
   extern __shared__ float4 tf_smem4[];
   float* sm = reinterpret_cast<float*>(tf_smem4);
   const DuvLayout& L = a.lay;
@@ -959,6 +961,8 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
 }
 
 __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float4 tf_smem4[];
   float* sm = reinterpret_cast<float*>(tf_smem4);
   const DuvLayout& L = a.lay;
@@ -1407,7 +1411,8 @@ int launch_tile_duv_fwd(const Batch* b, const TileDuvDesc& d, float* out, const 
   a.mse_denom = mse_denom;
   a.loss_part = target != nullptr ? loss_part : nullptr;
   const int grid = std::min((int)cdiv(b->num_tiles, ng), ctx().sm_count);
-  k_duv_fwd<<<grid, TF_GROUP * ng, a.lay.total_bytes[ng], ctx().stream>>>(a);
+  ATH_CUDA(launch_pdl(k_duv_fwd, dim3(grid), dim3(TF_GROUP * ng), a.lay.total_bytes[ng],
+                      ctx().stream, a));
   ATH_LAUNCHED_T(target != nullptr ? "tile_duv_fwd_mse" : "tile_duv_fwd");
   if (num_parts) *num_parts = grid * ng;
   return ATHENA_OK;
@@ -1432,7 +1437,8 @@ int launch_tile_duv_bwd(const Batch* b, const TileDuvDesc& d, const float* gout,
   a.gin = gin;
   a.part = part.as<float>();
   a.np = (int)num_params;
-  k_duv_bwd<<<grid, TF_GROUP * ng, a.lay.total_bytes[ng], ctx().stream>>>(a);
+  ATH_CUDA(launch_pdl(k_duv_bwd, dim3(grid), dim3(TF_GROUP * ng), a.lay.total_bytes[ng],
+                      ctx().stream, a));
   ATH_LAUNCHED_T("tile_duv_bwd");
   *nparts = grid * ng;
   return ATHENA_OK;
