@@ -213,10 +213,13 @@ struct TnCfg {
   static constexpr int STAGE = A1_BYTES + 2 * A2_HALF;
   static constexpr int SMEM = 1024 + 2 * STAGE + 64;
   static constexpr int TMEM_COLS = (N <= 32 ? 32 : 64);
+  // the loop is a load -> split -> MMA chain with one 64-row stage in flight per CTA: where two
+  // CTAs fit one SM (N = 32) the second one doubles the bytes in flight
+  static constexpr int CTAS_PER_SM = (2 * (SMEM + 1024) <= 227 * 1024) ? 2 : 1;
 };
 
 template <int KW, int N>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(512, TnCfg<KW, N>::CTAS_PER_SM)
 k_tc_tn(const float* __restrict__ A1, int lda1, const float* __restrict__ A2, int lda2,
         const float* __restrict__ Hact, int act_in, float* __restrict__ part, long long M) {
   using Cfg = TnCfg<KW, N>;
@@ -432,7 +435,7 @@ static int launch_tn_t(const float* A1, int lda1, const float* A2, int lda2, con
     attr = true;
   }
   int64_t ntiles = cdiv(M, Cfg::RS);
-  int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx().sm_count);
+  int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx().sm_count * Cfg::CTAS_PER_SM);
   ATH_TRY(scratch.reserve(sizeof(float) * (size_t)grid * Cfg::K * N));
   ATH_CUDA(launch_pdl(k_tc_tn<K, N>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, ctx().stream, A1,
                       lda1, A2, lda2, Hact, act_in, scratch.as<float>(), (long long)M));

@@ -506,7 +506,8 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
 }
 
 static int duvenaud_backward(Layer* L, Batch* b, const float* gout, float* gin,
-                             DeferList* defer = nullptr) {
+                             DeferList* defer = nullptr, int fold_act = ATHENA_ACT_NONE,
+                             bool* folded = nullptr) {
   const int64_t V = b->V;
   if (L->tile_fwd) {
     // the whole reverse sweep of the layer in ONE launch; A_t and S_t are recomputed from z_t
@@ -514,6 +515,14 @@ static int duvenaud_backward(Layer* L, Batch* b, const float* gout, float* gin,
     for (int t = 1; t <= L->T; ++t) Z[t - 1] = L->H[t - 1]->as<float>();
     TileDuvDesc d;
     duv_desc(L, L->fwd_x, L->fwd_e, Z, &d);
+    if (gin != nullptr && folded != nullptr && fold_act != ATHENA_ACT_NONE &&
+        fold_act != ATHENA_ACT_LINEAR && fold_act != ATHENA_ACT_SOFTMAX &&
+        fold_act != ATHENA_ACT_SWISH) {
+      // the input gradient leaves as the gradient w.r.t. the producing layer's pre-activation
+      // (its output is this layer's input X): no activation-derivative launch in between
+      d.fold_act = fold_act;
+      *folded = true;
+    }
     int nparts = 0;
     ATH_TRY(launch_tile_duv_bwd(b, d, gout, gin, L->num_params, L->tile_part, &nparts));
     DeferJob job{L->tile_part.as<float>(), nparts, (int)L->num_params, L->grads};
@@ -593,7 +602,7 @@ int layer_backward_dev(Layer* L, Batch* b, const float* gout, float* gin,
   if (L->kind == 2) return full_backward(L, b, gout, gin);
   if (L->kind == 0) return kipf_backward(L, b, gout, gin, opt);
   ATH_REQUIRE(!opt.gout_is_preact, ATHENA_ERR_STATE, "duvenaud backward: unexpected pre-activation gradient");
-  return duvenaud_backward(L, b, gout, gin, opt.defer);
+  return duvenaud_backward(L, b, gout, gin, opt.defer, opt.fold_act, opt.folded);
 }
 
 // ---- network ---------------------------------------------------------------------

@@ -147,6 +147,15 @@ struct RowWalk {
 
 // ---- tile movers ---------------------------------------------------------------------
 
+// pulls [p, p + bytes) into L2 ahead of the phase that loads it (the backward's tile loads sit
+// between two group barriers: their latency is exposed)
+__device__ __forceinline__ void tf_prefetch_l2(int tid, const void* p, int bytes) {
+  const char* c = static_cast<const char*>(p);
+  for (int o = tid * 128; o < bytes; o += TF_GROUP * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
+  if (tid == 0 && bytes > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + bytes - 1));
+}
+
 // global [rows][F] -> shared [rows][pitch]; columns F .. 4*ceil(F/4) are zeroed
 __device__ __forceinline__ void tf_load_rows(int tid, float* dst, int pitch,
                                              const float* __restrict__ src, int rows, int F) {
@@ -179,6 +188,31 @@ __device__ __forceinline__ void tf_store_rows(int tid, float* __restrict__ dst, 
     for (int i = tid; i < rows * F; i += TF_GROUP) {
       const int v = i / F, f = i - v * F;
       dst[static_cast<size_t>(v) * F + f] = src[v * pitch + f];
+    }
+  }
+}
+
+// shared [rows][pitch] -> global [rows][F], times act'(H) of the layer that produced this layer's
+// input (H = its saved output): the hand-over to a Kipf layer below needs no launch of its own
+__device__ __forceinline__ void tf_store_rows_actgrad(int tid, float* __restrict__ dst,
+                                                      const float* src, int pitch, int rows, int F,
+                                                      const float* __restrict__ H, int act) {
+  const int F4 = (F + 3) >> 2;
+  if ((F & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(H)) & 15) == 0) {
+    RowWalk w(tid, F4);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const float4* h4 = reinterpret_cast<const float4*>(H);
+    for (int i = tid; w.v < rows; i += TF_GROUP, w.next(F4)) {
+      const float4 g = *reinterpret_cast<const float4*>(src + w.v * pitch + 4 * w.c);
+      const float4 h = __ldg(h4 + i);
+      d4[i] = make_float4(tf_act_grad(act, h.x, g.x), tf_act_grad(act, h.y, g.y),
+                          tf_act_grad(act, h.z, g.z), tf_act_grad(act, h.w, g.w));
+    }
+  } else {
+    for (int i = tid; i < rows * F; i += TF_GROUP) {
+      const int v = i / F, f = i - v * F;
+      const size_t o = static_cast<size_t>(v) * F + f;
+      dst[o] = tf_act_grad(act, __ldg(H + o), src[v * pitch + f]);
     }
   }
 }
@@ -674,6 +708,7 @@ struct DuvArgs {
   // backward
   const float* gout;     // [B][no]
   float* gin;            // [V][F_0] or nullptr
+  int fold_act;          // gin leaves multiplied by fold_act'(X) (X = the producing layer's output)
   float* part;           // [grid * groups][np] group-private partial parameter gradients
   int np;
   DuvLayout lay;
@@ -901,7 +936,7 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
       // A = [ sum_w in(:,ja(1,w)) ; sum_w E(:,ja(2,w)) ] / d   (propagate; the division belongs
       // to duvenaud_update)
       tf_gather<false>(tid, AY, P, xin, P, (Fi + 3) >> 2, ptr_s, idx_s, nullptr, tv.rows, bkt_s);
-      tf_sync(grp);
+      if (Fi & 3) tf_sync(grp);  // else the two passes write disjoint 16-byte chunks
       tf_append_edges(tid, AY, P, Fi, a.nef, ae, L.pE, bkt_s, tv.rows);
       tf_sync(grp);
       // z = act( W_d(v) . A(:,v) )
@@ -999,9 +1034,9 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
       const int v = i / a.nef, f = i - v * a.nef;
       ae[v * L.pE + f] = __ldg(a.Ae + static_cast<size_t>(tv.r0) * a.nef + i);
     }
-    float* X = gsm + L.buf[0];  // z_t, then z_{t-1}, then dA
-    float* Y = gsm + L.buf[1];  // readout / dY, then A, then the new carry
-    float* Z = gsm + L.buf[2];  // carry -> gz
+    float* X = gsm + L.buf[0];  // z_t, then z_{t-1}
+    float* Y = gsm + L.buf[1];  // readout / dY, then A, then dA
+    float* Z = gsm + L.buf[2];  // carry -> gz -> the new carry
     tf_load_rows(tid, X, P, a.Z[T - 1] + static_cast<size_t>(tv.r0) * a.nvf[T], tv.rows, a.nvf[T]);
     tf_sync(grp);
     // vertices of the tile grouped by degree bucket (ascending vertex inside a bucket)
@@ -1020,9 +1055,20 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
       }
       if (lane == 0) seg_s[a.D] = base;
     }
+    {
+      // the next tile of this group: its z_T rows on their way to L2 while this tile computes
+      const int jn = j + gridDim.x * ngrp;
+      if (jn < a.num_tiles && tid < 64) {
+        const int4 nt = __ldg(a.tiles + jn);  // (first row, rows, first entry, entries)
+        tf_prefetch_l2(tid * (TF_GROUP / 64), a.Z[T - 1] + static_cast<size_t>(nt.x) * a.nvf[T],
+                       nt.y * a.nvf[T] * 4);
+      }
+    }
     for (int t = T; t >= 1; --t) {
       const int i = t - 1;
       const int Fi = a.nvf[t - 1], Fo = a.nvf[t], K = Fi + a.nef, no = a.no;
+      tf_prefetch_l2(tid, (t >= 2 ? a.Z[t - 2] : a.X) + static_cast<size_t>(tv.r0) * Fi,
+                     tv.rows * Fi * 4);  // step 4 loads it
       // 1. S = ract(R_t z_t) into Y, then dY in place (upstream row = gout of the vertex's graph)
       duv_update(tid, a.ract, Y, X, P, Fo, sm + L.r[i], L.pr[i], 0, nullptr, tv.rows, no);
       tf_sync(grp);
@@ -1059,31 +1105,32 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
       }
       tf_sync(grp);
       tf_gather<false>(tid, Y, P, X, P, (Fi + 3) >> 2, ptr_s, idx_s, nullptr, tv.rows, bkt_s);
-      tf_sync(grp);
+      if (Fi & 3) tf_sync(grp);  // else the two passes write disjoint 16-byte chunks
       tf_append_edges(tid, Y, P, Fi, a.nef, ae, L.pE, bkt_s, tv.rows);
       tf_sync(grp);
       // 5. dW_{t,d}(o,k) += sum_{v in bucket d} gz(o,v) A(k,v)      (A already divided by d)
       tf_outer(tid, part + a.woff[i], Y, P, K, Z, P, Fo, list_s, seg_s, a.D, tv.rows);
       const bool need_dx = t > 1 || a.gin != nullptr;
       if (need_dx) {
-        // 6. dA(k,v) = ( W_d^T gz(:,v) )(k) / d for k < Fi, into X (z_{t-1} is consumed)
+        // 6. dA(k,v) = ( W_d^T gz(:,v) )(k) / d for k < Fi, over A in Y once step 5 has read it:
+        //    X keeps z_{t-1}, which is the next iteration's z_t (no second load of the tile)
+        tf_sync(grp);
         const uint8_t* bk = bkt_s;
-        tf_gemm_nt(tid, X, P, Z, P, Fo, sm + L.w[i], L.pw[i], L.gs[i], bkt_s, tv.rows, Fi,
+        tf_gemm_nt(tid, Y, P, Z, P, Fo, sm + L.w[i], L.pw[i], L.gs[i], bkt_s, tv.rows, Fi,
                    [bk](int v, int, float s) { return s * (1.f / static_cast<float>(bk[v] + 1)); });
         tf_sync(grp);
-        // 7. d in(:,u) = sum over the CSC column of u of dA(1:Fi, v): the new carry, into Y
-        tf_gather<false>(tid, Y, P, X, P, (Fi + 3) >> 2, cptr_s, cidx_s, nullptr, tv.rows,
+        // 7. d in(:,u) = sum over the CSC column of u of dA(1:Fi, v): the new carry, over gz in Z
+        tf_gather<false>(tid, Z, P, Y, P, (Fi + 3) >> 2, cptr_s, cidx_s, nullptr, tv.rows,
                          nullptr);
         tf_sync(grp);
-        if (t == 1) tf_store_rows(tid, a.gin + static_cast<size_t>(tv.r0) * Fi, Y, P, tv.rows, Fi);
-      }
-      if (t > 1) {
-        // the carry sits in Y: rotate Y <-> Z; X receives z_{t-1} again (as the next z_t)
-        float* tmp = Y;
-        Y = Z;
-        Z = tmp;
-        tf_load_rows(tid, X, P, a.Z[t - 2] + static_cast<size_t>(tv.r0) * Fi, tv.rows, Fi);
-        tf_sync(grp);
+        if (t == 1) {
+          float* gdst = a.gin + static_cast<size_t>(tv.r0) * Fi;
+          if (a.fold_act == ATHENA_ACT_NONE)
+            tf_store_rows(tid, gdst, Z, P, tv.rows, Fi);
+          else
+            tf_store_rows_actgrad(tid, gdst, Z, P, tv.rows, Fi,
+                                  a.X + static_cast<size_t>(tv.r0) * Fi, a.fold_act);
+        }
       }
     }
   }
@@ -1435,6 +1482,7 @@ int launch_tile_duv_bwd(const Batch* b, const TileDuvDesc& d, const float* gout,
   ATH_TRY(part.reserve(sizeof(float) * (size_t)grid * ng * (size_t)num_params));
   a.gout = gout;
   a.gin = gin;
+  a.fold_act = gin != nullptr ? d.fold_act : ATHENA_ACT_NONE;
   a.part = part.as<float>();
   a.np = (int)num_params;
   ATH_CUDA(launch_pdl(k_duv_bwd, dim3(grid), dim3(TF_GROUP * ng), a.lay.total_bytes[ng],
