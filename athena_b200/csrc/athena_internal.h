@@ -307,8 +307,8 @@ int launch_pipe_gather_fwd_mse(const Batch* b, const float* X, const float* W, f
 int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const float* Hin,
                            float* out, int F, int N, int act, const uint32_t* mask_in = nullptr);
 // defer != nullptr: the fold of the per-CTA partials into dW is queued instead of launched
-int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int N, DevBuf& scratch,
-                   DeferList* defer = nullptr, bool queue = false);
+int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int K, int N,
+                   DevBuf& scratch, DeferList* defer = nullptr, bool queue = false);
 
 // fused FP32 (FFMA2) tile kernels for batches of small graphs (tile_fma.cu): one Kipf step of
 // any width up to 128, and the whole Duvenaud layer (all time steps + readout) per launch
@@ -405,7 +405,7 @@ struct TnPending {
   const float* G;
   float* dW;
   int64_t M;
-  int N;
+  int K, N;
   DevBuf* scratch;  // per-CTA partials of this product
 };
 struct DeferList {

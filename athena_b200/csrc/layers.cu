@@ -443,7 +443,7 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
     // fused path: one tcgen05 kernel gathers gY_t over the CSC, multiplies by W_t^T and applies
     // act'(H_{t-1}); the un-normalised scatter commutes with the linear map
     const bool fused_dp = need_dp && L->act != ATHENA_ACT_SOFTMAX && pipe_bwd_ok;
-    const bool fused_tn = Fi == 64 && pipe_tn_supported(Fi, Fo);
+    const bool fused_tn = pipe_tn_supported(Fi, Fo);
     const bool tn_tc = !fused_tn && tc_tn_supported(Fi, Fo, Fi, Fo, Pt, g);
     const bool nt_tc = need_dp && !fused_dp && tc_rows_supported(Fo, Fi, Fo, Fi, g, L->g1.as<float>());
     // the unfused tensor-core kernels can apply act'(H) while loading gH
@@ -460,7 +460,7 @@ static int kipf_backward(Layer* L, Batch* b, const float* gout, float* gin, cons
     if (fused_tn) {
       // a one-step layer never reuses its gradient buffers inside the sweep: the product can
       // join the batched launch at the end of the sweep
-      ATH_TRY(launch_pipe_tn(Pt, gy, dWt, V, Fo, *L->TN[t - 1], opt.defer, L->T == 1));
+      ATH_TRY(launch_pipe_tn(Pt, gy, dWt, V, Fi, Fo, *L->TN[t - 1], opt.defer, L->T == 1));
     } else if (tn_tc) {
       // per-step partial buffer: with a DeferList the fold waits for the finalize launch
       ATH_TRY(launch_tc_tn(Pt, Fi, gy, Fo, Hact, L->act, dWt, V, Fo, Fi, *L->TN[t - 1], opt.defer));

@@ -505,11 +505,13 @@ struct TnJobs {
   int evict_first;            // both operands are read for the last time: L2 evict_first
 };
 
-template <int N>
+template <int KW, int N>
 struct Tn2Cfg {
-  static constexpr int K = 64;
+  static constexpr int K = KW;                               // 64, or 32: hi(P)^T in TMEM lanes 0..31,
+                                                             // lo(P)^T in lanes 32..63, lanes 64..127 unused
+  static constexpr int HI_WARPS = K / 32;                    // lane quarters of one half of the A operand
   static constexpr int RS = 64;                              // rows per stage
-  static constexpr int NS = 3;
+  static constexpr int NS = 3 * 128 / (KW + N);              // 96 KB of raw rows in flight per SM
   static constexpr int G_THREADS = 128;                      // warps 0..3: gY -> hi/lo B operand
   static constexpr int A_WARP0 = 4;                          // warps 4..7: P^T -> TMEM A operand
   static constexpr int PRODUCER_WARP = 8;
@@ -521,7 +523,7 @@ struct Tn2Cfg {
   // into registers (IEEE round-to-nearest adds) every FLUSH stages: two TMEM accumulators
   // alternate, the MMAs of group g+1 overlap the drain of group g.
   static constexpr int FLUSH = 2;
-  static constexpr int P_RAW = RS * K * 4;                   // 16 KB
+  static constexpr int P_RAW = RS * K * 4;                   // 16 KB (K = 64)
   static constexpr int G_RAW = RS * N * 4;
   static constexpr int STAGE_BYTES = P_RAW + G_RAW;
   static constexpr int BLK = RS * 128;                       // [64 rows x 32 feats]
@@ -550,10 +552,10 @@ __device__ __forceinline__ void job_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
 }
 
-template <int N>
-__global__ void __launch_bounds__(Tn2Cfg<N>::THREADS, 1)
+template <int KW, int N>
+__global__ void __launch_bounds__(Tn2Cfg<KW, N>::THREADS, 1)
 k_pipe_tn(TnJobs jobs) {
-  using Cfg = Tn2Cfg<N>;
+  using Cfg = Tn2Cfg<KW, N>;
   constexpr int K = Cfg::K;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -694,15 +696,16 @@ k_pipe_tn(TnJobs jobs) {
       gcount += ngroups;
       // the two halves (TMEM lanes 0..63: hi(P)^T . G, lanes 64..127: lo(P)^T . G) are added
       // here, in a fixed order, so that the CTA writes ONE partial
-      const int feat = (lq & 1) * 32 + lane;
+      // (K = 32: quarters 2 and 3 hold nothing and only keep the barriers' head counts)
+      const int feat = (lq % Cfg::HI_WARPS) * 32 + lane;
       float* comb = reinterpret_cast<float*>(smem + Cfg::OFF_COMB) + feat * Cfg::COMB_PITCH;
-      if (lq >= 2) {
+      if (lq >= Cfg::HI_WARPS && lq < 2 * Cfg::HI_WARPS) {
 #pragma unroll
         for (int i = 0; i < N; i += 4)
           *reinterpret_cast<float4*>(comb + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");  // the four accumulate warps
-      if (lq < 2) {
+      if (lq < Cfg::HI_WARPS) {
         float* dst = jobs.part[q] + static_cast<size_t>(blockIdx.x) * K * N + feat * N;
 #pragma unroll
         for (int i = 0; i < N; i += 4) {
@@ -720,8 +723,9 @@ k_pipe_tn(TnJobs jobs) {
     // and stores them as 64 TMEM columns: the A operand never touches shared memory again
     // (no operand stores, no operand reads by the MMA: -25 % shared-memory traffic per stage).
     const int lq = warp & 3;
-    const int f = (lq & 1) * 32 + lane;
-    const bool lo_part = lq >= 2;
+    const int f = (lq % Cfg::HI_WARPS) * 32 + lane;
+    const bool lo_part = lq >= Cfg::HI_WARPS;
+    const bool a_live = lq < 2 * Cfg::HI_WARPS;  // K = 32: TMEM lanes 64..127 stay unwritten
     int j = 0;
     for (int q = 0; q < jobs.n; ++q) {
       const long long M = jobs.M[q], ntiles = tiles_of(q);
@@ -734,25 +738,27 @@ k_pipe_tn(TnJobs jobs) {
         mbar_wait(&full[s], ph);
         float x[Cfg::RS];
 #pragma unroll
-        for (int r = 0; r < Cfg::RS; ++r) x[r] = r < rows ? raw[r * K + f] : 0.f;
+        for (int r = 0; r < Cfg::RS; ++r) x[r] = (a_live && r < rows) ? raw[r * K + f] : 0.f;
         mbar_arrive(&empty[s]);
         const int ob = j & 1;
         mbar_wait(&ops_free[ob], ((j >> 1) & 1) ^ 1u);  // MMAs of stage j-2 have read this buffer
         tc_fence_after();
         const uint32_t ta =
             tmem + Cfg::T_A + ob * Cfg::RS + (static_cast<uint32_t>(lq * 32) << 16);
+        if (a_live) {
 #pragma unroll
-        for (int h = 0; h < Cfg::RS / 32; ++h) {
-          uint32_t v[32];
+          for (int h = 0; h < Cfg::RS / 32; ++h) {
+            uint32_t v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float xx = x[h * 32 + i];
-            const uint32_t hi = __float_as_uint(xx) & 0xffffe000u;
-            v[i] = lo_part ? __float_as_uint(xx - __uint_as_float(hi)) : hi;
+            for (int i = 0; i < 32; ++i) {
+              const float xx = x[h * 32 + i];
+              const uint32_t hi = __float_as_uint(xx) & 0xffffe000u;
+              v[i] = lo_part ? __float_as_uint(xx - __uint_as_float(hi)) : hi;
+            }
+            tmem_st32(ta + h * 32, v);
           }
-          tmem_st32(ta + h * 32, v);
+          tmem_st_wait();
         }
-        tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&a_ready[ob]);
       }
@@ -894,7 +900,9 @@ bool pipe_gather_supported(const Batch* b, int F, int N) {
          pipe_tcg_supported(const_cast<Batch*>(b), F, N);
 }
 
-bool pipe_tn_supported(int K, int N) { return pipe_enabled() && K == 64 && (N == 64 || N == 32); }
+bool pipe_tn_supported(int K, int N) {
+  return pipe_enabled() && (K == 64 || K == 32) && (N == 64 || N == 32);
+}
 
 // forward: out = act( (A_hat X) W ),  P = A_hat X           (W row-major [F][N])
 int launch_pipe_gather_fwd(const Batch* b, const float* X, const float* W, float* P, float* out,
@@ -982,12 +990,12 @@ int launch_pipe_gather_bwd(const Batch* b, const float* G, const float* W, const
   return launch_gather_t<64, 64, true, EPI_ACTGRAD>(a);
 }
 
-template <int N>
+template <int K, int N>
 static int launch_pipe_tn_t(const TnPending* jobs, int njobs, DeferList* defer) {
-  using Cfg = Tn2Cfg<N>;
+  using Cfg = Tn2Cfg<K, N>;
   static bool attr = false;
   if (!attr) {
-    ATH_CUDA(cudaFuncSetAttribute(k_pipe_tn<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ATH_CUDA(cudaFuncSetAttribute(k_pipe_tn<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM));
     attr = true;
   }
@@ -1008,7 +1016,8 @@ static int launch_pipe_tn_t(const TnPending* jobs, int njobs, DeferList* defer) 
     tj.part[q] = jobs[src].scratch->template as<float>();
     tj.M[q] = jobs[src].M;
   }
-  ATH_CUDA(launch_pdl(k_pipe_tn<N>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, ctx().stream, tj));
+  ATH_CUDA(launch_pdl(k_pipe_tn<K, N>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, ctx().stream,
+                      tj));
   ATH_LAUNCHED_T("pipe_tn");
   for (int q = 0; q < njobs; ++q) {
     float* part = jobs[q].scratch->template as<float>();
@@ -1023,16 +1032,26 @@ static int launch_pipe_tn_t(const TnPending* jobs, int njobs, DeferList* defer) 
   return ATHENA_OK;
 }
 
-// dW[64 x N] += P^T . G     (P [M][64], G [M][N], both dense row-major)
+static int launch_pipe_tn_shape(int K, int N, const TnPending* jobs, int njobs, DeferList* defer) {
+  if (K == 64) {
+    return N == 64 ? launch_pipe_tn_t<64, 64>(jobs, njobs, defer)
+                   : launch_pipe_tn_t<64, 32>(jobs, njobs, defer);
+  }
+  return N == 64 ? launch_pipe_tn_t<32, 64>(jobs, njobs, defer)
+                 : launch_pipe_tn_t<32, 32>(jobs, njobs, defer);
+}
+
+// dW[K x N] += P^T . G     (P [M][K], G [M][N], both dense row-major; K, N in {32, 64})
 // With a DeferList the product is only queued: launch_pipe_tn_pending runs every queued product
-// of the reverse sweep in one launch per width (before launch_finalize folds the partials).
+// of the reverse sweep in one launch per shape (before launch_finalize folds the partials).
 // queue: P and G stay untouched until the end of the sweep, so the product itself may wait;
 // otherwise only the fold of its partials is deferred.
-int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int N, DevBuf& scratch,
-                   DeferList* defer, bool queue) {
+int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int K, int N,
+                   DevBuf& scratch, DeferList* defer, bool queue) {
   if (M == 0) return ATHENA_OK;
-  ATH_REQUIRE(N == 64 || N == 32, ATHENA_ERR_ARG, "pipe_tn: unsupported N=%d", N);
-  const TnPending job{P, G, dW, M, N, &scratch};
+  ATH_REQUIRE((K == 64 || K == 32) && (N == 64 || N == 32), ATHENA_ERR_ARG,
+              "pipe_tn: unsupported shape %d x %d", K, N);
+  const TnPending job{P, G, dW, M, K, N, &scratch};
   static int nobatch = -1;
   if (nobatch < 0) {
     const char* e = getenv("ATHENA_DEBUG_TN_NOBATCH");  // A/B switch: one launch per product
@@ -1042,20 +1061,20 @@ int launch_pipe_tn(const float* P, const float* G, float* dW, int64_t M, int N, 
     defer->tn.push_back(job);
     return ATHENA_OK;
   }
-  return N == 64 ? launch_pipe_tn_t<64>(&job, 1, defer) : launch_pipe_tn_t<32>(&job, 1, defer);
+  return launch_pipe_tn_shape(K, N, &job, 1, defer);
 }
 
 int launch_pipe_tn_pending(DeferList* defer) {
-  for (int width : {64, 32}) {
+  for (int shape = 0; shape < 4; ++shape) {
+    const int K = (shape & 2) ? 32 : 64, width = (shape & 1) ? 32 : 64;
     std::vector<TnPending> batch;
     for (const TnPending& j : defer->tn)
-      if (j.N == width) batch.push_back(j);
+      if (j.K == K && j.N == width) batch.push_back(j);
     const char* e = getenv("ATHENA_DEBUG_TN_NOBATCH");
     const size_t per_launch = (e && atoi(e) == 2) ? 1 : TN_MAX_JOBS;
     for (size_t i = 0; i < batch.size(); i += per_launch) {
       const int n = (int)std::min<size_t>(per_launch, batch.size() - i);
-      ATH_TRY(width == 64 ? launch_pipe_tn_t<64>(batch.data() + i, n, defer)
-                          : launch_pipe_tn_t<32>(batch.data() + i, n, defer));
+      ATH_TRY(launch_pipe_tn_shape(K, width, batch.data() + i, n, defer));
     }
   }
   defer->tn.clear();
