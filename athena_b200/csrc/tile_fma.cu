@@ -33,6 +33,7 @@
 // reference's order; weight gradients are accumulated per group in a private partial
 // vector (no atomics) that k_finalize folds in a fixed order.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "athena_internal.h"
@@ -40,6 +41,26 @@
 namespace athena {
 
 namespace {
+
+#ifdef TF_TRACE  // debugging build: clock64 stamps of block 0 / thread 0 at the phase boundaries
+#define TFT()                                                              \
+  do {                                                                     \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && tft_n < 96) tft_m[tft_n++] = clock64(); \
+  } while (0)
+#define TFT_DECL() long long tft_m[96]; int tft_n = 0; TFT()
+#define TFT_DUMP(name)                                                     \
+  do {                                                                     \
+    if (threadIdx.x == 0 && blockIdx.x == 0) {                             \
+      printf("%s:", name);                                                 \
+      for (int q = 1; q < tft_n; ++q) printf(" %lld", tft_m[q] - tft_m[q - 1]); \
+      printf(" | total %lld\n", tft_m[tft_n - 1] - tft_m[0]);              \
+    }                                                                      \
+  } while (0)
+#else
+#define TFT() do { } while (0)
+#define TFT_DECL() do { } while (0)
+#define TFT_DUMP(name) do { } while (0)
+#endif
 
 constexpr int TF_GROUP = 512;                   // threads working on one tile
 constexpr int TF_GWARPS = TF_GROUP / 32;
@@ -67,7 +88,11 @@ __device__ __forceinline__ void tf_sync(int grp) {
 }
 
 // exp through ex2.approx (max relative error 2^-22): two instructions instead of ~10
-__device__ __forceinline__ float tf_exp(float x) { return __expf(x); }
+__device__ __forceinline__ float tf_exp(float x) {
+  float y;  // (.ftz: without the denormal rescue of __expf -- 2 instructions instead of 6)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
 __device__ __forceinline__ float tf_rcp(float x) { return __fdividef(1.f, x); }
 
 struct ActNone {
@@ -240,7 +265,7 @@ template <bool COEF>
 __device__ __forceinline__ void tf_gather(int tid, float* dst, int dpitch, const float* src,
                                           int spitch, int F4, const int* ptr_s,
                                           const uint8_t* idx_s, const float* coef_s, int rows,
-                                          const uint8_t* bkt_s) {
+                                          const uint8_t* bkt_s, const uint8_t* inv_s = nullptr) {
   RowWalk w(tid, F4);
   for (; w.v < rows; w.next(F4)) {
     const int v = w.v, c = w.c;
@@ -271,7 +296,8 @@ __device__ __forceinline__ void tf_gather(int tid, float* dst, int dpitch, const
       acc.z *= rd;
       acc.w *= rd;
     }
-    *reinterpret_cast<float4*>(dst + v * dpitch + 4 * c) = acc;
+    // inv_s: row v of the result is stored at position inv_s[v] (rows grouped by degree bucket)
+    *reinterpret_cast<float4*>(dst + (inv_s != nullptr ? inv_s[v] : v) * dpitch + 4 * c) = acc;
   }
 }
 
@@ -282,18 +308,23 @@ __device__ __forceinline__ void tf_gather(int tid, float* dst, int dpitch, const
 template <class Epi>
 __device__ __forceinline__ void tf_gemm(int tid, float* C, int pc, const float* A, int pa, int K,
                                         const float* W, int pw, int gs, const uint8_t* grp_s,
-                                        int rows, int N, Epi epi) {
+                                        int rows, int N, Epi epi,
+                                        const uint8_t* list_s = nullptr) {
+  // list_s: A holds the rows grouped by weight block (row p of A is vertex list_s[p]): the lanes
+  // of a warp then read ONE block -- every weight load is a broadcast, one shared-memory
+  // wavefront instead of one per block present in the warp
   const int warp = tid >> 5, lane = tid & 31;
   const int nvg = (rows + 31) >> 5, nnb = (N + TF_NB - 1) / TF_NB;
   const int N4 = ((N + 3) >> 2) << 2;
   const int K4 = K >> 2;
   for (int it = warp; it < nvg * nnb; it += TF_GWARPS) {
     const int nb = it / nvg, vg = it - nb * nvg;
-    const int v = vg * 32 + lane;
-    const bool live = v < rows;
-    const int vv = live ? v : rows - 1;
+    const int pos = vg * 32 + lane;
+    const bool live = pos < rows;
+    const int vv = live ? pos : rows - 1;
+    const int v = list_s != nullptr ? list_s[vv] : vv;  // the row of C, the vertex of grp_s
     const float4* a = reinterpret_cast<const float4*>(A + vv * pa);
-    const float* w = W + (grp_s != nullptr ? grp_s[vv] * gs : 0) + nb * TF_NB;
+    const float* w = W + (grp_s != nullptr ? grp_s[v] * gs : 0) + nb * TF_NB;
     float2 acc[TF_NB / 2];
 #pragma unroll
     for (int j = 0; j < TF_NB / 2; ++j) acc[j] = make_float2(0.f, 0.f);
@@ -814,14 +845,38 @@ __device__ __forceinline__ void tf_edge_sum(int tid, float* ae, int pe,
 // A[v][Fi .. Fi+Fe) = Ae[v][:] / d ; A[v][K .. 4*ceil(K/4)) = 0
 __device__ __forceinline__ void tf_append_edges(int tid, float* A, int pa, int Fi, int Fe,
                                                 const float* ae, int pe, const uint8_t* bkt_s,
-                                                int rows) {
+                                                int rows, const uint8_t* inv_s = nullptr) {
   const int K = Fi + Fe, Kp = ((K + 3) >> 2) << 2;
   const int w = Kp - Fi;
   if (w == 0) return;
   for (int i = tid; i < rows * w; i += TF_GROUP) {
     const int v = i / w, j = i - v * w;
-    A[v * pa + Fi + j] = j < Fe ? ae[v * pe + j] * (1.f / static_cast<float>(bkt_s[v] + 1)) : 0.f;
+    A[(inv_s != nullptr ? inv_s[v] : v) * pa + Fi + j] =
+        j < Fe ? ae[v * pe + j] * (1.f / static_cast<float>(bkt_s[v] + 1)) : 0.f;
   }
+}
+
+// one warp: the vertices of the tile grouped by degree bucket, ascending inside a bucket:
+// list_s[p] = vertex at position p, inv_s[v] = position of vertex v (optional), seg_s[d] = first
+// position of bucket d (seg_s[D] = rows)
+__device__ __forceinline__ void tf_bucket_list(int lane, const uint8_t* bkt_s, int rows, int D,
+                                               uint8_t* list_s, uint8_t* inv_s, int* seg_s) {
+  int base = 0;
+  for (int d = 0; d < D; ++d) {
+    if (lane == 0) seg_s[d] = base;
+    for (int c = 0; c < TILE_ROWS / 32; ++c) {
+      const int v = c * 32 + lane;
+      const bool m = v < rows && bkt_s[v] == d;
+      const unsigned bal = __ballot_sync(0xffffffffu, m);
+      if (m) {
+        const int pos = base + __popc(bal & ((1u << lane) - 1u));
+        list_s[pos] = static_cast<uint8_t>(v);
+        if (inv_s != nullptr) inv_s[v] = static_cast<uint8_t>(pos);
+      }
+      base += __popc(bal);
+    }
+  }
+  if (lane == 0) seg_s[D] = base;
 }
 
 __device__ __forceinline__ void duv_stage_weights(float* sm, const DuvArgs& a) {
@@ -868,12 +923,12 @@ __device__ __forceinline__ void duv_stage_weights(float* sm, const DuvArgs& a) {
 // z = act(A . W_d) with the activation hoisted out of the epilogue's inner loop
 __device__ __forceinline__ void duv_update(int tid, int act, float* Z, const float* A, int P, int K,
                                            const float* W, int pw, int gs, const uint8_t* bkt_s,
-                                           int rows, int Fo) {
+                                           int rows, int Fo, const uint8_t* list_s = nullptr) {
 #define TF_UPD(ACT)                                                                          \
   do {                                                                                       \
     if (bkt_s != nullptr)                                                                    \
       tf_gemm(tid, Z, P, A, P, K, W, pw, gs, bkt_s, rows, Fo,                                \
-              [](int, int, float s) { return ACT{}(s); });                                   \
+              [](int, int, float s) { return ACT{}(s); }, list_s);                           \
     else                                                                                     \
       tf_gemm2(tid, Z, P, A, P, K, W, pw, rows, Fo, [](int, int, float s) { return ACT{}(s); }); \
   } while (0)
@@ -888,8 +943,10 @@ __device__ __forceinline__ void duv_update(int tid, int act, float* Z, const flo
 }
 
 __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs a) {
+  TFT_DECL();
   pdl_wait();  // launched programmatically dependent: nothing of the previous kernel is read
   pdl_launch_dependents();  // (or overwritten) before it has completed
+  TFT();
   extern __shared__ float4 tf_smem4[];
   float* sm = reinterpret_cast<float*>(tf_smem4);
   const DuvLayout& L = a.lay;
@@ -899,12 +956,16 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
   int* ptr_s = reinterpret_cast<int*>(gsm + L.ints);
   float* red = reinterpret_cast<float*>(ptr_s + 132 + 132 + 260 + 128);
   uint8_t* idx_s = reinterpret_cast<uint8_t*>(gsm + L.bytes);
+  uint8_t* inv_s = idx_s + TF_IDX;  // (the CSC bytes of the backward's layout)
   uint8_t* bkt_s = idx_s + 2 * TF_IDX;
+  uint8_t* list_s = bkt_s + 128;
+  int* seg_s = ptr_s + 132 + 132;
   float* ae = gsm + L.ae;
   float* outs = gsm + L.outs;
   const int P = L.P;
   duv_stage_weights(sm, a);
   __syncthreads();
+  TFT();
   float lsum = 0.f;
   for (int j = blockIdx.x * ngrp + grp; j < a.num_tiles; j += gridDim.x * ngrp) {
     const TileView tv = tf_tile(a.tiles, j, a.num_tiles, a.vgraph, a.num_graphs);
@@ -919,6 +980,10 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
     float* zout = gsm + L.buf[2];
     tf_load_rows(tid, xin, P, a.X + static_cast<size_t>(tv.r0) * a.nvf[0], tv.rows, a.nvf[0]);
     tf_sync(grp);
+    TFT();
+    // A is built with its rows grouped by degree bucket (the barriers below order this before
+    // the first use)
+    if (tid < 32) tf_bucket_list(tid, bkt_s, tv.rows, a.D, list_s, inv_s, seg_s);
     if (a.nef > 0) {
       tf_edge_sum(tid, ae, L.pE, a.E, a.nef, a.eid, ptr_s, tv.e0, tv.rows);
       tf_sync(grp);
@@ -927,7 +992,10 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
           const int v = i / a.nef, f = i - v * a.nef;
           a.Ae[static_cast<size_t>(tv.r0) * a.nef + i] = ae[v * L.pE + f];
         }
+    } else {
+      tf_sync(grp);  // the bucket list is complete
     }
+    TFT();
     const int ng = tv.g_end - tv.g_begin;
     const bool outs_local = ng * a.no <= TF_OUTS;
     for (int t = 1; t <= a.T; ++t) {
@@ -935,21 +1003,27 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
       const int Fi = a.nvf[t - 1], Fo = a.nvf[t], K = Fi + a.nef;
       // A = [ sum_w in(:,ja(1,w)) ; sum_w E(:,ja(2,w)) ] / d   (propagate; the division belongs
       // to duvenaud_update)
-      tf_gather<false>(tid, AY, P, xin, P, (Fi + 3) >> 2, ptr_s, idx_s, nullptr, tv.rows, bkt_s);
+      tf_gather<false>(tid, AY, P, xin, P, (Fi + 3) >> 2, ptr_s, idx_s, nullptr, tv.rows, bkt_s,
+                       inv_s);
       if (Fi & 3) tf_sync(grp);  // else the two passes write disjoint 16-byte chunks
-      tf_append_edges(tid, AY, P, Fi, a.nef, ae, L.pE, bkt_s, tv.rows);
+      tf_append_edges(tid, AY, P, Fi, a.nef, ae, L.pE, bkt_s, tv.rows, inv_s);
       tf_sync(grp);
-      // z = act( W_d(v) . A(:,v) )
-      duv_update(tid, a.act, zout, AY, P, K, sm + L.w[i], L.pw[i], L.gs[i], bkt_s, tv.rows, Fo);
+      TFT();
+      // z = act( W_d(v) . A(:,v) ), rows of z back in vertex order
+      duv_update(tid, a.act, zout, AY, P, K, sm + L.w[i], L.pw[i], L.gs[i], bkt_s, tv.rows, Fo,
+                 list_s);
       tf_sync(grp);
+      TFT();
       tf_store_rows(tid, a.Z[i] + static_cast<size_t>(tv.r0) * Fo, zout, P, tv.rows, Fo);
       // readout: S = ract( R_t . z )
       duv_update(tid, a.ract, AY, zout, P, Fo, sm + L.r[i], L.pr[i], 0, nullptr, tv.rows, a.no);
       tf_sync(grp);
+      TFT();
       if (a.ract == ATHENA_ACT_SOFTMAX) {
         tf_softmax_rows(tid, AY, P, tv.rows, a.no);
         tf_sync(grp);
       }
+      TFT();
       // out(:,s) (+)= sum_v S(:,v), vertices ascending (sum(ptr2, dim=2), :848-852)
       for (int idx = tid; idx < ng * a.no; idx += TF_GROUP) {
         const int gl = idx / a.no, o = idx - gl * a.no;
@@ -978,8 +1052,10 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
       xin = zout;
       zout = tmp;
       tf_sync(grp);  // the readout buffer becomes A again
+      TFT();
     }
   }
+  TFT_DUMP("duv_fwd [wait, weights, tile-load, edge-sum; per t: gather+append, update, readout, softmax, segsum]");
   if (a.loss_part != nullptr) {
     // per-group loss partial, fixed combine order
 #pragma unroll
@@ -996,8 +1072,10 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
 }
 
 __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs a) {
+  TFT_DECL();
   pdl_wait();
   pdl_launch_dependents();
+  TFT();
   extern __shared__ float4 tf_smem4[];
   float* sm = reinterpret_cast<float*>(tf_smem4);
   const DuvLayout& L = a.lay;
@@ -1018,6 +1096,7 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
   for (int i = tid; i < a.np; i += TF_GROUP) part[i] = 0.f;
   duv_stage_weights(sm, a);
   __syncthreads();
+  TFT();
   const int T = a.T;
   for (int j = blockIdx.x * ngrp + grp; j < a.num_tiles; j += gridDim.x * ngrp) {
     const TileView tv = tf_tile(a.tiles, j, a.num_tiles, a.vgraph, a.num_graphs);
@@ -1040,21 +1119,8 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
     tf_load_rows(tid, X, P, a.Z[T - 1] + static_cast<size_t>(tv.r0) * a.nvf[T], tv.rows, a.nvf[T]);
     tf_sync(grp);
     // vertices of the tile grouped by degree bucket (ascending vertex inside a bucket)
-    if (tid < 32) {
-      const int lane = tid;
-      int base = 0;
-      for (int d = 0; d < a.D; ++d) {
-        if (lane == 0) seg_s[d] = base;
-        for (int c = 0; c < TILE_ROWS / 32; ++c) {
-          const int v = c * 32 + lane;
-          const bool m = v < tv.rows && bkt_s[v] == d;
-          const unsigned bal = __ballot_sync(0xffffffffu, m);
-          if (m) list_s[base + __popc(bal & ((1u << lane) - 1u))] = static_cast<uint8_t>(v);
-          base += __popc(bal);
-        }
-      }
-      if (lane == 0) seg_s[a.D] = base;
-    }
+    if (tid < 32) tf_bucket_list(tid, bkt_s, tv.rows, a.D, list_s, nullptr, seg_s);
+    TFT();
     {
       // the next tile of this group: its z_T rows on their way to L2 while this tile computes
       const int jn = j + gridDim.x * ngrp;
@@ -1083,6 +1149,7 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
                         [gout, vgs, no](int v) { return gout + static_cast<size_t>(vgs[v]) * no; });
       }
       tf_sync(grp);
+      TFT();
       // 2. dR_t(o,f) += sum_v dY(o,v) z_t(f,v)
       tf_outer(tid, part + a.roff[i], X, P, Fo, Y, P, no, nullptr, nullptr, 1, tv.rows);
       // 3. gz = ( R_t^T dY + carry ) .* act'(z_t), in place in Z
@@ -1098,16 +1165,19 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
                     });
       }
       tf_sync(grp);
+      TFT();
       // 4. z_{t-1} replaces z_t; A = [gather(z_{t-1}) ; Ae] / d is recomputed into Y (dY is dead)
       {
         const float* prev = t >= 2 ? a.Z[t - 2] : a.X;
         tf_load_rows(tid, X, P, prev + static_cast<size_t>(tv.r0) * Fi, tv.rows, Fi);
       }
       tf_sync(grp);
+      TFT();
       tf_gather<false>(tid, Y, P, X, P, (Fi + 3) >> 2, ptr_s, idx_s, nullptr, tv.rows, bkt_s);
       if (Fi & 3) tf_sync(grp);  // else the two passes write disjoint 16-byte chunks
       tf_append_edges(tid, Y, P, Fi, a.nef, ae, L.pE, bkt_s, tv.rows);
       tf_sync(grp);
+      TFT();
       // 5. dW_{t,d}(o,k) += sum_{v in bucket d} gz(o,v) A(k,v)      (A already divided by d)
       tf_outer(tid, part + a.woff[i], Y, P, K, Z, P, Fo, list_s, seg_s, a.D, tv.rows);
       const bool need_dx = t > 1 || a.gin != nullptr;
@@ -1115,14 +1185,17 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
         // 6. dA(k,v) = ( W_d^T gz(:,v) )(k) / d for k < Fi, over A in Y once step 5 has read it:
         //    X keeps z_{t-1}, which is the next iteration's z_t (no second load of the tile)
         tf_sync(grp);
+        TFT();
         const uint8_t* bk = bkt_s;
         tf_gemm_nt(tid, Y, P, Z, P, Fo, sm + L.w[i], L.pw[i], L.gs[i], bkt_s, tv.rows, Fi,
                    [bk](int v, int, float s) { return s * (1.f / static_cast<float>(bk[v] + 1)); });
         tf_sync(grp);
+        TFT();
         // 7. d in(:,u) = sum over the CSC column of u of dA(1:Fi, v): the new carry, over gz in Z
         tf_gather<false>(tid, Z, P, Y, P, (Fi + 3) >> 2, cptr_s, cidx_s, nullptr, tv.rows,
                          nullptr);
         tf_sync(grp);
+        TFT();
         if (t == 1) {
           float* gdst = a.gin + static_cast<size_t>(tv.r0) * Fi;
           if (a.fold_act == ATHENA_ACT_NONE)
@@ -1134,6 +1207,7 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
       }
     }
   }
+  TFT_DUMP("duv_bwd [wait, zero+weights, tile-load+buckets; per t: readout+softmax+dY, dR+gz, load z, gather+append, dW, dA, scatter]");
 }
 
 // ======================================================================================
@@ -1299,6 +1373,12 @@ static KipfLayout kipf_layout(int Fi, int Fo, bool backward) {
 static int tf_groups(const int* total_bytes, int num_tiles) {
   const size_t lim = ctx().max_smem_optin;
   if ((size_t)total_bytes[1] > lim) return 0;
+  static int one = -1;
+  if (one < 0) {
+    const char* e = getenv("ATHENA_DEBUG_TILE_ONE_GROUP");  // experiments: one group per CTA
+    one = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  if (one) return 1;
   if (num_tiles >= 2 && (size_t)total_bytes[2] <= lim) return 2;
   return 1;
 }
