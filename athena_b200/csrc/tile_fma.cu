@@ -187,10 +187,22 @@ __device__ __forceinline__ void tf_load_rows(int tid, float* dst, int pitch,
   const int F4 = (F + 3) >> 2;
   if ((F & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     // the tile is contiguous in global memory: chunk i of the tile is chunk (i % F4) of row i / F4
+    // (two chunks requested before the first is stored)
     RowWalk w(tid, F4);
     const float4* s4 = reinterpret_cast<const float4*>(src);
-    for (int i = tid; w.v < rows; i += TF_GROUP, w.next(F4))
-      *reinterpret_cast<float4*>(dst + w.v * pitch + 4 * w.c) = __ldg(s4 + i);
+    for (int i = tid; w.v < rows; i += 2 * TF_GROUP) {
+      float* d0 = dst + w.v * pitch + 4 * w.c;
+      w.next(F4);
+      const bool two = w.v < rows;
+      float* d1 = dst + w.v * pitch + 4 * w.c;
+      const float4 x0 = __ldg(s4 + i);
+      const float4 x1 = two ? __ldg(s4 + i + TF_GROUP) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(d0) = x0;
+      if (two) {
+        *reinterpret_cast<float4*>(d1) = x1;
+        w.next(F4);
+      }
+    }
   } else {
     const int Fp = F4 * 4;
     for (int i = tid; i < rows * Fp; i += TF_GROUP) {
@@ -256,6 +268,39 @@ __device__ __forceinline__ void tf_load_struct(int tid, int* ptr_s, uint8_t* idx
   } else {
     for (int i = tid; i < ents; i += TF_GROUP) idx_s[i] = __ldg(idx_g + e0 + i);
   }
+}
+
+// The same in two halves, so that the loads of several structures (and of the tile's rows) are
+// in flight together: tf_struct_fetch requests, tf_struct_put stores and returns the address of
+// the tile's first neighbour byte.  The bytes are copied as aligned words from the word that
+// holds entry e0, i.e. idx_raw keeps e0 % 4 leading bytes of the previous tile.
+struct StructRegs {
+  int ptr;
+  uint32_t w[2];  // TILE_ENTRIES + 6 bytes <= 2 * TF_GROUP words
+};
+static_assert((TILE_ENTRIES + 3 + 3) / 4 <= 2 * TF_GROUP, "StructRegs: two words per thread");
+static_assert(TILE_ROWS < TF_GROUP, "StructRegs: one row pointer per thread");
+__device__ __forceinline__ StructRegs tf_struct_fetch(int tid, const int32_t* __restrict__ ptr_g,
+                                                      const uint8_t* __restrict__ idx_g, int r0,
+                                                      int rows, int e0, int ents) {
+  StructRegs r;
+  r.ptr = tid <= rows ? __ldg(ptr_g + r0 + tid) - e0 : 0;
+  const int sh = e0 & 3, words = (ents + sh + 3) >> 2;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(idx_g + (e0 - sh));
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+    r.w[q] = tid + q * TF_GROUP < words ? __ldg(src + tid + q * TF_GROUP) : 0u;
+  return r;
+}
+__device__ __forceinline__ uint8_t* tf_struct_put(int tid, const StructRegs& r, int* ptr_s,
+                                                  uint8_t* idx_raw, int rows, int e0, int ents) {
+  if (tid <= rows) ptr_s[tid] = r.ptr;
+  const int sh = e0 & 3, words = (ents + sh + 3) >> 2;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(idx_raw);
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+    if (tid + q * TF_GROUP < words) dst[tid + q * TF_GROUP] = r.w[q];
+  return idx_raw + sh;
 }
 
 // dst[v][4c .. 4c+3] = ( sum_{e in row v, ascending} c_e * src[idx[e]][4c .. 4c+3] ) [/ (bkt[v]+1)]
@@ -387,16 +432,20 @@ __device__ __forceinline__ void tf_gemm(int tid, float* C, int pc, const float* 
 template <class Epi>
 __device__ __forceinline__ void tf_gemm_nt(int tid, float* C, int pc, const float* A, int pa,
                                            int K, const float* W, int pw, int gs,
-                                           const uint8_t* grp_s, int rows, int N, Epi epi) {
+                                           const uint8_t* grp_s, int rows, int N, Epi epi,
+                                           const uint8_t* list_s = nullptr) {
+  // list_s: lane p works on vertex list_s[p] (vertices grouped by weight block): the lanes of a
+  // warp read ONE block, every weight load is a broadcast (A and C stay in vertex order)
   const int warp = tid >> 5, lane = tid & 31;
   const int nvg = (rows + 31) >> 5, nnb = (N + TF_NB - 1) / TF_NB;
   const int N4 = ((N + 3) >> 2) << 2;
   const int K4 = K >> 2;
   for (int it = warp; it < nvg * nnb; it += TF_GWARPS) {
     const int nb = it / nvg, vg = it - nb * nvg;
-    const int v = vg * 32 + lane;
-    const bool live = v < rows;
-    const int vv = live ? v : rows - 1;
+    const int pos = vg * 32 + lane;
+    const bool live = pos < rows;
+    const int vv = list_s != nullptr ? list_s[live ? pos : rows - 1] : (live ? pos : rows - 1);
+    const int v = vv;
     const float4* a = reinterpret_cast<const float4*>(A + vv * pa);
     const float* w = W + (grp_s != nullptr ? grp_s[vv] * gs : 0) + nb * TF_NB * pw;
     float2 acc[TF_NB];
@@ -564,7 +613,7 @@ __device__ __forceinline__ void tf_gemm_nt2(int tid, float* C, int pc, const flo
 // One warp owns 8 k x 32 n of one group: lane = (k pair, n quad), i.e. a 2 x 4 register tile
 // fed by one LDS.64 of A (4 distinct addresses per warp) and one LDS.128 of G (one contiguous
 // 128-byte row piece per warp) per vertex -- 4 FFMA2 per 2 loads.  The group-private partial
-// is read before the loop and written after it.  list_s == nullptr: identity (one segment
+// is read and written after the loop.  list_s == nullptr: identity (one segment
 // with all rows).  G must be zero in columns N .. 4*ceil(N/4).
 // (Measured and dropped: cutting the rows of an ungrouped product into slices for otherwise
 // idle warps -- the extra barrier and the combine through shared memory cost more.)
@@ -585,20 +634,33 @@ __device__ __forceinline__ void tf_outer(int tid, float* __restrict__ part, cons
     if (p0 >= p1) continue;
     const int k0 = 8 * kb + 2 * kp, n0 = 32 * np + 4 * nq;
     const bool active = k0 < K && n0 < N4;
-    float old[2][4];
     float2 acc[2][2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float* row = part + (static_cast<size_t>(g) * K + k0 + i) * N + n0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        old[i][j] = (active && k0 + i < K && n0 + j < N) ? row[j] : 0.f;
-      acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
-    }
+    for (int i = 0; i < 2; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
     const float* Ak = A + (active ? k0 : 0);
     const float* Gn = G + (active ? n0 : 0);
-#pragma unroll 4
-    for (int p = p0; p < p1; ++p) {
+    // four vertices per round, all eight loads requested before the first FFMA2 (left to the
+    // compiler the loop ran one vertex at a time: load, load, wait, 4 x FFMA2)
+    int p = p0;
+    for (; p + 4 <= p1; p += 4) {
+      float2 a2[4];
+      float4 g4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int v = list_s != nullptr ? list_s[p + q] : p + q;
+        a2[q] = *reinterpret_cast<const float2*>(Ak + v * pa);
+        g4[q] = *reinterpret_cast<const float4*>(Gn + v * pg);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 glo = make_float2(g4[q].x, g4[q].y), ghi = make_float2(g4[q].z, g4[q].w);
+        fma2s(acc[0][0], a2[q].x, glo);
+        fma2s(acc[0][1], a2[q].x, ghi);
+        fma2s(acc[1][0], a2[q].y, glo);
+        fma2s(acc[1][1], a2[q].y, ghi);
+      }
+    }
+    for (; p < p1; ++p) {
       const int v = list_s != nullptr ? list_s[p] : p;
       const float2 a2 = *reinterpret_cast<const float2*>(Ak + v * pa);
       const float4 g4 = *reinterpret_cast<const float4*>(Gn + v * pg);
@@ -613,9 +675,18 @@ __device__ __forceinline__ void tf_outer(int tid, float* __restrict__ part, cons
       for (int i = 0; i < 2; ++i) {
         float* row = part + (static_cast<size_t>(g) * K + k0 + i) * N + n0;
         const float r4[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
+        if (k0 + i < K && n0 + 4 <= N && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+          float4 o = *reinterpret_cast<const float4*>(row);
+          o.x += r4[0];
+          o.y += r4[1];
+          o.z += r4[2];
+          o.w += r4[3];
+          *reinterpret_cast<float4*>(row) = o;
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (k0 + i < K && n0 + j < N) row[j] = old[i][j] + r4[j];
+          for (int j = 0; j < 4; ++j)
+            if (k0 + i < K && n0 + j < N) row[j] += r4[j];
+        }
       }
     }
   }
@@ -811,8 +882,8 @@ __device__ __forceinline__ TileView tf_tile(const int4* tiles, int j, int num_ti
 }
 
 // Ae[v][:] = sum_w E(:, ja(2,w))  (time-step invariant part of duvenaud_propagate).  The edge
-// ids and rows of four entries are requested before the first is added (independent loads;
-// the additions keep the entry order).
+// ids and rows of eight entries are requested before the first is added (two dependent global
+// latencies per row of up to eight entries; the additions keep the entry order).
 __device__ __forceinline__ void tf_edge_sum(int tid, float* ae, int pe,
                                             const float* __restrict__ E, int Fe,
                                             const int32_t* __restrict__ eid, const int* ptr_s,
@@ -821,22 +892,17 @@ __device__ __forceinline__ void tf_edge_sum(int tid, float* ae, int pe,
     const int v = i / Fe, f = i - v * Fe;
     const int b = ptr_s[v], e1 = ptr_s[v + 1];
     float s = 0.f;
-    int e = b;
-    for (; e + 4 <= e1; e += 4) {
-      int id[4];
-      float x[4];
+    for (int e = b; e < e1; e += 8) {
+      int id[8];
+      float x[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) id[q] = __ldg(eid + e0 + e + q);
+      for (int q = 0; q < 8; ++q) id[q] = e + q < e1 ? __ldg(eid + e0 + e + q) : -1;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < 8; ++q)
         x[q] = id[q] >= 0 ? __ldg(E + static_cast<size_t>(id[q]) * Fe + f) : 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < 8; ++q)
         if (id[q] >= 0) s += x[q];
-    }
-    for (; e < e1; ++e) {
-      const int id = __ldg(eid + e0 + e);
-      if (id >= 0) s += __ldg(E + static_cast<size_t>(id) * Fe + f);
     }
     ae[v * pe + f] = s;
   }
@@ -955,9 +1021,9 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
   float* gsm = sm + L.group0 + grp * L.group_stride;
   int* ptr_s = reinterpret_cast<int*>(gsm + L.ints);
   float* red = reinterpret_cast<float*>(ptr_s + 132 + 132 + 260 + 128);
-  uint8_t* idx_s = reinterpret_cast<uint8_t*>(gsm + L.bytes);
-  uint8_t* inv_s = idx_s + TF_IDX;  // (the CSC bytes of the backward's layout)
-  uint8_t* bkt_s = idx_s + 2 * TF_IDX;
+  uint8_t* idx_raw = reinterpret_cast<uint8_t*>(gsm + L.bytes);
+  uint8_t* inv_s = idx_raw + TF_IDX;  // (the CSC bytes of the backward's layout)
+  uint8_t* bkt_s = idx_raw + 2 * TF_IDX;
   uint8_t* list_s = bkt_s + 128;
   int* seg_s = ptr_s + 132 + 132;
   float* ae = gsm + L.ae;
@@ -967,18 +1033,26 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
   __syncthreads();
   TFT();
   float lsum = 0.f;
+  // the descriptor of the next tile (a chain of dependent loads) is requested a whole tile ahead
+  TileView tvn{};
+  if (blockIdx.x * ngrp + grp < a.num_tiles)
+    tvn = tf_tile(a.tiles, blockIdx.x * ngrp + grp, a.num_tiles, a.vgraph, a.num_graphs);
   for (int j = blockIdx.x * ngrp + grp; j < a.num_tiles; j += gridDim.x * ngrp) {
-    const TileView tv = tf_tile(a.tiles, j, a.num_tiles, a.vgraph, a.num_graphs);
+    const TileView tv = tvn;
+    if (j + gridDim.x * ngrp < a.num_tiles)
+      tvn = tf_tile(a.tiles, j + gridDim.x * ngrp, a.num_tiles, a.vgraph, a.num_graphs);
     tf_sync(grp);  // the previous tile is done with every buffer
-    tf_load_struct(tid, ptr_s, idx_s, a.row_ptr, a.col8, tv.r0, tv.rows, tv.e0, tv.ents);
-    for (int v = tid; v < tv.rows; v += TF_GROUP) {
-      const int deg = __ldg(a.row_ptr + tv.r0 + v + 1) - __ldg(a.row_ptr + tv.r0 + v);
-      bkt_s[v] = static_cast<uint8_t>(max(a.min_deg, min(deg, a.max_deg)) - a.min_deg);
-    }
+    // every global load of the tile is requested before the first one is stored
+    const StructRegs sr = tf_struct_fetch(tid, a.row_ptr, a.col8, tv.r0, tv.rows, tv.e0, tv.ents);
+    int deg = 0;
+    if (tid < tv.rows) deg = __ldg(a.row_ptr + tv.r0 + tid + 1) - __ldg(a.row_ptr + tv.r0 + tid);
     float* xin = gsm + L.buf[0];
     float* AY = gsm + L.buf[1];   // A, then the readout
     float* zout = gsm + L.buf[2];
     tf_load_rows(tid, xin, P, a.X + static_cast<size_t>(tv.r0) * a.nvf[0], tv.rows, a.nvf[0]);
+    const uint8_t* idx_s = tf_struct_put(tid, sr, ptr_s, idx_raw, tv.rows, tv.e0, tv.ents);
+    if (tid < tv.rows)
+      bkt_s[tid] = static_cast<uint8_t>(max(a.min_deg, min(deg, a.max_deg)) - a.min_deg);
     tf_sync(grp);
     TFT();
     // A is built with its rows grouped by degree bucket (the barriers below order this before
@@ -1086,9 +1160,9 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
   int* cptr_s = ptr_s + 132;
   int* seg_s = cptr_s + 132;
   int* vg_s = seg_s + 260;
-  uint8_t* idx_s = reinterpret_cast<uint8_t*>(gsm + L.bytes);
-  uint8_t* cidx_s = idx_s + TF_IDX;
-  uint8_t* bkt_s = cidx_s + TF_IDX;
+  uint8_t* idx_raw = reinterpret_cast<uint8_t*>(gsm + L.bytes);
+  uint8_t* cidx_raw = idx_raw + TF_IDX;
+  uint8_t* bkt_s = cidx_raw + TF_IDX;
   uint8_t* list_s = bkt_s + 128;
   float* ae = gsm + L.ae;
   const int P = L.P;
@@ -1098,15 +1172,23 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
   __syncthreads();
   TFT();
   const int T = a.T;
+  int4 tin = make_int4(0, 0, 0, 0);  // (first row, rows, first entry, entries) of the next tile
+  if (blockIdx.x * ngrp + grp < a.num_tiles) tin = __ldg(a.tiles + blockIdx.x * ngrp + grp);
   for (int j = blockIdx.x * ngrp + grp; j < a.num_tiles; j += gridDim.x * ngrp) {
-    const TileView tv = tf_tile(a.tiles, j, a.num_tiles, a.vgraph, a.num_graphs);
+    TileView tv;
+    tv.r0 = tin.x;
+    tv.rows = tin.y;
+    tv.e0 = tin.z;
+    tv.ents = tin.w;
+    if (j + gridDim.x * ngrp < a.num_tiles) tin = __ldg(a.tiles + j + gridDim.x * ngrp);
     tf_sync(grp);
-    tf_load_struct(tid, ptr_s, idx_s, a.row_ptr, a.col8, tv.r0, tv.rows, tv.e0, tv.ents);
-    tf_load_struct(tid, cptr_s, cidx_s, a.csc_ptr, a.csc8, tv.r0, tv.rows, tv.e0, tv.ents);
-    for (int v = tid; v < tv.rows; v += TF_GROUP) {
-      const int deg = __ldg(a.row_ptr + tv.r0 + v + 1) - __ldg(a.row_ptr + tv.r0 + v);
-      bkt_s[v] = static_cast<uint8_t>(max(a.min_deg, min(deg, a.max_deg)) - a.min_deg);
-      vg_s[v] = __ldg(a.vgraph + tv.r0 + v);
+    // every global load of the tile is requested before the first one is stored
+    const StructRegs sr = tf_struct_fetch(tid, a.row_ptr, a.col8, tv.r0, tv.rows, tv.e0, tv.ents);
+    const StructRegs sc = tf_struct_fetch(tid, a.csc_ptr, a.csc8, tv.r0, tv.rows, tv.e0, tv.ents);
+    int deg = 0, vgv = 0;
+    if (tid < tv.rows) {
+      deg = __ldg(a.row_ptr + tv.r0 + tid + 1) - __ldg(a.row_ptr + tv.r0 + tid);
+      vgv = __ldg(a.vgraph + tv.r0 + tid);
     }
     // edge-feature sums saved by the forward
     for (int i = tid; i < tv.rows * a.nef; i += TF_GROUP) {
@@ -1117,6 +1199,12 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
     float* Y = gsm + L.buf[1];  // readout / dY, then A, then dA
     float* Z = gsm + L.buf[2];  // carry -> gz -> the new carry
     tf_load_rows(tid, X, P, a.Z[T - 1] + static_cast<size_t>(tv.r0) * a.nvf[T], tv.rows, a.nvf[T]);
+    const uint8_t* idx_s = tf_struct_put(tid, sr, ptr_s, idx_raw, tv.rows, tv.e0, tv.ents);
+    const uint8_t* cidx_s = tf_struct_put(tid, sc, cptr_s, cidx_raw, tv.rows, tv.e0, tv.ents);
+    if (tid < tv.rows) {
+      bkt_s[tid] = static_cast<uint8_t>(max(a.min_deg, min(deg, a.max_deg)) - a.min_deg);
+      vg_s[tid] = vgv;
+    }
     tf_sync(grp);
     // vertices of the tile grouped by degree bucket (ascending vertex inside a bucket)
     if (tid < 32) tf_bucket_list(tid, bkt_s, tv.rows, a.D, list_s, nullptr, seg_s);
@@ -1124,11 +1212,9 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
     {
       // the next tile of this group: its z_T rows on their way to L2 while this tile computes
       const int jn = j + gridDim.x * ngrp;
-      if (jn < a.num_tiles && tid < 64) {
-        const int4 nt = __ldg(a.tiles + jn);  // (first row, rows, first entry, entries)
-        tf_prefetch_l2(tid * (TF_GROUP / 64), a.Z[T - 1] + static_cast<size_t>(nt.x) * a.nvf[T],
-                       nt.y * a.nvf[T] * 4);
-      }
+      if (jn < a.num_tiles && tid < 64)
+        tf_prefetch_l2(tid * (TF_GROUP / 64), a.Z[T - 1] + static_cast<size_t>(tin.x) * a.nvf[T],
+                       tin.y * a.nvf[T] * 4);
     }
     for (int t = T; t >= 1; --t) {
       const int i = t - 1;
@@ -1188,7 +1274,8 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
         TFT();
         const uint8_t* bk = bkt_s;
         tf_gemm_nt(tid, Y, P, Z, P, Fo, sm + L.w[i], L.pw[i], L.gs[i], bkt_s, tv.rows, Fi,
-                   [bk](int v, int, float s) { return s * (1.f / static_cast<float>(bk[v] + 1)); });
+                   [bk](int v, int, float s) { return s * (1.f / static_cast<float>(bk[v] + 1)); },
+                   list_s);
         tf_sync(grp);
         TFT();
         // 7. d in(:,u) = sum over the CSC column of u of dA(1:Fi, v): the new carry, over gz in Z
