@@ -329,6 +329,8 @@ struct TileDuvDesc {
   const float* E;         // [E][F_e]
   float* Ae;              // [V][F_e] per-vertex edge-feature sums (forward writes, backward reads)
   float* const* Z;        // z_t, t = 1..T (written by the forward, read by the backward)
+  float* const* S = nullptr;  // optional readouts S_t = ract(R_t z_t), [V][no]: the forward saves
+                              // them, the backward reads them back instead of recomputing them
   int fold_act = 0;       // backward: the input gradient leaves multiplied by fold_act'(X)
 };
 bool tile_duv_supported(const Batch* b, int T, const int* nvf, int nef, int D, int no);

@@ -34,6 +34,7 @@ struct Layer : Object {
   std::vector<char> mask_valid;                          // MK[t] written by the last forward
   DevBuf Ae, out_buf, g0, g1, g2, tn_scratch, stage_x, stage_e, stage_g, stage_gin;
   DevBuf tile_part;          // CTA partials of the fused Duvenaud reverse sweep (tile_fma.cu)
+  bool tile_S = false;       // the fused forward saved the readouts S_t
   bool tile_fwd = false;     // the last forward ran on the fused tile kernel (saved: z_t only)
   const float* fwd_e = nullptr;  // device edge features of the last forward
   std::vector<char> staged;  // per-sample marks of athena_cuda_layer_backward_stage
@@ -234,16 +235,26 @@ static int duvenaud_forward(Layer* L, Batch* b, const float* x, const float* e,
     ATH_REQUIRE(L->nef == 0 || e != nullptr, ATHENA_ERR_ARG,
                 "duvenaud forward: edge_features is null");
     float* Z[16];
+    float* S[16];
     for (int t = 1; t <= L->T; ++t) {
       DevBuf& Zt = *L->H[t - 1];
       ATH_TRY(Zt.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * L->nvf[t], 1)));
       Z[t - 1] = Zt.as<float>();
+      // the readouts S_t are kept for the reverse sweep (not in inference mode)
+      S[t - 1] = nullptr;
+      if (!L->inference) {
+        DevBuf& St = *L->S[t - 1];
+        ATH_TRY(St.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * L->n_out, 1)));
+        S[t - 1] = St.as<float>();
+      }
     }
+    L->tile_S = !L->inference;
     ATH_TRY(L->out_buf.reserve(sizeof(float) * (size_t)b->B * L->n_out));
     if (L->nef > 0)
       ATH_TRY(L->Ae.reserve(sizeof(float) * (size_t)std::max<int64_t>(V * L->nef, 1)));
     TileDuvDesc d;
     duv_desc(L, x, e, Z, &d);
+    if (L->tile_S) d.S = S;
     const bool mse = fo != nullptr && fo->mse_target != nullptr;
     if (mse) {
       ATH_TRY(main_wait(fo->target_ready));
@@ -512,9 +523,14 @@ static int duvenaud_backward(Layer* L, Batch* b, const float* gout, float* gin,
   if (L->tile_fwd) {
     // the whole reverse sweep of the layer in ONE launch; A_t and S_t are recomputed from z_t
     float* Z[16];
-    for (int t = 1; t <= L->T; ++t) Z[t - 1] = L->H[t - 1]->as<float>();
+    float* S[16];
+    for (int t = 1; t <= L->T; ++t) {
+      Z[t - 1] = L->H[t - 1]->as<float>();
+      S[t - 1] = L->tile_S ? L->S[t - 1]->as<float>() : nullptr;
+    }
     TileDuvDesc d;
     duv_desc(L, L->fwd_x, L->fwd_e, Z, &d);
+    if (L->tile_S) d.S = S;
     if (gin != nullptr && folded != nullptr && fold_act != ATHENA_ACT_NONE &&
         fold_act != ATHENA_ACT_LINEAR && fold_act != ATHENA_ACT_SOFTMAX &&
         fold_act != ATHENA_ACT_SWISH) {

@@ -798,6 +798,7 @@ struct DuvArgs {
                         // (nullable), read by the backward
   const float* params;  // W_1..W_T, R_1..R_T (flat, the reference's packing)
   float* Z[TF_MAX_T];   // z_t, [V][F_t]
+  float* S[TF_MAX_T];   // S_t = ract(R_t z_t), [V][no], or nullptr (the backward recomputes it)
   int woff[TF_MAX_T], roff[TF_MAX_T];
   int nvf[TF_MAX_T + 1];
   int T, nef, D, min_deg, max_deg, no, act, ract;
@@ -1098,6 +1099,10 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
         tf_sync(grp);
       }
       TFT();
+      // S_t for the reverse sweep (the kernels are bound by shared-memory traffic, not by HBM:
+      // 128 bytes per vertex and step here save the backward a product and a softmax)
+      if (a.S[i] != nullptr)
+        tf_store_rows(tid, a.S[i] + static_cast<size_t>(tv.r0) * a.no, AY, P, tv.rows, a.no);
       // out(:,s) (+)= sum_v S(:,v), vertices ascending (sum(ptr2, dim=2), :848-852)
       for (int idx = tid; idx < ng * a.no; idx += TF_GROUP) {
         const int gl = idx / a.no, o = idx - gl * a.no;
@@ -1199,6 +1204,8 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
     float* Y = gsm + L.buf[1];  // readout / dY, then A, then dA
     float* Z = gsm + L.buf[2];  // carry -> gz -> the new carry
     tf_load_rows(tid, X, P, a.Z[T - 1] + static_cast<size_t>(tv.r0) * a.nvf[T], tv.rows, a.nvf[T]);
+    if (a.S[T - 1] != nullptr)
+      tf_load_rows(tid, Y, P, a.S[T - 1] + static_cast<size_t>(tv.r0) * a.no, tv.rows, a.no);
     const uint8_t* idx_s = tf_struct_put(tid, sr, ptr_s, idx_raw, tv.rows, tv.e0, tv.ents);
     const uint8_t* cidx_s = tf_struct_put(tid, sc, cptr_s, cidx_raw, tv.rows, tv.e0, tv.ents);
     if (tid < tv.rows) {
@@ -1221,12 +1228,22 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
       const int Fi = a.nvf[t - 1], Fo = a.nvf[t], K = Fi + a.nef, no = a.no;
       tf_prefetch_l2(tid, (t >= 2 ? a.Z[t - 2] : a.X) + static_cast<size_t>(tv.r0) * Fi,
                      tv.rows * Fi * 4);  // step 4 loads it
-      // 1. S = ract(R_t z_t) into Y, then dY in place (upstream row = gout of the vertex's graph)
-      duv_update(tid, a.ract, Y, X, P, Fo, sm + L.r[i], L.pr[i], 0, nullptr, tv.rows, no);
-      tf_sync(grp);
-      if (a.ract == ATHENA_ACT_SOFTMAX) {
-        tf_softmax_rows(tid, Y, P, tv.rows, no);
+      if (t >= 2 && a.S[t - 2] != nullptr)  // step 1 of the next iteration loads it
+        tf_prefetch_l2(tid, a.S[t - 2] + static_cast<size_t>(tv.r0) * no, tv.rows * no * 4);
+      // 1. S = ract(R_t z_t) into Y (read back if the forward saved it), then dY in place
+      //    (upstream row = gout of the vertex's graph)
+      if (a.S[i] != nullptr) {
+        if (t < T) {
+          tf_load_rows(tid, Y, P, a.S[i] + static_cast<size_t>(tv.r0) * no, tv.rows, no);
+          tf_sync(grp);
+        }
+      } else {
+        duv_update(tid, a.ract, Y, X, P, Fo, sm + L.r[i], L.pr[i], 0, nullptr, tv.rows, no);
         tf_sync(grp);
+        if (a.ract == ATHENA_ACT_SOFTMAX) {
+          tf_softmax_rows(tid, Y, P, tv.rows, no);
+          tf_sync(grp);
+        }
       }
       {
         const float* gout = a.gout;
@@ -1601,6 +1618,7 @@ static void duv_fill(DuvArgs* a, const Batch* b, const TileDuvDesc& d) {
   for (int t = 0; t <= d.T; ++t) a->nvf[t] = d.nvf[t];
   for (int t = 0; t < d.T; ++t) {
     a->Z[t] = d.Z[t];
+    a->S[t] = d.S != nullptr ? d.S[t] : nullptr;
     a->woff[t] = (int)d.poff[t];
     a->roff[t] = (int)d.poff[d.T + t];
   }
