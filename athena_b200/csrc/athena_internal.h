@@ -390,6 +390,7 @@ struct OptimState {
   // > 0: launch_finalize already clamped the gradients and left this many partial sums of
   // squares in `scratch`; launch_update then goes straight to the step
   int presum_nb = 0;
+  DevBuf tail;     // block counter of the finalize launch that also steps (short vectors)
 };
 // clip + optimiser step + zero the gradients (athena_network_sub.f90:2904-2927)
 int launch_update(float* params, float* grads, int64_t n, OptimState& st);
@@ -421,7 +422,7 @@ bool finalize_can_step(const OptimState& st);
 int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts, float* loss_acc,
                     float* params, float* grads, int64_t n, OptimState* st,
                     float* xout = nullptr, const P2PSignal* sig = nullptr, int exchange = 0,
-                    OptimState* presum = nullptr);
+                    OptimState* presum = nullptr, bool* presum_stepped = nullptr);
 // exchange != 0: the peer-memory sum (+ the step when st != nullptr) rides on the same launch
 bool finalize_can_exchange(int64_t n);
 

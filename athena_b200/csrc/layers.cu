@@ -859,10 +859,12 @@ static int net_loss_grads(Network* N, Batch* b, const float* x, const float* e, 
     // norm clipping on one GPU: the finalize launch clamps and pre-sums for the step that follows
     OptimState* presum = (step_too && fst == nullptr && !use_p2p && comm_world_size() == 1 &&
                           N->opt.d.clip_norm_on) ? &N->opt : nullptr;
+    bool tail_stepped = false;  // short parameter vectors: the clipped step rode along
     ATH_TRY(launch_finalize(defer, fo.fused ? fo.loss_part : nullptr, fo.num_parts, gflat + N->n,
                             N->flat_params.as<float>(), gflat, N->n, fst, xout,
-                            use_p2p ? &sig : nullptr, fuse_exchange ? 1 : 0, presum));
-    if (stepped) *stepped = fuse_exchange ? p2p_step : fuse_step;
+                            use_p2p ? &sig : nullptr, fuse_exchange ? 1 : 0, presum,
+                            stepped ? &tail_stepped : nullptr));
+    if (stepped) *stepped = (fuse_exchange ? p2p_step : fuse_step) || tail_stepped;
   }
   if (use_p2p && !fuse_exchange) {
     // signal (done by the finalize launch) + wait + sum over NVLink + (when no clipping

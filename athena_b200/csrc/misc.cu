@@ -286,6 +286,7 @@ k_step(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
 // pattern and the group totals are added in group order.
 constexpr int FIN_ELEMS = 32, FIN_GROUPS = 32, FIN_THREADS = FIN_ELEMS * FIN_GROUPS;
 constexpr int FIN_MAX_JOBS = 8;
+constexpr int64_t FIN_TAIL_MAX = 16384;  // parameters one block steps through at the end
 struct FinJob {
   const float* part;  // [nparts][count]
   int nparts, count;
@@ -308,6 +309,10 @@ struct FinArgs {
   float* sumsq_part;
   int clamp;
   float cmin, cmax;
+  // small parameter vectors with norm clipping: the LAST block to finish adds up the partial
+  // sums of squares (in block order) and applies the whole clipped step -- no second launch
+  int tail_step;
+  unsigned int* tail_counter;
   int xfused, xstep;
   const float* xin[P2P_MAX_WORLD];
   long long timeout_ns;
@@ -393,6 +398,33 @@ k_finalize(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     if (e == 0) f.sumsq_part[blockIdx.x] = sq;
+  }
+  if (f.tail_step) {
+    __shared__ int is_last;
+    __syncthreads();  // this block's gradients and its partial are written
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int prev = atomicAdd(f.tail_counter, 1u);
+      is_last = prev + 1 == gridDim.x;
+      if (is_last) *f.tail_counter = 0;
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      float local = 0.f;
+      for (int k = threadIdx.x; k < (int)gridDim.x; k += FIN_THREADS) local += __ldcg(f.sumsq_part + k);
+      const float tot = block_sum<FIN_THREADS>(local);
+      __shared__ float scale_sh;
+      if (threadIdx.x == 0) scale_sh = fminf(1.f, a.clip_norm / sqrtf(tot));
+      __syncthreads();
+      const float scale = scale_sh;
+      for (long long k = threadIdx.x; k < n; k += FIN_THREADS) {
+        float gr = __ldcg(g + k);
+        if (scale < 1.f) gr = gr * scale;
+        step_one(p, s1, s2, k, gr, a);
+        g[k] = 0.f;  // reset_gradients, athena_network_sub.f90:2927
+      }
+    }
   }
   if (blockIdx.x == 0 && (f.loss_part != nullptr || f.xout != nullptr)) {
     __syncthreads();
@@ -686,7 +718,8 @@ bool finalize_can_exchange(int64_t n) {
 
 int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts, float* loss_acc,
                     float* params, float* grads, int64_t n, OptimState* st, float* xout,
-                    const P2PSignal* sig, int exchange, OptimState* presum) {
+                    const P2PSignal* sig, int exchange, OptimState* presum, bool* presum_stepped) {
+  if (presum_stepped) *presum_stepped = false;
   if (n == 0) return ATHENA_OK;
   // norm clipping: this launch clamps and leaves the partial sums of squares for the step
   const int fin_grid = (int)cdiv(n, FIN_ELEMS);
@@ -697,6 +730,16 @@ int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts
   cudaStream_t s = ctx().stream;
   StepArgs a{};
   if (st) ATH_TRY(step_prepare(n, *st, &a));
+  // a short parameter vector: the clipped step rides on this launch (its last block does it)
+  const bool tail = presum != nullptr && presum_stepped != nullptr && n <= FIN_TAIL_MAX;
+  if (tail) {
+    if (!presum->tail.p) {
+      ATH_TRY(presum->tail.reserve(sizeof(unsigned int)));
+      ATH_CUDA(cudaMemsetAsync(presum->tail.p, 0, sizeof(unsigned int), s));
+    }
+    ATH_TRY(step_prepare(n, *presum, &a));
+    ATH_TRY(presum->scratch.reserve(sizeof(float) * (size_t)std::max(fin_grid, 1024)));
+  }
   P2PState& PS = p2p();
   if (exchange) {
     ATH_REQUIRE(sig && xout && PS.ready && dl.jobs.size() <= (size_t)FIN_MAX_JOBS, ATHENA_ERR_STATE,
@@ -704,6 +747,7 @@ int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts
     ATH_REQUIRE(!PS.failed, ATHENA_ERR_COMM,
                 "p2p exchange: an earlier exchange timed out waiting for a peer");
   }
+  OptimState* sst = st ? st : (tail ? presum : nullptr);  // whose moments the launch updates
   size_t done = 0;
   do {
     FinArgs f{};
@@ -726,7 +770,12 @@ int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts
       f.clamp = presum->d.clip_min_max;
       f.cmin = presum->d.clip_min;
       f.cmax = presum->d.clip_max;
-      presum->presum_nb = fin_grid;
+      presum->presum_nb = tail ? 0 : fin_grid;
+      if (tail) {
+        f.tail_step = 1;
+        f.tail_counter = presum->tail.as<unsigned int>();
+        *presum_stepped = true;
+      }
     }
     f.xout = last ? xout : nullptr;
     if (last && xout && sig) f.sig = *sig;
@@ -739,10 +788,10 @@ int launch_finalize(const DeferList& dl, const float* loss_part, int loss_nparts
       PS.epoch += 1;  // this launch IS the exchange
     }
     ATH_CUDA(launch_pdl(k_finalize, dim3((unsigned)cdiv(n, FIN_ELEMS)), dim3(FIN_THREADS), 0, s,
-                        params, grads, st ? st->s1.as<float>() : nullptr,
-                        st ? st->s2.as<float>() : nullptr, (long long)n, f, a));
+                        params, grads, sst ? sst->s1.as<float>() : nullptr,
+                        sst ? sst->s2.as<float>() : nullptr, (long long)n, f, a));
     ATH_LAUNCHED_T(f.xfused ? (f.xstep ? "finalize_exchange_step" : "finalize_exchange")
-                            : f.do_step ? "finalize_step" : "finalize");
+                            : (f.do_step || f.tail_step) ? "finalize_step" : "finalize");
   } while (done < dl.jobs.size());
   return ATHENA_OK;
 }

@@ -946,6 +946,20 @@ __device__ __forceinline__ void tf_bucket_list(int lane, const uint8_t* bkt_s, i
   if (lane == 0) seg_s[D] = base;
 }
 
+// one asynchronous 4-byte global -> shared copy: the staging loops below issue all of them
+// without waiting for one another (as plain loads each loop exposed its own memory latency:
+// 3 T loops in a row, a fifth of the forward kernel on a one-tile batch)
+__device__ __forceinline__ void tf_cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(dst))),
+               "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void tf_cp_async_wait() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// (ends with tf_cp_async_wait(); the caller's __syncthreads() publishes the weights)
 __device__ __forceinline__ void duv_stage_weights(float* sm, const DuvArgs& a) {
   const int D = a.D, nt = blockDim.x;
   for (int t = 1; t <= a.T; ++t) {
@@ -961,15 +975,21 @@ __device__ __forceinline__ void duv_stage_weights(float* sm, const DuvArgs& a) {
       const int n = threadIdx.x % pw;
       for (int row = threadIdx.x / pw; row < D * rows_w; row += nt / pw) {
         const int d = row / rows_w, k = row - d * rows_w;
-        ws[d * gs + k * pw + n] =
-            (k < K && n < Fo) ? __ldg(Wg + (static_cast<size_t>(d) * K + k) * Fo + n) : 0.f;
+        float* dst = ws + d * gs + k * pw + n;
+        if (k < K && n < Fo)
+          tf_cp_async4(dst, Wg + (static_cast<size_t>(d) * K + k) * Fo + n);
+        else
+          *dst = 0.f;
       }
     } else {
       for (int idx = threadIdx.x; idx < D * rows_w * pw; idx += nt) {
         const int row = idx / pw, n = idx - row * pw;
         const int d = row / rows_w, k = row - d * rows_w;
-        ws[d * gs + k * pw + n] =
-            (k < K && n < Fo) ? __ldg(Wg + (static_cast<size_t>(d) * K + k) * Fo + n) : 0.f;
+        float* dst = ws + d * gs + k * pw + n;
+        if (k < K && n < Fo)
+          tf_cp_async4(dst, Wg + (static_cast<size_t>(d) * K + k) * Fo + n);
+        else
+          *dst = 0.f;
       }
     }
     // the bank-shift pad at the end of every bucket block
@@ -982,9 +1002,13 @@ __device__ __forceinline__ void duv_stage_weights(float* sm, const DuvArgs& a) {
     const int pr = a.lay.pr[i];
     for (int idx = threadIdx.x; idx < tf_up(Fo, TF_NB) * pr; idx += nt) {
       const int f = idx / pr, n = idx - f * pr;
-      rs[idx] = (f < Fo && n < a.no) ? __ldg(Rg + static_cast<size_t>(f) * a.no + n) : 0.f;
+      if (f < Fo && n < a.no)
+        tf_cp_async4(rs + idx, Rg + static_cast<size_t>(f) * a.no + n);
+      else
+        rs[idx] = 0.f;
     }
   }
+  tf_cp_async_wait();
 }
 
 // z = act(A . W_d) with the activation hoisted out of the epilogue's inner loop
