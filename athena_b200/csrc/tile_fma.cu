@@ -555,11 +555,15 @@ __device__ __forceinline__ void tf_gemm2(int tid, float* C, int pc, const float*
 template <class Epi>
 __device__ __forceinline__ void tf_gemm_nt2(int tid, float* C, int pc, const float* A, int pa,
                                             int K, const float* W, int pw, int rows, int N,
-                                            Epi epi) {
+                                            Epi epi, int busy_warps = 0) {
+  // busy_warps: the first warps of the group are still inside an outer product that nothing
+  // separates from this call: the others take the work
   const int warp = tid >> 5, lane = tid & 31;
   const int nrg = (rows + 63) >> 6, nnb = (N + 3) >> 2;
   const int K4 = K >> 2;
-  for (int it = warp; it < nrg * nnb; it += TF_GWARPS) {
+  if (busy_warps > TF_GWARPS / 2) busy_warps = 0;
+  for (int it = warp >= busy_warps ? warp - busy_warps : nrg * nnb; it < nrg * nnb;
+       it += TF_GWARPS - busy_warps) {
     const int nb = it / nrg, rg = it - nb * nrg;
     const int v0 = rg * 64 + lane, v1 = v0 + 32;
     const bool live0 = v0 < rows, live1 = v1 < rows;
@@ -1127,13 +1131,25 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
       // 128 bytes per vertex and step here save the backward a product and a softmax)
       if (a.S[i] != nullptr)
         tf_store_rows(tid, a.S[i] + static_cast<size_t>(tv.r0) * a.no, AY, P, tv.rows, a.no);
-      // out(:,s) (+)= sum_v S(:,v), vertices ascending (sum(ptr2, dim=2), :848-852)
-      for (int idx = tid; idx < ng * a.no; idx += TF_GROUP) {
-        const int gl = idx / a.no, o = idx - gl * a.no;
-        const int g = tv.g_begin + gl;
-        const int v0 = __ldg(a.voff + g) - tv.r0, v1 = __ldg(a.voff + g + 1) - tv.r0;
+      // out(:,s) (+)= sum_v S(:,v) (sum(ptr2, dim=2), :848-852).  Four lanes per (graph, output)
+      // pair add every fourth vertex and are combined in a fixed order: a quarter of the
+      // dependent-add chain of one lane per pair
+      const int npairs = ng * a.no;
+      for (int base = 0; base < npairs; base += TF_GROUP / 4) {
+        const int idx = base + (tid >> 2), q = tid & 3;
+        const bool live = idx < npairs;
+        int g = 0, o = 0;
         float s = 0.f;
-        for (int v = v0; v < v1; ++v) s += AY[v * P + o];
+        if (live) {
+          const int gl = idx / a.no;
+          o = idx - gl * a.no;
+          g = tv.g_begin + gl;
+          const int v0 = __ldg(a.voff + g) - tv.r0, v1 = __ldg(a.voff + g + 1) - tv.r0;
+          for (int v = v0 + q; v < v1; v += 4) s += AY[v * P + o];
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (!live || q != 0) continue;
         float* dst = a.out + static_cast<size_t>(g) * a.no + o;
         float tot;
         if (outs_local) {
@@ -1289,7 +1305,8 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
                     [act, has_carry, zt, cc, P](int v, int n, float s) {
                       const float dz = has_carry ? s + cc[v * P + n] : s;
                       return tf_act_grad(act, zt[v * P + n], dz);
-                    });
+                    },
+                    ((Fo + 7) >> 3) * ((no + 31) >> 5) /* warps inside step 2 */);
       }
       tf_sync(grp);
       TFT();
