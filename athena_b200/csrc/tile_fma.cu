@@ -14,7 +14,10 @@
 //               softmax athena_diffstruc_extd_sub.f90:309-313, sum over vertices :848-852)
 //               + optionally the [num_outputs, batch] MSE cell (athena_loss.f90:414)
 //   k_duv_bwd   the reverse sweep through all of it (:284-368, :115-142, softmax :355-379),
-//               recomputing A_t and S_t from the saved z_t instead of reading stored copies
+//               recomputing A_t from the saved z_t and reading the readouts S_t back (the
+//               kernels are bound by shared-memory traffic, not by HBM: DESIGN.md 3.2); the
+//               activation derivative of the layer that produced the input rides on the
+//               input-gradient store
 //   k_kipf_fwd  kipf_propagate + matmul + activation   (_sub_kipf.f90:29-46,
 //               athena_kipf_msgpass_layer.f90:943-952), any widths up to 128
 //   k_kipf_bwd  act', dW = gY^T P, dP = gY W^T, un-normalised CSC scatter (_sub_kipf.f90:101-109)
@@ -29,7 +32,9 @@
 // block read as broadcast LDS.128; per-bucket weight blocks are offset by an odd number of
 // 16-byte chunks so that lanes of different buckets hit different banks.  The same [k][n]
 // weight block serves Y = A.W (n-blocked, scalar x pair FFMA2) and dA = G.W^T (row-blocked,
-// pair x pair FFMA2 over the contraction index).  Sums over CSR entries run in the
+// pair x pair FFMA2 over the contraction index).  The rows of a tile are grouped by degree
+// bucket (tf_bucket_list) wherever a per-bucket weight block is read, so that the lanes of a
+// warp read ONE block and every weight load is a broadcast.  Sums over CSR entries run in the
 // reference's order; weight gradients are accumulated per group in a private partial
 // vector (no atomics) that k_finalize folds in a fixed order.
 #include <algorithm>
