@@ -144,24 +144,33 @@ __device__ __forceinline__ void fma2p(float2& d, float2 a, float2 b) {  // pair 
   d = *reinterpret_cast<float2*>(&dd);
 }
 
+// floor(n / d) for 0 <= n < 4096 and 1 <= d <= 64 as one multiply and one shift: the quotients
+// the tile walks need (thread -> row / chunk, item -> row / column) have run-time divisors, and
+// the ~20-instruction integer division sequences were 8 % of the forward kernel's instructions.
+// (n * ceil(2^20 / d)) >> 20 is exact in that range (checked exhaustively: tests/test_abi_cpu.py).
+__constant__ uint32_t tf_inv20[65] = {
+    0,      1048576, 524288, 349526, 262144, 209716, 174763, 149797, 131072, 116509, 104858,
+    95326,  87382,   80660,  74899,  69906,  65536,  61681,  58255,  55189,  52429,  49933,
+    47663,  45591,   43691,  41944,  40330,  38837,  37450,  36158,  34953,  33826,  32768,
+    31776,  30841,   29960,  29128,  28340,  27595,  26887,  26215,  25576,  24967,  24386,
+    23832,  23302,   22796,  22311,  21846,  21400,  20972,  20561,  20165,  19785,  19419,
+    19066,  18725,   18397,  18079,  17773,  17477,  17190,  16913,  16645,  16384};
+__device__ __forceinline__ int tf_div(int n, int d) {
+  return (d <= 64 && n < 4096) ? static_cast<int>((static_cast<uint32_t>(n) * tf_inv20[d]) >> 20)
+                               : n / d;
+}
+
 // (row, chunk) walk of a [rows][F4 chunks] tile by the 512 threads of a group without a
 // division per element: when F4 divides the group size a thread keeps its chunk
 struct RowWalk {
   int v, c, dv, dc;
   bool fast;
   __device__ __forceinline__ RowWalk(int tid, int F4) {
-    fast = (TF_GROUP % F4) == 0;
-    if (fast) {
-      v = tid / F4;
-      c = tid - v * F4;
-      dv = TF_GROUP / F4;
-      dc = 0;
-    } else {
-      v = tid / F4;
-      c = tid - v * F4;
-      dv = TF_GROUP / F4;
-      dc = TF_GROUP - dv * F4;
-    }
+    v = tf_div(tid, F4);
+    c = tid - v * F4;
+    dv = tf_div(TF_GROUP, F4);
+    dc = TF_GROUP - dv * F4;
+    fast = dc == 0;
   }
   __device__ __forceinline__ void next(int F4) {
     v += dv;
@@ -211,7 +220,7 @@ __device__ __forceinline__ void tf_load_rows(int tid, float* dst, int pitch,
   } else {
     const int Fp = F4 * 4;
     for (int i = tid; i < rows * Fp; i += TF_GROUP) {
-      const int v = i / Fp, f = i - v * Fp;
+      const int v = tf_div(i, Fp), f = i - v * Fp;
       dst[v * pitch + f] = f < F ? __ldg(src + static_cast<size_t>(v) * F + f) : 0.f;
     }
   }
@@ -368,7 +377,7 @@ __device__ __forceinline__ void tf_gemm(int tid, float* C, int pc, const float* 
   const int N4 = ((N + 3) >> 2) << 2;
   const int K4 = K >> 2;
   for (int it = warp; it < nvg * nnb; it += TF_GWARPS) {
-    const int nb = it / nvg, vg = it - nb * nvg;
+    const int nb = tf_div(it, nvg), vg = it - nb * nvg;
     const int pos = vg * 32 + lane;
     const bool live = pos < rows;
     const int vv = live ? pos : rows - 1;
@@ -446,7 +455,7 @@ __device__ __forceinline__ void tf_gemm_nt(int tid, float* C, int pc, const floa
   const int N4 = ((N + 3) >> 2) << 2;
   const int K4 = K >> 2;
   for (int it = warp; it < nvg * nnb; it += TF_GWARPS) {
-    const int nb = it / nvg, vg = it - nb * nvg;
+    const int nb = tf_div(it, nvg), vg = it - nb * nvg;
     const int pos = vg * 32 + lane;
     const bool live = pos < rows;
     const int vv = list_s != nullptr ? list_s[live ? pos : rows - 1] : (live ? pos : rows - 1);
@@ -507,7 +516,7 @@ __device__ __forceinline__ void tf_gemm2(int tid, float* C, int pc, const float*
   const int nrg = (rows + 63) >> 6, nnb = (N + 3) >> 2;
   const int K4 = K >> 2;
   for (int it = warp; it < nrg * nnb; it += TF_GWARPS) {
-    const int nb = it / nrg, rg = it - nb * nrg;
+    const int nb = tf_div(it, nrg), rg = it - nb * nrg;
     const int v0 = rg * 64 + lane, v1 = v0 + 32;
     const bool live0 = v0 < rows, live1 = v1 < rows;
     const float* A0 = A + (live0 ? v0 : rows - 1) * pa;
@@ -569,7 +578,7 @@ __device__ __forceinline__ void tf_gemm_nt2(int tid, float* C, int pc, const flo
   if (busy_warps > TF_GWARPS / 2) busy_warps = 0;
   for (int it = warp >= busy_warps ? warp - busy_warps : nrg * nnb; it < nrg * nnb;
        it += TF_GWARPS - busy_warps) {
-    const int nb = it / nrg, rg = it - nb * nrg;
+    const int nb = tf_div(it, nrg), rg = it - nb * nrg;
     const int v0 = rg * 64 + lane, v1 = v0 + 32;
     const bool live0 = v0 < rows, live1 = v1 < rows;
     const float* A0 = A + (live0 ? v0 : rows - 1) * pa;
@@ -899,7 +908,7 @@ __device__ __forceinline__ void tf_edge_sum(int tid, float* ae, int pe,
                                             const int32_t* __restrict__ eid, const int* ptr_s,
                                             int e0, int rows) {
   for (int i = tid; i < rows * Fe; i += TF_GROUP) {
-    const int v = i / Fe, f = i - v * Fe;
+    const int v = tf_div(i, Fe), f = i - v * Fe;
     const int b = ptr_s[v], e1 = ptr_s[v + 1];
     float s = 0.f;
     for (int e = b; e < e1; e += 8) {
@@ -926,7 +935,7 @@ __device__ __forceinline__ void tf_append_edges(int tid, float* A, int pa, int F
   const int w = Kp - Fi;
   if (w == 0) return;
   for (int i = tid; i < rows * w; i += TF_GROUP) {
-    const int v = i / w, j = i - v * w;
+    const int v = tf_div(i, w), j = i - v * w;
     A[(inv_s != nullptr ? inv_s[v] : v) * pa + Fi + j] =
         j < Fe ? ae[v * pe + j] * (1.f / static_cast<float>(bkt_s[v] + 1)) : 0.f;
   }
@@ -1097,7 +1106,7 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
       tf_sync(grp);
       if (a.Ae != nullptr)
         for (int i = tid; i < tv.rows * a.nef; i += TF_GROUP) {
-          const int v = i / a.nef, f = i - v * a.nef;
+          const int v = tf_div(i, a.nef), f = i - v * a.nef;
           a.Ae[static_cast<size_t>(tv.r0) * a.nef + i] = ae[v * L.pE + f];
         }
     } else {
@@ -1146,7 +1155,7 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
         int g = 0, o = 0;
         float s = 0.f;
         if (live) {
-          const int gl = idx / a.no;
+          const int gl = tf_div(idx, a.no);
           o = idx - gl * a.no;
           g = tv.g_begin + gl;
           const int v0 = __ldg(a.voff + g) - tv.r0, v1 = __ldg(a.voff + g + 1) - tv.r0;
@@ -1242,7 +1251,7 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
     }
     // edge-feature sums saved by the forward
     for (int i = tid; i < tv.rows * a.nef; i += TF_GROUP) {
-      const int v = i / a.nef, f = i - v * a.nef;
+      const int v = tf_div(i, a.nef), f = i - v * a.nef;
       ae[v * L.pE + f] = __ldg(a.Ae + static_cast<size_t>(tv.r0) * a.nef + i);
     }
     float* X = gsm + L.buf[0];  // z_t, then z_{t-1}

@@ -226,3 +226,21 @@ def test_lr_decay_mirrors_follow_the_reference_formulas():
     assert exp_lr_decay_type().decay_rate == 0.9 and step_lr_decay_type().decay_steps == 100
     i = inv_lr_decay_type(0.01, 2.0)
     assert abs(i.get_lr(0.1, 10) - 0.1 / 1.1 ** 2) <= 1e-8
+
+
+def test_tile_kernel_reciprocal_division_table_is_exact():
+    """csrc/tile_fma.cu replaces floor(n / d) by (n * tf_inv20[d]) >> 20 for n < 4096, d <= 64:
+    the table in the source must be ceil(2^20 / d) and the formula exact over the whole range
+    (and the product must fit 32 bits)."""
+    import re
+    src = open(os.path.join(ROOT, "athena_b200", "csrc", "tile_fma.cu")).read()
+    m = re.search(r"tf_inv20\[65\] = \{(.*?)\};", src, re.S)
+    assert m is not None
+    table = [int(x) for x in m.group(1).replace("\n", " ").split(",")]
+    assert len(table) == 65
+    n = np.arange(4096, dtype=np.uint64)
+    for d in range(1, 65):
+        assert table[d] == (2 ** 20 + d - 1) // d
+        prod = n * np.uint64(table[d])
+        assert int(prod.max()) < 2 ** 32
+        assert np.array_equal(prod >> np.uint64(20), n // np.uint64(d))
