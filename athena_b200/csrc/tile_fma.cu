@@ -75,7 +75,7 @@ constexpr int TF_MAX_T = 16;
 constexpr int TF_NB = 8;                        // outputs per thread in the products
 constexpr int TF_IDX = TILE_ENTRIES + 16;       // tile-local neighbour bytes
 constexpr int TF_OUTS = 2048;                   // per-group [graphs x outputs] readout sums
-constexpr int TF_INTS = 132 + 132 + 260 + 128 + 16;
+constexpr int TF_INTS = 132 + 132 + 260 + 128 + 16 + 128;  // ptr, cptr, seg, vg, red, rd
 
 // row pitch (floats) of a shared-memory tile: a multiple of 4 whose quarter is odd, so that
 // row-per-lane LDS.128 / STS.128 of a quarter warp cover all 32 banks
@@ -324,7 +324,7 @@ template <bool COEF>
 __device__ __forceinline__ void tf_gather(int tid, float* dst, int dpitch, const float* src,
                                           int spitch, int F4, const int* ptr_s,
                                           const uint8_t* idx_s, const float* coef_s, int rows,
-                                          const uint8_t* bkt_s, const uint8_t* inv_s = nullptr) {
+                                          const float* rd_s, const uint8_t* inv_s = nullptr) {
   RowWalk w(tid, F4);
   for (; w.v < rows; w.next(F4)) {
     const int v = w.v, c = w.c;
@@ -347,9 +347,10 @@ __device__ __forceinline__ void tf_gather(int tid, float* dst, int dpitch, const
         acc.w += x.w;
       }
     }
-    if (bkt_s != nullptr) {
-      // A(:,v) / real(d), _sub_duvenaud.f90:208 (as a product with the rounded reciprocal)
-      const float rd = 1.f / static_cast<float>(bkt_s[v] + 1);
+    if (rd_s != nullptr) {
+      // A(:,v) / real(d), _sub_duvenaud.f90:208 (as a product with the rounded reciprocal, which
+      // the tile prologue leaves in rd_s: one division per vertex and tile)
+      const float rd = rd_s[v];
       acc.x *= rd;
       acc.y *= rd;
       acc.z *= rd;
@@ -929,7 +930,7 @@ __device__ __forceinline__ void tf_edge_sum(int tid, float* ae, int pe,
 
 // A[v][Fi .. Fi+Fe) = Ae[v][:] / d ; A[v][K .. 4*ceil(K/4)) = 0
 __device__ __forceinline__ void tf_append_edges(int tid, float* A, int pa, int Fi, int Fe,
-                                                const float* ae, int pe, const uint8_t* bkt_s,
+                                                const float* ae, int pe, const float* rd_s,
                                                 int rows, const uint8_t* inv_s = nullptr) {
   const int K = Fi + Fe, Kp = ((K + 3) >> 2) << 2;
   const int w = Kp - Fi;
@@ -937,7 +938,7 @@ __device__ __forceinline__ void tf_append_edges(int tid, float* A, int pa, int F
   for (int i = tid; i < rows * w; i += TF_GROUP) {
     const int v = tf_div(i, w), j = i - v * w;
     A[(inv_s != nullptr ? inv_s[v] : v) * pa + Fi + j] =
-        j < Fe ? ae[v * pe + j] * (1.f / static_cast<float>(bkt_s[v] + 1)) : 0.f;
+        j < Fe ? ae[v * pe + j] * rd_s[v] : 0.f;
   }
 }
 
@@ -1069,6 +1070,7 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
   uint8_t* bkt_s = idx_raw + 2 * TF_IDX;
   uint8_t* list_s = bkt_s + 128;
   int* seg_s = ptr_s + 132 + 132;
+  float* rd_s = reinterpret_cast<float*>(ptr_s + 132 + 132 + 260 + 128 + 16);  // 1 / d per vertex
   float* ae = gsm + L.ae;
   float* outs = gsm + L.outs;
   const int P = L.P;
@@ -1094,8 +1096,11 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
     float* zout = gsm + L.buf[2];
     tf_load_rows(tid, xin, P, a.X + static_cast<size_t>(tv.r0) * a.nvf[0], tv.rows, a.nvf[0]);
     const uint8_t* idx_s = tf_struct_put(tid, sr, ptr_s, idx_raw, tv.rows, tv.e0, tv.ents);
-    if (tid < tv.rows)
-      bkt_s[tid] = static_cast<uint8_t>(max(a.min_deg, min(deg, a.max_deg)) - a.min_deg);
+    if (tid < tv.rows) {
+      const int bk = max(a.min_deg, min(deg, a.max_deg)) - a.min_deg;
+      bkt_s[tid] = static_cast<uint8_t>(bk);
+      rd_s[tid] = 1.f / static_cast<float>(bk + 1);
+    }
     tf_sync(grp);
     TFT();
     // A is built with its rows grouped by degree bucket (the barriers below order this before
@@ -1120,10 +1125,10 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_fwd(const DuvArgs
       const int Fi = a.nvf[t - 1], Fo = a.nvf[t], K = Fi + a.nef;
       // A = [ sum_w in(:,ja(1,w)) ; sum_w E(:,ja(2,w)) ] / d   (propagate; the division belongs
       // to duvenaud_update)
-      tf_gather<false>(tid, AY, P, xin, P, (Fi + 3) >> 2, ptr_s, idx_s, nullptr, tv.rows, bkt_s,
+      tf_gather<false>(tid, AY, P, xin, P, (Fi + 3) >> 2, ptr_s, idx_s, nullptr, tv.rows, rd_s,
                        inv_s);
       if (Fi & 3) tf_sync(grp);  // else the two passes write disjoint 16-byte chunks
-      tf_append_edges(tid, AY, P, Fi, a.nef, ae, L.pE, bkt_s, tv.rows, inv_s);
+      tf_append_edges(tid, AY, P, Fi, a.nef, ae, L.pE, rd_s, tv.rows, inv_s);
       tf_sync(grp);
       TFT();
       // z = act( W_d(v) . A(:,v) ), rows of z back in vertex order
@@ -1218,6 +1223,7 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
   int* ptr_s = reinterpret_cast<int*>(gsm + L.ints);
   int* cptr_s = ptr_s + 132;
   int* seg_s = cptr_s + 132;
+  float* rd_s = reinterpret_cast<float*>(ptr_s + 132 + 132 + 260 + 128 + 16);  // 1 / d per vertex
   int* vg_s = seg_s + 260;
   uint8_t* idx_raw = reinterpret_cast<uint8_t*>(gsm + L.bytes);
   uint8_t* cidx_raw = idx_raw + TF_IDX;
@@ -1263,7 +1269,9 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
     const uint8_t* idx_s = tf_struct_put(tid, sr, ptr_s, idx_raw, tv.rows, tv.e0, tv.ents);
     const uint8_t* cidx_s = tf_struct_put(tid, sc, cptr_s, cidx_raw, tv.rows, tv.e0, tv.ents);
     if (tid < tv.rows) {
-      bkt_s[tid] = static_cast<uint8_t>(max(a.min_deg, min(deg, a.max_deg)) - a.min_deg);
+      const int bk = max(a.min_deg, min(deg, a.max_deg)) - a.min_deg;
+      bkt_s[tid] = static_cast<uint8_t>(bk);
+      rd_s[tid] = 1.f / static_cast<float>(bk + 1);
       vg_s[tid] = vgv;
     }
     tf_sync(grp);
@@ -1331,9 +1339,9 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
       }
       tf_sync(grp);
       TFT();
-      tf_gather<false>(tid, Y, P, X, P, (Fi + 3) >> 2, ptr_s, idx_s, nullptr, tv.rows, bkt_s);
+      tf_gather<false>(tid, Y, P, X, P, (Fi + 3) >> 2, ptr_s, idx_s, nullptr, tv.rows, rd_s);
       if (Fi & 3) tf_sync(grp);  // else the two passes write disjoint 16-byte chunks
-      tf_append_edges(tid, Y, P, Fi, a.nef, ae, L.pE, bkt_s, tv.rows);
+      tf_append_edges(tid, Y, P, Fi, a.nef, ae, L.pE, rd_s, tv.rows);
       tf_sync(grp);
       TFT();
       // 5. dW_{t,d}(o,k) += sum_{v in bucket d} gz(o,v) A(k,v)      (A already divided by d)
@@ -1344,9 +1352,9 @@ __global__ void __launch_bounds__(TF_GROUP * TF_MAXG, 1) k_duv_bwd(const DuvArgs
         //    X keeps z_{t-1}, which is the next iteration's z_t (no second load of the tile)
         tf_sync(grp);
         TFT();
-        const uint8_t* bk = bkt_s;
+        const float* rd = rd_s;
         tf_gemm_nt(tid, Y, P, Z, P, Fo, sm + L.w[i], L.pw[i], L.gs[i], bkt_s, tv.rows, Fi,
-                   [bk](int v, int, float s) { return s * (1.f / static_cast<float>(bk[v] + 1)); },
+                   [rd](int v, int, float s) { return s * rd[v]; },
                    list_s);
         tf_sync(grp);
         TFT();
