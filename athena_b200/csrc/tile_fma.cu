@@ -991,9 +991,9 @@ __device__ __forceinline__ void duv_stage_weights(float* sm, const DuvArgs& a) {
     const int rows_w = tf_up(K, TF_NB);  // rows per bucket block (pad rows are zero)
     if (nt % pw == 0) {
       // a thread keeps its column: one division per row instead of two per element
-      const int n = threadIdx.x % pw;
-      for (int row = threadIdx.x / pw; row < D * rows_w; row += nt / pw) {
-        const int d = row / rows_w, k = row - d * rows_w;
+      const int row0 = tf_div(threadIdx.x, pw), n = threadIdx.x - row0 * pw;
+      for (int row = row0; row < D * rows_w; row += nt / pw) {
+        const int d = tf_div(row, rows_w), k = row - d * rows_w;
         float* dst = ws + d * gs + k * pw + n;
         if (k < K && n < Fo)
           tf_cp_async4(dst, Wg + (static_cast<size_t>(d) * K + k) * Fo + n);
@@ -1002,8 +1002,8 @@ __device__ __forceinline__ void duv_stage_weights(float* sm, const DuvArgs& a) {
       }
     } else {
       for (int idx = threadIdx.x; idx < D * rows_w * pw; idx += nt) {
-        const int row = idx / pw, n = idx - row * pw;
-        const int d = row / rows_w, k = row - d * rows_w;
+        const int row = tf_div(idx, pw), n = idx - row * pw;
+        const int d = tf_div(row, rows_w), k = row - d * rows_w;
         float* dst = ws + d * gs + k * pw + n;
         if (k < K && n < Fo)
           tf_cp_async4(dst, Wg + (static_cast<size_t>(d) * K + k) * Fo + n);
@@ -1020,7 +1020,7 @@ __device__ __forceinline__ void duv_stage_weights(float* sm, const DuvArgs& a) {
     float* rs = sm + a.lay.r[i];
     const int pr = a.lay.pr[i];
     for (int idx = threadIdx.x; idx < tf_up(Fo, TF_NB) * pr; idx += nt) {
-      const int f = idx / pr, n = idx - f * pr;
+      const int f = tf_div(idx, pr), n = idx - f * pr;
       if (f < Fo && n < a.no)
         tf_cp_async4(rs + idx, Rg + static_cast<size_t>(f) * a.no + n);
       else
