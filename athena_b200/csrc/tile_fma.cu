@@ -772,7 +772,27 @@ __device__ __forceinline__ void tf_act_bwd_rows(int tid, int act, float* Y, int 
   const bool live = v < rows;
   float* y = Y + (live ? v : 0) * py;
   const float* g = grow(live ? v : 0);
-  if (act == ATHENA_ACT_SOFTMAX) {
+  if (act == ATHENA_ACT_SOFTMAX && N <= 8 * TF_LPR) {
+    // rows of up to 32 columns stay in registers between the two passes (S and the upstream
+    // gradient row are read once)
+    float sv[8], gv[8];
+    float dot = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int n = h + TF_LPR * q;
+      const bool in = live && n < N;
+      sv[q] = in ? y[n] : 0.f;
+      gv[q] = in ? g[n] : 0.f;  // (generic: the Kipf reverse kernel keeps this row in shared memory)
+      dot += sv[q] * gv[q];
+    }
+#pragma unroll
+    for (int o = 1; o < TF_LPR; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int n = h + TF_LPR * q;
+      if (live && n < N) y[n] = sv[q] * gv[q] - sv[q] * dot;
+    }
+  } else if (act == ATHENA_ACT_SOFTMAX) {
     float dot = 0.f;
     if (live)
       for (int n = h; n < N; n += TF_LPR) dot += y[n] * g[n];
