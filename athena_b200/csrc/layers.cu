@@ -230,8 +230,8 @@ static int duvenaud_forward(Layer* L, Batch* b, const float* x, const float* e,
   const bool swish = L->act == ATHENA_ACT_SWISH;
   if (!swish &&
       tile_duv_supported(b, L->T, L->nvf.data(), L->nef, L->max_deg - L->min_deg + 1, L->n_out)) {
-    // every time step and the readout of the whole layer in ONE launch (tile_fma.cu); only
-    // z_t is kept for the reverse sweep
+    // every time step and the readout of the whole layer in ONE launch (tile_fma.cu); z_t, the
+    // readouts S_t and the per-vertex edge-feature sums are kept for the reverse sweep
     ATH_REQUIRE(L->nef == 0 || e != nullptr, ATHENA_ERR_ARG,
                 "duvenaud forward: edge_features is null");
     float* Z[16];
